@@ -1,0 +1,682 @@
+"""CPU oracle for the RJ-MCMC proposal-scoring hot path of dyban (charx7/DynamicBayesianNetworks).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under `dynamicbayesiannetworks_b200/` imports this module; only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may use it,
+and only as the checker / the timed CPU baseline.  The product path is the CUDA library.
+
+What it is: a NumPy FP64 restatement of the reference's algorithm for the path, function by function, each
+citing the reference file:line it follows (paths relative to /root/reference/src/dyban/).  Two forms of the
+scoring arithmetic are provided:
+
+  * `log_ml_literal`  — the reference's own T_h x T_h formulation (C_h = I + w X_h X_h^T, det and inverse
+                        per segment) with only the overflow-prone scalars moved to the log domain
+                        (lgamma for log(gamma()), -(T/2) ln(pi) for log(pi**(-T/2)), slogdet for
+                        log(det**0.5)).  O(T_h^3); the literal CPU cost of the reference.
+  * `log_ml`          — the same quantity on k x k sufficient statistics G_h = X_h^T X_h, g_h = X_h^T y_h,
+                        s_h = y_h^T y_h (matrix-determinant lemma + Woodbury).  The
+                        statistics are accumulated directly from the data rows of each segment (NOT from
+                        prefix sums), so it is an independent check of the GPU's prefix-difference layout.
+
+Parity pinning: PINNED.  `tests/test_oracle_golden.py` checks every function here against outputs of the
+unmodified reference run in the build container (`tests/golden/make_golden.py`, fixtures `tests/golden/*.npz`):
+log-ML / beta-tilde / mu-sampler / prior known-answer vectors on yeast (N=33), mTOR (N=119) and synthetic
+N=199 / N=340 series, and full replayed chains (every Gibbs parameter, every log-ML, every accept flag, pi and
+tau after every iteration) for h-dbn, nh-dbn, seq-dbn and glob-dbn.  The reference's own unit tests pin
+nothing for this path, and its log-ML overflows for T >= 344 (marginalLikelihood.py:116),
+so beyond that size this oracle stands on the algebraic identity plus the `log_ml` == `log_ml_literal` check.
+"""
+import math
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------
+# method table: the per-method constants the reference hard-codes
+# ------------------------------------------------------------------------------------------------
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN = 0, 1, 2, 3
+METHOD_IDS = {
+    'h_dbn': H_DBN, 'h-dbn': H_DBN,
+    'varying_nh_dbn': NH_DBN, 'nh-dbn': NH_DBN,
+    'seq_coup_nh_dbn': SEQ_DBN, 'seq-dbn': SEQ_DBN,
+    'glob_coup_nh_dbn': GLOB_DBN, 'glob-dbn': GLOB_DBN,
+}
+
+
+def method_constants(method, N):
+    """Constructor arguments and hyper-parameters per method.
+
+    network.py:157-163 (nh: num_samples=N), :193-197 (h: N+1), :213-219 (seq: N-1), :237-243 (glob: N);
+    sigma^2 ~ IG(0.005,0.005) for nh/seq (bayesianPwLinearRegression.py:69-70,
+    seqCoupledBayesianPwLinReg.py:44-45) and IG(0.01,0.01) for h/glob (bayesianLinearRegression.py:110-111,
+    globCoupBayesianPwLinReg.py:43-44); lambda^2, delta^2 ~ IG(2,0.2) everywhere.
+    Returns dict(T_ml, T_sigma, num_samples, a_sig, b_sig, a_lam, b_lam, a_del, b_del).
+    """
+    m = METHOD_IDS[method] if isinstance(method, str) else method
+    c = dict(a_lam=2.0, b_lam=0.2, a_del=2.0, b_del=0.2)
+    if m == H_DBN:
+        # fit(): T = self.num_samples = N+1 (bayesianLinearRegression.py:96); ML gets num_samples-1 = N (:134-135)
+        c.update(T_ml=N, T_sigma=N + 1, num_samples=N, a_sig=0.01, b_sig=0.01)
+    elif m == NH_DBN:
+        c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.005, b_sig=0.005)
+    elif m == SEQ_DBN:
+        c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
+    elif m == GLOB_DBN:
+        c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.01, b_sig=0.01)
+    else:
+        raise ValueError(method)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 — data slicing (network.py:54-141, utils.py:128-269)
+# ------------------------------------------------------------------------------------------------
+def lagged_matrices(data_list):
+    """Lag-1 feature/response matrices shared by all nodes.
+
+    network.py:105-118: features of a segment are rows [:len-1]; :126-130: responses are rows [1:len];
+    segments are concatenated.  Returns (X[N, n], Y[N, n]); node i regresses Y[:, i] on X[:, j != i].
+    """
+    X = np.concatenate([np.asarray(s, dtype=np.float64)[:-1, :] for s in data_list], axis=0)
+    Y = np.concatenate([np.asarray(s, dtype=np.float64)[1:, :] for s in data_list], axis=0)
+    return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def segment_bounds(tau, N):
+    """0-based [a, b) row ranges of the segments defined by the changepoint list `tau`.
+
+    utils.py:162-224 / :226-269: segment h covers rows [c_{h-1}-1, c_h-1) with c_{-1}=1; the last entry of tau is
+    the pseudo changepoint (N+2), reduced by one for X (utils.py:179) and clipped by slicing for y (:262), i.e. the
+    last segment ends at N.
+    """
+    bounds = []
+    lo = 1
+    for h, c in enumerate(tau):
+        a = lo - 1
+        b = N if h == len(tau) - 1 else c - 1
+        bounds.append((a, b))
+        lo = c
+    return bounds
+
+
+def design_columns(pi):
+    """Design-matrix column order = intercept, then parents sorted by label (utils.py:202-204)."""
+    return sorted(int(p) for p in pi)
+
+
+def segment_design(X, y, pi, tau):
+    """Per-segment design matrices [1, X_pi] and responses, as the reference's constructNdArray builds them."""
+    cols = design_columns(pi)
+    N = X.shape[0]
+    Xs, ys = [], []
+    for a, b in segment_bounds(tau, N):
+        D = np.ones((b - a, 1 + len(cols)))
+        if cols:
+            D[:, 1:] = X[a:b, cols]
+        Xs.append(D)
+        ys.append(y[a:b])
+    return Xs, ys
+
+
+def segment_stats(X, y, pi, tau):
+    """(G_h, g_h, s_h, T_h) per segment, accumulated directly from the rows."""
+    Xs, ys = segment_design(X, y, pi, tau)
+    return [(D.T @ D, D.T @ yy, float(yy @ yy), D.shape[0]) for D, yy in zip(Xs, ys)]
+
+
+# ------------------------------------------------------------------------------------------------
+# a2 / a3 — marginal likelihood
+# ------------------------------------------------------------------------------------------------
+def _omega(h, lam, dlt, seq):
+    # marginalLikelihood.py:104-107: delta^2 replaces lambda^2 for idx > 0 when method == 'seq-coup'
+    return dlt if (seq and h > 0) else lam
+
+
+def log_ml_literal(Xs, ys, mus, alpha, beta, lam, T, seq=False, dlt=None):
+    """marginalLikelihood.py:91-150 in its own T_h x T_h form; `mus` is a list (one prior mean per segment)."""
+    acc_logdet = 0.0
+    acc_q = 0.0
+    for h, (D, yy) in enumerate(zip(Xs, ys)):
+        w = _omega(h, lam, dlt, seq)
+        C = np.eye(D.shape[0]) + w * (D @ D.T)                      # :104-107
+        sign, ld = np.linalg.slogdet(C)                             # :110-112 (log(det ** 0.5))
+        acc_logdet += 0.5 * ld
+        r = yy.reshape(-1, 1) - D @ np.asarray(mus[h], dtype=float).reshape(-1, 1)   # :133
+        acc_q += float((r.T @ np.linalg.solve(C, r)).item())               # :137-144
+    el1 = math.lgamma(T / 2 + alpha) - math.lgamma(alpha)           # :116
+    el2 = -(T / 2) * math.log(math.pi) + alpha * math.log(2 * beta) - acc_logdet   # :118
+    el3 = -(T / 2 + alpha) * math.log(2 * beta + acc_q)             # :146
+    return el1 + el2 + el3
+
+
+def seg_quadratic(G, g, s, mu, w):
+    """Returns (ln det(I + w X X^T), r^T C^-1 r) for one segment from k x k statistics.
+
+    ln det C = ln det(I_k + w G) (matrix determinant lemma), r^T C^-1 r = rho - w v^T A^-1 v with
+    v = g - G mu, rho = s - 2 mu^T g + mu^T G mu, A = I_k + w G (Woodbury) — SURVEY.md Appendix A.
+    """
+    k = G.shape[0]
+    A = np.eye(k) + w * G
+    L = np.linalg.cholesky(A)
+    logdet = 2.0 * float(np.sum(np.log(np.diag(L))))
+    mu = np.asarray(mu, dtype=float).ravel()
+    v = g - G @ mu
+    rho = s - 2.0 * float(mu @ g) + float(mu @ G @ mu)
+    z = np.linalg.solve(L, v)
+    return logdet, rho - w * float(z @ z)
+
+
+def log_ml(stats, mus, alpha, beta, lam, T, seq=False, dlt=None):
+    """marginalLikelihood.py:91-150 on sufficient statistics (the form the GPU kernels evaluate)."""
+    acc_logdet = 0.0
+    acc_q = 0.0
+    for h, (G, g, s, _) in enumerate(stats):
+        ld, q = seg_quadratic(G, g, s, mus[h], _omega(h, lam, dlt, seq))
+        acc_logdet += 0.5 * ld
+        acc_q += q
+    return (math.lgamma(T / 2 + alpha) - math.lgamma(alpha) - (T / 2) * math.log(math.pi)
+            + alpha * math.log(2 * beta) - acc_logdet - (T / 2 + alpha) * math.log(2 * beta + acc_q))
+
+
+def log_ml_h(stats, alpha, beta, lam, T):
+    """log of calculateMarginalLikelihood (marginalLikelihood.py:152-166): one segment, mu = 0."""
+    k = stats[0][0].shape[0]
+    return log_ml(stats[:1], [np.zeros(k)], alpha, beta, lam, T)
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 — priors
+# ------------------------------------------------------------------------------------------------
+CP_PRIOR_P = 0.125
+
+
+def log_cp_prior(tau):
+    """log of calculateChangePointsSetPrior (priors.py:4-46); -inf if more than 9 entries (:23-24)."""
+    cc = [1] + list(tau)
+    if len(cc) > 10:
+        return -math.inf
+    p = CP_PRIOR_P
+    out = ((cc[-1] - 1) - cc[-2]) * math.log(1 - p)                 # :28-31
+    for idx in range(len(tau) - 1):                                 # :35-42
+        out += math.log(p) + (cc[idx + 1] - cc[idx] - 1) * math.log(1 - p)
+    return out
+
+
+def pi_prior(pi, F, fan_in):
+    """calculateFeatureSetPriorProb (priors.py:48-68): uniform over sets of size <= fan_in, else 0."""
+    if len(pi) > fan_in:
+        return 0.0
+    return 1.0 / sum(math.comb(F, i) for i in range(fan_in + 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# a8 — sequentially coupled prior means
+# ------------------------------------------------------------------------------------------------
+def beta_tilde(stats, lam, dlt):
+    """betaTildeSampler (samplers.py:4-54) on sufficient statistics.
+
+    bt[0] = mu (zeros, :47-48); bt[1] = (I/lam + G_1)^-1 g_1 from segment 1's OWN data (:36-39);
+    bt[h>=2] = (I/dlt + G_{h-1})^-1 (bt[h-2]/dlt + g_{h-1}) (:40-46, note the idx-2).
+    """
+    k = stats[0][0].shape[0]
+    bt = []
+    for h in range(len(stats)):
+        if h == 0:
+            bt.append(np.zeros(k))
+        elif h == 1:
+            G, g = stats[1][0], stats[1][1]
+            bt.append(np.linalg.solve(np.eye(k) / lam + G, g))
+        else:
+            G, g = stats[h - 1][0], stats[h - 1][1]
+            bt.append(np.linalg.solve(np.eye(k) / dlt + G, bt[h - 2] / dlt + g))
+    return bt
+
+
+# ------------------------------------------------------------------------------------------------
+# a9 — global-coupling mean sampler
+# ------------------------------------------------------------------------------------------------
+def mu_posterior(stats, mu_in, sigma2, lam):
+    """Mean and covariance of the MVN that muSampler draws from (samplers.py:307-351).
+
+    X_h^T (s2 C_h)^-1 X_h = A_h^-1 G_h / s2 and X_h^T (s2 C_h)^-1 y_h = A_h^-1 g_h / s2 with A_h = I + lam G_h;
+    Sigma = (I + sum_h ...)^-1 (:324); mean = Sigma (sum_h ... + mu_in) (:336-337: the INPUT mu is added).
+    Returns (mean, Sigma, precision).
+    """
+    k = stats[0][0].shape[0]
+    Q = np.eye(k)
+    m = np.asarray(mu_in, dtype=float).ravel().copy()
+    for G, g, _, _ in stats:
+        A = np.eye(k) + lam * G
+        Q = Q + np.linalg.solve(A, G) / sigma2
+        m = m + np.linalg.solve(A, g) / sigma2
+    Sigma = np.linalg.inv(Q)
+    return Sigma @ m, Sigma, Q
+
+
+def mvn_logpdf_prec(x, mean, Q):
+    """log N(x; mean, Q^-1) (what scipy.stats.multivariate_normal.pdf returns, logged; moves.py:106-116)."""
+    x = np.asarray(x, dtype=float).ravel()
+    d = x - np.asarray(mean, dtype=float).ravel()
+    L = np.linalg.cholesky(Q)
+    logdetQ = 2.0 * float(np.sum(np.log(np.diag(L))))
+    return -0.5 * (x.size * math.log(2 * math.pi) - logdetQ + float(d @ Q @ d))
+
+
+def std_normal_logpdf(x):
+    """log N(x; 0, I) — the mu prior in moves.py:102-109, :501-508."""
+    x = np.asarray(x, dtype=float).ravel()
+    return -0.5 * (x.size * math.log(2 * math.pi) + float(x @ x))
+
+
+# ------------------------------------------------------------------------------------------------
+# a10-a12 — Gibbs full conditionals (parameters only; the draw itself comes from the draw source)
+# ------------------------------------------------------------------------------------------------
+def sigma2_params(stats, mus, lam, a_sig, b_sig, T, seq=False, dlt=None):
+    """(shape, rate) of the Gamma whose reciprocal is sigma^2.
+
+    samplers.py:103-127 (nh/glob), :56-88 (seq: beta-tilde means, delta^2 for h>0), :129-143 (h):
+    shape = a + T/2, rate = b + 0.5 sum_h r_h^T C_h^-1 r_h.
+    """
+    q = 0.0
+    for h, (G, g, s, _) in enumerate(stats):
+        q += seg_quadratic(G, g, s, mus[h], _omega(h, lam, dlt, seq))[1]
+    return a_sig + T / 2, b_sig + 0.5 * q
+
+
+def beta_params(stats, mus, lam, sigma2, seq=False, dlt=None):
+    """Per-segment (mean, cov) passed to np.random.multivariate_normal (samplers.py:207-218).
+
+    mean = (I/w + G)^-1 (mu/w + g), cov = sigma2 (I/w + G)^-1, with w = lambda^2, or delta^2 for h > 0 in the
+    sequentially coupled model (samplers.py:158-163) whose prior means are the beta-tildes (:156).
+    """
+    out = []
+    for h, (G, g, _, _) in enumerate(stats):
+        w = _omega(h, lam, dlt, seq)
+        k = G.shape[0]
+        P = np.eye(k) / w + G
+        Pinv = np.linalg.inv(P)
+        out.append((Pinv @ (np.asarray(mus[h], dtype=float).ravel() / w + g), sigma2 * Pinv))
+    return out
+
+
+def lambda2_params(method, betas, mu, sigma2, a_lam, b_lam):
+    """(shape, rate) for lambda^2.
+
+    h:       samplers.py:296-305  shape a + k/2,        rate b + |beta - mu|^2 / (2 sigma2)
+    nh/glob: samplers.py:265-294  shape a + S k / 2,    rate b + 0.5 sum_h |beta_h - mu|^2 / sigma2
+    seq:     samplers.py:249-263  shape a + (k + 1)/2,  rate b + beta_0^T beta_0 / (2 sigma2)
+    """
+    k = len(betas[0])
+    mu = np.asarray(mu, dtype=float).ravel()
+    if method == H_DBN:
+        d = betas[0] - mu
+        return a_lam + k / 2, b_lam + 0.5 * float(d @ d) / sigma2
+    if method == SEQ_DBN:
+        return a_lam + (k + 1) / 2, b_lam + 0.5 * float(betas[0] @ betas[0]) / sigma2
+    acc = 0.0
+    for b in betas:
+        d = b - mu
+        acc += float(d @ d) / sigma2
+    return a_lam + len(betas) * k / 2, b_lam + 0.5 * acc
+
+
+def delta2_params(betas, bt, sigma2, a_del, b_del):
+    """(shape, rate) for delta^2 (samplers.py:220-247): beta_h is centred on bt[h-1] (:228) for h >= 1."""
+    k = len(betas[0])
+    acc = 0.0
+    for h in range(1, len(betas)):
+        d = betas[h] - bt[h - 1]
+        acc += float(d @ d)
+    return a_del + (len(betas) - 1) * k / 2, b_del + 0.5 * acc / sigma2
+
+
+# ------------------------------------------------------------------------------------------------
+# a4 / a5 — proposals (pure index manipulation; `pick(n)` returns an index in [0, n))
+# ------------------------------------------------------------------------------------------------
+ADD, DELETE, EXCHANGE = 0, 1, 2
+BIRTH, DEATH, REALLOC = 0, 1, 2
+
+
+def propose_pi(pi, move, features, fan_in, pick):
+    """addMove / deleteMove / exchangeMove (utils.py:271-323). Returns (pi_star | None, hr).
+
+    `pi` keeps the reference's order: add/exchange append (utils.py:305,323), delete returns sorted (:290).
+    `features` = the candidate parent labels (all genes but the node), ascending (np.setdiff1d sorts).
+    hr per moves.py:610-618.
+    """
+    pi = [int(p) for p in pi]
+    F = len(features)
+    if move == ADD:
+        if len(pi) > fan_in - 1:                                    # utils.py:294-295
+            return None, 0.0
+        cand = [f for f in features if f not in pi]                 # :301
+        if not cand:
+            return None, 0.0
+        star = pi + [cand[pick(len(cand))]]                         # :303-305
+        return star, (F - len(pi)) / len(star)
+    if move == DELETE:
+        if len(pi) < 1:                                             # :285-286
+            return None, 0.0
+        el = pi[pick(len(pi))]                                      # :289
+        star = sorted(p for p in pi if p != el)                     # :290
+        return star, len(pi) / (F - len(star))
+    if len(pi) < 1:                                                 # :308-309
+        return None, 0.0
+    el = pi[pick(len(pi))]                                          # :314
+    cand = [f for f in features if f not in pi]                     # :317
+    rest = sorted(p for p in pi if p != el)                         # :318
+    if not cand:
+        return None, 0.0
+    return rest + [cand[pick(len(cand))]], 1.0                      # :320-323
+
+
+def propose_tau(tau, move, num_samples, pick, glob=False):
+    """cpBirthMove / cpDeathMove / cpRellocationMove (changepointMoves.py) + validity and hr.
+
+    nh/seq: moves.py:154-175 (birth invalid when len == 10, hr = (n - |tau|)/(|tau*| - 1);
+            death hr = (|tau| - 1)/(n - |tau*|)).
+    glob:   moves.py:40-64 (birth invalid when len > 9, hr = (n - 1 - |tau|)/|tau*|; death hr = |tau|/(n - 1 - |tau*|)).
+    Returns (tau_star | None, hr).
+    """
+    tau = [int(c) for c in tau]
+    n = num_samples
+    if move == BIRTH:
+        cand = [c for c in range(2, n + 1) if c not in tau]        # changepointMoves.py:112-117
+        if not cand:
+            return None, 0.0
+        star = sorted(tau + [cand[pick(len(cand))]])                # :118-122
+        if len(star) > 9:
+            return None, 0.0
+        hr = (n - 1 - len(tau)) / len(star) if glob else (n - len(tau)) / (len(star) - 1)
+        return star, hr
+    if move == DEATH:
+        if len(tau) < 2:                                            # :81-82
+            return None, 0.0
+        star = list(tau)
+        star.pop(pick(len(tau) - 1))                                # :86-89
+        hr = len(tau) / (n - 1 - len(star)) if glob else (len(tau) - 1) / (n - len(star))
+        return star, hr
+    if len(tau) < 2:                                                # :21-22
+        return None, 0.0
+    idx = pick(len(tau) - 1)                                        # :28-30
+    last = tau[-1] - 1                                              # :26
+    left = 1 if idx == 0 else tau[idx - 1]                          # :33-37
+    right = last if idx + 1 == len(tau) - 1 else tau[idx + 1]       # :39-43
+    cand = [c for c in range(left + 1, right) if c != tau[idx]]     # :47-49
+    if not cand:                                                    # :50-51
+        return None, 0.0
+    new = cand[pick(len(cand))]                                     # :55
+    star = sorted(tau[:idx] + tau[idx + 1:-1] + [new]) + [tau[-1]]  # :56-58
+    return star, 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# draw sources
+# ------------------------------------------------------------------------------------------------
+class ReplayDraws:
+    """Feeds a recorded reference run (tests/golden/chain_*.npz) back, one node at a time."""
+
+    def __init__(self, golden, node):
+        self.g, self.i = golden, node
+
+    def inv_gamma(self, it, which, shape, rate):
+        return float(self.g[{'sigma': 'sigma2', 'lambda': 'lambda2', 'delta': 'delta2'}[which]][self.i, it])
+
+    def beta(self, it, h, mean, cov):
+        k = len(mean)
+        return np.array(self.g['beta'][self.i, it, h, :k])
+
+    def move(self, it, which):
+        return int(self.g[which + '_move'][self.i, it])
+
+    def picker(self, it, which):
+        picks = list(self.g[which + '_pick'][self.i, it])
+        return lambda n, _p=picks: int(_p.pop(0))
+
+    def mu_draw(self, it, slot, mean, Sigma):
+        k = len(mean)
+        return np.array(self.g['mus_val'][self.i, it, slot, :k])
+
+    def uniform(self, it, which):
+        return float(self.g['u_' + which][self.i, it])
+
+
+class RngDraws:
+    """Free-running draws from a numpy Generator (statistical parity only)."""
+
+    def __init__(self, rng):
+        self.rng = rng
+
+    def inv_gamma(self, it, which, shape, rate):
+        return 1.0 / self.rng.gamma(shape, 1.0 / rate)
+
+    def beta(self, it, h, mean, cov):
+        L = np.linalg.cholesky(cov)
+        return mean + L @ self.rng.standard_normal(len(mean))
+
+    def move(self, it, which):
+        return int(self.rng.integers(0, 3))
+
+    def picker(self, it, which):
+        return lambda n: int(self.rng.integers(0, n))
+
+    def mu_draw(self, it, slot, mean, Sigma):
+        L = np.linalg.cholesky(Sigma)
+        return mean + L @ self.rng.standard_normal(len(mean))
+
+    def uniform(self, it, which):
+        return float(self.rng.uniform())
+
+
+# ------------------------------------------------------------------------------------------------
+# a13 — the per-node chain (regressor loops)
+# ------------------------------------------------------------------------------------------------
+def _accept_plain(log_ratio, u):
+    """moves.py:225-232, :620-637: u < min(1, exp(delta))."""
+    return u < min(1.0, math.exp(min(log_ratio, 700.0)))
+
+
+def _accept_glob(log_ratio, u):
+    """moves.py:112-120, :512-520: u < exp(min(1, delta))."""
+    return u < math.exp(min(1.0, log_ratio))
+
+
+def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
+    """One (node, chain) unit for `n_iter` iterations; returns a trace dict shaped like the golden files.
+
+    Order of updates per iteration follows bayesianLinearRegression.py:114-147 (h),
+    bayesianPwLinearRegression.py:89-132 (nh), seqCoupledBayesianPwLinReg.py:68-121 (seq),
+    globCoupBayesianPwLinReg.py:64-116 (glob): sigma^2, beta, lambda^2 (, delta^2), pi move, tau move.
+    """
+    m = METHOD_IDS[method] if isinstance(method, str) else method
+    N, n = X.shape
+    y = Y[:, node]
+    features = [j for j in range(n) if j != node]
+    F = len(features)
+    c = method_constants(m, N)
+    seq, glob = m == SEQ_DBN, m == GLOB_DBN
+    has_tau = with_tau and m != H_DBN
+    KM, SM = 5, 10
+
+    pi, tau = [], [N + 2]
+    lam = sig = dlt = 1.0
+    mu = np.zeros(1)                                                # glob: current global mean (k entries)
+    tr = {k_: np.full(n_iter, np.nan) for k_ in (
+        'sigma2', 'lambda2', 'delta2', 'sig_shape', 'sig_scale', 'lam_shape', 'lam_scale', 'del_shape', 'del_scale')}
+    tr['beta_mean'] = np.full((n_iter, SM, KM), np.nan)
+    tr['beta_cov'] = np.full((n_iter, SM, KM, KM), np.nan)
+    tr['logml'] = np.full((n_iter, 4), np.nan)
+    for k_ in ('pi_valid', 'tau_valid', 'pi_accept', 'tau_accept', 'npi', 'S'):
+        tr[k_] = np.full(n_iter, -1, dtype=np.int32)
+    tr['pi_after'] = np.full((n_iter, KM - 1), -1, dtype=np.int32)
+    tr['tau_after'] = np.full((n_iter, SM), -1, dtype=np.int32)
+    tr['mus_mean'] = np.full((n_iter, 4, KM), np.nan)
+    tr['mus_cov'] = np.full((n_iter, 4, KM, KM), np.nan)
+    tr['mus_logdens'] = np.full((n_iter, 4, 2), np.nan)
+    tr['mu_after'] = np.full((n_iter, KM), np.nan)
+    tr['n_evals'] = 0
+
+    def prior_means(stats, lam_, dlt_, mu_):
+        if seq:
+            return beta_tilde(stats, lam_, dlt_)
+        k = stats[0][0].shape[0]
+        return [np.asarray(mu_, dtype=float).ravel() if glob else np.zeros(k)] * len(stats)
+
+    def score(stats, lam_, dlt_, mu_):
+        tr['n_evals'] += 1
+        return log_ml(stats, prior_means(stats, lam_, dlt_, mu_), c['a_sig'], c['b_sig'], lam_, c['T_ml'], seq, dlt_)
+
+    for it in range(n_iter):
+        stats = segment_stats(X, y, pi, tau)
+        S, k = len(stats), len(pi) + 1
+        tr['S'][it] = S
+        # ---- sigma^2
+        mus = prior_means(stats, lam, dlt, mu)
+        shape, rate = sigma2_params(stats, mus, lam, c['a_sig'], c['b_sig'], c['T_sigma'], seq, dlt)
+        tr['sig_shape'][it], tr['sig_scale'][it] = shape, 1.0 / rate
+        sig = draws.inv_gamma(it, 'sigma', shape, rate)
+        tr['sigma2'][it] = sig
+        # ---- beta
+        betas = []
+        for h, (mean, cov) in enumerate(beta_params(stats, mus, lam, sig, seq, dlt)):
+            tr['beta_mean'][it, h, :k] = mean
+            tr['beta_cov'][it, h, :k, :k] = cov
+            betas.append(draws.beta(it, h, mean, cov))
+        # ---- lambda^2 (and delta^2)
+        shape, rate = lambda2_params(m, betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
+        tr['lam_shape'][it], tr['lam_scale'][it] = shape, 1.0 / rate
+        lam_new = draws.inv_gamma(it, 'lambda', shape, rate)
+        tr['lambda2'][it] = lam_new
+        dlt_new = dlt
+        if seq:
+            bt = beta_tilde(stats, lam_new, dlt)                    # samplers.py:223 (lambda[it+1], delta[it])
+            shape, rate = delta2_params(betas, bt, sig, c['a_del'], c['b_del'])
+            tr['del_shape'][it], tr['del_scale'][it] = shape, 1.0 / rate
+            dlt_new = draws.inv_gamma(it, 'delta', shape, rate)
+            tr['delta2'][it] = dlt_new
+        lam, dlt = lam_new, dlt_new
+
+        # ---- pi move
+        move = draws.move(it, 'pi')
+        star, hr = propose_pi(pi, move, features, fan_in, draws.picker(it, 'pi'))
+        tr['pi_valid'][it] = int(star is not None)
+        tr['pi_accept'][it] = 0
+        if star is not None:
+            stats_star = segment_stats(X, y, star, tau)
+            lp = math.log(pi_prior(star, F, fan_in)) - math.log(pi_prior(pi, F, fan_in))
+            if glob:
+                # moves.py:476-491: mu* ~ q(.|pi*, mu_in = 0); reverse density with mu_in = current mu
+                mean_s, Sig_s, Q_s = mu_posterior(stats_star, np.zeros(len(star) + 1), sig, lam)
+                mu_star = draws.mu_draw(it, 0, mean_s, Sig_s)
+                ml_star = score(stats_star, lam, dlt, mu_star)
+                ml_cur = score(stats, lam, dlt, mu)
+                mean_c, Sig_c, Q_c = mu_posterior(stats, mu, sig, lam)
+                ld_star = mvn_logpdf_prec(mu_star, mean_s, Q_s)
+                ld_cur = mvn_logpdf_prec(mu, mean_c, Q_c)
+                tr['mus_mean'][it, 0, :len(mean_s)] = mean_s
+                tr['mus_cov'][it, 0, :len(mean_s), :len(mean_s)] = Sig_s
+                tr['mus_mean'][it, 1, :k] = mean_c
+                tr['mus_cov'][it, 1, :k, :k] = Sig_c
+                tr['mus_logdens'][it, 0, 0] = ld_star
+                tr['mus_logdens'][it, 1, 1] = ld_cur
+                ratio = (ml_star - ml_cur + lp + ld_cur - ld_star
+                         + std_normal_logpdf(mu_star) - std_normal_logpdf(mu) + math.log(hr))
+                acc = _accept_glob(ratio, draws.uniform(it, 'pi'))
+            else:
+                if m == H_DBN:
+                    ml_star = log_ml_h(stats_star, c['a_sig'], c['b_sig'], lam, c['T_ml']); tr['n_evals'] += 1
+                    ml_cur = log_ml_h(stats, c['a_sig'], c['b_sig'], lam, c['T_ml']); tr['n_evals'] += 1
+                else:
+                    ml_star = score(stats_star, lam, dlt, None)
+                    ml_cur = score(stats, lam, dlt, None)
+                acc = _accept_plain(ml_star - ml_cur + lp + math.log(hr), draws.uniform(it, 'pi'))
+            tr['logml'][it, 0], tr['logml'][it, 1] = ml_star, ml_cur
+            tr['pi_accept'][it] = int(acc)
+            if acc:
+                pi, stats = star, stats_star
+                if glob:
+                    mu = mu_star
+        tr['npi'][it] = len(pi)
+        tr['pi_after'][it, :len(pi)] = pi
+
+        # ---- tau move
+        if has_tau:
+            move = draws.move(it, 'tau')
+            star, hr = propose_tau(tau, move, c['num_samples'], draws.picker(it, 'tau'), glob)
+            tr['tau_valid'][it] = int(star is not None)
+            tr['tau_accept'][it] = 0
+            if star is not None:
+                stats_star = segment_stats(X, y, pi, star)
+                lp = log_cp_prior(star) - log_cp_prior(tau)
+                k = len(pi) + 1
+                if glob:
+                    # moves.py:66-93: current density first (mu_in = mu), then mu* ~ q(.|tau*, mu_in = 0)
+                    ml_cur = score(stats, lam, dlt, mu)
+                    mean_c, Sig_c, Q_c = mu_posterior(stats, mu, sig, lam)
+                    ld_cur = mvn_logpdf_prec(mu, mean_c, Q_c)
+                    mean_s, Sig_s, Q_s = mu_posterior(stats_star, np.zeros(k), sig, lam)
+                    mu_star = draws.mu_draw(it, 3, mean_s, Sig_s)
+                    ld_star = mvn_logpdf_prec(mu_star, mean_s, Q_s)
+                    ml_star = score(stats_star, lam, dlt, mu_star)
+                    tr['mus_mean'][it, 2, :k] = mean_c
+                    tr['mus_cov'][it, 2, :k, :k] = Sig_c
+                    tr['mus_mean'][it, 3, :k] = mean_s
+                    tr['mus_cov'][it, 3, :k, :k] = Sig_s
+                    tr['mus_logdens'][it, 2, 1] = ld_cur
+                    tr['mus_logdens'][it, 3, 0] = ld_star
+                    ratio = (ml_star - ml_cur + lp + std_normal_logpdf(mu_star) - std_normal_logpdf(mu)
+                             + ld_cur - ld_star + math.log(hr))
+                    acc = _accept_glob(ratio, draws.uniform(it, 'tau'))
+                else:
+                    ml_cur = score(stats, lam, dlt, None)
+                    ml_star = score(stats_star, lam, dlt, None)
+                    acc = _accept_plain(ml_star - ml_cur + lp + math.log(hr), draws.uniform(it, 'tau'))
+                tr['logml'][it, 2], tr['logml'][it, 3] = ml_cur, ml_star
+                tr['tau_accept'][it] = int(acc)
+                if acc:
+                    tau = star
+                    if glob:
+                        mu = mu_star
+        tr['tau_after'][it, :len(tau)] = tau
+        if glob:
+            tr['mu_after'][it, :len(mu)] = mu
+    return tr
+
+
+# ------------------------------------------------------------------------------------------------
+# a14 — edge-frequency and changepoint-histogram reductions
+# ------------------------------------------------------------------------------------------------
+THIN = 10
+
+
+def edge_kept(idx, burn_in):
+    """pi_vector[idx] is kept iff idx >= burn_in and (idx - burn_in) % 10 != 0 (network.py:358-359)."""
+    return idx >= burn_in and (idx - burn_in) % THIN != 0
+
+
+def tau_kept(j, burn_in):
+    """tau_vector[j] is kept iff j >= burn_in and (j - burn_in) % 10 == 0 (network.py:388-389)."""
+    return j >= burn_in and (j - burn_in) % THIN == 0
+
+
+def accumulate_counts(trace, node, n, N, burn_in, edge, nonempty, cp_hist, cp_kept):
+    """Add one unit's samples to the count matrices that get all-reduced (scores.py:155-194,
+    examples/plot_diagnostics.py:226-240).  pi_vector[0] is the initial empty list, pi_vector[it+1] = pi_after[it];
+    tau_vector[it] = tau_after[it]."""
+    n_iter = trace['npi'].shape[0]
+    for it in range(n_iter):
+        if edge_kept(it + 1, burn_in):
+            k = int(trace['npi'][it])
+            if k > 0:
+                nonempty[node] += 1
+                for p in trace['pi_after'][it, :k]:
+                    edge[node, int(p)] += 1
+        if tau_kept(it, burn_in) and trace['tau_valid'][it] >= 0:
+            cp_kept[node] += 1
+            for c_ in trace['tau_after'][it]:
+                if 0 <= c_ <= N:
+                    cp_hist[node, int(c_)] += 1
+
+
+def edge_scores(edge, nonempty):
+    """proposed_adj_matrix (row = child): count / number of kept non-empty parent sets (scores.py:184-192)."""
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return edge / nonempty[:, None]

@@ -1,0 +1,97 @@
+"""The oracle (oracle/dbn_oracle.py) against outputs of the unmodified reference (tests/golden/*.npz)."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import KAT_FILES, CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from oracle import dbn_oracle as O
+
+
+@pytest.mark.parametrize('path', KAT_FILES, ids=ids(KAT_FILES))
+def test_function_kats(path):
+    g = load(path)
+    X, Y = O.lagged_matrices(data_list(g))
+    N = int(g['N'])
+    assert X.shape[0] == N
+    n_cases = g['node'].shape[0]
+    for c in range(n_cases):
+        node, npi, S = int(g['node'][c]), int(g['npi'][c]), int(g['S'][c])
+        pi = [int(v) for v in g['pi'][c, :npi]]
+        tau = [int(v) for v in g['tau'][c, :S]]
+        lam, dlt, sig = float(g['lambda2'][c]), float(g['delta2'][c]), float(g['sigma2'][c])
+        a, b, T = float(g['alpha'][c]), float(g['beta'][c]), float(g['T'][c])
+        k = npi + 1
+        mu = g['mu'][c, :k]
+        y = Y[:, node]
+        stats = O.segment_stats(X, y, pi, tau)
+        Xs, ys = O.segment_design(X, y, pi, tau)
+        zero = [np.zeros(k)] * S
+        # log-ML, Gram form and literal form, vs the reference (1e-9 relative, north_star)
+        for name, mus, seq in (('logml_plain', zero, False), ('logml_mu', [mu] * S, False)):
+            ref = float(g[name][c])
+            if not math.isfinite(ref):
+                continue  # reference overflow (T >= 344 never reached in these fixtures)
+            assert_close(O.log_ml(stats, mus, a, b, lam, T), ref, LOGML_RTOL, what='%s[%d]' % (name, c))
+            assert_close(O.log_ml_literal(Xs, ys, mus, a, b, lam, T), ref, LOGML_RTOL, what='%s-literal[%d]' % (name, c))
+        bt = O.beta_tilde(stats, lam, dlt)
+        for h in range(S):
+            assert_close(bt[h], g['beta_tilde'][c, h, :k], 1e-8, 1e-11, what='beta_tilde[%d,%d]' % (c, h))
+        assert_close(O.log_ml(stats, bt, a, b, lam, T, True, dlt), float(g['logml_seq'][c]), LOGML_RTOL,
+                     what='logml_seq[%d]' % c)
+        assert_close(O.log_ml_literal(Xs, ys, bt, a, b, lam, T, True, dlt), float(g['logml_seq'][c]), LOGML_RTOL,
+                     what='logml_seq-literal[%d]' % c)
+        raw = float(g['rawml_h'][c])
+        if S == 1 and math.isfinite(raw) and raw > 0:
+            assert_close(O.log_ml_h(stats, a, b, lam, N), math.log(raw), LOGML_RTOL, what='rawml_h[%d]' % c)
+        # priors
+        assert_close(O.log_cp_prior(tau), math.log(float(g['cp_prior'][c])), 1e-12, what='cp_prior[%d]' % c)
+        F = X.shape[1] - 1
+        assert_close(O.pi_prior(pi, F, int(g['fan_in'][c])), float(g['pi_prior'][c]), 1e-14, what='pi_prior[%d]' % c)
+        # muSampler: MVN arguments and the density of the input mu
+        mean, Sigma, Q = O.mu_posterior(stats, mu, sig, lam)
+        assert_close(mean, g['mus_mean'][c, :k], 1e-8, 1e-11, what='mus_mean[%d]' % c)
+        assert_close(Sigma, g['mus_cov'][c, :k, :k], 1e-8, 1e-12, what='mus_cov[%d]' % c)
+        ref_ld = float(g['mus_logdens_before'][c])
+        if math.isfinite(ref_ld):
+            assert_close(O.mvn_logpdf_prec(mu, mean, Q), ref_ld, 1e-8, 1e-9, what='mus_logdens_before[%d]' % c)
+
+
+@pytest.mark.parametrize('path', CHAIN_FILES, ids=ids(CHAIN_FILES))
+def test_chain_replay(path):
+    """Replay the reference's recorded draw stream: accept flags, pi and tau must match bit-exactly, every Gibbs
+    parameter and log-ML to 1e-9 relative."""
+    g = load(path)
+    method = str(g['method'])
+    X, Y = O.lagged_matrices(data_list(g))
+    n = X.shape[1]
+    n_iter, burn_in, N = int(g['n_iter']), int(g['burn_in']), int(g['N'])
+    edge = np.zeros((n, n)); nonempty = np.zeros(n)
+    cp_hist = np.zeros((n, N + 3)); cp_kept = np.zeros(n)
+    for node in range(n):
+        tr = O.run_chain(method, X, Y, node, n_iter, O.ReplayDraws(g, node))
+        for key in ('pi_valid', 'pi_accept', 'npi', 'pi_after', 'S', 'tau_after'):
+            assert np.array_equal(tr[key], g[key][node]), (key, node)
+        if method != 'h_dbn':
+            for key in ('tau_valid', 'tau_accept'):
+                assert np.array_equal(tr[key], g[key][node]), (key, node)
+        for key in ('sig_shape', 'sig_scale', 'lam_shape', 'lam_scale', 'del_shape', 'del_scale', 'beta_mean'):
+            assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+        assert_close(tr['beta_cov'], g['beta_cov'][node], 1e-9, 1e-13, what='beta_cov node %d' % node)
+        assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
+        if method == 'glob_coup_nh_dbn':
+            assert_close(tr['mus_mean'], g['mus_mean'][node], 1e-8, 1e-11, what='mus_mean node %d' % node)
+            assert_close(tr['mus_cov'], g['mus_cov'][node], 1e-8, 1e-12, what='mus_cov node %d' % node)
+            ref = g['mus_logdens'][node].copy()
+            mine = tr['mus_logdens']
+            ref[np.isnan(mine)] = np.nan       # the oracle only fills the densities the acceptance ratio uses
+            assert_close(mine, ref, 1e-8, 1e-9, what='mus_logdens node %d' % node)
+            assert_close(tr['mu_after'], g['mu_after'][node], 0, 0, what='mu_after node %d' % node)
+        O.accumulate_counts(tr, node, n, N, burn_in, edge, nonempty, cp_hist, cp_kept)
+    adj = O.edge_scores(edge, nonempty)
+    ref_adj = g['proposed_adj_matrix']
+    ok = np.isfinite(ref_adj).all(axis=1)
+    assert_close(adj[ok], ref_adj[ok], 1e-14, what='proposed_adj_matrix')
+    if 'cp_hist' in g:
+        assert np.array_equal(cp_hist, g['cp_hist'])
+        assert np.array_equal(cp_kept, g['cp_kept'])
