@@ -1,0 +1,811 @@
+// Kernel 3 — the chain step: one thread per (node, chain) unit runs the regressor loop of the reference
+// (a13: bayesianLinearRegression.py:114-147, bayesianPwLinearRegression.py:89-132,
+// seqCoupledBayesianPwLinReg.py:68-121, globCoupBayesianPwLinReg.py:64-116) for `n_iter` iterations with its
+// state in registers / shared memory, scoring every proposal from the prefix table.
+#pragma once
+#include "dbn_score.cuh"
+#include "dbn_rng.cuh"
+#include "../../include/dbn_b200.h"
+
+namespace dbn {
+
+constexpr int KMAX = DBN_KMAX;
+constexpr int PMAX = DBN_PMAX;
+constexpr int SMAX = DBN_SMAX;
+constexpr int CHAIN_BLOCK = 128;
+
+struct ChainArgs {
+  Table tb;
+  int method, fan_in, with_tau, num_samples, burn_in, thin;
+  int C;        // local chains per node
+  int U;        // units = n * C
+  int it0;      // global index of the first iteration of this launch
+  int n_iter;
+  unsigned int chain_offset;
+  unsigned long long seed;
+  double T_sigma_half, a_sig, b_sig, a_lam, b_lam, a_del, b_del, log_p, log_1mp;
+  double c0, T_half_plus_a, two_b;  // marginal-likelihood constants
+  // state, struct of arrays over units
+  int* st_npi;
+  int* st_pi;   // [PMAX][U]
+  int* st_S;
+  int* st_tau;  // [SMAX][U]
+  double* st_sig;
+  double* st_lam;
+  double* st_del;
+  double* st_mu;  // [KMAX][U]
+  // counts (contiguous block): edge[n][n], nonempty[n], cp_hist[n][N+3], cp_kept[n]
+  unsigned long long* edge;
+  unsigned long long* nonempty;
+  unsigned long long* cp_hist;
+  unsigned long long* cp_kept;
+  unsigned long long* counters;  // [8]
+  // replay / trace (device copies, may be null)
+  const double* rd;
+  const int* ri;
+  double* td;
+  int* ti;
+};
+
+// ---- small sorted-set helpers on register arrays -------------------------------------------------------------
+__device__ __forceinline__ void sort4(int (&a)[PMAX], int n) {
+  // insertion sort of the first n entries, n <= 4, fully predicated
+#pragma unroll
+  for (int i = 1; i < PMAX; ++i) {
+#pragma unroll
+    for (int j = i; j > 0; --j) {
+      if (j < n && a[j - 1] > a[j]) {
+        int t = a[j];
+        a[j] = a[j - 1];
+        a[j - 1] = t;
+      }
+    }
+  }
+}
+
+// p-th (0-based) gene id in {0..n-1} \ ({node} u pi), ascending  (np.setdiff1d(possibleFeaturesSet, pi)[p])
+__device__ __forceinline__ int nth_candidate(int p, int node, const int (&sorted_pi)[PMAX], int npi) {
+  int c = p;
+  bool node_done = false;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) {
+    if (j < npi) {
+      const int e = sorted_pi[j];
+      if (!node_done && node < e) {
+        if (node <= c) ++c;
+        node_done = true;
+      }
+      if (e <= c) ++c;
+    }
+  }
+  if (!node_done && node <= c) ++c;
+  return c;
+}
+
+// design columns of a parent set: f[0] = 0, f[1..] = sorted ids + 1
+__device__ __forceinline__ void design_cols(const int (&pi)[PMAX], int npi, int (&f)[KMAX]) {
+  int s[PMAX];
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) s[j] = pi[j];
+  sort4(s, npi);
+  f[0] = 0;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) f[j + 1] = (j < npi) ? s[j] + 1 : 0;
+}
+
+// log of calculateChangePointsSetPrior (priors.py:4-46), tau(j) accessor, S = len(tau) <= 9
+template <class TauFn>
+__device__ __forceinline__ double log_cp_prior(TauFn tau, int S, double log_p, double log_1mp) {
+  int prev = 1;
+  double acc = 0.0;
+  for (int j = 0; j < S - 1; ++j) {
+    const int c = tau(j);
+    acc += log_p + (double)(c - prev - 1) * log_1mp;
+    prev = c;
+  }
+  return acc + (double)((tau(S - 1) - 1) - prev) * log_1mp;
+}
+
+// packed lower-triangular inverse covariance -> covariance (trace only)
+template <int KM>
+__device__ void invert_spd(const double (&Q)[KM * (KM + 1) / 2], double scale, double* out_packed) {
+  double A[KM * (KM + 1) / 2], dinv[KM];
+#pragma unroll
+  for (int e = 0; e < KM * (KM + 1) / 2; ++e) A[e] = Q[e];
+  ldl_factor<KM>(A, dinv);
+#pragma unroll
+  for (int col = 0; col < KM; ++col) {
+    double x[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) x[i] = (i == col) ? 1.0 : 0.0;
+    solve_ldl<KM>(A, dinv, x);
+#pragma unroll
+    for (int i = col; i < KM; ++i) out_packed[DBN_TRI(i, col)] = scale * x[i];
+  }
+}
+
+// Gaussian defined by precision Q and mean numerator m (mean = Q^-1 m): factor once, then sample / evaluate
+template <int KM>
+struct GaussQ {
+  double L[KM * (KM + 1) / 2], dinv[KM], mean[KM], logdetQ;
+  __device__ __forceinline__ void setup(const double (&Q)[KM * (KM + 1) / 2], const double (&m)[KM]) {
+#pragma unroll
+    for (int e = 0; e < KM * (KM + 1) / 2; ++e) L[e] = Q[e];
+    logdetQ = log(ldl_factor<KM>(L, dinv));
+#pragma unroll
+    for (int i = 0; i < KM; ++i) mean[i] = m[i];
+    solve_ldl<KM>(L, dinv, mean);
+  }
+  // log N(x; mean, Q^-1) with k real dimensions
+  __device__ __forceinline__ double logpdf(const double (&x)[KM], const double (&Q)[KM * (KM + 1) / 2], int k) const {
+    double d[KM], Qd[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) d[i] = x[i] - mean[i];
+    symv<KM>(Q, d, Qd);
+    return -0.5 * ((double)k * 1.8378770664093454836 - logdetQ + dot<KM>(d, Qd));
+  }
+  // x = mean + L^-T D^-1/2 z
+  __device__ __forceinline__ void sample(const double (&z)[KM], double (&x)[KM]) const {
+#pragma unroll
+    for (int i = 0; i < KM; ++i) x[i] = z[i] * sqrt(dinv[i]);
+    solve_upper<KM>(L, x);
+#pragma unroll
+    for (int i = 0; i < KM; ++i) x[i] += mean[i];
+  }
+};
+
+template <int KM>
+__device__ __forceinline__ double sqnorm_k(const double (&x)[KM]) {
+  return dot<KM>(x, x);
+}
+
+template <int METHOD, int KM, bool TRACE>
+__global__ void __launch_bounds__(CHAIN_BLOCK) chain_kernel(const ChainArgs a) {
+  constexpr bool SEQ = METHOD == DBN_SEQ_DBN;
+  constexpr bool GLOB = METHOD == DBN_GLOB_DBN;
+  constexpr bool HOMOG = METHOD == DBN_H_DBN;
+  constexpr int KT = KM * (KM + 1) / 2;
+  constexpr int NB = (TRACE || SEQ) ? SMAX : 1;
+
+  __shared__ int s_tau[SMAX * CHAIN_BLOCK];
+  __shared__ int s_tas[SMAX * CHAIN_BLOCK];
+  const int tid = threadIdx.x;
+  const int u_raw = blockIdx.x * CHAIN_BLOCK + tid;
+  const bool active = u_raw < a.U;   // lanes past the end run zero iterations so warp-wide reductions stay full
+  const int u = active ? u_raw : 0;
+  const int n_it = active ? a.n_iter : 0;
+  const int node = u / a.C;
+  const int chain = u - node * a.C;
+  const int n = a.tb.n, N = a.tb.N, F = n - 1;
+  auto TAU = [&](int j) -> int& { return s_tau[j * CHAIN_BLOCK + tid]; };
+  auto TAS = [&](int j) -> int& { return s_tas[j * CHAIN_BLOCK + tid]; };
+  auto tau_cur = [&](int j) { return s_tau[j * CHAIN_BLOCK + tid]; };
+  auto tau_star = [&](int j) { return s_tas[j * CHAIN_BLOCK + tid]; };
+
+  // ---- load state
+  int npi = a.st_npi[u];
+  int pi[PMAX];
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) pi[j] = a.st_pi[j * a.U + u];
+  int S = a.st_S[u];
+  for (int j = 0; j < SMAX; ++j) TAU(j) = a.st_tau[j * a.U + u];
+  double sig2 = a.st_sig[u], lam = a.st_lam[u], dlt = a.st_del[u];
+  double mu[KM];
+#pragma unroll
+  for (int i = 0; i < KM; ++i) mu[i] = GLOB ? a.st_mu[i * a.U + u] : 0.0;
+
+  Rng rng;
+  rng.init(a.seed, a.chain_offset + (unsigned)chain, (unsigned)node);
+  Work wk = {0, 0, 0, 0};
+  const bool replay = TRACE && a.rd != nullptr;
+
+  for (int li = 0; li < n_it; ++li) {
+    const int it = a.it0 + li;
+    rng.start_iteration((unsigned)it);
+    const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * DBN_RD_STRIDE : nullptr;
+    const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * DBN_RI_STRIDE : nullptr;
+    double* td = (TRACE && a.td) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
+    int* ti = (TRACE && a.ti) ? a.ti + ((long long)u * a.n_iter + li) * DBN_TI_STRIDE : nullptr;
+    if (TRACE && ti) ti[DBN_TI_S_BEFORE] = S;
+
+    int f[KMAX];
+    design_cols(pi, npi, f);
+    int k = npi + 1;
+    Cols<KM> cols;
+    {
+      int fk[KM];
+#pragma unroll
+      for (int i = 0; i < KM; ++i) fk[i] = f[i];
+      make_cols<KM>(cols, a.tb, node, fk, k);
+    }
+
+    // =========================== Gibbs pass: sigma^2, beta, lambda^2 (, delta^2) ===========================
+    // One sweep over the segments with the OLD lambda^2/delta^2.  beta_h = mean_h + sqrt(sigma^2) e_h with
+    // e_h = sqrt(w) L^-T D^-1/2 z_h independent of sigma^2, so sum_h |beta_h - c_h|^2 is assembled from
+    // (|d|^2, d.e, |e|^2) after sigma^2 has been drawn: no second sweep, no per-segment storage (nh/glob/h).
+    double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
+    double bm[NB][KM], be[NB][KM];  // seq / trace: per-segment mean and e (or injected beta in replay)
+    {
+      double bt_cur[KM], bt_prev[KM];
+#pragma unroll
+      for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
+      int lo = 0;
+      for (int h = 0; h < S; ++h) {
+        const int hi = DBN_SEG_END(tau_cur(h), h, S, N);
+        double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
+        load_segment<KM>(a.tb, cols, lo, hi, G, g, s);
+        if (SEQ && h == 1) {
+          form_a<KM>(G, lam, A);
+          ldl_factor<KM>(A, dinv);
+#pragma unroll
+          for (int i = 0; i < KM; ++i) bt_cur[i] = lam * g[i];
+          solve_ldl<KM>(A, dinv, bt_cur);
+          wk.segment(k, false);
+        }
+        const double w = (SEQ && h > 0) ? dlt : lam;
+        form_a<KM>(G, w, A);
+        ldl_factor<KM>(A, dinv);
+        double pm[KM];  // prior mean of this segment
+#pragma unroll
+        for (int i = 0; i < KM; ++i) pm[i] = SEQ ? bt_cur[i] : mu[i];
+        if constexpr (SEQ || GLOB)
+          q_sum += segment_q<KM, true>(G, g, s, pm, w, A, dinv, wv);
+        else
+          q_sum += segment_q<KM, false>(G, g, s, pm, w, A, dinv, wv);
+        wk.segment(k, SEQ || GLOB);
+        // posterior mean of beta_h: (I/w + G)^-1 (pm/w + g) = A^-1 (pm + w g)   (samplers.py:210-212)
+        double mean[KM];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) mean[i] = pm[i] + w * g[i];
+        solve_ldl<KM>(A, dinv, mean);
+        double e[KM];
+        if (!replay) {
+          // e = sqrt(w) L^-T D^-1/2 z  (cov = sigma^2 w A^-1, samplers.py:214-216)
+          double z[KM];
+#pragma unroll
+          for (int i = 0; i < KM; i += 2) {
+            double z0, z1;
+            rng.normal2(z0, z1);
+            z[i] = (i < k) ? z0 : 0.0;
+            if (i + 1 < KM) z[i + 1] = (i + 1 < k) ? z1 : 0.0;
+          }
+          const double sw = sqrt(w);
+#pragma unroll
+          for (int i = 0; i < KM; ++i) e[i] = sw * z[i] * sqrt(dinv[i]);
+          solve_upper<KM>(A, e);
+        } else {
+#pragma unroll
+          for (int i = 0; i < KM; ++i) e[i] = (i < k) ? rd[DBN_RD_BETA + h * KMAX + i] : 0.0;  // injected beta_h
+        }
+        if (TRACE && td) {
+#pragma unroll
+          for (int i = 0; i < KM; ++i) td[DBN_TD_BETA_MEAN + h * KMAX + i] = (i < k) ? mean[i] : NAN;
+          // cov / sigma^2 = w A^-1 ; scaled by sigma^2 below
+          double Aorig[KT];
+          form_a<KM>(G, w, Aorig);
+          double covp[KT];
+          invert_spd<KM>(Aorig, w, covp);
+#pragma unroll
+          for (int i = 0; i < KM; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) td[DBN_TD_BETA_COV + h * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? covp[DBN_TRI(i, j)] : NAN;
+        }
+        if constexpr (NB > 1) {
+#pragma unroll
+          for (int i = 0; i < KM; ++i) {
+            bm[h][i] = mean[i];
+            be[h][i] = e[i];
+          }
+        }
+        if (!SEQ) {
+          // centre c_h = mu (zeros for nh/h): samplers.py:279, :299
+          if (!replay) {
+            double d[KM];
+#pragma unroll
+            for (int i = 0; i < KM; ++i) d[i] = mean[i] - pm[i];
+            acc_dd += dot<KM>(d, d);
+            acc_de += dot<KM>(d, e);
+            acc_ee += dot<KM>(e, e);
+          } else {
+            double d[KM];
+#pragma unroll
+            for (int i = 0; i < KM; ++i) d[i] = (i < k) ? e[i] - pm[i] : 0.0;
+            acc_dd += dot<KM>(d, d);
+          }
+        }
+        if (SEQ && h >= 1) {
+          double nxt[KM];
+#pragma unroll
+          for (int i = 0; i < KM; ++i) nxt[i] = bt_prev[i] + dlt * g[i];
+          solve_ldl<KM>(A, dinv, nxt);
+#pragma unroll
+          for (int i = 0; i < KM; ++i) {
+            bt_prev[i] = bt_cur[i];
+            bt_cur[i] = nxt[i];
+          }
+        }
+        lo = hi;
+      }
+    }
+    // ---- sigma^2 ~ IG: shape a + T/2, rate b + q/2 (samplers.py:118-125, :81-86, :135-141)
+    {
+      const double shape = a.a_sig + a.T_sigma_half;
+      const double rate = a.b_sig + 0.5 * q_sum;
+      sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / rng.gamma(shape);
+      if (TRACE && td) {
+        td[DBN_TD_SIG_SHAPE] = shape;
+        td[DBN_TD_SIG_RATE] = rate;
+        td[DBN_TD_SIGMA2] = sig2;
+      }
+    }
+    const double sg = sqrt(sig2);
+    if (TRACE && td) {
+      for (int h = 0; h < S; ++h) {
+        for (int i = 0; i < KM; ++i) {
+          const double b = replay ? be[h < NB ? h : 0][i] : bm[h < NB ? h : 0][i] + sg * be[h < NB ? h : 0][i];
+          td[DBN_TD_BETA + h * KMAX + i] = (i < k) ? b : NAN;
+        }
+        for (int e = 0; e < DBN_KTRI; ++e) td[DBN_TD_BETA_COV + h * DBN_KTRI + e] *= sig2;
+      }
+    }
+    // ---- lambda^2
+    {
+      double shape, rate;
+      if constexpr (SEQ) {
+        // samplers.py:249-263: shape a + (k+1)/2, rate b + beta_0.beta_0 / (2 sigma^2)
+        double b0[KM];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) b0[i] = replay ? be[0][i] : bm[0][i] + sg * be[0][i];
+        shape = a.a_lam + 0.5 * (double)(k + 1);
+        rate = a.b_lam + 0.5 * dot<KM>(b0, b0) / sig2;
+      } else {
+        const double ss = replay ? acc_dd : (acc_dd + 2.0 * sg * acc_de + sig2 * acc_ee);
+        // nh/glob: samplers.py:285-289 shape a + S k/2 ; h: :301 shape a + k/2 ; rate b + ss / (2 sigma^2)
+        shape = a.a_lam + 0.5 * (double)(HOMOG ? k : S * k);
+        rate = a.b_lam + 0.5 * ss / sig2;
+      }
+      const double lam_new = replay ? rd[DBN_RD_LAMBDA2] : rate / rng.gamma(shape);
+      if (TRACE && td) {
+        td[DBN_TD_LAM_SHAPE] = shape;
+        td[DBN_TD_LAM_RATE] = rate;
+        td[DBN_TD_LAMBDA2] = lam_new;
+      }
+      if constexpr (SEQ) {
+        // delta^2 (samplers.py:220-247): beta-tildes recomputed with (lambda^2 new, delta^2 old), beta_h centred
+        // on bt[h-1] for h >= 1
+        double acc = 0.0;
+        double bt_cur[KM], bt_prev[KM];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
+        int lo = 0;
+        for (int h = 0; h < S; ++h) {
+          const int hi = DBN_SEG_END(tau_cur(h), h, S, N);
+          if (h >= 1) {
+            double G[KT], g[KM], s, A[KT], dinv[KM];
+            load_segment<KM>(a.tb, cols, lo, hi, G, g, s);
+            if (h == 1) {
+              form_a<KM>(G, lam_new, A);
+              ldl_factor<KM>(A, dinv);
+#pragma unroll
+              for (int i = 0; i < KM; ++i) bt_cur[i] = lam_new * g[i];
+              solve_ldl<KM>(A, dinv, bt_cur);
+              wk.segment(k, false);
+            }
+            double d[KM];
+#pragma unroll
+            for (int i = 0; i < KM; ++i) {
+              const double b = replay ? be[h < NB ? h : 0][i] : bm[h < NB ? h : 0][i] + sg * be[h < NB ? h : 0][i];
+              d[i] = b - bt_prev[i];
+            }
+            acc += dot<KM>(d, d);
+            if (h + 1 < S) {
+              form_a<KM>(G, dlt, A);
+              ldl_factor<KM>(A, dinv);
+              double nxt[KM];
+#pragma unroll
+              for (int i = 0; i < KM; ++i) nxt[i] = bt_prev[i] + dlt * g[i];
+              solve_ldl<KM>(A, dinv, nxt);
+#pragma unroll
+              for (int i = 0; i < KM; ++i) {
+                bt_prev[i] = bt_cur[i];
+                bt_cur[i] = nxt[i];
+              }
+              wk.segment(k, false);
+            }
+          }
+          lo = hi;
+        }
+        const double dshape = a.a_del + 0.5 * (double)((S - 1) * k);
+        const double drate = a.b_del + 0.5 * acc / sig2;
+        const double dlt_new = replay ? rd[DBN_RD_DELTA2] : drate / rng.gamma(dshape);
+        if (TRACE && td) {
+          td[DBN_TD_DEL_SHAPE] = dshape;
+          td[DBN_TD_DEL_RATE] = drate;
+          td[DBN_TD_DELTA2] = dlt_new;
+        }
+        dlt = dlt_new;
+      }
+      lam = lam_new;
+    }
+
+    // unified scorer for the current method
+    auto score = [&](const Cols<KM>& c, auto tau_fn, int S_, const double(&mu_)[KM]) -> double {
+      if constexpr (SEQ)
+        return score_seq<KM>(a.tb, c, tau_fn, S_, lam, dlt, a.c0, a.T_half_plus_a, a.two_b, wk);
+      else if constexpr (GLOB)
+        return score_plain<KM, true>(a.tb, c, tau_fn, S_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
+      else
+        return score_plain<KM, false>(a.tb, c, tau_fn, S_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
+    };
+
+    // ======================================= parent-set move (a4 / a6) =======================================
+    double ml_now = NAN;   // log-ML of the state after the pi move (reused by the tau move)
+    bool have_ml_now = false;
+    double Qc[KT], m0c[KM];  // glob: muSampler precision / mean numerator of the current state
+    bool have_qc = false;
+    {
+      const int move = replay ? ri[DBN_RI_PI_MOVE] : rng.below(3);
+      int star[PMAX];
+      int nstar = npi;
+      bool valid = true;
+      double log_hr = 0.0;
+      int spi[PMAX];
+#pragma unroll
+      for (int j = 0; j < PMAX; ++j) spi[j] = pi[j];
+      sort4(spi, npi);
+#pragma unroll
+      for (int j = 0; j < PMAX; ++j) star[j] = pi[j];
+      if (move == 0) {  // addMove (utils.py:293-305)
+        const int ncand = F - npi;
+        if (npi > a.fan_in - 1 || ncand <= 0) {
+          valid = false;
+        } else {
+          const int p = replay ? ri[DBN_RI_PI_PICK] : rng.below(ncand);
+          const int c = nth_candidate(p, node, spi, npi);
+#pragma unroll
+          for (int j = 0; j < PMAX; ++j)
+            if (j == npi) star[j] = c;
+          nstar = npi + 1;
+          log_hr = log((double)(F - npi) / (double)nstar);  // moves.py:612
+        }
+      } else {
+        if (npi < 1) {
+          valid = false;  // utils.py:285-286, :308-309
+        } else {
+          const int idx = replay ? ri[DBN_RI_PI_PICK] : rng.below(npi);
+          int el = pi[0];
+#pragma unroll
+          for (int j = 1; j < PMAX; ++j)
+            if (j == idx) el = pi[j];
+          // sorted(pi \ el)  (np.setdiff1d, utils.py:290, :318)
+          int w_ = 0;
+#pragma unroll
+          for (int j = 0; j < PMAX; ++j) {
+            if (j < npi && spi[j] != el) {
+#pragma unroll
+              for (int q = 0; q < PMAX; ++q)
+                if (q == w_) star[q] = spi[j];
+              ++w_;
+            }
+          }
+          if (move == 1) {  // deleteMove
+            nstar = npi - 1;
+            log_hr = log((double)npi / (double)(F - nstar));  // moves.py:615
+          } else {  // exchangeMove (utils.py:307-323)
+            const int ncand = F - npi;
+            if (ncand <= 0) {
+              valid = false;
+            } else {
+              const int p = replay ? ri[DBN_RI_PI_PICK + 1] : rng.below(ncand);
+              const int c = nth_candidate(p, node, spi, npi);
+#pragma unroll
+              for (int j = 0; j < PMAX; ++j)
+                if (j == npi - 1) star[j] = c;
+              nstar = npi;
+            }
+          }
+        }
+      }
+      if (TRACE && ti) {
+        ti[DBN_TI_PI_MOVE] = move;
+        ti[DBN_TI_PI_VALID] = valid;
+        ti[DBN_TI_PI_ACCEPT] = 0;
+      }
+      if (TRACE && td) {
+        td[DBN_TD_LOGML + 0] = NAN;
+        td[DBN_TD_LOGML + 1] = NAN;
+        td[DBN_TD_LOGML + 2] = NAN;
+        td[DBN_TD_LOGML + 3] = NAN;
+        for (int e = DBN_TD_MUS_LOGDENS; e < DBN_TD_BETA_MEAN; ++e) td[e] = NAN;
+      }
+      if (valid) {
+        int fs[KMAX];
+        design_cols(star, nstar, fs);
+        const int ks = nstar + 1;
+        Cols<KM> cstar;
+        {
+          int fk[KM];
+#pragma unroll
+          for (int i = 0; i < KM; ++i) fk[i] = fs[i];
+          make_cols<KM>(cstar, a.tb, node, fk, ks);
+        }
+        double ml_star, ml_cur, log_ratio;
+        double mu_star[KM];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) mu_star[i] = 0.0;
+        double Qs[KT], m0s[KM];
+        if constexpr (GLOB) {
+          // moves.py:476-491: mu* ~ muSampler(0 | pi*), reverse density muSampler(mu | pi) at the current mu
+          mu_posterior<KM>(a.tb, cstar, tau_cur, S, lam, sig2, Qs, m0s, wk);
+          GaussQ<KM> gs;
+          gs.setup(Qs, m0s);
+          if (replay) {
+#pragma unroll
+            for (int i = 0; i < KM; ++i) mu_star[i] = (i < ks) ? rd[DBN_RD_MU_PI + i] : 0.0;
+          } else {
+            double z[KM];
+#pragma unroll
+            for (int i = 0; i < KM; i += 2) {
+              double z0, z1;
+              rng.normal2(z0, z1);
+              z[i] = (i < ks) ? z0 : 0.0;
+              if (i + 1 < KM) z[i + 1] = (i + 1 < ks) ? z1 : 0.0;
+            }
+            gs.sample(z, mu_star);
+          }
+          const double ld_star = gs.logpdf(mu_star, Qs, ks);
+          ml_star = score(cstar, tau_cur, S, mu_star);
+          ml_cur = score(cols, tau_cur, S, mu);
+          mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig2, Qc, m0c, wk);
+          have_qc = true;
+          double mc[KM];
+#pragma unroll
+          for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + mu[i];  // samplers.py:336: the input mu is the prior mean term
+          GaussQ<KM> gc;
+          gc.setup(Qc, mc);
+          const double ld_cur = gc.logpdf(mu, Qc, k);
+          // moves.py:501-516
+          const double lp_star = -0.5 * ((double)ks * 1.8378770664093454836 + sqnorm_k<KM>(mu_star));
+          const double lp_cur = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu));
+          log_ratio = ml_star - ml_cur + ld_cur - ld_star + lp_star - lp_cur + log_hr;
+          if (TRACE && td) {
+            td[DBN_TD_MUS_LOGDENS + 0] = ld_star;
+            td[DBN_TD_MUS_LOGDENS + 1] = ld_cur;
+            for (int i = 0; i < KM; ++i) {
+              td[DBN_TD_MUS_MEAN + 0 * KMAX + i] = (i < ks) ? gs.mean[i] : NAN;
+              td[DBN_TD_MUS_MEAN + 1 * KMAX + i] = (i < k) ? gc.mean[i] : NAN;
+            }
+            double cv[KT];
+            invert_spd<KM>(Qs, 1.0, cv);
+            for (int i = 0; i < KM; ++i)
+              for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 0 * DBN_KTRI + DBN_TRI(i, j)] = (i < ks) ? cv[DBN_TRI(i, j)] : NAN;
+            invert_spd<KM>(Qc, 1.0, cv);
+            for (int i = 0; i < KM; ++i)
+              for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 1 * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? cv[DBN_TRI(i, j)] : NAN;
+          }
+        } else {
+          ml_star = score(cstar, tau_cur, S, mu_star);   // moves.py:574-576 / :569-571 / :672
+          ml_cur = score(cols, tau_cur, S, mu);          // moves.py:599-600 / :594-595 / :681
+          log_ratio = ml_star - ml_cur + log_hr;         // uniform parent-set prior cancels (priors.py:48-68)
+        }
+        const double uacc = replay ? rd[DBN_RD_U_PI] : rng.uniform();
+        // nh/seq/h: u < min(1, exp(d)) (moves.py:620-633, :699-702); glob: u < exp(min(1, d)) (moves.py:512-520)
+        const bool acc = GLOB ? (uacc < exp(fmin(1.0, log_ratio))) : (uacc < fmin(1.0, exp(log_ratio)));
+        if (TRACE && td) {
+          td[DBN_TD_LOGML + 0] = ml_star;
+          td[DBN_TD_LOGML + 1] = ml_cur;
+        }
+        if (TRACE && ti) ti[DBN_TI_PI_ACCEPT] = acc;
+        ml_now = acc ? ml_star : ml_cur;
+        have_ml_now = true;
+        if (acc) {
+          npi = nstar;
+          k = ks;
+#pragma unroll
+          for (int j = 0; j < PMAX; ++j) pi[j] = star[j];
+          cols = cstar;
+          if (GLOB) {
+#pragma unroll
+            for (int i = 0; i < KM; ++i) {
+              mu[i] = mu_star[i];
+              m0c[i] = m0s[i];
+            }
+#pragma unroll
+            for (int e = 0; e < KT; ++e) Qc[e] = Qs[e];
+          }
+        }
+      }
+      // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
+      const int idx = it + 1;
+      if (idx >= a.burn_in && ((idx - a.burn_in) % a.thin) != 0 && npi > 0) {
+        atomicAdd(&a.nonempty[node], 1ull);
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j)
+          if (j < npi) atomicAdd(&a.edge[(long long)node * n + pi[j]], 1ull);
+      }
+      if (TRACE && ti) {
+        ti[DBN_TI_NPI] = npi;
+        for (int j = 0; j < PMAX; ++j) ti[DBN_TI_PI + j] = (j < npi) ? pi[j] : -1;
+      }
+    }
+
+    // ======================================= changepoint move (a5 / a6) ======================================
+    if (!HOMOG && a.with_tau) {
+      const int move = replay ? ri[DBN_RI_TAU_MOVE] : rng.below(3);
+      const int ns = a.num_samples;
+      bool valid = true;
+      int Ss = S;
+      double log_hr = 0.0;
+      if (move == 0) {  // cpBirthMove (changepointMoves.py:93-124)
+        int inside = 0;
+        for (int j = 0; j < S - 1; ++j) inside += (TAU(j) >= 2 && TAU(j) <= ns) ? 1 : 0;
+        const int ncand = ns - 1 - inside;
+        if (ncand <= 0) {
+          valid = false;
+        } else {
+          const int p = replay ? ri[DBN_RI_TAU_PICK] : rng.below(ncand);
+          int c = 2 + p;
+          for (int j = 0; j < S - 1; ++j)
+            if (TAU(j) <= c) ++c;
+          int w_ = 0;
+          bool placed = false;
+          for (int j = 0; j < S; ++j) {
+            if (!placed && c < TAU(j)) {
+              TAS(w_++) = c;
+              placed = true;
+            }
+            TAS(w_++) = TAU(j);
+          }
+          Ss = S + 1;
+          if (Ss > 9) valid = false;  // moves.py:156 (== 10) / :42 (> 9)
+          // moves.py:159 (nh/seq) / :46 (glob)
+          log_hr = GLOB ? log((double)(ns - 1 - S) / (double)Ss) : log((double)(ns - S) / (double)(Ss - 1));
+        }
+      } else if (S < 2) {
+        valid = false;  // changepointMoves.py:81-82, :21-22
+      } else if (move == 1) {  // cpDeathMove (:63-91)
+        const int idx = replay ? ri[DBN_RI_TAU_PICK] : rng.below(S - 1);
+        int w_ = 0;
+        for (int j = 0; j < S; ++j)
+          if (j != idx) TAS(w_++) = TAU(j);
+        Ss = S - 1;
+        // moves.py:163 (nh/seq) / :55 (glob)
+        log_hr = GLOB ? log((double)S / (double)(ns - 1 - Ss)) : log((double)(S - 1) / (double)(ns - Ss));
+      } else {  // cpRellocationMove (:3-61)
+        const int idx = replay ? ri[DBN_RI_TAU_PICK] : rng.below(S - 1);
+        const int last = TAU(S - 1) - 1;
+        const int left = (idx == 0) ? 1 : TAU(idx - 1);
+        const int right = (idx + 1 == S - 1) ? last : TAU(idx + 1);
+        const int ncand = right - left - 2;
+        if (ncand <= 0) {
+          valid = false;
+        } else {
+          const int p = replay ? ri[DBN_RI_TAU_PICK + 1] : rng.below(ncand);
+          int c = left + 1 + p;
+          if (c >= TAU(idx)) ++c;
+          for (int j = 0; j < S; ++j) TAS(j) = (j == idx) ? c : TAU(j);
+        }
+      }
+      if (TRACE && ti) {
+        ti[DBN_TI_TAU_MOVE] = move;
+        ti[DBN_TI_TAU_VALID] = valid;
+        ti[DBN_TI_TAU_ACCEPT] = 0;
+      }
+      if (valid) {
+        double ml_cur = have_ml_now ? ml_now : score(cols, tau_cur, S, mu);  // moves.py:184-191 / :67-69
+        double ml_star, log_ratio;
+        const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
+        double mu_star[KM];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) mu_star[i] = 0.0;
+        if constexpr (GLOB) {
+          // moves.py:72-93: density of the current mu under muSampler(mu | tau), then mu* ~ muSampler(0 | tau*)
+          if (!have_qc) mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig2, Qc, m0c, wk);
+          double mc[KM];
+#pragma unroll
+          for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + mu[i];
+          GaussQ<KM> gc;
+          gc.setup(Qc, mc);
+          const double ld_cur = gc.logpdf(mu, Qc, k);
+          double Qs[KT], m0s[KM];
+          mu_posterior<KM>(a.tb, cols, tau_star, Ss, lam, sig2, Qs, m0s, wk);
+          GaussQ<KM> gs;
+          gs.setup(Qs, m0s);
+          if (replay) {
+#pragma unroll
+            for (int i = 0; i < KM; ++i) mu_star[i] = (i < k) ? rd[DBN_RD_MU_TAU + i] : 0.0;
+          } else {
+            double z[KM];
+#pragma unroll
+            for (int i = 0; i < KM; i += 2) {
+              double z0, z1;
+              rng.normal2(z0, z1);
+              z[i] = (i < k) ? z0 : 0.0;
+              if (i + 1 < KM) z[i + 1] = (i + 1 < k) ? z1 : 0.0;
+            }
+            gs.sample(z, mu_star);
+          }
+          const double ld_star = gs.logpdf(mu_star, Qs, k);
+          ml_star = score(cols, tau_star, Ss, mu_star);
+          const double lp_star = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu_star));
+          const double lp_cur = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu));
+          log_ratio = ml_star - ml_cur + lprior + lp_star - lp_cur + ld_cur - ld_star + log_hr;  // moves.py:112-117
+          if (TRACE && td) {
+            td[DBN_TD_MUS_LOGDENS + 2] = ld_cur;
+            td[DBN_TD_MUS_LOGDENS + 3] = ld_star;
+            for (int i = 0; i < KM; ++i) {
+              td[DBN_TD_MUS_MEAN + 2 * KMAX + i] = (i < k) ? gc.mean[i] : NAN;
+              td[DBN_TD_MUS_MEAN + 3 * KMAX + i] = (i < k) ? gs.mean[i] : NAN;
+            }
+            double cv[KT];
+            invert_spd<KM>(Qc, 1.0, cv);
+            for (int i = 0; i < KM; ++i)
+              for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 2 * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? cv[DBN_TRI(i, j)] : NAN;
+            invert_spd<KM>(Qs, 1.0, cv);
+            for (int i = 0; i < KM; ++i)
+              for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 3 * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? cv[DBN_TRI(i, j)] : NAN;
+          }
+        } else {
+          ml_star = score(cols, tau_star, Ss, mu_star);  // moves.py:209-216
+          log_ratio = ml_star - ml_cur + lprior + log_hr;  // moves.py:225
+        }
+        const double uacc = replay ? rd[DBN_RD_U_TAU] : rng.uniform();
+        const bool acc = GLOB ? (uacc < exp(fmin(1.0, log_ratio))) : (uacc < fmin(1.0, exp(log_ratio)));
+        if (TRACE && td) {
+          td[DBN_TD_LOGML + 2] = ml_cur;
+          td[DBN_TD_LOGML + 3] = ml_star;
+        }
+        if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = acc;
+        if (acc) {
+          S = Ss;
+          for (int j = 0; j < Ss; ++j) TAU(j) = TAS(j);
+          if (GLOB) {
+#pragma unroll
+            for (int i = 0; i < KM; ++i) mu[i] = mu_star[i];
+          }
+        }
+      }
+      // ---- counts: tau_vector[it] is kept iff it >= burn_in and (it - burn_in) % thin == 0 (network.py:388-389)
+      if (it >= a.burn_in && ((it - a.burn_in) % a.thin) == 0) {
+        atomicAdd(&a.cp_kept[node], 1ull);
+        for (int j = 0; j < S - 1; ++j) atomicAdd(&a.cp_hist[(long long)node * (N + 3) + TAU(j)], 1ull);
+      }
+    }
+    if (TRACE && ti) {
+      ti[DBN_TI_S] = S;
+      for (int j = 0; j < SMAX; ++j) ti[DBN_TI_TAU + j] = (j < S) ? TAU(j) : -1;
+    }
+    if (TRACE && td) {
+      if (!SEQ) td[DBN_TD_DEL_SHAPE] = td[DBN_TD_DEL_RATE] = td[DBN_TD_DELTA2] = NAN;
+      for (int i = 0; i < KMAX; ++i) td[DBN_TD_MU + i] = (GLOB && i < k && i < KM) ? mu[i < KM ? i : 0] : NAN;
+    }
+  }
+
+  // ---- store state
+  if (active) {
+  a.st_npi[u] = npi;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) a.st_pi[j * a.U + u] = pi[j];
+  a.st_S[u] = S;
+  for (int j = 0; j < SMAX; ++j) a.st_tau[j * a.U + u] = TAU(j);
+  a.st_sig[u] = sig2;
+  a.st_lam[u] = lam;
+  a.st_del[u] = dlt;
+  if (GLOB) {
+#pragma unroll
+    for (int i = 0; i < KM; ++i) a.st_mu[i * a.U + u] = mu[i];
+  }
+  }
+  // ---- work counters: one atomic per warp
+  unsigned long long v[5] = {(unsigned long long)n_it, wk.evals, wk.segs, wk.bytes, wk.flops};
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    unsigned long long x = v[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&a.counters[c], x);
+  }
+}
+
+}  // namespace dbn

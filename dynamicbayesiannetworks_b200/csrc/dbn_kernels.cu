@@ -1,0 +1,732 @@
+// Kernels 1 and 2 (prefix statistics, batched scorer), the FP64 peak probe, and the C ABI of include/dbn_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dbn_chain.cuh"
+
+namespace dbn {
+
+// =====================================================================================================
+// Kernel 1 — time-prefix sufficient statistics (replaces utils.py:128-269 re-slicing)
+// =====================================================================================================
+// Every table column p is the running sum over regression rows of a product of two entries of
+//   v_t = [1, x_t(0..n-1), y_t(0..n-1)]        (x_t = data row t, y_t = data row t+1 within a series segment)
+// colA[p], colB[p] name the two entries.  The table is written once, row-major in t, so the kernel is a pure
+// HBM write stream: 8 * (N+1) * row_doubles bytes out, 16 * N * n bytes in.
+
+constexpr int PREFIX_BLOCK = 256;
+
+// gather the lag-1 matrices: V[t] = [1, raw[xrow[t]], raw[xrow[t] + 1]]
+__global__ void build_v_kernel(const double* __restrict__ raw, const int* __restrict__ xrow, int N, int n,
+                               double* __restrict__ V) {
+  const int W = 2 * n + 1;
+  const long long total = (long long)N * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / W), c = (int)(i - (long long)t * W);
+    double v = 1.0;
+    if (c >= 1 && c <= n) v = raw[(long long)xrow[t] * n + (c - 1)];
+    if (c > n) v = raw[(long long)(xrow[t] + 1) * n + (c - n - 1)];
+    V[i] = v;
+  }
+}
+
+// WRITE == false: per-(chunk, column) totals.  WRITE == true: running sums from the chunk's scanned offset.
+template <bool WRITE>
+__global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
+                                                              const unsigned short* __restrict__ colB, int N, int W, long long R,
+                                                              int Lc, double* __restrict__ chunk, double* __restrict__ table) {
+  extern __shared__ double sv[];  // [Lc][W]
+  const int t0 = blockIdx.y * Lc;
+  const int len = min(Lc, N - t0);
+  for (int i = threadIdx.x; i < len * W; i += PREFIX_BLOCK) sv[i] = V[(long long)t0 * W + i];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * PREFIX_BLOCK + threadIdx.x;
+  if (p >= R) return;
+  const int ca = colA[p], cb = colB[p];
+  if (!WRITE) {
+    double acc = 0.0;
+    for (int t = 0; t < len; ++t) acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
+    chunk[(long long)blockIdx.y * R + p] = acc;
+  } else {
+    double acc = chunk[(long long)blockIdx.y * R + p];
+    double* out = table + (long long)(t0 + 1) * R + p;
+    for (int t = 0; t < len; ++t) {
+      acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
+      __stcs(out, acc);  // streaming store: the table is far larger than L2
+      out += R;
+    }
+  }
+}
+
+// exclusive scan over chunks, one thread per column
+__global__ void prefix_scan_chunks(double* __restrict__ chunk, int n_chunks, long long R) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= R) return;
+  double acc = 0.0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const double v = chunk[(long long)c * R + p];
+    chunk[(long long)c * R + p] = acc;
+    acc += v;
+  }
+}
+
+// =====================================================================================================
+// Kernel 2 — batched scorer (replaces marginalLikelihood.py:91-166)
+// =====================================================================================================
+__global__ void __launch_bounds__(128) score_batch_kernel(Table tb, int mode, double c0, double T_half_plus_a, double two_b, int B,
+                                                          const int* __restrict__ node, const int* __restrict__ pi,
+                                                          const int* __restrict__ pi_len, const int* __restrict__ tau,
+                                                          const int* __restrict__ tau_len, const double* __restrict__ lam,
+                                                          const double* __restrict__ dlt, const double* __restrict__ mu,
+                                                          double* __restrict__ out, unsigned long long* counters) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int p[PMAX];
+  const int npi = pi_len[b];
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) p[j] = pi[b * PMAX + j];
+  int f[KMAX];
+  design_cols(p, npi, f);
+  Cols<KMAX> cols;
+  make_cols<KMAX>(cols, tb, node[b], f, npi + 1);
+  const int S = tau_len[b];
+  const int* tb_ = tau + (long long)b * SMAX;
+  auto tau_fn = [&](int j) { return __ldg(tb_ + j); };
+  double m[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) m[i] = (i < npi + 1) ? mu[b * KMAX + i] : 0.0;
+  Work wk = {0, 0, 0, 0};
+  double r;
+  if (mode == 1)
+    r = score_seq<KMAX>(tb, cols, tau_fn, S, lam[b], dlt[b], c0, T_half_plus_a, two_b, wk);
+  else
+    r = score_plain<KMAX, true>(tb, cols, tau_fn, S, lam[b], m, c0, T_half_plus_a, two_b, wk);
+  out[b] = r;
+  atomicAdd(&counters[1], wk.evals);
+  atomicAdd(&counters[2], wk.segs);
+  atomicAdd(&counters[3], wk.bytes);
+  atomicAdd(&counters[4], wk.flops);
+}
+
+// =====================================================================================================
+// FP64 peak probe: 8 independent DFMA chains per thread
+// =====================================================================================================
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.999999, c = 1e-9 * (threadIdx.x + 1);
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace dbn
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace dbn;
+
+struct dbn_handle {
+  dbn_config cfg;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  // data / table
+  int n = 0, N = 0, W = 0, n_chunks = 0, Lc = 0;
+  long long R = 0;
+  int zz_size = 0;
+  double* d_raw = nullptr;
+  int* d_xrow = nullptr;
+  double* d_V = nullptr;
+  unsigned short *d_colA = nullptr, *d_colB = nullptr;
+  double* d_chunk = nullptr;
+  double* d_table = nullptr;
+  bool have_stats = false;
+  // chain
+  bool have_chain = false;
+  dbn_run_params rp;
+  int U = 0;
+  int it_done = 0;
+  int *st_npi = nullptr, *st_pi = nullptr, *st_S = nullptr, *st_tau = nullptr;
+  double *st_sig = nullptr, *st_lam = nullptr, *st_del = nullptr, *st_mu = nullptr;
+  unsigned long long* d_counts = nullptr;
+  long long counts_elems = 0;
+  unsigned long long* d_counters = nullptr;
+};
+
+// ---- chain ------------------------------------------------------------------------------------------
+__global__ void init_state_kernel(int U, int N, int* npi, int* pi, int* S, int* tau, double* sig, double* lam, double* del, double* mu) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  npi[u] = 0;
+  for (int j = 0; j < PMAX; ++j) pi[j * U + u] = 0;
+  S[u] = 1;
+  tau[u] = N + 2;  // network.py:162 — only the pseudo changepoint
+  for (int j = 1; j < SMAX; ++j) tau[j * U + u] = 0;
+  sig[u] = lam[u] = del[u] = 1.0;  // bayesianPwLinearRegression.py:84-85
+  for (int i = 0; i < KMAX; ++i) mu[i * U + u] = 0.0;
+}
+
+
+typedef void (*chain_fn)(const ChainArgs);
+
+template <int KM, bool TRACE>
+static chain_fn pick_method(int method) {
+  switch (method) {
+    case DBN_H_DBN: return chain_kernel<DBN_H_DBN, KM, TRACE>;
+    case DBN_NH_DBN: return chain_kernel<DBN_NH_DBN, KM, TRACE>;
+    case DBN_SEQ_DBN: return chain_kernel<DBN_SEQ_DBN, KM, TRACE>;
+    default: return chain_kernel<DBN_GLOB_DBN, KM, TRACE>;
+  }
+}
+
+
+static std::string g_create_error;
+static std::mutex g_mu;
+
+#define DBN_FAIL(h, code, ...)                       \
+  do {                                               \
+    char buf_[512];                                  \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);       \
+    (h)->err = buf_;                                 \
+    return (code);                                   \
+  } while (0)
+
+#define CU(h, expr)                                                                                      \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) DBN_FAIL(h, DBN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T>
+static void free_dev(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+extern "C" {
+
+int dbn_abi_version(void) { return DBN_ABI_VERSION; }
+
+const char* dbn_last_error(const dbn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dbn_create(const dbn_config* cfg, dbn_handle** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!cfg || !out) {
+    g_create_error = "dbn_create: null argument";
+    return DBN_ERR_INVALID;
+  }
+  if (cfg->n_chains < 1) {
+    g_create_error = "dbn_create: n_chains must be >= 1";
+    return DBN_ERR_INVALID;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("dbn_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return DBN_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= count) {
+    g_create_error = "dbn_create: device ordinal out of range";
+    return DBN_ERR_INVALID;
+  }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return DBN_ERR_CUDA;
+  }
+  dbn_handle* h = new dbn_handle();
+  h->cfg = *cfg;
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete h;
+    return DBN_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  e = cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DBN_ERR_CUDA;
+  }
+  *out = h;
+  return DBN_OK;
+}
+
+static void free_stats(dbn_handle* h) {
+  free_dev(h->d_raw);
+  free_dev(h->d_xrow);
+  free_dev(h->d_V);
+  free_dev(h->d_colA);
+  free_dev(h->d_colB);
+  free_dev(h->d_chunk);
+  free_dev(h->d_table);
+  h->have_stats = false;
+}
+
+static void free_chain(dbn_handle* h) {
+  free_dev(h->st_npi);
+  free_dev(h->st_pi);
+  free_dev(h->st_S);
+  free_dev(h->st_tau);
+  free_dev(h->st_sig);
+  free_dev(h->st_lam);
+  free_dev(h->st_del);
+  free_dev(h->st_mu);
+  free_dev(h->d_counts);
+  h->have_chain = false;
+}
+
+void dbn_destroy(dbn_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  free_stats(h);
+  free_chain(h);
+  free_dev(h->d_counters);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int dbn_set_stream(dbn_handle* h, void* cuda_stream) {
+  if (!h) return DBN_ERR_INVALID;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return DBN_OK;
+}
+
+int dbn_sync(dbn_handle* h) {
+  if (!h) return DBN_ERR_INVALID;
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return DBN_OK;
+}
+
+static int launch_prefix(dbn_handle* h) {
+  const int n = h->n, N = h->N, W = h->W;
+  build_v_kernel<<<296, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, N, n, h->d_V);
+  CU(h, cudaGetLastError());
+  const size_t smem = (size_t)h->Lc * W * sizeof(double);
+  dim3 grid((unsigned)((h->R + PREFIX_BLOCK - 1) / PREFIX_BLOCK), (unsigned)h->n_chunks);
+  prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  CU(h, cudaGetLastError());
+  prefix_scan_chunks<<<(unsigned)((h->R + 255) / 256), 256, 0, h->stream>>>(h->d_chunk, h->n_chunks, h->R);
+  CU(h, cudaGetLastError());
+  CU(h, cudaMemsetAsync(h->d_table, 0, (size_t)h->R * sizeof(double), h->stream));  // row 0
+  prefix_kernel<true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  CU(h, cudaGetLastError());
+  return DBN_OK;
+}
+
+int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, int32_t n_seg, int32_t n, int32_t lag) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!data || !seg_len || n_seg < 1 || n < 2) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: bad arguments (need n >= 2, n_seg >= 1)");
+  if (lag != 1) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: only lag == 1 is implemented (network.py:92-122 lag > 1 is a 'next' row)");
+  if (2 * n + 1 > 65535) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: n too large for the 16-bit column map");
+  CU(h, cudaSetDevice(h->cfg.device));
+  long long rows = 0, N = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    if (seg_len[s] < 2) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: every series segment needs >= 2 rows");
+    rows += seg_len[s];
+    N += seg_len[s] - 1;
+  }
+  free_stats(h);
+  free_chain(h);
+  h->n = n;
+  h->N = (int)N;
+  h->W = 2 * n + 1;
+  h->zz_size = (n + 1) * (n + 2) / 2;
+  h->R = (long long)h->zz_size + (long long)n * (n + 2);
+  // regression row t -> raw row of x_t (network.py:105-118: rows [:len-1] of each segment, concatenated)
+  std::vector<int> xrow((size_t)N);
+  {
+    long long base = 0, t = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      for (int j = 0; j + 1 < seg_len[s]; ++j) xrow[(size_t)t++] = (int)(base + j);
+      base += seg_len[s];
+    }
+  }
+  // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[n+1+i]; YY(i) = v[n+1+i]^2
+  std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
+  {
+    size_t p = 0;
+    for (int a = 0; a <= n; ++a)
+      for (int b = 0; b <= a; ++b) {
+        ca[p] = (unsigned short)a;
+        cb[p] = (unsigned short)b;
+        ++p;
+      }
+    for (int i = 0; i < n; ++i) {
+      for (int a = 0; a <= n; ++a) {
+        ca[p] = (unsigned short)a;
+        cb[p] = (unsigned short)(n + 1 + i);
+        ++p;
+      }
+      ca[p] = cb[p] = (unsigned short)(n + 1 + i);
+      ++p;
+    }
+  }
+  const size_t row_bytes = (size_t)h->W * sizeof(double);
+  int Lc = (int)(96 * 1024 / row_bytes);
+  if (Lc > 64) Lc = 64;
+  if (Lc < 1) Lc = 1;
+  h->Lc = Lc;
+  h->n_chunks = (int)((N + Lc - 1) / Lc);
+  CU(h, cudaFuncSetAttribute(prefix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+  CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+  CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
+  CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));
+  CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
+  CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
+  CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
+  cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
+  if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
+  CU(h, cudaMemcpyAsync(h->d_raw, data, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_colB, cb.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  int rc = launch_prefix(h);
+  if (rc != DBN_OK) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
+  h->have_stats = true;
+  return DBN_OK;
+}
+
+int dbn_rebuild_stats(dbn_handle* h) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_rebuild_stats: call dbn_build_stats first");
+  CU(h, cudaSetDevice(h->cfg.device));
+  return launch_prefix(h);
+}
+
+int dbn_stats_info(const dbn_handle* h, int32_t* N, int64_t* row_doubles, int64_t* algorithmic_bytes) {
+  if (!h || !h->have_stats) return DBN_ERR_STATE;
+  if (N) *N = h->N;
+  if (row_doubles) *row_doubles = h->R;
+  // 8 * [ N*n*2 (read x_t, y_t) + (N+1) * ((n+1)(n+2)/2 + (n+1) n + n) ]
+  if (algorithmic_bytes) *algorithmic_bytes = 8ll * ((long long)h->N * h->n * 2 + (long long)(h->N + 1) * h->R);
+  return DBN_OK;
+}
+
+int dbn_read_stats_row(dbn_handle* h, int32_t t, double* out_row) {
+  if (!h || !out_row) return DBN_ERR_INVALID;
+  if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_read_stats_row: call dbn_build_stats first");
+  if (t < 0 || t > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_read_stats_row: t out of range");
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemcpyAsync(out_row, h->d_table + (long long)t * h->R, (size_t)h->R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return DBN_OK;
+}
+
+static Table make_table(const dbn_handle* h) {
+  Table t;
+  t.base = h->d_table;
+  t.row_stride = h->R;
+  t.n = h->n;
+  t.N = h->N;
+  t.zz_size = h->zz_size;
+  return t;
+}
+
+static double ml_const(double T, double alpha, double beta) {
+  return lgamma(T / 2 + alpha) - lgamma(alpha) - (T / 2) * log(M_PI) + alpha * log(2 * beta);
+}
+
+int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, double T, int32_t B, const int32_t* node,
+                    const int32_t* pi, const int32_t* pi_len, const int32_t* tau, const int32_t* tau_len,
+                    const double* lambda2, const double* delta2, const double* mu, double* out_logml) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_score_batch: call dbn_build_stats first");
+  if (B < 0 || !node || !pi || !pi_len || !tau || !tau_len || !lambda2 || !delta2 || !mu || !out_logml)
+    DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: null argument");
+  if (mode != 0 && mode != 1) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: mode must be 0 (shared prior mean) or 1 (seq-coup)");
+  if (B == 0) return DBN_OK;
+  for (int b = 0; b < B; ++b) {
+    if (node[b] < 0 || node[b] >= h->n || pi_len[b] < 0 || pi_len[b] > PMAX || tau_len[b] < 1 || tau_len[b] > SMAX)
+      DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d out of range", b);
+    for (int j = 0; j < pi_len[b]; ++j)
+      if (pi[b * PMAX + j] < 0 || pi[b * PMAX + j] >= h->n || pi[b * PMAX + j] == node[b])
+        DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d has an invalid parent", b);
+    int prev = 1;
+    for (int j = 0; j + 1 < tau_len[b]; ++j) {
+      const int c = tau[b * SMAX + j];
+      if (c <= prev || c > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d has an invalid changepoint list", b);
+      prev = c;
+    }
+  }
+  CU(h, cudaSetDevice(h->cfg.device));
+  int *d_node = nullptr, *d_pi = nullptr, *d_pl = nullptr, *d_tau = nullptr, *d_tl = nullptr;
+  double *d_lam = nullptr, *d_dlt = nullptr, *d_mu = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    free_dev(d_node); free_dev(d_pi); free_dev(d_pl); free_dev(d_tau); free_dev(d_tl);
+    free_dev(d_lam); free_dev(d_dlt); free_dev(d_mu); free_dev(d_out);
+  };
+#define CUX(expr)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      DBN_FAIL(h, DBN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));                   \
+    }                                                                                              \
+  } while (0)
+  const size_t b4 = (size_t)B * sizeof(int), b8 = (size_t)B * sizeof(double);
+  CUX(cudaMalloc(&d_node, b4)); CUX(cudaMalloc(&d_pi, b4 * PMAX)); CUX(cudaMalloc(&d_pl, b4));
+  CUX(cudaMalloc(&d_tau, b4 * SMAX)); CUX(cudaMalloc(&d_tl, b4));
+  CUX(cudaMalloc(&d_lam, b8)); CUX(cudaMalloc(&d_dlt, b8)); CUX(cudaMalloc(&d_mu, b8 * KMAX)); CUX(cudaMalloc(&d_out, b8));
+  CUX(cudaMemcpyAsync(d_node, node, b4, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_pi, pi, b4 * PMAX, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_pl, pi_len, b4, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_tau, tau, b4 * SMAX, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_tl, tau_len, b4, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_lam, lambda2, b8, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_dlt, delta2, b8, cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(d_mu, mu, b8 * KMAX, cudaMemcpyHostToDevice, h->stream));
+  score_batch_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(make_table(h), mode, ml_const(T, alpha, beta), T / 2 + alpha, 2 * beta, B,
+                                                            d_node, d_pi, d_pl, d_tau, d_tl, d_lam, d_dlt, d_mu, d_out, h->d_counters);
+  CUX(cudaGetLastError());
+  CUX(cudaMemcpyAsync(out_logml, d_out, b8, cudaMemcpyDeviceToHost, h->stream));
+  CUX(cudaStreamSynchronize(h->stream));
+  cleanup();
+#undef CUX
+  return DBN_OK;
+}
+
+int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
+  if (!h || !p) return DBN_ERR_INVALID;
+  if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
+  if (p->method < DBN_H_DBN || p->method > DBN_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (p->fan_in < 1 || p->fan_in > PMAX) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
+  if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
+  if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
+  const long long U = (long long)h->n * h->cfg.n_chains;
+  if (U > 0x7fffffffll) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: too many units");
+  CU(h, cudaSetDevice(h->cfg.device));
+  free_chain(h);
+  h->rp = *p;
+  h->U = (int)U;
+  h->it_done = 0;
+  CU(h, cudaMalloc(&h->st_npi, U * sizeof(int)));
+  CU(h, cudaMalloc(&h->st_pi, U * PMAX * sizeof(int)));
+  CU(h, cudaMalloc(&h->st_S, U * sizeof(int)));
+  CU(h, cudaMalloc(&h->st_tau, U * SMAX * sizeof(int)));
+  CU(h, cudaMalloc(&h->st_sig, U * sizeof(double)));
+  CU(h, cudaMalloc(&h->st_lam, U * sizeof(double)));
+  CU(h, cudaMalloc(&h->st_del, U * sizeof(double)));
+  CU(h, cudaMalloc(&h->st_mu, U * KMAX * sizeof(double)));
+  h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
+  CU(h, cudaMalloc(&h->d_counts, (size_t)h->counts_elems * sizeof(unsigned long long)));
+  CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->counts_elems * sizeof(unsigned long long), h->stream));
+  CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
+  init_state_kernel<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>((int)U, h->N, h->st_npi, h->st_pi, h->st_S, h->st_tau, h->st_sig,
+                                                                       h->st_lam, h->st_del, h->st_mu);
+  CU(h, cudaGetLastError());
+  h->have_chain = true;
+  return DBN_OK;
+}
+
+int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d, int32_t* trace_i) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: call dbn_chain_init first");
+  if (n_iter < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: n_iter < 0");
+  if ((replay_d == nullptr) != (replay_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay_d and replay_i must be given together");
+  if ((replay_d != nullptr) && !(trace_d && trace_i)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay mode requires trace buffers");
+  if ((trace_d == nullptr) != (trace_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: trace_d and trace_i must be given together");
+  if (n_iter == 0) return DBN_OK;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const dbn_run_params& p = h->rp;
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tb = make_table(h);
+  a.method = p.method;
+  a.fan_in = p.fan_in;
+  a.with_tau = p.with_tau;
+  a.num_samples = p.num_samples;
+  a.burn_in = p.burn_in;
+  a.thin = p.thin;
+  a.C = h->cfg.n_chains;
+  a.U = h->U;
+  a.it0 = h->it_done;
+  a.n_iter = n_iter;
+  a.chain_offset = (unsigned)h->cfg.chain_offset;
+  a.seed = h->cfg.seed;
+  a.T_sigma_half = p.T_sigma / 2;
+  a.a_sig = p.a_sigma; a.b_sig = p.b_sigma;
+  a.a_lam = p.a_lambda; a.b_lam = p.b_lambda;
+  a.a_del = p.a_delta; a.b_del = p.b_delta;
+  a.log_p = log(p.cp_p);
+  a.log_1mp = log(1.0 - p.cp_p);
+  a.c0 = ml_const(p.T_ml, p.a_sigma, p.b_sigma);
+  a.T_half_plus_a = p.T_ml / 2 + p.a_sigma;
+  a.two_b = 2 * p.b_sigma;
+  a.st_npi = h->st_npi; a.st_pi = h->st_pi; a.st_S = h->st_S; a.st_tau = h->st_tau;
+  a.st_sig = h->st_sig; a.st_lam = h->st_lam; a.st_del = h->st_del; a.st_mu = h->st_mu;
+  a.edge = h->d_counts;
+  a.nonempty = a.edge + (long long)h->n * h->n;
+  a.cp_hist = a.nonempty + h->n;
+  a.cp_kept = a.cp_hist + (long long)h->n * (h->N + 3);
+  a.counters = h->d_counters;
+
+  const bool trace = trace_d != nullptr;
+  const bool replay = replay_d != nullptr;
+  double *d_rd = nullptr, *d_td = nullptr;
+  int *d_ri = nullptr, *d_ti = nullptr;
+  auto cleanup = [&]() { free_dev(d_rd); free_dev(d_td); free_dev(d_ri); free_dev(d_ti); };
+#define CUX(expr)                                                                \
+  do {                                                                           \
+    cudaError_t e_ = (expr);                                                     \
+    if (e_ != cudaSuccess) {                                                     \
+      cleanup();                                                                 \
+      DBN_FAIL(h, DBN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    }                                                                            \
+  } while (0)
+  const size_t rec = (size_t)h->U * n_iter;
+  if (trace) {
+    CUX(cudaMalloc(&d_td, rec * DBN_TD_STRIDE * sizeof(double)));
+    CUX(cudaMalloc(&d_ti, rec * DBN_TI_STRIDE * sizeof(int)));
+    CUX(cudaMemsetAsync(d_td, 0xFF, rec * DBN_TD_STRIDE * sizeof(double), h->stream));  // NaN
+    CUX(cudaMemsetAsync(d_ti, 0xFF, rec * DBN_TI_STRIDE * sizeof(int), h->stream));     // -1
+    a.td = d_td;
+    a.ti = d_ti;
+  }
+  if (replay) {
+    CUX(cudaMalloc(&d_rd, rec * DBN_RD_STRIDE * sizeof(double)));
+    CUX(cudaMalloc(&d_ri, rec * DBN_RI_STRIDE * sizeof(int)));
+    CUX(cudaMemcpyAsync(d_rd, replay_d, rec * DBN_RD_STRIDE * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMemcpyAsync(d_ri, replay_i, rec * DBN_RI_STRIDE * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    a.rd = d_rd;
+    a.ri = d_ri;
+  }
+  const bool km4 = p.fan_in <= 3;
+  chain_fn fn = trace ? (km4 ? pick_method<4, true>(p.method) : pick_method<5, true>(p.method))
+                      : (km4 ? pick_method<4, false>(p.method) : pick_method<5, false>(p.method));
+  const unsigned grid = (unsigned)((h->U + CHAIN_BLOCK - 1) / CHAIN_BLOCK);
+  fn<<<grid, CHAIN_BLOCK, 0, h->stream>>>(a);
+  CUX(cudaGetLastError());
+  unsigned long long one = 1;
+  (void)one;
+  h->it_done += n_iter;
+  if (trace) {
+    CUX(cudaMemcpyAsync(trace_d, d_td, rec * DBN_TD_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaMemcpyAsync(trace_i, d_ti, rec * DBN_TI_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));
+  }
+  cleanup();
+#undef CUX
+  return DBN_OK;
+}
+
+int dbn_counts_size(const dbn_handle* h, int64_t* n_elems) {
+  if (!h || !n_elems) return DBN_ERR_INVALID;
+  if (!h->have_chain) return DBN_ERR_STATE;
+  *n_elems = h->counts_elems;
+  return DBN_OK;
+}
+
+int dbn_read_counts(dbn_handle* h, int64_t* out) {
+  if (!h || !out) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_read_counts: call dbn_chain_init first");
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemcpyAsync(out, h->d_counts, (size_t)h->counts_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return DBN_OK;
+}
+
+int dbn_device_counts(dbn_handle* h, void** device_ptr) {
+  if (!h || !device_ptr) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_device_counts: call dbn_chain_init first");
+  *device_ptr = h->d_counts;
+  return DBN_OK;
+}
+
+int dbn_read_state(dbn_handle* h, int32_t* pi, int32_t* pi_len, int32_t* tau, int32_t* tau_len, double* scalars, double* mu) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_read_state: call dbn_chain_init first");
+  CU(h, cudaSetDevice(h->cfg.device));
+  const size_t U = (size_t)h->U;
+  CU(h, cudaStreamSynchronize(h->stream));
+  std::vector<int> ti(U * SMAX);
+  std::vector<double> td(U * KMAX);
+  if (pi) {
+    CU(h, cudaMemcpy(ti.data(), h->st_pi, U * PMAX * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t u = 0; u < U; ++u)
+      for (int j = 0; j < PMAX; ++j) pi[u * PMAX + j] = ti[j * U + u];
+  }
+  if (pi_len) CU(h, cudaMemcpy(pi_len, h->st_npi, U * sizeof(int), cudaMemcpyDeviceToHost));
+  if (tau) {
+    CU(h, cudaMemcpy(ti.data(), h->st_tau, U * SMAX * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t u = 0; u < U; ++u)
+      for (int j = 0; j < SMAX; ++j) tau[u * SMAX + j] = ti[j * U + u];
+  }
+  if (tau_len) CU(h, cudaMemcpy(tau_len, h->st_S, U * sizeof(int), cudaMemcpyDeviceToHost));
+  if (scalars) {
+    std::vector<double> s(U);
+    double* src[3] = {h->st_sig, h->st_lam, h->st_del};
+    for (int c = 0; c < 3; ++c) {
+      CU(h, cudaMemcpy(s.data(), src[c], U * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t u = 0; u < U; ++u) scalars[u * 3 + c] = s[u];
+    }
+  }
+  if (mu) {
+    CU(h, cudaMemcpy(td.data(), h->st_mu, U * KMAX * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t u = 0; u < U; ++u)
+      for (int i = 0; i < KMAX; ++i) mu[u * KMAX + i] = td[i * U + u];
+  }
+  return DBN_OK;
+}
+
+int dbn_read_counters(dbn_handle* h, uint64_t out[8]) {
+  if (!h || !out) return DBN_ERR_INVALID;
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemcpyAsync(out, h->d_counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return DBN_OK;
+}
+
+int dbn_reset_counters(dbn_handle* h) {
+  if (!h) return DBN_ERR_INVALID;
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(uint64_t), h->stream));
+  return DBN_OK;
+}
+
+int dbn_measure_fp64_peak(dbn_handle* h, double* gflops) {
+  if (!h || !gflops) return DBN_ERR_INVALID;
+  CU(h, cudaSetDevice(h->cfg.device));
+  cudaDeviceProp prop;
+  CU(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* d_out = nullptr;
+  CU(h, cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, h->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d_out, iters, 1.0 + rep);
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double gf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e9;
+    if (rep > 0 && gf > best) best = gf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  CU(h, cudaGetLastError());
+  *gflops = best;
+  return DBN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// Device building blocks of the scorer: prefix-table gather, k x k LDL^T, and the per-state passes.
+//
+// One thread evaluates one (node, chain) state: every matrix is at most KM x KM (KM = 1 + fan-in <= 5) and is
+// held in registers as a packed lower triangle with all loops unrolled.  A state with k < KM design columns is
+// padded with identity rows (G = 0 there), which leaves every real entry's arithmetic untouched, so threads of
+// a warp with different parent-set sizes execute the same instruction stream.
+//
+// Math = SURVEY.md Appendix A: with A_h = I + w G_h = L D L^T,
+//   ln det C_h = sum ln d_j,   r^T C_h^-1 r = rho - w (L^-1 v)^T D^-1 (L^-1 v),  v = g - G mu, rho = s - 2 mu.g + mu.G.mu
+// replacing the T_h x T_h det/inv of marginalLikelihood.py:104-144 and samplers.py:112-116.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+namespace dbn {
+
+#define DBN_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// ----- prefix table geometry (one row per t = 0..N) -------------------------------------------------------
+// row = [ ZZ packed lower triangle over z = (1, x_0..x_{n-1}) : (n+1)(n+2)/2 doubles |
+//         for each node i: ZY[i][0..n] (sum z_a * y_i), YY[i] (sum y_i^2) : n * (n + 2) doubles ]
+struct Table {
+  const double* base;
+  long long row_stride;  // doubles per row
+  int n;
+  int N;        // regression rows; table has N+1 rows, row 0 is all zeros
+  int zz_size;  // (n+1)(n+2)/2
+};
+
+template <int KM>
+struct Cols {
+  int zz[KM * (KM + 1) / 2];
+  int zy[KM];
+  int yy;
+  int k;
+};
+
+// f[0] = 0 (intercept); f[1..k-1] = sorted parent gene ids + 1 (utils.py:202-204: columns sorted by label)
+template <int KM>
+__device__ __forceinline__ void make_cols(Cols<KM>& c, const Table& t, int node, const int (&f)[KM], int k) {
+  c.k = k;
+  const int nb = t.zz_size + node * (t.n + 2);
+#pragma unroll
+  for (int i = 0; i < KM; ++i) {
+    const int fi = f[i];
+    c.zy[i] = nb + fi;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) c.zz[DBN_TRI(i, j)] = fi * (fi + 1) / 2 + f[j];
+  }
+  c.yy = nb + t.n + 1;
+}
+
+// segment statistics of rows [lo, hi): difference of two table rows restricted to the state's columns
+template <int KM>
+__device__ __forceinline__ void load_segment(const Table& t, const Cols<KM>& c, int lo, int hi,
+                                             double (&G)[KM * (KM + 1) / 2], double (&g)[KM], double& s) {
+  const double* __restrict__ ph = t.base + (long long)hi * t.row_stride;
+  const double* __restrict__ pl = t.base + (long long)lo * t.row_stride;
+#pragma unroll
+  for (int i = 0; i < KM; ++i) {
+    const bool on = i < c.k;
+    g[i] = on ? (__ldg(ph + c.zy[i]) - __ldg(pl + c.zy[i])) : 0.0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) G[DBN_TRI(i, j)] = on ? (__ldg(ph + c.zz[DBN_TRI(i, j)]) - __ldg(pl + c.zz[DBN_TRI(i, j)])) : 0.0;
+  }
+  s = __ldg(ph + c.yy) - __ldg(pl + c.yy);
+}
+
+// ----- KM x KM symmetric positive definite algebra on packed lower triangles ------------------------------
+// In place A -> unit-lower L (strict part) ; returns prod_j d_j and fills dinv[j] = 1/d_j.
+template <int KM>
+__device__ __forceinline__ double ldl_factor(double (&A)[KM * (KM + 1) / 2], double (&dinv)[KM]) {
+  double prod = 1.0;
+#pragma unroll
+  for (int j = 0; j < KM; ++j) {
+    const double d = A[DBN_TRI(j, j)];
+    prod *= d;
+    const double di = 1.0 / d;
+    dinv[j] = di;
+#pragma unroll
+    for (int i = j + 1; i < KM; ++i) {
+      const double l = A[DBN_TRI(i, j)] * di;
+#pragma unroll
+      for (int m = j + 1; m <= i; ++m) A[DBN_TRI(i, m)] -= l * A[DBN_TRI(m, j)];
+    }
+#pragma unroll
+    for (int i = j + 1; i < KM; ++i) A[DBN_TRI(i, j)] *= di;
+  }
+  return prod;
+}
+
+// w <- L^-1 w (unit lower)
+template <int KM>
+__device__ __forceinline__ void solve_lower(const double (&L)[KM * (KM + 1) / 2], double (&w)[KM]) {
+#pragma unroll
+  for (int i = 1; i < KM; ++i)
+#pragma unroll
+    for (int p = 0; p < i; ++p) w[i] -= L[DBN_TRI(i, p)] * w[p];
+}
+
+// x <- L^-T x (unit lower transposed)
+template <int KM>
+__device__ __forceinline__ void solve_upper(const double (&L)[KM * (KM + 1) / 2], double (&x)[KM]) {
+#pragma unroll
+  for (int i = KM - 2; i >= 0; --i)
+#pragma unroll
+    for (int p = i + 1; p < KM; ++p) x[i] -= L[DBN_TRI(p, i)] * x[p];
+}
+
+// x <- (L D L^T)^-1 x
+template <int KM>
+__device__ __forceinline__ void solve_ldl(const double (&L)[KM * (KM + 1) / 2], const double (&dinv)[KM], double (&x)[KM]) {
+  solve_lower<KM>(L, x);
+#pragma unroll
+  for (int i = 0; i < KM; ++i) x[i] *= dinv[i];
+  solve_upper<KM>(L, x);
+}
+
+// y = G x for packed symmetric G
+template <int KM>
+__device__ __forceinline__ void symv(const double (&G)[KM * (KM + 1) / 2], const double (&x)[KM], double (&y)[KM]) {
+#pragma unroll
+  for (int i = 0; i < KM; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < KM; ++j) a += G[(i >= j) ? DBN_TRI(i, j) : DBN_TRI(j, i)] * x[j];
+    y[i] = a;
+  }
+}
+
+template <int KM>
+__device__ __forceinline__ double dot(const double (&a)[KM], const double (&b)[KM]) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < KM; ++i) s += a[i] * b[i];
+  return s;
+}
+
+// A = I + w G (packed)
+template <int KM>
+__device__ __forceinline__ void form_a(const double (&G)[KM * (KM + 1) / 2], double w, double (&A)[KM * (KM + 1) / 2]) {
+#pragma unroll
+  for (int i = 0; i < KM; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[DBN_TRI(i, j)] = (i == j ? 1.0 : 0.0) + w * G[DBN_TRI(i, j)];
+}
+
+// quadratic form r^T C^-1 r of one segment given the factorisation of A = I + w G
+template <int KM, bool HAS_MU>
+__device__ __forceinline__ double segment_q(const double (&G)[KM * (KM + 1) / 2], const double (&g)[KM], double s,
+                                            const double (&mu)[KM], double w, const double (&L)[KM * (KM + 1) / 2],
+                                            const double (&dinv)[KM], double (&wv)[KM]) {
+  double rho = s;
+  if (HAS_MU) {
+    double Gmu[KM];
+    symv<KM>(G, mu, Gmu);
+#pragma unroll
+    for (int i = 0; i < KM; ++i) wv[i] = g[i] - Gmu[i];
+    rho = s - 2.0 * dot<KM>(mu, g) + dot<KM>(mu, Gmu);
+  } else {
+#pragma unroll
+    for (int i = 0; i < KM; ++i) wv[i] = g[i];
+  }
+  solve_lower<KM>(L, wv);
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < KM; ++i) acc += wv[i] * wv[i] * dinv[i];
+  return rho - w * acc;
+}
+
+// work accounting: algorithmic bytes and FP64 flops of one segment evaluation with k columns
+struct Work {
+  unsigned long long evals, segs, bytes, flops;
+  __device__ __forceinline__ void segment(int k, bool has_mu) {
+    segs += 1;
+    bytes += 16ull * (unsigned)(k * (k + 1) / 2 + k + 1);
+    flops += (unsigned)((k * k * k) / 3 + 2 * k * k + 5 * k + (has_mu ? 2 * k * k : 0));
+  }
+  __device__ __forceinline__ void eval() {
+    evals += 1;
+    flops += 12;
+  }
+};
+
+// end row (exclusive) of segment h: tau[h] - 1, N for the last one (utils.py:179,262)
+#define DBN_SEG_END(tau_h, h, S, N) (((h) == (S)-1) ? (N) : ((tau_h)-1))
+
+// ----- a2/a3: log marginal likelihood, one prior mean for all segments (nh/h: zeros; glob: mu) ------------
+// tau(h) is a callable returning the h-th changepoint.  c0 = lgamma(T/2+a) - lgamma(a) - (T/2) ln(pi) + a ln(2b).
+template <int KM, bool HAS_MU, class TauFn>
+__device__ __forceinline__ double score_plain(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam,
+                                              const double (&mu)[KM], double c0, double T_half_plus_a, double two_b,
+                                              Work& wk) {
+  double acc_ld = 0.0, acc_q = 0.0;
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
+    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
+    load_segment<KM>(t, c, lo, hi, G, g, s);
+    form_a<KM>(G, lam, A);
+    acc_ld += log(ldl_factor<KM>(A, dinv));
+    acc_q += segment_q<KM, HAS_MU>(G, g, s, mu, lam, A, dinv, wv);
+    wk.segment(c.k, HAS_MU);
+    lo = hi;
+  }
+  wk.eval();
+  return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+}
+
+// ----- a2 + a8: sequentially coupled log marginal likelihood ------------------------------------------------
+// Prior means are betaTildeSampler's (samplers.py:4-54): bt[0] = 0, bt[1] = (I/lam + G_1)^-1 g_1,
+// bt[h] = (I/dlt + G_{h-1})^-1 (bt[h-2]/dlt + g_{h-1}); C_h uses dlt for h > 0 (marginalLikelihood.py:104-107).
+template <int KM, class TauFn>
+__device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, double dlt,
+                                            double c0, double T_half_plus_a, double two_b, Work& wk) {
+  double acc_ld = 0.0, acc_q = 0.0;
+  double bt_cur[KM], bt_prev[KM];
+#pragma unroll
+  for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
+    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
+    load_segment<KM>(t, c, lo, hi, G, g, s);
+    if (h == 1) {  // bt[1] from this segment's own data with lambda^2
+      form_a<KM>(G, lam, A);
+      ldl_factor<KM>(A, dinv);
+#pragma unroll
+      for (int i = 0; i < KM; ++i) bt_cur[i] = lam * g[i];
+      solve_ldl<KM>(A, dinv, bt_cur);
+      wk.segment(c.k, false);
+    }
+    const double w = (h == 0) ? lam : dlt;
+    form_a<KM>(G, w, A);
+    acc_ld += log(ldl_factor<KM>(A, dinv));
+    acc_q += segment_q<KM, true>(G, g, s, bt_cur, w, A, dinv, wv);
+    wk.segment(c.k, true);
+    if (h >= 1) {  // bt[h+1] = A_dlt(h)^-1 (bt[h-1] + dlt g_h)
+      double nxt[KM];
+#pragma unroll
+      for (int i = 0; i < KM; ++i) nxt[i] = bt_prev[i] + dlt * g[i];
+      solve_ldl<KM>(A, dinv, nxt);
+#pragma unroll
+      for (int i = 0; i < KM; ++i) {
+        bt_prev[i] = bt_cur[i];
+        bt_cur[i] = nxt[i];
+      }
+    }
+    lo = hi;
+  }
+  wk.eval();
+  return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+}
+
+// ----- a9: muSampler's Gaussian (samplers.py:307-351) on sufficient statistics ----------------------------
+// Q = I + sum_h A_h^-1 G_h / s2 (precision), m0 = sum_h A_h^-1 g_h / s2 (mean numerator WITHOUT the mu_in term).
+template <int KM, class TauFn>
+__device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, double sig2,
+                                             double (&Q)[KM * (KM + 1) / 2], double (&m0)[KM], Work& wk) {
+  const double is2 = 1.0 / sig2;
+#pragma unroll
+  for (int i = 0; i < KM; ++i) {
+    m0[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) Q[DBN_TRI(i, j)] = (i == j) ? 1.0 : 0.0;
+  }
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
+    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM];
+    load_segment<KM>(t, c, lo, hi, G, g, s);
+    form_a<KM>(G, lam, A);
+    ldl_factor<KM>(A, dinv);
+    double x[KM];
+#pragma unroll
+    for (int i = 0; i < KM; ++i) x[i] = g[i];
+    solve_ldl<KM>(A, dinv, x);
+#pragma unroll
+    for (int i = 0; i < KM; ++i) m0[i] += x[i] * is2;
+    // columns of A^-1 G (symmetric): only the lower triangle is accumulated
+#pragma unroll
+    for (int col = 0; col < KM; ++col) {
+#pragma unroll
+      for (int i = 0; i < KM; ++i) x[i] = G[(i >= col) ? DBN_TRI(i, col) : DBN_TRI(col, i)];
+      solve_ldl<KM>(A, dinv, x);
+#pragma unroll
+      for (int i = col; i < KM; ++i) Q[DBN_TRI(i, col)] += x[i] * is2;
+    }
+    wk.segment(c.k, true);
+    lo = hi;
+  }
+}
+
+}  // namespace dbn

@@ -39,3 +39,38 @@ def assert_close(a, b, rtol, atol=0.0, what=''):
     bad = err > tol
     assert not bad.any(), '%s: max rel err %.3e (rtol %.1e) at %d/%d entries' % (
         what, float((err / np.maximum(np.abs(b[fb]), 1e-300)).max()), rtol, int(bad.sum()), bad.size)
+
+
+def golden_replay(g):
+    """Replay dict (engine.pack_replay layout, unit = node, one chain) from a chain golden file."""
+    n, n_iter = g['sigma2'].shape
+    K, S = 5, 10
+    r = dict(sigma2=g['sigma2'], lambda2=g['lambda2'], delta2=g['delta2'], u_pi=g['u_pi'], u_tau=g['u_tau'],
+             beta=g['beta'], pi_move=g['pi_move'], pi_pick=g['pi_pick'], tau_move=g['tau_move'], tau_pick=g['tau_pick'])
+    if 'mus_val' in g:
+        r['mu_pi'] = g['mus_val'][:, :, 0, :]
+        r['mu_tau'] = g['mus_val'][:, :, 3, :]
+    return r
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def assert_close_mat(a, b, rtol, what=''):
+    """Matrix-wise tolerance: |a - b| <= rtol * max|b| over the trailing two axes (covariances: entries that are
+    tiny relative to the matrix scale carry cancellation noise in the reference's own np.linalg.inv)."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    assert (fa == fb).all(), '%s: finite masks differ at %s' % (what, np.argwhere(fa != fb)[:5])
+    scale = np.nanmax(np.where(fb, np.abs(b), 0.0), axis=(-1, -2), keepdims=True)
+    err = np.where(fb, np.abs(np.where(fa, a, 0.0) - np.where(fb, b, 0.0)), 0.0)
+    bad = err > rtol * scale
+    assert not bad.any(), '%s: max matrix-relative err %.3e (rtol %.1e) at %d entries' % (
+        what, float((err / np.maximum(scale, 1e-300)).max()), rtol, int(bad.sum()))

@@ -1,0 +1,207 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the reference goldens."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import KAT_FILES, CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
+from oracle import dbn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng_mod():
+    from dynamicbayesiannetworks_b200.engine import DbnEngine
+    return DbnEngine
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 1: prefix statistics == cumulative sums of outer products of the lag-1 rows
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', KAT_FILES, ids=ids(KAT_FILES))
+def test_prefix_rows(eng_mod, path):
+    g = load(path)
+    data = data_list(g)
+    X, Y = O.lagged_matrices(data)
+    N, n = X.shape
+    Z = np.concatenate([np.ones((N, 1)), X], axis=1)
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data)
+        assert e.stats_info()['N'] == N
+        for t in sorted({0, 1, 2, N // 3, N // 2, N - 1, N}):
+            zz, zy, yy = e.stats_row(t)
+            assert_close(zz, Z[:t].T @ Z[:t], 1e-12, 1e-12, what='ZZ[%d]' % t)
+            assert_close(zy, (Z[:t].T @ Y[:t]).T, 1e-12, 1e-12, what='ZY[%d]' % t)
+            assert_close(yy, (Y[:t] ** 2).sum(axis=0), 1e-12, 1e-12, what='YY[%d]' % t)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 2: batched scorer vs the reference's own log-ML values (1e-9 relative, north_star)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', KAT_FILES, ids=ids(KAT_FILES))
+def test_score_batch_vs_reference(eng_mod, path):
+    g = load(path)
+    B = g['node'].shape[0]
+    pi = [list(g['pi'][c, :g['npi'][c]]) for c in range(B)]
+    tau = [list(g['tau'][c, :g['S'][c]]) for c in range(B)]
+    mu = [g['mu'][c, :g['npi'][c] + 1] for c in range(B)]
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data_list(g))
+        for ab in (0.005, 0.01):
+            for T in sorted(set(g['T'])):
+                sel = np.nonzero((g['alpha'] == ab) & (g['T'] == T))[0]
+                if sel.size == 0:
+                    continue
+                sub = lambda lst: [lst[c] for c in sel]
+                args = (list(g['node'][sel]), sub(pi), sub(tau), g['lambda2'][sel])
+                plain = e.score_batch(*args, alpha=ab, beta=ab, T=T)
+                with_mu = e.score_batch(*args, mu=sub(mu), alpha=ab, beta=ab, T=T)
+                seq = e.score_batch(*args, delta2=g['delta2'][sel], alpha=ab, beta=ab, T=T, seq=True)
+                assert_close(plain, g['logml_plain'][sel], LOGML_RTOL, what='plain')
+                assert_close(with_mu, g['logml_mu'][sel], LOGML_RTOL, what='mu')
+                assert_close(seq, g['logml_seq'][sel], LOGML_RTOL, what='seq')
+        # h-dbn: log of the un-logged calculateMarginalLikelihood (marginalLikelihood.py:152-166), N rows, T = N
+        N = int(g['N'])
+        raw = g['rawml_h']
+        sel = np.nonzero(np.isfinite(raw) & (raw > 0))[0]
+        if sel.size:
+            for ab in (0.005, 0.01):
+                s2 = sel[g['alpha'][sel] == ab]
+                if s2.size:
+                    out = e.score_batch(list(g['node'][s2]), [pi[c] for c in s2], [[N + 2]] * s2.size, g['lambda2'][s2],
+                                        alpha=ab, beta=ab, T=N)
+                    assert_close(out, np.log(raw[s2]), LOGML_RTOL, what='h')
+
+
+def test_score_batch_large_T_vs_oracle(eng_mod):
+    """BASELINE config 4 shape (n=100, T=2000): beyond the reference's overflow limit, the oracle is the check."""
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    data, _, _ = make_synthetic(100, 2000, n_changepoints=3, max_fan_in=4, seed=20260119)
+    X, Y = O.lagged_matrices([data])
+    N, n = X.shape
+    rng = np.random.default_rng(5)
+    B = 300
+    node = rng.integers(0, n, B)
+    pi, tau, mu, lam, dlt = [], [], [], [], []
+    for b in range(B):
+        feats = [j for j in range(n) if j != node[b]]
+        pi.append([int(v) for v in rng.choice(feats, size=rng.integers(0, 5), replace=False)])
+        S = int(rng.integers(1, 10))
+        tau.append(sorted(int(v) for v in rng.choice(np.arange(2, N + 1), size=S - 1, replace=False)) + [N + 2])
+        mu.append(rng.normal(0, 0.3, len(pi[-1]) + 1))
+        lam.append(float(np.exp(rng.uniform(-3, 3)))); dlt.append(float(np.exp(rng.uniform(-3, 3))))
+    with eng_mod(n_chains=1) as e:
+        e.build_stats([data])
+        out_mu = e.score_batch(list(node), pi, tau, lam, mu=mu, alpha=0.005, beta=0.005, T=N)
+        out_seq = e.score_batch(list(node), pi, tau, lam, delta2=dlt, alpha=0.005, beta=0.005, T=N - 1, seq=True)
+    for b in range(B):
+        stats = O.segment_stats(X, Y[:, node[b]], pi[b], tau[b])
+        ref = O.log_ml(stats, [mu[b]] * len(tau[b]), 0.005, 0.005, lam[b], N)
+        assert_close(out_mu[b], ref, LOGML_RTOL, what='large-T mu[%d]' % b)
+        ref = O.log_ml(stats, O.beta_tilde(stats, lam[b], dlt[b]), 0.005, 0.005, lam[b], N - 1, True, dlt[b])
+        assert_close(out_seq[b], ref, LOGML_RTOL, what='large-T seq[%d]' % b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 3: replay of the reference's recorded draw stream
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', CHAIN_FILES, ids=ids(CHAIN_FILES))
+def test_chain_replay_vs_reference(eng_mod, path):
+    """Given the identical injected draw stream, accept/reject flags, parent sets and changepoints must match the
+    reference bit-exactly; Gibbs parameters and log-MLs to 1e-9 relative."""
+    g = load(path)
+    method = str(g['method'])
+    n, n_iter = g['sigma2'].shape
+    N, burn_in = int(g['N']), int(g['burn_in'])
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data_list(g))
+        e.chain_init(method, burn_in=burn_in)
+        tr = e.run(n_iter, replay=golden_replay(g), trace=True)
+        counts = e.counts()
+    for key in ('pi_valid', 'pi_accept', 'npi', 'S'):
+        assert np.array_equal(tr[key], g[key]), key
+    assert np.array_equal(tr['pi_after'], g['pi_after']), 'pi_after'
+    if method != 'h_dbn':
+        for key in ('tau_valid', 'tau_accept'):
+            assert np.array_equal(tr[key], g[key]), key
+    assert np.array_equal(tr['tau_after'], g['tau_after']), 'tau_after'
+    assert_close(tr['sig_shape'], g['sig_shape'], 1e-12, what='sig_shape')
+    assert_close(1.0 / tr['sig_rate'], g['sig_scale'], 1e-9, what='sig_scale')
+    assert_close(tr['lam_shape'], g['lam_shape'], 1e-12, what='lam_shape')
+    assert_close(1.0 / tr['lam_rate'], g['lam_scale'], 1e-9, what='lam_scale')
+    if method == 'seq_coup_nh_dbn':
+        assert_close(tr['del_shape'], g['del_shape'], 1e-12, what='del_shape')
+        assert_close(1.0 / tr['del_rate'], g['del_scale'], 1e-9, what='del_scale')
+    assert_close(tr['logml'], g['logml'], LOGML_RTOL, what='logml')
+    assert_close(tr['beta_mean'], g['beta_mean'], 1e-8, 1e-11, what='beta_mean')
+    assert_close_mat(tr['beta_cov'], g['beta_cov'], 1e-9, what='beta_cov')
+    if method == 'glob_coup_nh_dbn':
+        assert_close(tr['mus_mean'], g['mus_mean'], 1e-8, 1e-11, what='mus_mean')
+        assert_close_mat(tr['mus_cov'], g['mus_cov'], 1e-9, what='mus_cov')
+        ref = np.stack([g['mus_logdens'][:, :, 0, 0], g['mus_logdens'][:, :, 1, 1], g['mus_logdens'][:, :, 2, 1],
+                        g['mus_logdens'][:, :, 3, 0]], axis=-1)
+        assert_close(tr['mus_logdens'], ref, 1e-8, 1e-9, what='mus_logdens')
+        assert_close(tr['mu_after'], g['mu_after'], 0, 0, what='mu_after')
+    # thinned-chain counts -> proposed_adj_matrix / changepoint histogram (network.py:355-368,388-389)
+    adj = counts['edge'] / np.maximum(counts['nonempty'], 1)[:, None]
+    ref_adj = g['proposed_adj_matrix']
+    ok = np.isfinite(ref_adj).all(axis=1)
+    assert_close(adj[ok], ref_adj[ok], 1e-14, what='proposed_adj_matrix')
+    if 'cp_hist' in g:
+        assert np.array_equal(counts['cp_hist'], g['cp_hist'].astype(np.int64))
+        assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
+
+
+def test_chain_replay_split_launches(eng_mod):
+    """State carried across dbn_run calls: two launches of n/2 iterations == one launch of n."""
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    n, n_iter = g['sigma2'].shape
+    r = golden_replay(g)
+    half = n_iter // 2
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data_list(g))
+        e.chain_init('varying_nh_dbn', burn_in=int(g['burn_in']))
+        a = e.run(half, replay={k: v[:, :half] for k, v in r.items()}, trace=True)
+        b = e.run(n_iter - half, replay={k: v[:, half:] for k, v in r.items()}, trace=True)
+    assert np.array_equal(np.concatenate([a['tau_after'], b['tau_after']], axis=1), g['tau_after'])
+    assert np.array_equal(np.concatenate([a['pi_after'], b['pi_after']], axis=1), g['pi_after'])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# free-running Philox chains: statistical agreement with the oracle's free-running chains
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn'])
+def test_free_running_edge_posteriors(eng_mod, method):
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    data = data_list(g)
+    X, Y = O.lagged_matrices(data)
+    n = X.shape[1]
+    N = X.shape[0]
+    n_iter, burn = 1500, 500
+    C = 256
+    with eng_mod(n_chains=C, seed=1234) as e:
+        e.build_stats(data)
+        e.chain_init(method, burn_in=burn)
+        e.run(n_iter)
+        c = e.counts()
+        st = e.state()
+        ctr = e.counters()
+    assert ctr['unit_iterations'] == n * C * n_iter
+    assert np.isfinite(st['sigma2']).all() and (st['sigma2'] > 0).all()
+    assert np.isfinite(st['lambda2']).all() and (st['lambda2'] > 0).all()
+    gpu = c['edge'] / np.maximum(c['nonempty'], 1)[:, None]
+    # oracle free-running chains (fewer, they are slow): compare edge frequencies within Monte-Carlo error
+    edge = np.zeros((n, n)); nonempty = np.zeros(n); cph = np.zeros((n, N + 3)); cpk = np.zeros(n)
+    rng = np.random.default_rng(99)
+    n_or = 6
+    for node in range(n):
+        for _ in range(n_or):
+            tr = O.run_chain(method, X, Y, node, 600, O.RngDraws(rng))
+            O.accumulate_counts(tr, node, n, N, 200, edge, nonempty, cph, cpk)
+    ref = O.edge_scores(edge, nonempty)
+    off = ~np.eye(n, dtype=bool)
+    # autocorrelated chains: effective sample size of the oracle side is small, so the bound is loose but it
+    # catches a wrong acceptance rule / prior / Hastings ratio (those shift frequencies by >0.2)
+    assert np.abs(gpu[off] - ref[off]).max() < 0.2, (gpu, ref)
+    assert np.abs(gpu[off] - ref[off]).mean() < 0.07, (gpu, ref)
