@@ -140,6 +140,7 @@ struct dbn_handle {
   std::string err;
   // data / table
   int n = 0, N = 0, W = 0, n_chunks = 0, Lc = 0;
+  long long raw_rows = 0;
   long long R = 0;
   int zz_size = 0;
   double* d_raw = nullptr;
@@ -339,13 +340,6 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     rows += seg_len[s];
     N += seg_len[s] - 1;
   }
-  free_stats(h);
-  free_chain(h);
-  h->n = n;
-  h->N = (int)N;
-  h->W = 2 * n + 1;
-  h->zz_size = (n + 1) * (n + 2) / 2;
-  h->R = (long long)h->zz_size + (long long)n * (n + 2);
   // regression row t -> raw row of x_t (network.py:105-118: rows [:len-1] of each segment, concatenated)
   std::vector<int> xrow((size_t)N);
   {
@@ -355,46 +349,59 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
       base += seg_len[s];
     }
   }
-  // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[n+1+i]; YY(i) = v[n+1+i]^2
-  std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
-  {
-    size_t p = 0;
-    for (int a = 0; a <= n; ++a)
-      for (int b = 0; b <= a; ++b) {
-        ca[p] = (unsigned short)a;
-        cb[p] = (unsigned short)b;
+  const bool same_geometry = h->have_stats && h->n == n && h->N == (int)N && h->raw_rows == rows;
+  if (!same_geometry) {
+    free_stats(h);
+    free_chain(h);
+    h->n = n;
+    h->N = (int)N;
+    h->raw_rows = rows;
+    h->W = 2 * n + 1;
+    h->zz_size = (n + 1) * (n + 2) / 2;
+    h->R = (long long)h->zz_size + (long long)n * (n + 2);
+    // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[n+1+i]; YY(i) = v[n+1+i]^2
+    std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
+    {
+      size_t p = 0;
+      for (int a = 0; a <= n; ++a)
+        for (int b = 0; b <= a; ++b) {
+          ca[p] = (unsigned short)a;
+          cb[p] = (unsigned short)b;
+          ++p;
+        }
+      for (int i = 0; i < n; ++i) {
+        for (int a = 0; a <= n; ++a) {
+          ca[p] = (unsigned short)a;
+          cb[p] = (unsigned short)(n + 1 + i);
+          ++p;
+        }
+        ca[p] = cb[p] = (unsigned short)(n + 1 + i);
         ++p;
       }
-    for (int i = 0; i < n; ++i) {
-      for (int a = 0; a <= n; ++a) {
-        ca[p] = (unsigned short)a;
-        cb[p] = (unsigned short)(n + 1 + i);
-        ++p;
-      }
-      ca[p] = cb[p] = (unsigned short)(n + 1 + i);
-      ++p;
     }
+    const size_t row_bytes = (size_t)h->W * sizeof(double);
+    int Lc = (int)(96 * 1024 / row_bytes);
+    if (Lc > 64) Lc = 64;
+    if (Lc < 1) Lc = 1;
+    h->Lc = Lc;
+    h->n_chunks = (int)((N + Lc - 1) / Lc);
+    CU(h, cudaFuncSetAttribute(prefix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+    CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+    CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
+    CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
+    CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
+    CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
+    cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
+    if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
+    CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_colB, cb.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));  // ca/cb go out of scope
   }
-  const size_t row_bytes = (size_t)h->W * sizeof(double);
-  int Lc = (int)(96 * 1024 / row_bytes);
-  if (Lc > 64) Lc = 64;
-  if (Lc < 1) Lc = 1;
-  h->Lc = Lc;
-  h->n_chunks = (int)((N + Lc - 1) / Lc);
-  CU(h, cudaFuncSetAttribute(prefix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
-  CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
-  CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
-  CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
-  CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));
-  CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
-  CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
-  CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
-  cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
-  if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
+  // same geometry: the table is rebuilt in place and the chain state (if any) carries on over the new data
   CU(h, cudaMemcpyAsync(h->d_raw, data, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_colB, cb.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
   int rc = launch_prefix(h);
   if (rc != DBN_OK) return rc;
   CU(h, cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
@@ -612,8 +619,6 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   const unsigned grid = (unsigned)((h->U + CHAIN_BLOCK - 1) / CHAIN_BLOCK);
   fn<<<grid, CHAIN_BLOCK, 0, h->stream>>>(a);
   CUX(cudaGetLastError());
-  unsigned long long one = 1;
-  (void)one;
   h->it_done += n_iter;
   if (trace) {
     CUX(cudaMemcpyAsync(trace_d, d_td, rec * DBN_TD_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

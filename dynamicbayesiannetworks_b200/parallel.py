@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing: one process per GPU, (node, chain) units sharded by chain, one all-reduce of the count
+matrices per thinning window.
+
+Nodes are independent regressions (network.py:413-416) and chains are independent by construction, so the sampling
+itself needs no collective.  Only the edge-count / changepoint-histogram block (engine.counts()) is summed over
+ranks.  torch.distributed is used for the rendezvous and the NCCL (GPU) / gloo (CPU tests) all-reduce.
+"""
+import numpy as np
+
+
+def shard_chains(total_chains, rank, world_size):
+    """Contiguous split of the chain index space: returns (chain_offset, n_local).  Every rank keeps all nodes, so
+    the prefix table is replicated and unit u = node * n_local + chain_local; Philox counters use the GLOBAL chain
+    id (chain_offset + chain_local), which makes the union of the shards identical to an unsharded run."""
+    base, rem = divmod(int(total_chains), int(world_size))
+    n_local = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, n_local
+
+
+class _DevicePtr:
+    """Minimal __cuda_array_interface__ view of library-owned device memory (no copy)."""
+
+    def __init__(self, ptr, n_elems, typestr='<i8'):
+        self.__cuda_array_interface__ = {'shape': (int(n_elems),), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2}
+
+
+def counts_tensor(engine):
+    """torch int64 view (device memory of the engine) of the contiguous count block."""
+    import torch
+    ptr, n = engine.counts_device_ptr()
+    return torch.as_tensor(_DevicePtr(ptr, n), device='cuda:%d' % engine.device)
+
+
+def allreduce_counts(local, out=None, async_op=False):
+    """Sum the count block over all ranks.  `local` is a torch tensor (CUDA for NCCL, CPU for gloo); the sum is
+    written to `out` (a copy) so that the local accumulators keep counting only their own shard."""
+    import torch
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty_like(local)
+    out.copy_(local)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        work = dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            return out, work
+    return (out, None) if async_op else out
+
+
+def edge_scores_from_counts(edge, nonempty):
+    """proposed_adj_matrix: edge[i][j] / #kept non-empty parent sets of node i (scores.py:184-192).  A node whose
+    every kept sample had an empty parent set makes the reference divide by zero; 0.0 is returned here."""
+    edge = np.asarray(edge, dtype=np.float64)
+    den = np.asarray(nonempty, dtype=np.float64)[:, None]
+    return np.divide(edge, den, out=np.zeros_like(edge), where=den > 0)

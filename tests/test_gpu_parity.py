@@ -205,3 +205,30 @@ def test_free_running_edge_posteriors(eng_mod, method):
     # catches a wrong acceptance rule / prior / Hastings ratio (those shift frequencies by >0.2)
     assert np.abs(gpu[off] - ref[off]).max() < 0.2, (gpu, ref)
     assert np.abs(gpu[off] - ref[off]).mean() < 0.07, (gpu, ref)
+
+
+def test_network_dropin(eng_mod):
+    """dyban.Network surface on the device path: result attributes, history lengths, pickling."""
+    import pickle
+    from dynamicbayesiannetworks_b200 import Network
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    data = data_list(g)
+    for method in ('h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn'):
+        net = Network(data, 300, 100, 1)
+        net.infer_network(method)
+        adj = np.array(net.proposed_adj_matrix)
+        assert adj.shape == (5, 5) and np.isfinite(adj).all() and (adj >= 0).all() and (adj <= 1).all()
+        assert np.allclose(np.diag(adj), 0)
+        r = net.chain_results
+        assert len(r['pi_vector']) == 301 and len(r['sigma_sqr_vector']) == 301 and len(r['lambda_sqr_vector']) == 301
+        if method != 'h_dbn':
+            assert len(r['tau_vector']) == 300 and all(t[-1] == 35 for t in r['tau_vector'])
+            assert len(net.cps_over_response) == 5 and len(net.cps_over_response[0]) == 20
+        if method == 'seq_coup_nh_dbn':
+            assert len(r['delta_sqr_vector']) == 301
+        pickle.loads(pickle.dumps(net))
+    big = Network(data, 400, 100, 1, n_chains=128)
+    big.infer_network('nh-dbn')
+    assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)
+    with pytest.raises(NotImplementedError):
+        Network(data, 10, 0, 1).infer_network('fp_glob_coup_nh_dbn')
