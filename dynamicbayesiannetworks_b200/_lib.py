@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'libdbn_b200.so')
+# DBN_B200_LIB points at an alternative build of the same library (kernel A/B experiments); never a CPU fallback
+LIB_PATH = os.environ.get('DBN_B200_LIB') or os.path.join(PKG, 'libdbn_b200.so')
 
 KMAX, PMAX, SMAX = 5, 4, 10
 KTRI = KMAX * (KMAX + 1) // 2

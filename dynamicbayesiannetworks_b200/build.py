@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libdbn_b200.so')
 SOURCES = [os.path.join(CSRC, 'dbn_kernels.cu')]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('dbn_chain.cuh', 'dbn_score.cuh', 'dbn_rng.cuh')] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('dbn_chain.cuh', 'dbn_chain_fast.cuh', 'dbn_score.cuh', 'dbn_rng.cuh')] + [
     os.path.join(ROOT, 'include', 'dbn_b200.h')]
 
 
@@ -32,12 +32,14 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out` / `defines`: build a variant (e.g. a different launch bound) beside the default library."""
+    if out is None and not force and not is_stale():
         return LIB
+    out = out or LIB
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-I', os.path.join(ROOT, 'include'),
-           '-o', LIB] + SOURCES
+           '-o', out] + ['-D' + d for d in defines] + SOURCES
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
@@ -46,8 +48,11 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), res.stdout))
     if verbose:
         print(res.stdout)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    argv = sys.argv[1:]
+    out = argv[argv.index('--out') + 1] if '--out' in argv else None
+    defines = [a[2:] for a in argv if a.startswith('-D')]
+    print(build(force='--force' in argv, verbose='--verbose' in argv, out=out, defines=defines))

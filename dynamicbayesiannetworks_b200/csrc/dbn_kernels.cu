@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "dbn_chain.cuh"
+#include "dbn_chain_fast.cuh"
 
 namespace dbn {
 
@@ -157,6 +157,10 @@ struct dbn_handle {
   int it_done = 0;
   int *st_npi = nullptr, *st_pi = nullptr, *st_S = nullptr, *st_tau = nullptr;
   double *st_sig = nullptr, *st_lam = nullptr, *st_del = nullptr, *st_mu = nullptr;
+  // h / nh fast path: boundary-row cache, column slots, boundary slots
+  double* d_cache = nullptr;
+  int *st_cg = nullptr, *st_bslot = nullptr;
+  bool cache_valid = false;
   unsigned long long* d_counts = nullptr;
   long long counts_elems = 0;
   unsigned long long* d_counters = nullptr;
@@ -181,8 +185,8 @@ typedef void (*chain_fn)(const ChainArgs);
 template <int KM, bool TRACE>
 static chain_fn pick_method(int method) {
   switch (method) {
-    case DBN_H_DBN: return chain_kernel<DBN_H_DBN, KM, TRACE>;
-    case DBN_NH_DBN: return chain_kernel<DBN_NH_DBN, KM, TRACE>;
+    case DBN_H_DBN: return chain_fast_kernel<DBN_H_DBN, KM, TRACE>;
+    case DBN_NH_DBN: return chain_fast_kernel<DBN_NH_DBN, KM, TRACE>;
     case DBN_SEQ_DBN: return chain_kernel<DBN_SEQ_DBN, KM, TRACE>;
     default: return chain_kernel<DBN_GLOB_DBN, KM, TRACE>;
   }
@@ -284,6 +288,10 @@ static void free_chain(dbn_handle* h) {
   free_dev(h->st_lam);
   free_dev(h->st_del);
   free_dev(h->st_mu);
+  free_dev(h->d_cache);
+  free_dev(h->st_cg);
+  free_dev(h->st_bslot);
+  h->cache_valid = false;
   free_dev(h->d_counts);
   h->have_chain = false;
 }
@@ -406,6 +414,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
   if (rc != DBN_OK) return rc;
   CU(h, cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
   h->have_stats = true;
+  h->cache_valid = false;  // the chain (if any) re-gathers its boundary rows from the new table
   return DBN_OK;
 }
 
@@ -413,6 +422,7 @@ int dbn_rebuild_stats(dbn_handle* h) {
   if (!h) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_rebuild_stats: call dbn_build_stats first");
   CU(h, cudaSetDevice(h->cfg.device));
+  h->cache_valid = false;
   return launch_prefix(h);
 }
 
@@ -530,6 +540,14 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   CU(h, cudaMalloc(&h->st_lam, U * sizeof(double)));
   CU(h, cudaMalloc(&h->st_del, U * sizeof(double)));
   CU(h, cudaMalloc(&h->st_mu, U * KMAX * sizeof(double)));
+  if (p->method == DBN_H_DBN || p->method == DBN_NH_DBN) {
+    const int km = p->fan_in <= 3 ? 4 : 5;
+    const size_t cache_bytes = (size_t)BSLOTS * fast_cache_row_doubles(km) * U * sizeof(double);
+    cudaError_t e = cudaMalloc(&h->d_cache, cache_bytes);
+    if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "boundary-row cache of %.2f GB does not fit: %s", cache_bytes / 1e9, cudaGetErrorString(e));
+    CU(h, cudaMalloc(&h->st_cg, U * PMAX * sizeof(int)));
+    CU(h, cudaMalloc(&h->st_bslot, U * SMAX * sizeof(int)));
+  }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
   CU(h, cudaMalloc(&h->d_counts, (size_t)h->counts_elems * sizeof(unsigned long long)));
   CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->counts_elems * sizeof(unsigned long long), h->stream));
@@ -582,6 +600,10 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   a.cp_hist = a.nonempty + h->n;
   a.cp_kept = a.cp_hist + (long long)h->n * (h->N + 3);
   a.counters = h->d_counters;
+  a.cache = h->d_cache;
+  a.st_cg = h->st_cg;
+  a.st_bslot = h->st_bslot;
+  a.refresh = h->cache_valid ? 0 : 1;
 
   const bool trace = trace_d != nullptr;
   const bool replay = replay_d != nullptr;
@@ -619,6 +641,7 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   const unsigned grid = (unsigned)((h->U + CHAIN_BLOCK - 1) / CHAIN_BLOCK);
   fn<<<grid, CHAIN_BLOCK, 0, h->stream>>>(a);
   CUX(cudaGetLastError());
+  h->cache_valid = true;
   h->it_done += n_iter;
   if (trace) {
     CUX(cudaMemcpyAsync(trace_d, d_td, rec * DBN_TD_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
