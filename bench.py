@@ -294,6 +294,9 @@ def main():
         'data': 'synthetic', 'config': workload(),
         'ml_evals_per_sec': tot_evals / (ms * 1e-3),
         'ml_evals_per_iteration': ctr['ml_evals'] / max(1, ctr['unit_iterations']),
+        'accept_rate': {'pi': ctr['pi_accepts'] / max(1, ctr['unit_iterations']),
+                        'tau': ctr['tau_accepts'] / max(1, ctr['unit_iterations'])},
+        'segment_factorisations_per_iteration': ctr['segment_factorisations'] / max(1, ctr['unit_iterations']),
         'roofline': {'kernel': 'chain_kernel<nh-dbn, KM=5>', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,
                      'algorithmic_bytes_per_launch': per_launch_bytes,

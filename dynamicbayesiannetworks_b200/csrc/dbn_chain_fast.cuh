@@ -5,14 +5,21 @@
 // Why (profiles/r1_v0): with every pass re-gathering 2 x 21 scattered doubles per segment, the v0 kernel was bound
 // by the L1 miss-request path (one 32-byte sector request per gathered double, ~1 request/cycle/SM) at 12 warps/SM.
 // Here
-//   * cache[slot][entry][unit] holds the prefix-table row of each of the unit's <= 9 segment boundaries, restricted
-//     to the unit's design columns (15 + 5 + 1 doubles at KM = 5).  Threads of a warp read the same (slot, entry) of
-//     consecutive units: fully coalesced, 4 sectors per request instead of 1.
+//   * cache[j][entry][unit], j < 9, holds the statistics (G_h, g_h, s_h) of the unit's j-th segment in time order,
+//     restricted to the unit's design columns (15 + 5 + 1 doubles at KM = 5): the difference of the two prefix-table
+//     rows at the segment's boundaries, taken once when the state changes.  Threads of a warp read the same
+//     (j, entry) of consecutive units: fully coalesced, 21 loads per segment and sweep.  Rows are kept physically
+//     ordered, because a per-unit row indirection scatters the warp's addresses again (measured: profiles/r1_v1).
 //   * the parent-set move scores pi and pi* in ONE sweep: both column sets share a base of <= KM-1 columns, which is
 //     factorised once per segment (A_B = L D L^T); the column only pi has and the column only pi* has are two
 //     alternative last rows of that factorisation.  Only the new column (<= KM+1 values per boundary) is gathered.
 //   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new)
-//     and gathers one table row (the new boundary) into a scratch slot of the cache.
+//     from the <= 4 prefix-table rows involved, staged in three scratch rows of the cache.
+//   * accepted moves are rare per unit but not per warp, so the cache updates they need (new column in every row;
+//     rows shifted behind an inserted / removed segment) are done by the whole warp for one accepting lane at a
+//     time, 32 entries per step, instead of by the accepting lane alone while 31 lanes idle.
+// Every cached row is an exact function of (pi, tau) and the table (no running sums), so the state does not depend
+// on the history of moves.
 // Columns are kept in cache-slot order, not sorted by gene id: for mu = 0 (h, nh) the marginal likelihood and the
 // Gibbs parameters are invariant to the column order (only rounding differs, ~1e-15 relative); traces are written
 // in the reference's sorted order.
@@ -25,7 +32,10 @@ constexpr int FAST_BLOCK = 128;
 #ifndef DBN_FAST_MINB
 #define DBN_FAST_MINB 1
 #endif
-constexpr int BSLOTS = DBN_SMAX;  // cached rows per unit: <= 9 boundaries (8 changepoints + the final row) + 1 scratch
+constexpr int SEG_ROWS = DBN_SMAX - 1;  // <= 9 segments
+constexpr int ROW_L = SEG_ROWS, ROW_X = SEG_ROWS + 1, ROW_R = SEG_ROWS + 2;  // scratch: prefix rows left / moving / right
+constexpr int BSLOTS = SEG_ROWS + 3;    // cached rows per unit
+constexpr unsigned FULL = 0xffffffffu;
 
 template <int KM>
 struct FastDims {
@@ -35,6 +45,22 @@ struct FastDims {
 };
 
 __host__ __device__ inline int fast_cache_row_doubles(int km) { return km * (km + 1) / 2 + km + 1; }
+inline size_t fast_smem_bytes(int km) {
+  return (size_t)2 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(int) +
+         (FAST_BLOCK / 32) * 16 * sizeof(int);
+}
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): the staged row of the next segment is in flight while the
+// current one is factorised; no registers are held for it
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <int METHOD, int KM, bool TRACE>
 __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(const ChainArgs a) {
@@ -42,21 +68,24 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NE = FastDims<KM>::NE;
   constexpr int KBT = KB * (KB + 1) / 2;
 
-  __shared__ int s_tau[SMAX * FAST_BLOCK];
-  __shared__ int s_tas[SMAX * FAST_BLOCK];
-  __shared__ unsigned char s_bs[SMAX * FAST_BLOCK];  // cache slot of boundary j+1 (rows tau_j - 1, last = N)
+  // dynamic shared memory: [2][NE][BLOCK] doubles (segment rows staged by cp.async) | tau | tau* | per-warp scratch
+  extern __shared__ double s_dyn[];
+  double* const s_row = s_dyn;
+  int* const s_tau = reinterpret_cast<int*>(s_dyn + 2 * NE * FAST_BLOCK);
+  int* const s_tas = s_tau + SMAX * FAST_BLOCK;
+  int* const s_coop = s_tas + SMAX * FAST_BLOCK;  // per warp: what the accepting lane publishes to the others
   const int tid = threadIdx.x;
   const int u_raw = blockIdx.x * FAST_BLOCK + tid;
   const bool active = u_raw < a.U;
   const int u = active ? u_raw : 0;
-  const int n_it = active ? a.n_iter : 0;
+  const int lane = tid & 31;
+  int* const coop = s_coop + (tid >> 5) * 16;
   const int node = u / a.C;
   const int chain = u - node * a.C;
   const int n = a.tb.n, N = a.tb.N, F = n - 1;
   const long long U = a.U;
   auto TAU = [&](int j) -> int& { return s_tau[j * FAST_BLOCK + tid]; };
   auto TAS = [&](int j) -> int& { return s_tas[j * FAST_BLOCK + tid]; };
-  auto BS = [&](int j) -> unsigned char& { return s_bs[j * FAST_BLOCK + tid]; };
   auto tau_cur = [&](int j) { return s_tau[j * FAST_BLOCK + tid]; };
   auto tau_star = [&](int j) { return s_tas[j * FAST_BLOCK + tid]; };
   double* const cbase = a.cache + u;
@@ -68,16 +97,19 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   int pi[PMAX];
 #pragma unroll
   for (int j = 0; j < PMAX; ++j) pi[j] = a.st_pi[j * a.U + u];
-  int S = a.st_S[u];
+  int S = active ? a.st_S[u] : 0;  // lanes past the end keep step with the warp (ballots below) on an empty state
   for (int j = 0; j < SMAX; ++j) TAU(j) = a.st_tau[j * a.U + u];
   double sig2 = a.st_sig[u], lam = a.st_lam[u];
   int cg[KM];  // gene id held by column slot s (>= 1), -1 = empty; slot 0 is the intercept
   cg[0] = -1;
 
-  // table row `t` restricted to the slots' columns -> cache row `slot` (zeros for empty slots)
-  auto gather_row = [&](int t, int slot) {
+  // prefix-table row `t` restricted to the slots' columns (zeros for empty slots), minus the same of row `t0`
+  // when t0 >= 0, -> cache row `dst`
+  auto gather_row = [&](int t, int t0, int dst) {
     const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
-    double* c = crow(slot);
+    const double* __restrict__ row0 = a.tb.base + (long long)(t0 < 0 ? t : t0) * a.tb.row_stride;
+    const bool sub = t0 >= 0;
+    double* c = crow(dst);
 #pragma unroll
     for (int i = 0; i < KM; ++i) {
       const bool oi = (i == 0) || cg[i] >= 0;
@@ -86,36 +118,48 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       for (int j = 0; j <= i; ++j) {
         const bool oj = (j == 0) || cg[j] >= 0;
         const int fj = (j == 0) ? 0 : cg[j] + 1;
-        const int hi = max(fi, fj), lo = min(fi, fj);
-        c[(long long)DBN_TRI(i, j) * U] = (oi && oj) ? __ldg(row + hi * (hi + 1) / 2 + lo) : 0.0;
+        const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
+        c[(long long)DBN_TRI(i, j) * U] = (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0;
       }
-      c[(long long)(KT + i) * U] = oi ? __ldg(row + nb + fi) : 0.0;
+      c[(long long)(KT + i) * U] = oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0;
     }
-    c[(long long)(KT + KM) * U] = __ldg(row + nb + n + 1);
+    c[(long long)(KT + KM) * U] = __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0);
   };
 
   if (a.refresh) {
-    // (re)build the cache from the table: canonical slots = parent positions, boundary j -> slot j
+    // (re)build the cache from the table: canonical slots = parent positions, segment j -> row j
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = (s - 1 < npi) ? pi[s - 1] : -1;
-    for (int j = 0; j < S; ++j) {
-      BS(j) = (unsigned char)j;
-      if (active) gather_row(DBN_SEG_END(TAU(j), j, S, N), j);
-    }
+    for (int j = 0; j < S; ++j) gather_row(DBN_SEG_END(TAU(j), j, S, N), j == 0 ? -1 : TAU(j - 1) - 1, j);
   } else {
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = a.st_cg[(s - 1) * a.U + u];
-    for (int j = 0; j < SMAX; ++j) BS(j) = (unsigned char)a.st_bslot[j * a.U + u];
   }
 
-  Rng rng;
-  rng.init(a.seed, a.chain_offset + (unsigned)chain, (unsigned)node);
+  // Philox counter = (global chain, node, iteration, slot); slots: Gibbs normals 4h + {0,1,2}, discrete picks and
+  // accept uniforms 48..50, sigma^2 gamma 64.., lambda^2 gamma 256..
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const uint32_t gchain = a.chain_offset + (unsigned)chain, unode = (unsigned)node;
   Work wk = {0, 0, 0, 0};
   unsigned long long n_fact = 0;  // segment factorisations actually executed
+  unsigned n_pacc = 0, n_tacc = 0;  // accepted parent-set / changepoint moves
   const bool replay = TRACE && a.rd != nullptr;
 
-  // statistics of one segment in slot order: cache row `hi` minus cache row `lo` (lo < 0: table row 0 = zeros)
-  auto load_seg = [&](int lo, int hi, double(&G)[KT], double(&g)[KM], double& s) {
+  // start the asynchronous copy of segment row j into staging buffer `buf` (one commit group per call, possibly
+  // empty, so that wait_group<1> always means "the previous call's row has landed")
+  auto stage_row = [&](int j, int buf) {
+    if (j < S) {
+      const double* src = crow(j);
+      double* dst = s_row + buf * NE * FAST_BLOCK + tid;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) cp_async8(dst + e * FAST_BLOCK, src + (long long)e * U);
+    }
+    cp_async_commit();
+  };
+  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment between two staged prefix
+  // rows: cache row `hi` minus cache row `lo` (lo < 0: table row 0 = zeros)
+  auto seg_eval = [&](int lo, int hi, double& prod, double& q) {
+    double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
     const double* ph = crow(hi);
     const double* pl = crow(lo < 0 ? hi : lo);
     const bool has_lo = lo >= 0;
@@ -124,24 +168,19 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
     for (int i = 0; i < KM; ++i) g[i] = ph[(long long)(KT + i) * U] - (has_lo ? pl[(long long)(KT + i) * U] : 0.0);
     s = ph[(long long)(KT + KM) * U] - (has_lo ? pl[(long long)(KT + KM) * U] : 0.0);
-  };
-  // pivot product and quadratic form r^T C^-1 r of one segment (mu = 0), all KM slots
-  auto seg_eval = [&](int lo, int hi, double& prod, double& q) {
-    double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
-    load_seg(lo, hi, G, g, s);
     form_a<KM>(G, lam, A);
     prod = ldl_factor<KM>(A, dinv);
     q = segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
     ++n_fact;
   };
 
-  for (int li = 0; li < n_it; ++li) {
+  for (int li = 0; li < a.n_iter; ++li) {
     const int it = a.it0 + li;
-    rng.start_iteration((unsigned)it);
+    const uint32_t uit = (uint32_t)it;
     const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * DBN_RD_STRIDE : nullptr;
     const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * DBN_RI_STRIDE : nullptr;
-    double* td = (TRACE && a.td) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
-    int* ti = (TRACE && a.ti) ? a.ti + ((long long)u * a.n_iter + li) * DBN_TI_STRIDE : nullptr;
+    double* td = (TRACE && a.td && active) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
+    int* ti = (TRACE && a.ti && active) ? a.ti + ((long long)u * a.n_iter + li) * DBN_TI_STRIDE : nullptr;
     if (TRACE && ti) ti[DBN_TI_S_BEFORE] = S;
     int k = npi + 1;
 
@@ -163,11 +202,17 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // e_h independent of sigma^2, so sum_h |beta_h|^2 is assembled from (|m|^2, m.e, |e|^2) after sigma^2 is drawn.
     double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
     {
-      int lo = -1;
+      stage_row(0, 0);
       for (int h = 0; h < S; ++h) {
-        const int hi = BS(h);
+        stage_row(h + 1, (h + 1) & 1);
+        cp_async_wait<1>();
+        const double* sr = s_row + (h & 1) * NE * FAST_BLOCK + tid;
         double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
-        load_seg(lo, hi, G, g, s);
+#pragma unroll
+        for (int e = 0; e < KT; ++e) G[e] = sr[e * FAST_BLOCK];
+#pragma unroll
+        for (int i = 0; i < KM; ++i) g[i] = sr[(KT + i) * FAST_BLOCK];
+        s = sr[(KT + KM) * FAST_BLOCK];
         form_a<KM>(G, lam, A);
         ldl_factor<KM>(A, dinv);
         ++n_fact;
@@ -183,10 +228,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           const double sw = sqrt(lam);
 #pragma unroll
           for (int i = 0; i < KM; i += 2) {
-            double z0, z1;
-            rng.normal2(z0, z1);
-            e[i] = ((i == 0) || cg[i] >= 0) ? sw * z0 * sqrt(dinv[i]) : 0.0;
-            if (i + 1 < KM) e[i + 1] = (cg[i + 1] >= 0) ? sw * z1 * sqrt(dinv[i + 1]) : 0.0;
+            const double2 z = normal_pair(gchain, unode, uit, (uint32_t)(4 * h + i / 2), key);
+            e[i] = ((i == 0) || cg[i] >= 0) ? sw * z.x * sqrt(dinv[i]) : 0.0;
+            if (i + 1 < KM) e[i + 1] = (cg[i + 1] >= 0) ? sw * z.y * sqrt(dinv[i + 1]) : 0.0;
           }
           solve_upper<KM>(A, e);  // e = sqrt(lam) L^-T D^-1/2 z: cov = sigma^2 lam A^-1 (samplers.py:214-216)
           acc_dd += dot<KM>(mean, mean);
@@ -224,13 +268,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
             }
           }
         }
-        lo = hi;
       }
     }
     {
       const double shape = a.a_sig + a.T_sigma_half;
       const double rate = a.b_sig + 0.5 * q_sum;
-      sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / rng.gamma(shape);
+      sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / gamma_draw(gchain, unode, uit, 64u, key, shape);
       if (TRACE && td) {
         td[DBN_TD_SIG_SHAPE] = shape;
         td[DBN_TD_SIG_RATE] = rate;
@@ -252,7 +295,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       // nh: samplers.py:285-289 shape a + S k/2 ; h: :301 shape a + k/2 ; rate b + ss / (2 sigma^2)
       const double shape = a.a_lam + 0.5 * (double)(HOMOG ? k : S * k);
       const double rate = a.b_lam + 0.5 * ss / sig2;
-      lam = replay ? rd[DBN_RD_LAMBDA2] : rate / rng.gamma(shape);
+      lam = replay ? rd[DBN_RD_LAMBDA2] : rate / gamma_draw(gchain, unode, uit, 256u, key, shape);
       if (TRACE && td) {
         td[DBN_TD_LAM_SHAPE] = shape;
         td[DBN_TD_LAM_RATE] = rate;
@@ -265,12 +308,21 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     }
 
     // ============================ proposals (no scoring yet) ==================================================
+    // all discrete picks and both accept uniforms of the iteration come from three Philox blocks
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
+    if (!replay) {
+      wa = philox_block(gchain, unode, uit, 48u, key);
+      wb = philox_block(gchain, unode, uit, 49u, key);
+      wc = philox_block(gchain, unode, uit, 50u, key);
+    }
+    auto pick = [](uint32_t word, int m) { return (int)__umulhi(word, (uint32_t)m); };
+    auto unif = [](uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; };
     // ---- parent-set proposal: addMove / deleteMove / exchangeMove (utils.py:271-323)
-    const int pmove = replay ? ri[DBN_RI_PI_MOVE] : rng.below(3);
-    bool pvalid = true;
+    const int pmove = replay ? ri[DBN_RI_PI_MOVE] : pick(wa.x, 3);
+    bool pvalid = active;
     int star[PMAX], nstar = npi;
     int el = -1, cnew = -1;  // gene leaving / entering the parent set
-    double p_log_hr = 0.0;
+    int hr_num = 1, hr_den = 1;  // Hastings ratio of the parent-set move (moves.py:612, :615)
     {
       int spi[PMAX];
 #pragma unroll
@@ -281,18 +333,18 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (npi > a.fan_in - 1 || ncand <= 0) {
           pvalid = false;
         } else {
-          const int p = replay ? ri[DBN_RI_PI_PICK] : rng.below(ncand);
+          const int p = replay ? ri[DBN_RI_PI_PICK] : pick(wa.y, ncand);
           cnew = nth_candidate(p, node, spi, npi);
 #pragma unroll
           for (int j = 0; j < PMAX; ++j)
             if (j == npi) star[j] = cnew;
           nstar = npi + 1;
-          p_log_hr = log((double)(F - npi) / (double)nstar);  // moves.py:612
+          hr_num = F - npi, hr_den = nstar;  // moves.py:612
         }
       } else if (npi < 1) {
         pvalid = false;  // utils.py:285-286, :308-309
       } else {
-        const int idx = replay ? ri[DBN_RI_PI_PICK] : rng.below(npi);
+        const int idx = replay ? ri[DBN_RI_PI_PICK] : pick(wa.y, npi);
         el = pi[0];
 #pragma unroll
         for (int j = 1; j < PMAX; ++j)
@@ -309,13 +361,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
         if (pmove == 1) {
           nstar = npi - 1;
-          p_log_hr = log((double)npi / (double)(F - nstar));  // moves.py:615
+          hr_num = npi, hr_den = F - nstar;  // moves.py:615
         } else {
           const int ncand = F - npi;
           if (ncand <= 0) {
             pvalid = false;
           } else {
-            const int p = replay ? ri[DBN_RI_PI_PICK + 1] : rng.below(ncand);
+            const int p = replay ? ri[DBN_RI_PI_PICK + 1] : pick(wa.z, ncand);
             cnew = nth_candidate(p, node, spi, npi);
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
@@ -331,11 +383,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     bool tvalid = false;
     int tj = 0;      // boundary index (1-based among b_1..b_S) that is inserted / removed / moved
     int trow = 0;    // table row of the new boundary (birth / reallocation)
-    double t_log_hr = 0.0;
+    int t_num = 1, t_den = 1;  // Hastings ratio of the changepoint move (moves.py:159, :163)
     if (do_tau) {
-      tmove = replay ? ri[DBN_RI_TAU_MOVE] : rng.below(3);
+      tmove = replay ? ri[DBN_RI_TAU_MOVE] : pick(wa.w, 3);
       const int ns = a.num_samples;
-      tvalid = true;
+      tvalid = active;
       if (tmove == 0) {
         int inside = 0;
         for (int j = 0; j < S - 1; ++j) inside += (TAU(j) >= 2 && TAU(j) <= ns) ? 1 : 0;
@@ -343,7 +395,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (ncand <= 0) {
           tvalid = false;
         } else {
-          const int p = replay ? ri[DBN_RI_TAU_PICK] : rng.below(ncand);
+          const int p = replay ? ri[DBN_RI_TAU_PICK] : pick(wb.x, ncand);
           int c = 2 + p;
           for (int j = 0; j < S - 1; ++j)
             if (TAU(j) <= c) ++c;
@@ -360,20 +412,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           trow = c - 1;
           Ss = S + 1;
           if (Ss > 9 || !placed || trow >= N) tvalid = false;  // moves.py:156
-          t_log_hr = log((double)(ns - S) / (double)(Ss - 1));  // moves.py:159
+          t_num = ns - S, t_den = Ss - 1;  // moves.py:159
         }
       } else if (S < 2) {
         tvalid = false;  // changepointMoves.py:81-82, :21-22
       } else if (tmove == 1) {
-        const int idx = replay ? ri[DBN_RI_TAU_PICK] : rng.below(S - 1);
+        const int idx = replay ? ri[DBN_RI_TAU_PICK] : pick(wb.x, S - 1);
         int w_ = 0;
         for (int j = 0; j < S; ++j)
           if (j != idx) TAS(w_++) = TAU(j);
         tj = idx + 1;
         Ss = S - 1;
-        t_log_hr = log((double)(S - 1) / (double)(ns - Ss));  // moves.py:163
+        t_num = S - 1, t_den = ns - Ss;  // moves.py:163
       } else {
-        const int idx = replay ? ri[DBN_RI_TAU_PICK] : rng.below(S - 1);
+        const int idx = replay ? ri[DBN_RI_TAU_PICK] : pick(wb.x, S - 1);
         const int last = TAU(S - 1) - 1;
         const int left = (idx == 0) ? 1 : TAU(idx - 1);
         const int right = (idx + 1 == S - 1) ? last : TAU(idx + 1);
@@ -381,7 +433,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (ncand <= 0) {
           tvalid = false;
         } else {
-          const int p = replay ? ri[DBN_RI_TAU_PICK + 1] : rng.below(ncand);
+          const int p = replay ? ri[DBN_RI_TAU_PICK + 1] : pick(wb.y, ncand);
           int c = left + 1 + p;
           if (c >= TAU(idx)) ++c;
           for (int j = 0; j < S; ++j) TAS(j) = (j == idx) ? c : TAU(j);
@@ -406,8 +458,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // position p of the sweep holds slot perm[p]; the last position is the slot that leaves (delete / exchange) or
     // the free slot that would be filled (add).  current = base + last position, star = base + new column.
     double ld_now = 0.0, q_now = 0.0, ml_now = NAN;
+    bool p_acc = false;
+    int tslot = KM - 1;
+    int et[KB], o2[KB], ett = 0, ezyt = 0, o2d = -1, o2y = -1;  // cache entries / table offsets of the changing column
+#pragma unroll
+    for (int p = 0; p < KB; ++p) et[p] = o2[p] = 0;
     if (pvalid || tvalid) {
-      int tslot = KM - 1;
       if (pvalid) {
         if (pmove == 0) {
 #pragma unroll
@@ -425,8 +481,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       for (int p = 1; p < KB; ++p) perm[p] = (p < tslot) ? p : p + 1;
       perm[KB] = tslot;
       const bool has_new = pvalid && cnew >= 0;
-      // cache entries of the sweep's positions, table offsets of the new column
-      int eb[KBT], et[KB], ezy[KM], o2[KB];
+      int eb[KBT], ezy[KB];
       const int cf = cnew + 1;
 #pragma unroll
       for (int p = 0; p < KB; ++p) {
@@ -439,31 +494,30 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         const int hi = max(cf, fp), lo = min(cf, fp);
         o2[p] = (has_new && occ) ? hi * (hi + 1) / 2 + lo : -1;
       }
-      ezy[KB] = KT + tslot;
-      const int ett = DBN_TRI(tslot, tslot);
-      const int o2d = cf * (cf + 1) / 2 + cf, o2y = nb + cf;
+      ezyt = KT + tslot;
+      ett = DBN_TRI(tslot, tslot);
+      o2d = has_new ? cf * (cf + 1) / 2 + cf : -1;
+      o2y = has_new ? nb + cf : -1;
 
       double ldB = 0.0, R1 = 1.0, R2 = 1.0, q1 = 0.0, q2 = 0.0;
       double n_prev[KB + 2];  // new column at the previous boundary: cross terms, diagonal, ZY
 #pragma unroll
       for (int i = 0; i < KB + 2; ++i) n_prev[i] = 0.0;
-      int lo = -1;
+      stage_row(0, 0);
       for (int h = 0; h < S; ++h) {
-        const int hi = BS(h);
-        const double* ph = crow(hi);
-        const double* pl = crow(lo < 0 ? hi : lo);
-        const bool has_lo = lo >= 0;
-        auto diff = [&](int e) { return ph[(long long)e * U] - (has_lo ? pl[(long long)e * U] : 0.0); };
+        stage_row(h + 1, (h + 1) & 1);
+        cp_async_wait<1>();
+        const double* sr = s_row + (h & 1) * NE * FAST_BLOCK + tid;
         double A[KBT], gB[KB], t1[KB], t2[KB], dinv[KB];
 #pragma unroll
-        for (int e = 0; e < KBT; ++e) A[e] = diff(eb[e]);
+        for (int e = 0; e < KBT; ++e) A[e] = sr[eb[e] * FAST_BLOCK];
 #pragma unroll
         for (int p = 0; p < KB; ++p) {
-          gB[p] = diff(ezy[p]);
-          t1[p] = diff(et[p]);
+          gB[p] = sr[ezy[p] * FAST_BLOCK];
+          t1[p] = sr[et[p] * FAST_BLOCK];
         }
-        const double t1d = diff(ett), t1y = diff(ezy[KB]);
-        const double s = diff(KT + KM);
+        const double t1d = sr[ett * FAST_BLOCK], t1y = sr[ezyt * FAST_BLOCK];
+        const double s = sr[(KT + KM) * FAST_BLOCK];
         double t2d = 0.0, t2y = 0.0;
         if (has_new) {
           const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(h), h, S, N) * a.tb.row_stride;
@@ -511,15 +565,14 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         double d1, c1, d2, c2;
         tail(t1, t1d, t1y, d1, c1);
         tail(t2, t2d, t2y, d2, c2);
-        ldB += log(prodB);
+        ldB += dlog(prodB);
         R1 *= d1;
         R2 *= d2;
         q1 += s - lam * (accB + c1);
         q2 += s - lam * (accB + c2);
-        lo = hi;
       }
-      const double ld_cur = ldB + log(R1), ld_star = ldB + log(R2);
-      const double ml_cur = a.c0 - 0.5 * ld_cur - a.T_half_plus_a * log(a.two_b + q1);  // moves.py:599-600 / :681
+      const double ld_cur = ldB + dlog(R1), ld_star = ldB + dlog(R2);
+      const double ml_cur = a.c0 - 0.5 * ld_cur - a.T_half_plus_a * dlog(a.two_b + q1);  // moves.py:599-600 / :681
       wk.eval();
       for (int h = 0; h < S; ++h) wk.segment(k, false);
       ld_now = ld_cur;
@@ -527,18 +580,18 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       ml_now = ml_cur;
       if (pvalid) {
         const int ks = nstar + 1;
-        const double ml_star = a.c0 - 0.5 * ld_star - a.T_half_plus_a * log(a.two_b + q2);  // moves.py:574-576 / :672
+        const double ml_star = a.c0 - 0.5 * ld_star - a.T_half_plus_a * dlog(a.two_b + q2);  // moves.py:574-576 / :672
         wk.eval();
         for (int h = 0; h < S; ++h) wk.segment(ks, false);
-        const double log_ratio = ml_star - ml_cur + p_log_hr;  // uniform parent-set prior cancels (priors.py:48-68)
-        const double uacc = replay ? rd[DBN_RD_U_PI] : rng.uniform();
-        const bool acc = uacc < fmin(1.0, exp(log_ratio));  // moves.py:620-633, :699-702
+        const double log_ratio = ml_star - ml_cur + dlog((double)hr_num / (double)hr_den);  // uniform parent-set prior cancels (priors.py:48-68)
+        const double uacc = replay ? rd[DBN_RD_U_PI] : unif(wb.z, wb.w);
+        p_acc = uacc < fmin(1.0, dexp(log_ratio));  // moves.py:620-633, :699-702
         if (TRACE && td) {
           td[DBN_TD_LOGML + 0] = ml_star;
           td[DBN_TD_LOGML + 1] = ml_cur;
         }
-        if (TRACE && ti) ti[DBN_TI_PI_ACCEPT] = acc;
-        if (acc) {
+        if (TRACE && ti) ti[DBN_TI_PI_ACCEPT] = p_acc;
+        if (p_acc) {
           npi = nstar;
           k = ks;
 #pragma unroll
@@ -546,25 +599,52 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           ld_now = ld_star;
           q_now = q2;
           ml_now = ml_star;
-          // the new column (or zeros, for a delete) takes slot `tslot` in every cached boundary row
-          for (int h = 0; h < S; ++h) {
-            double* c = crow(BS(h));
-            const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(h), h, S, N) * a.tb.row_stride;
-#pragma unroll
-            for (int p = 0; p < KB; ++p) c[(long long)et[p] * U] = (o2[p] >= 0) ? __ldg(row + o2[p]) : 0.0;
-            c[(long long)ett * U] = has_new ? __ldg(row + o2d) : 0.0;
-            c[(long long)ezy[KB] * U] = has_new ? __ldg(row + o2y) : 0.0;
-          }
 #pragma unroll
           for (int s = 1; s < KM; ++s)
             if (s == tslot) cg[s] = has_new ? cnew : -1;
+          ++n_pacc;
         }
+      }
+    }
+    // ---- accepted parent-set moves: the new column (zeros for a delete) takes slot `tslot` in every cached row.
+    // The warp serves one accepting lane at a time: item (j, p) = entry p of the changing column in segment row j.
+    {
+      unsigned m = __ballot_sync(FULL, p_acc);
+      while (m) {
+        const int L = __ffs(m) - 1;
+        m &= m - 1;
+        if (lane == L) {
+#pragma unroll
+          for (int p = 0; p < KB; ++p) {
+            coop[p] = o2[p];
+            coop[8 + p] = et[p];
+          }
+          coop[KB] = o2d;
+          coop[KB + 1] = o2y;
+          coop[8 + KB] = ett;
+          coop[8 + KB + 1] = ezyt;
+        }
+        __syncwarp();
+        const int uL = __shfl_sync(FULL, u, L), SL = __shfl_sync(FULL, S, L);
+        const int tL = (tid & ~31) + L;
+        for (int idx = lane; idx < SL * (KB + 2); idx += 32) {
+          const int j = idx / (KB + 2), p = idx - j * (KB + 2);
+          const int off = coop[p], ent = coop[8 + p];
+          double v = 0.0;
+          if (off >= 0) {
+            const int bhi = DBN_SEG_END(s_tau[j * FAST_BLOCK + tL], j, SL, N);
+            v = __ldg(a.tb.base + (long long)bhi * a.tb.row_stride + off);
+            if (j > 0) v -= __ldg(a.tb.base + (long long)(s_tau[(j - 1) * FAST_BLOCK + tL] - 1) * a.tb.row_stride + off);
+          }
+          a.cache[((long long)j * NE + ent) * U + uL] = v;
+        }
+        __syncwarp();
       }
     }
     // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
     {
       const int idx = it + 1;
-      if (idx >= a.burn_in && ((idx - a.burn_in) % a.thin) != 0 && npi > 0) {
+      if (active && idx >= a.burn_in && ((idx - a.burn_in) % a.thin) != 0 && npi > 0) {
         atomicAdd(&a.nonempty[node], 1ull);
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
@@ -578,58 +658,106 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 
     // ============================ changepoint move: only the changed segments (a5) ============================
     if (do_tau) {
+      bool t_acc = false;
+      const bool birth = tmove == 0, death = tmove == 1;
       if (tvalid) {
-        // boundaries around the change: left = b_{tj-1}, mid = b_tj (absent for a birth), right = the next one
-        unsigned used = 0;
-        for (int j = 0; j < S; ++j) used |= 1u << BS(j);
-        const int scratch = __ffs(~used) - 1;
-        const bool birth = tmove == 0, death = tmove == 1;
-        const int left = (tj >= 2) ? (int)BS(tj - 2) : -1;
-        const int mid = birth ? -1 : (int)BS(tj - 1);
-        const int right = birth ? (int)BS(tj - 1) : (int)BS(tj);
-        if (!death) gather_row(trow, scratch);
-        double prod_old = 1.0, q_old = 0.0, prod_new = 1.0, q_new = 0.0, pr, qq;
-        if (birth) {
-          seg_eval(left, right, pr, qq); prod_old *= pr; q_old += qq;
-        } else {
-          seg_eval(left, mid, pr, qq); prod_old *= pr; q_old += qq;
-          seg_eval(mid, right, pr, qq); prod_old *= pr; q_old += qq;
+        // boundaries around the change (table rows): left = b_{tj-1}, mid = b_tj (absent for a birth), right = next.
+        // They are staged in the scratch rows ROW_L, ROW_X, ROW_R (current columns); ROW_X first holds the old
+        // boundary, then the new one.  Old segments: (left, mid), (mid, right) or, for a birth, (left, right);
+        // new segments: (left, new), (new, right) or, for a death, (left, right).
+        const int b_left = (tj >= 2) ? TAU(tj - 2) - 1 : -1;
+        const int b_mid = birth ? -1 : TAU(tj - 1) - 1;
+        const int jr = birth ? tj - 1 : tj;  // index in tau of the right boundary
+        const int b_right = DBN_SEG_END(TAU(jr), jr, S, N);
+        const int rl = (b_left >= 0) ? ROW_L : -1;
+        double prod_old = 1.0, q_old = 0.0, prod_new = 1.0, q_new = 0.0;
+        // steps: stage left, stage right, old side (through the old boundary, if any), new side (through the new one)
+        for (int step = 0; step < 4; ++step) {
+          const int t = (step == 0) ? b_left : (step == 1) ? b_right : (step == 2) ? b_mid : (death ? -1 : trow);
+          const int dst = (step == 0) ? ROW_L : (step == 1) ? ROW_R : ROW_X;
+          if (t >= 0) gather_row(t, -1, dst);
+          if (step >= 2) {
+            const int n_e = (t >= 0) ? 2 : 1;
+            double pp = 1.0, qs = 0.0;
+            for (int e = 0; e < n_e; ++e) {
+              double pr, qq;
+              seg_eval(e == 0 ? rl : ROW_X, e == n_e - 1 ? ROW_R : ROW_X, pr, qq);
+              pp *= pr;
+              qs += qq;
+            }
+            if (step == 2) {
+              prod_old = pp;
+              q_old = qs;
+            } else {
+              prod_new = pp;
+              q_new = qs;
+            }
+          }
         }
-        if (death) {
-          seg_eval(left, right, pr, qq); prod_new *= pr; q_new += qq;
-        } else {
-          seg_eval(left, scratch, pr, qq); prod_new *= pr; q_new += qq;
-          seg_eval(scratch, right, pr, qq); prod_new *= pr; q_new += qq;
-        }
-        const double ld_star = ld_now + log(prod_new / prod_old);
+        const double ld_star = ld_now + dlog(prod_new / prod_old);
         const double q_star = q_now - q_old + q_new;
-        const double ml_star = a.c0 - 0.5 * ld_star - a.T_half_plus_a * log(a.two_b + q_star);  // moves.py:209-216
+        const double ml_star = a.c0 - 0.5 * ld_star - a.T_half_plus_a * dlog(a.two_b + q_star);  // moves.py:209-216
         wk.eval();
         for (int h = 0; h < Ss; ++h) wk.segment(k, false);
         const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
-        const double log_ratio = ml_star - ml_now + lprior + t_log_hr;  // moves.py:225
-        const double uacc = replay ? rd[DBN_RD_U_TAU] : rng.uniform();
-        const bool acc = uacc < fmin(1.0, exp(log_ratio));
+        const double log_ratio = ml_star - ml_now + lprior + dlog((double)t_num / (double)t_den);  // moves.py:225
+        const double uacc = replay ? rd[DBN_RD_U_TAU] : unif(wc.x, wc.y);
+        t_acc = uacc < fmin(1.0, dexp(log_ratio));
         if (TRACE && td) {
           td[DBN_TD_LOGML + 2] = ml_now;
           td[DBN_TD_LOGML + 3] = ml_star;
         }
-        if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = acc;
-        if (acc) {
-          if (birth) {
-            for (int j = S; j >= tj; --j) BS(j) = BS(j - 1);
-            BS(tj - 1) = (unsigned char)scratch;
-          } else if (death) {
-            for (int j = tj - 1; j < S - 1; ++j) BS(j) = BS(j + 1);
-          } else {
-            BS(tj - 1) = (unsigned char)scratch;
+        if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = t_acc;
+      }
+      // ---- accepted changepoint moves: shift the segment rows behind the change, write the new segments' rows
+      // from the staged prefix rows.  One accepting lane at a time, the warp moves 32 entries per step.
+      {
+        unsigned m = __ballot_sync(FULL, t_acc);
+        while (m) {
+          const int L = __ffs(m) - 1;
+          m &= m - 1;
+          const int uL = __shfl_sync(FULL, u, L), SL = __shfl_sync(FULL, S, L);
+          const int mvL = __shfl_sync(FULL, tmove, L), tjL = __shfl_sync(FULL, tj, L);
+          double* cu = a.cache + uL;
+          // birth splits segment tj-1: rows tj .. S-1 move up by one; death merges tj-1 and tj: rows tj+1 .. S-1
+          // move down by one; a reallocation moves nothing
+          const int src0 = (mvL == 0) ? tjL : tjL + 1;
+          const int n_mv = (mvL == 2) ? 0 : SL - src0;
+          const int dlt_ = (mvL == 0) ? 1 : -1;
+          double v[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < n_mv * NE) v[i] = cu[((long long)src0 * NE + idx) * U];
           }
-          S = Ss;
-          for (int j = 0; j < Ss; ++j) TAU(j) = TAS(j);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < n_mv * NE) cu[((long long)(src0 + dlt_) * NE + idx) * U] = v[i];
+          }
+          __syncwarp();
+          if (lane < NE) {
+            const double xl = (tjL >= 2) ? cu[((long long)ROW_L * NE + lane) * U] : 0.0;
+            const double xr = cu[((long long)ROW_R * NE + lane) * U];
+            if (mvL == 1) {
+              cu[((long long)(tjL - 1) * NE + lane) * U] = xr - xl;
+            } else {
+              const double xx = cu[((long long)ROW_X * NE + lane) * U];
+              cu[((long long)(tjL - 1) * NE + lane) * U] = xx - xl;
+              cu[((long long)tjL * NE + lane) * U] = xr - xx;
+            }
+          }
+          __syncwarp();
         }
       }
+      if (t_acc) {
+        S = Ss;
+        for (int j = 0; j < Ss; ++j) TAU(j) = TAS(j);
+        ++n_tacc;
+      }
       // ---- counts: tau_vector[it] is kept iff it >= burn_in and (it - burn_in) % thin == 0 (network.py:388-389)
-      if (it >= a.burn_in && ((it - a.burn_in) % a.thin) == 0) {
+      if (active && it >= a.burn_in && ((it - a.burn_in) % a.thin) == 0) {
         atomicAdd(&a.cp_kept[node], 1ull);
         for (int j = 0; j < S - 1; ++j) atomicAdd(&a.cp_hist[(long long)node * (N + 3) + TAU(j)], 1ull);
       }
@@ -651,17 +779,17 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     a.st_lam[u] = lam;
 #pragma unroll
     for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
-    for (int j = 0; j < SMAX; ++j) a.st_bslot[j * a.U + u] = BS(j);
   }
   // ---- work counters: one atomic per warp
-  unsigned long long v[6] = {(unsigned long long)n_it, wk.evals, wk.segs, wk.bytes, wk.flops, n_fact};
+  unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
+                             (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
+  for (int c = 0; c < 8; ++c) {
     unsigned long long x = v[c];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&a.counters[c == 5 ? 6 : c], x);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&a.counters[c], x);
   }
 }
 

@@ -87,4 +87,49 @@ struct Rng {
   }
 };
 
+// ---- out-of-line variants for the h / nh kernel (dbn_chain_fast.cuh) ------------------------------------------------
+// The chain step is one long program per thread; inlining Philox and the FP64 log / exp / sincospi expansions at
+// every use made it ~31k SASS instructions and instruction-fetch bound (profiles/r1_v1).  These are called instead.
+// They are stateless: every consumer owns a fixed range of the per-iteration counter word.
+__device__ __noinline__ inline uint4 philox_block(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr, uint2 key) {
+  return philox4x32_10(make_uint4(chain, node, it, ctr), key);
+}
+__device__ __noinline__ inline double dlog(double x) { return log(x); }
+__device__ __noinline__ inline double dexp(double x) { return exp(x); }
+
+// two independent N(0,1) from one Philox block (Box-Muller on two 53-bit uniforms)
+__device__ __noinline__ inline double2 normal_pair(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr, uint2 key) {
+  const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr), key);
+  const double u = (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+  const double v = (double)((((uint64_t)r.z << 32) | r.w) >> 11) * 0x1.0p-53;
+  const double rad = sqrt(-2.0 * log(1.0 - u));
+  double s, c;
+  sincospi(2.0 * v, &s, &c);
+  return make_double2(rad * c, rad * s);
+}
+
+// Gamma(shape, 1) by Marsaglia-Tsang on the counter range [ctr0, ctr0 + 192)
+__device__ __noinline__ inline double gamma_draw(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr0, uint2 key, double shape) {
+  double boost = 1.0;
+  uint32_t ctr = ctr0;
+  if (shape < 1.0) {
+    const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
+    const double u = (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+    boost = pow(1.0 - u, 1.0 / shape);
+    shape += 1.0;
+  }
+  const double d = shape - 1.0 / 3.0;
+  const double c = rsqrt(9.0 * d);
+  for (int tries = 0; tries < 64; ++tries) {
+    const double2 z = normal_pair(chain, node, it, ctr++, key);
+    const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
+    double v = 1.0 + c * z.x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = 1.0 - (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+    if (log(u) < 0.5 * z.x * z.x + d - d * v + d * log(v)) return boost * d * v;
+  }
+  return boost * d;  // unreachable in practice (acceptance > 0.95 per try)
+}
+
 }  // namespace dbn

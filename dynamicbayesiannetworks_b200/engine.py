@@ -181,7 +181,8 @@ class DbnEngine:
     def counters(self):
         out = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.dbn_read_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))), 'dbn_read_counters')
-        keys = ('unit_iterations', 'ml_evals', 'segment_evals', 'algorithmic_bytes', 'algorithmic_flops')
+        keys = ('unit_iterations', 'ml_evals', 'segment_evals', 'algorithmic_bytes', 'algorithmic_flops', 'pi_accepts',
+                'segment_factorisations', 'tau_accepts')
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def reset_counters(self):

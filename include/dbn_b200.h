@@ -211,7 +211,10 @@ int dbn_read_state(dbn_handle* h, int32_t* pi, int32_t* pi_len, int32_t* tau, in
 /* work counters accumulated by dbn_run since the last dbn_chain_init / dbn_reset_counters:
  * [0] unit-iterations, [1] marginal-likelihood evaluations executed, [2] segment evaluations (all passes),
  * [3] algorithmic bytes of those segment evaluations (2*8*(k(k+1)/2+k+1) per segment, actual k),
- * [4] algorithmic FP64 flops of those segment evaluations, [5] chain-kernel launches */
+ * [4] algorithmic FP64 flops of those segment evaluations, [5] accepted parent-set moves, [6] segment
+ * factorisations actually executed (the h / nh kernel scores pi and pi* in one sweep and re-evaluates only the
+ * segments a changepoint move changes, so this is smaller than [2]), [7] accepted changepoint moves
+ * ([5]-[7] are filled by the h / nh kernel only) */
 int dbn_read_counters(dbn_handle* h, uint64_t out[8]);
 int dbn_reset_counters(dbn_handle* h);
 
