@@ -28,10 +28,16 @@
 
 namespace dbn {
 
-constexpr int FAST_BLOCK = 128;
-#ifndef DBN_FAST_MINB
-#define DBN_FAST_MINB 1
+#ifndef DBN_FAST_BLOCK
+#define DBN_FAST_BLOCK 128
 #endif
+#ifndef DBN_FAST_MINB
+#define DBN_FAST_MINB 3
+#endif
+#ifndef DBN_FAST_SYNC
+#define DBN_FAST_SYNC 1
+#endif
+constexpr int FAST_BLOCK = DBN_FAST_BLOCK;
 constexpr int SEG_ROWS = DBN_SMAX - 1;  // <= 9 segments
 constexpr int ROW_L = SEG_ROWS, ROW_X = SEG_ROWS + 1, ROW_R = SEG_ROWS + 2;  // scratch: prefix rows left / moving / right
 constexpr int BSLOTS = SEG_ROWS + 3;    // cached rows per unit
@@ -177,6 +183,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   for (int li = 0; li < a.n_iter; ++li) {
     const int it = a.it0 + li;
     const uint32_t uit = (uint32_t)it;
+    // The step is ~8k instructions of mostly straight-line code per thread, far more than the instruction cache
+    // holds; warps that drift apart each stream it from L2 on their own (stall_no_instruction, profiles/r1_v4).
+    // Block-wide barriers keep the block's warps on the same stretch of code so one fetch serves all of them.
+    if (DBN_FAST_SYNC >= 1) __syncthreads();
     const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * DBN_RD_STRIDE : nullptr;
     const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * DBN_RI_STRIDE : nullptr;
     double* td = (TRACE && a.td && active) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       }
     }
 
+    if (DBN_FAST_SYNC >= 2) __syncthreads();
     // ============================ proposals (no scoring yet) ==================================================
     // all discrete picks and both accept uniforms of the iteration come from three Philox blocks
     uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
@@ -499,7 +510,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       o2d = has_new ? cf * (cf + 1) / 2 + cf : -1;
       o2y = has_new ? nb + cf : -1;
 
-      double ldB = 0.0, R1 = 1.0, R2 = 1.0, q1 = 0.0, q2 = 0.0;
+      // ln det of the base blocks: the pivot products are accumulated as mantissa x 2^exponent (one log per sweep)
+      double mB = 1.0, R1 = 1.0, R2 = 1.0, q1 = 0.0, q2 = 0.0;
+      int eB = 0;
       double n_prev[KB + 2];  // new column at the previous boundary: cross terms, diagonal, ZY
 #pragma unroll
       for (int i = 0; i < KB + 2; ++i) n_prev[i] = 0.0;
@@ -560,18 +573,23 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
             w -= yd * gB[p];
           }
           dt = d;
-          contrib = w * w / d;
+          contrib = w * w * pivot_rcp(d);
         };
         double d1, c1, d2, c2;
         tail(t1, t1d, t1y, d1, c1);
         tail(t2, t2d, t2y, d2, c2);
-        ldB += dlog(prodB);
+        {
+          int ex;
+          mB = frexp(mB * prodB, &ex);
+          eB += ex;
+        }
         R1 *= d1;
         R2 *= d2;
         q1 += s - lam * (accB + c1);
         q2 += s - lam * (accB + c2);
       }
-      const double ld_cur = ldB + dlog(R1), ld_star = ldB + dlog(R2);
+      const double ldB = (double)eB * 0.69314718055994530942;
+      const double ld_cur = ldB + dlog(mB * R1), ld_star = ldB + dlog(mB * R2);
       const double ml_cur = a.c0 - 0.5 * ld_cur - a.T_half_plus_a * dlog(a.two_b + q1);  // moves.py:599-600 / :681
       wk.eval();
       for (int h = 0; h < S; ++h) wk.segment(k, false);
@@ -606,6 +624,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     }
+    if (DBN_FAST_SYNC >= 2) __syncthreads();
     // ---- accepted parent-set moves: the new column (zeros for a delete) takes slot `tslot` in every cached row.
     // The warp serves one accepting lane at a time: item (j, p) = entry p of the changing column in segment row j.
     {

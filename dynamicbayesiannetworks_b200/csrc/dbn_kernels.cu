@@ -638,13 +638,15 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   const bool km4 = p.fan_in <= 3;
   chain_fn fn = trace ? (km4 ? pick_method<4, true>(p.method) : pick_method<5, true>(p.method))
                       : (km4 ? pick_method<4, false>(p.method) : pick_method<5, false>(p.method));
-  const unsigned grid = (unsigned)((h->U + CHAIN_BLOCK - 1) / CHAIN_BLOCK);
   size_t smem = 0;
+  int block = CHAIN_BLOCK;
   if (p.method == DBN_H_DBN || p.method == DBN_NH_DBN) {
+    block = FAST_BLOCK;
     smem = fast_smem_bytes(km4 ? 4 : 5);
     CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  fn<<<grid, CHAIN_BLOCK, smem, h->stream>>>(a);
+  const unsigned grid = (unsigned)((h->U + block - 1) / block);
+  fn<<<grid, block, smem, h->stream>>>(a);
   CUX(cudaGetLastError());
   h->cache_valid = true;
   h->it_done += n_iter;
