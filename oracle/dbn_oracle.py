@@ -32,8 +32,9 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN = 0, 1, 2, 3
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN = 0, 1, 2, 3, 4
 METHOD_IDS = {
+    'fp_glob_coup_nh_dbn': FP_GLOB_DBN, 'fp-glob-dbn': FP_GLOB_DBN,
     'h_dbn': H_DBN, 'h-dbn': H_DBN,
     'varying_nh_dbn': NH_DBN, 'nh-dbn': NH_DBN,
     'seq_coup_nh_dbn': SEQ_DBN, 'seq-dbn': SEQ_DBN,
@@ -59,7 +60,8 @@ def method_constants(method, N):
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.005, b_sig=0.005)
     elif m == SEQ_DBN:
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
-    elif m == GLOB_DBN:
+    elif m in (GLOB_DBN, FP_GLOB_DBN):
+        # network.py:237-243, :249-255 (num_samples = N for both); fpGlobCoupBpwLinReg.py:49-50 (IG(0.01, 0.01))
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.01, b_sig=0.01)
     else:
         raise ValueError(method)
@@ -485,6 +487,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
     Order of updates per iteration follows bayesianLinearRegression.py:114-147 (h),
     bayesianPwLinearRegression.py:89-132 (nh), seqCoupledBayesianPwLinReg.py:68-121 (seq),
     globCoupBayesianPwLinReg.py:64-116 (glob): sigma^2, beta, lambda^2 (, delta^2), pi move, tau move.
+    Full-parents globally coupled (fpGlobCoupBpwLinReg.py:16-119): pi is fixed to all other genes (:27-31), there is
+    no parent-set move, the changepoint move is the globally coupled one (:88-98); trace arrays are n wide.
     """
     m = METHOD_IDS[method] if isinstance(method, str) else method
     N, n = X.shape
@@ -492,13 +496,14 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
     features = [j for j in range(n) if j != node]
     F = len(features)
     c = method_constants(m, N)
-    seq, glob = m == SEQ_DBN, m == GLOB_DBN
+    fp = m == FP_GLOB_DBN
+    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN)
     has_tau = with_tau and m != H_DBN
-    KM, SM = 5, 10
+    KM, SM = (max(5, n) if fp else 5), 10
 
-    pi, tau = [], [N + 2]
+    pi, tau = (list(features) if fp else []), [N + 2]
     lam = sig = dlt = 1.0
-    mu = np.zeros(1)                                                # glob: current global mean (k entries)
+    mu = np.zeros(len(pi) + 1)                                      # glob: current global mean (k entries)
     tr = {k_: np.full(n_iter, np.nan) for k_ in (
         'sigma2', 'lambda2', 'delta2', 'sig_shape', 'sig_scale', 'lam_shape', 'lam_scale', 'del_shape', 'del_scale')}
     tr['beta_mean'] = np.full((n_iter, SM, KM), np.nan)
@@ -541,7 +546,10 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
             tr['beta_cov'][it, h, :k, :k] = cov
             betas.append(draws.beta(it, h, mean, cov))
         # ---- lambda^2 (and delta^2)
-        shape, rate = lambda2_params(m, betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
+        tr.setdefault('beta', np.full((n_iter, SM, KM), np.nan))
+        for h, b_ in enumerate(betas):
+            tr['beta'][it, h, :k] = b_
+        shape, rate = lambda2_params(GLOB_DBN if fp else m, betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
         tr['lam_shape'][it], tr['lam_scale'][it] = shape, 1.0 / rate
         lam_new = draws.inv_gamma(it, 'lambda', shape, rate)
         tr['lambda2'][it] = lam_new
@@ -555,10 +563,12 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
         lam, dlt = lam_new, dlt_new
 
         # ---- pi move
-        move = draws.move(it, 'pi')
-        star, hr = propose_pi(pi, move, features, fan_in, draws.picker(it, 'pi'))
-        tr['pi_valid'][it] = int(star is not None)
-        tr['pi_accept'][it] = 0
+        star = None
+        if not fp:
+            move = draws.move(it, 'pi')
+            star, hr = propose_pi(pi, move, features, fan_in, draws.picker(it, 'pi'))
+            tr['pi_valid'][it] = int(star is not None)
+            tr['pi_accept'][it] = 0
         if star is not None:
             stats_star = segment_stats(X, y, star, tau)
             lp = math.log(pi_prior(star, F, fan_in)) - math.log(pi_prior(pi, F, fan_in))
@@ -674,6 +684,24 @@ def accumulate_counts(trace, node, n, N, burn_in, edge, nonempty, cp_hist, cp_ke
             for c_ in trace['tau_after'][it]:
                 if 0 <= c_ <= N:
                     cp_hist[node, int(c_)] += 1
+
+
+def credible_scores(mu_samples, features, n):
+    """Edge-score row of a full-parents globally coupled node (network.py:303-347, scores.py:196-205, :223-253):
+    for every parent, max(fraction of thinned mu samples >= 0, fraction <= 0); `mu_samples` is [n_kept, k] with
+    column 0 the intercept and column 1 + j the j-th feature (sorted by label); the node's own column stays 0."""
+    mu_samples = np.asarray(mu_samples, dtype=float)
+    row = np.zeros(n)
+    for j, f in enumerate(features):
+        col = mu_samples[:, j + 1]
+        row[f] = max(np.mean(col >= 0), np.mean(col <= 0))
+    return row
+
+
+def mu_kept(idx, burn_in):
+    """mu_vector[idx] (idx = 0 is the initial zero vector, idx = it + 1 the state after iteration it) is kept iff
+    idx >= burn_in and (idx - burn_in) % 10 == 0 (network.py:309-311)."""
+    return idx >= burn_in and (idx - burn_in) % THIN == 0
 
 
 def edge_scores(edge, nonempty):

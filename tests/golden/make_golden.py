@@ -169,7 +169,9 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
     n = data_list[0].shape[1]
     has_tau = method != 'h_dbn'
     is_seq = method == 'seq_coup_nh_dbn'
-    is_glob = method == 'glob_coup_nh_dbn'
+    is_fp = method == 'fp_glob_coup_nh_dbn'       # full parents: no parent-set move, design width = n
+    is_glob = method == 'glob_coup_nh_dbn' or is_fp
+    KM = globals()['KM'] if not is_fp else max(globals()['KM'], n)
     EVENTS.clear()
     np.random.seed(seed)
     random.seed(seed)
@@ -184,6 +186,21 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
                 net.fit(method)
                 res = net.chain_results
                 per_node.append((start, len(EVENTS), res))
+                if is_fp:
+                    # network.py:303-347 without the plotting of scores.py:223-231 (credible_interval draws a
+                    # histogram): thin the mu chain, stack it, credible_score per feature (scores.py:196-205,:245-246)
+                    import dyban.scores as ref_scores
+                    feats = [int(s_[1:]) for s_ in list(net.network_configuration['features'])]
+                    burned = res['mu_vector'][burn_in:]
+                    thinned = [[burned[x]] for x in range(len(burned)) if x % 10 == 0]
+                    bm = ref_scores.beta_post_matrix(thinned)
+                    row = [0.0] * n
+                    for j, f in enumerate(feats):
+                        row[f] = ref_scores.credible_score(bm[:, j + 1])
+                    net.proposed_adj_matrix.append(row)
+                    burned_cps = res['tau_vector'][burn_in:]
+                    net.cps_over_response.append([burned_cps[x] for x in range(len(burned_cps)) if x % 10 == 0])
+                    continue
                 try:
                     net.score_edges(i, method)
                 except AttributeError:
@@ -225,8 +242,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
         pi_vec = res['pi_vector']
         tau_vec = res['tau_vector']
         cur_tau = [N + 2]
-        cur_pi = []
-        cur_mu = np.zeros(1)
+        cur_pi = [j for j in range(n) if j != i] if is_fp else []
+        cur_mu = np.zeros(len(cur_pi) + 1)
         for it in range(n_iter):
             S = len(cur_tau)
             g['S'][i, it] = S
@@ -247,23 +264,26 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
                 g['del_shape'][i, it], g['del_scale'][i, it], g['delta2'][i, it] = e[1], e[2], 1.0 / e[3]
                 pos += 1
             # ---- pi move
-            rec, pos = _parse_move(ev, pos, end)
+            if is_fp:
+                rec = dict(move=-1, valid=-1, u=NAN, picks=[], ncand=[], mvn=[], mus=[], logml=[], rawml=[])
+            else:
+                rec, pos = _parse_move(ev, pos, end)
             g['pi_move'][i, it] = rec['move']
             g['pi_valid'][i, it] = rec['valid']
             g['u_pi'][i, it] = rec['u']
             for j, (p, c) in enumerate(zip(rec['picks'], rec['ncand'])):
                 g['pi_pick'][i, it, j] = p
                 g['pi_ncand'][i, it, j] = c
-            new_pi = [int(v) for v in np.asarray(pi_vec[it + 1]).ravel()]
-            g['pi_accept'][i, it] = int(new_pi != cur_pi)
+            new_pi = cur_pi if is_fp else [int(v) for v in np.asarray(pi_vec[it + 1]).ravel()]
+            g['pi_accept'][i, it] = -1 if is_fp else int(new_pi != cur_pi)
             if method == 'h_dbn':
                 if rec['valid']:
                     g['logml'][i, it, 0] = np.log(rec['rawml'][0])
                     g['logml'][i, it, 1] = np.log(rec['rawml'][1])
-            elif rec['valid']:
+            elif rec['valid'] > 0:
                 g['logml'][i, it, 0] = rec['logml'][0]
                 g['logml'][i, it, 1] = rec['logml'][1]
-            if is_glob and rec['valid']:
+            if is_glob and rec['valid'] > 0:
                 for j, m in enumerate(rec['mvn']):
                     g['mus_mean'][i, it, j] = _pad_vec(m[1], KM)
                     g['mus_cov'][i, it, j] = _pad_mat(m[2], KM)
@@ -311,6 +331,11 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
         assert pos == end, (i, pos, end, ev[pos] if pos < end else None)
 
     out = dict(g)
+    if is_fp:
+        # n-wide covariances would make the fixture several MB: keep their diagonals (the means, log-densities and
+        # log-MLs recorded beside them pin the same matrices through Q^-1 and ln det Q)
+        out['beta_cov_diag'] = np.diagonal(out.pop('beta_cov'), axis1=-2, axis2=-1).copy()
+        out['mus_cov_diag'] = np.diagonal(out.pop('mus_cov'), axis1=-2, axis2=-1).copy()
     out['method'] = np.array(method)
     out['n_iter'] = np.array(n_iter)
     out['burn_in'] = np.array(burn_in)
@@ -449,6 +474,11 @@ def main():
     syn, _, _ = make_synthetic(8, 200, n_changepoints=3, max_fan_in=3, seed=7)
     syn_long, _, _ = make_synthetic(6, 341, n_changepoints=2, max_fan_in=3, seed=11)
 
+    if 'fp-only' in sys.argv:       # add the full-parents fixtures without re-minting the others
+        run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+        run_chain_golden('synth200', [syn], 'fp_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
+        return
     run_kat('yeast', yeast, 160, seed=101)
     run_kat('mtor', mtor, 160, seed=102)
     run_kat('synth200', [syn], 120, seed=103)
@@ -461,6 +491,9 @@ def main():
         run_chain_golden('mtor', mtor, m, n_iter=80, burn_in=20, seed=2)
     for m in methods[1:]:
         run_chain_golden('synth200', [syn], m, n_iter=120, burn_in=20, seed=3)
+    run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+    run_chain_golden('synth200', [syn], 'fp_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
 
 
 if __name__ == '__main__':

@@ -11,7 +11,9 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 LOGML_RTOL = 1e-9
 
 KAT_FILES = sorted(glob.glob(os.path.join(GOLDEN, 'kat_logml_*.npz')))
-CHAIN_FILES = sorted(glob.glob(os.path.join(GOLDEN, 'chain_*.npz')))
+_ALL_CHAINS = sorted(glob.glob(os.path.join(GOLDEN, 'chain_*.npz')))
+FP_CHAIN_FILES = [p for p in _ALL_CHAINS if '_fp_' in os.path.basename(p)]      # full-parents glob-coupled (n-wide)
+CHAIN_FILES = [p for p in _ALL_CHAINS if p not in FP_CHAIN_FILES]
 
 
 def load(path):

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
 from oracle import dbn_oracle as O
 
 
@@ -95,3 +95,38 @@ def test_chain_replay(path):
     if 'cp_hist' in g:
         assert np.array_equal(cp_hist, g['cp_hist'])
         assert np.array_equal(cp_kept, g['cp_kept'])
+
+
+@pytest.mark.parametrize('path', FP_CHAIN_FILES, ids=ids(FP_CHAIN_FILES))
+def test_fp_glob_chain_replay(path):
+    """Full-parents globally coupled chains (fpGlobCoupBpwLinReg.py:16-119) replayed from the reference's recorded
+    draws: changepoint lists and accept flags bit-exact, Gibbs parameters / log-MLs / mu-sampler means and densities
+    to 1e-9..1e-8, and the credible-score row of network.py:303-347 from the thinned mu chain."""
+    g = load(path)
+    X, Y = O.lagged_matrices(data_list(g))
+    n = X.shape[1]
+    n_iter, burn_in = int(g['n_iter']), int(g['burn_in'])
+    adj = np.zeros((n, n))
+    for node in range(n):
+        tr = O.run_chain('fp_glob_coup_nh_dbn', X, Y, node, n_iter, O.ReplayDraws(g, node))
+        for key in ('S', 'tau_after', 'tau_valid', 'tau_accept'):
+            assert np.array_equal(tr[key], g[key][node]), (key, node)
+        for key in ('sig_shape', 'sig_scale', 'lam_shape', 'lam_scale'):
+            assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+        # n-wide posterior means on the GP-smoothed (near-collinear) mTOR series: the reference's own inv() carries
+        # ~1e-9 relative noise in single entries, so entries are compared at 1e-7 of the vector's scale
+        assert_close(tr['beta_mean'], g['beta_mean'][node], 1e-7, 1e-9, what='beta_mean node %d' % node)
+        assert_close(np.diagonal(tr['beta_cov'], axis1=-2, axis2=-1), g['beta_cov_diag'][node], 1e-7, 1e-13, what='beta_cov')
+        assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
+        assert_close(tr['mus_mean'], g['mus_mean'][node], 1e-7, 1e-9, what='mus_mean node %d' % node)
+        assert_close(np.diagonal(tr['mus_cov'], axis1=-2, axis2=-1), g['mus_cov_diag'][node], 1e-7, 1e-12, what='mus_cov')
+        ref = g['mus_logdens'][node].copy()
+        mine = tr['mus_logdens']
+        ref[np.isnan(mine)] = np.nan
+        assert_close(mine, ref, 1e-8, 1e-8, what='mus_logdens node %d' % node)
+        assert_close(tr['mu_after'], g['mu_after'][node], 0, 0, what='mu_after node %d' % node)
+        # thinned mu chain: index 0 is the initial zero vector (fpGlobCoupBpwLinReg.py:66)
+        mu_vec = [np.zeros(n)] + [tr['mu_after'][it, :n] for it in range(n_iter)]
+        kept = [mu_vec[i] for i in range(len(mu_vec)) if O.mu_kept(i, burn_in)]
+        adj[node] = O.credible_scores(np.array(kept), [j for j in range(n) if j != node], n)
+    assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
