@@ -31,6 +31,19 @@ TI_PI_VALID, TI_PI_ACCEPT, TI_TAU_VALID, TI_TAU_ACCEPT, TI_NPI, TI_PI, TI_S, TI_
 TI_PI_MOVE, TI_TAU_MOVE, TI_S_BEFORE, TI_STRIDE = 20, 21, 22, 24
 
 
+def fp_rd_stride(k):
+    """doubles per replay record of dbn_run_fp (include/dbn_b200.h)"""
+    return 3 + k + SMAX * k
+
+
+def fp_td_stride(k):
+    """doubles per trace record of dbn_run_fp"""
+    return 10 + 3 * k + 3 * SMAX * k
+
+
+FP_RI_STRIDE, FP_TI_STRIDE = 4, 16
+
+
 class DbnConfig(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_chains', C.c_int32), ('chain_offset', C.c_int64), ('seed', C.c_uint64)]
 
@@ -61,12 +74,14 @@ SYMBOLS = {
                                   _ip, _ip, _ip, _ip, _ip, _dp, _dp, _dp, _dp]),
     'dbn_chain_init': (C.c_int, [_P, C.POINTER(DbnRunParams)]),
     'dbn_run': (C.c_int, [_P, C.c_int32, _dp, _ip, _dp, _ip]),
+    'dbn_run_fp': (C.c_int, [_P, C.c_int32, _dp, _ip, _dp, _ip]),
     'dbn_counts_size': (C.c_int, [_P, _lp]),
     'dbn_read_counts': (C.c_int, [_P, _lp]),
     'dbn_device_counts': (C.c_int, [_P, C.POINTER(_P)]),
     'dbn_read_state': (C.c_int, [_P, _ip, _ip, _ip, _ip, _dp, _dp]),
     'dbn_read_counters': (C.c_int, [_P, _up]),
     'dbn_reset_counters': (C.c_int, [_P]),
+    'dbn_verify_cache': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'dbn_measure_fp64_peak': (C.c_int, [_P, _dp]),
 }
 

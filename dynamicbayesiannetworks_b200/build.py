@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libdbn_b200.so')
 SOURCES = [os.path.join(CSRC, 'dbn_kernels.cu')]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('dbn_chain.cuh', 'dbn_chain_fast.cuh', 'dbn_score.cuh', 'dbn_rng.cuh')] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('dbn_chain.cuh', 'dbn_chain_fast.cuh', 'dbn_fp.cuh', 'dbn_score.cuh', 'dbn_rng.cuh')] + [
     os.path.join(ROOT, 'include', 'dbn_b200.h')]
 
 

@@ -15,9 +15,10 @@
 //     alternative last rows of that factorisation.  Only the new column (<= KM+1 values per boundary) is gathered.
 //   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new)
 //     from the <= 4 prefix-table rows involved, staged in three scratch rows of the cache.
-//   * accepted moves are rare per unit but not per warp, so the cache updates they need (new column in every row;
-//     rows shifted behind an inserted / removed segment) are done by the whole warp for one accepting lane at a
-//     time, 32 entries per step, instead of by the accepting lane alone while 31 lanes idle.
+//   * accepted moves rewrite the owner's rows: the new column in every row (parent-set move) or the rows behind an
+//     inserted / removed segment (changepoint move), as 16-byte pairs.  Only the thread that owns a unit ever writes
+//     that unit's rows: handing this work to the other lanes of the warp (v4/v5) needs votes and shuffles, and those
+//     were measured to run on a split warp on rare occasions (profiles/r1_notes.md).
 // Every cached row is an exact function of (pi, tau) and the table (no running sums), so the state does not depend
 // on the history of moves.
 // Columns are kept in cache-slot order, not sorted by gene id: for mu = 0 (h, nh) the marginal likelihood and the
@@ -34,33 +35,35 @@ namespace dbn {
 #ifndef DBN_FAST_MINB
 #define DBN_FAST_MINB 3
 #endif
-#ifndef DBN_FAST_SYNC
-#define DBN_FAST_SYNC 1
-#endif
 constexpr int FAST_BLOCK = DBN_FAST_BLOCK;
 constexpr int SEG_ROWS = DBN_SMAX - 1;  // <= 9 segments
 constexpr int ROW_L = SEG_ROWS, ROW_X = SEG_ROWS + 1, ROW_R = SEG_ROWS + 2;  // scratch: prefix rows left / moving / right
 constexpr int BSLOTS = SEG_ROWS + 3;    // cached rows per unit
-constexpr unsigned FULL = 0xffffffffu;
 
 template <int KM>
 struct FastDims {
   static constexpr int KB = KM - 1;
   static constexpr int KT = KM * (KM + 1) / 2;
-  static constexpr int NE = KT + KM + 1;  // doubles per cached row: ZZ packed by slot | ZY by slot | YY
+  static constexpr int NE = KT + KM + 1;  // entries per cached row: ZZ packed by slot | ZY by slot | YY
+  static constexpr int NP = (NE + 1) / 2; // 16-byte pairs per cached row
 };
 
-__host__ __device__ inline int fast_cache_row_doubles(int km) { return km * (km + 1) / 2 + km + 1; }
+// Cache layout: row r of unit u is NP pairs of doubles, pair p at doubles ((r * NP + p) * U + u) * 2: the two
+// entries of a pair are adjacent, so a row moves as NP 16-byte copies per thread, consecutive threads 16 bytes apart.
+__host__ __device__ inline int fast_cache_row_doubles(int km) { return 2 * ((km * (km + 1) / 2 + km + 1 + 1) / 2); }
 inline size_t fast_smem_bytes(int km) {
-  return (size_t)2 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(int) +
-         (FAST_BLOCK / 32) * 16 * sizeof(int);
+  return (size_t)2 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(int);
 }
+// entry e of a row whose pair 0 is at `p` (global: pair stride = 2 * U doubles; shared staging: 2 * FAST_BLOCK doubles)
+#define DBN_CE(p, e) (p)[(long long)((e) >> 1) * (2 * U) + ((e) & 1)]
+#define DBN_SE(p, e) (p)[((e) >> 1) * (2 * FAST_BLOCK) + ((e) & 1)]
 
-// 8-byte asynchronous global -> shared copy (LDGSTS): the staged row of the next segment is in flight while the
-// current one is factorised; no registers are held for it
-__device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
+// 16-byte asynchronous global -> shared copy (LDGSTS): the staged row of the next segment is in flight while the
+// current one is factorised; no registers are held for it.  .cg = through L2 only (the rows are streamed, never reused
+// from L1).
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -71,21 +74,18 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int METHOD, int KM, bool TRACE>
 __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(const ChainArgs a) {
   constexpr bool HOMOG = METHOD == DBN_H_DBN;
-  constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NE = FastDims<KM>::NE;
+  constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NE = FastDims<KM>::NE, NP = FastDims<KM>::NP;
   constexpr int KBT = KB * (KB + 1) / 2;
 
-  // dynamic shared memory: [2][NE][BLOCK] doubles (segment rows staged by cp.async) | tau | tau* | per-warp scratch
-  extern __shared__ double s_dyn[];
+  // dynamic shared memory: [2][NP][BLOCK][2] doubles (segment rows staged by cp.async) | tau | tau*
+  extern __shared__ __align__(16) double s_dyn[];
   double* const s_row = s_dyn;
-  int* const s_tau = reinterpret_cast<int*>(s_dyn + 2 * NE * FAST_BLOCK);
+  int* const s_tau = reinterpret_cast<int*>(s_dyn + 2 * (2 * NP) * FAST_BLOCK);
   int* const s_tas = s_tau + SMAX * FAST_BLOCK;
-  int* const s_coop = s_tas + SMAX * FAST_BLOCK;  // per warp: what the accepting lane publishes to the others
   const int tid = threadIdx.x;
   const int u_raw = blockIdx.x * FAST_BLOCK + tid;
   const bool active = u_raw < a.U;
   const int u = active ? u_raw : 0;
-  const int lane = tid & 31;
-  int* const coop = s_coop + (tid >> 5) * 16;
   const int node = u / a.C;
   const int chain = u - node * a.C;
   const int n = a.tb.n, N = a.tb.N, F = n - 1;
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   auto TAS = [&](int j) -> int& { return s_tas[j * FAST_BLOCK + tid]; };
   auto tau_cur = [&](int j) { return s_tau[j * FAST_BLOCK + tid]; };
   auto tau_star = [&](int j) { return s_tas[j * FAST_BLOCK + tid]; };
-  double* const cbase = a.cache + u;
-  auto crow = [&](int slot) -> double* { return cbase + (long long)slot * NE * U; };
+  double* const cbase = a.cache + 2ll * u;
+  auto crow = [&](int row) -> double* { return cbase + (long long)row * NP * (2 * U); };  // pair 0 of cached row `row`
   const int nb = a.tb.zz_size + node * (n + 2);  // table offset of this node's ZY / YY block
 
   // ---- load state
@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         const bool oj = (j == 0) || cg[j] >= 0;
         const int fj = (j == 0) ? 0 : cg[j] + 1;
         const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
-        c[(long long)DBN_TRI(i, j) * U] = (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0;
+        DBN_CE(c, DBN_TRI(i, j)) = (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0;
       }
-      c[(long long)(KT + i) * U] = oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0;
+      DBN_CE(c, KT + i) = oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0;
     }
-    c[(long long)(KT + KM) * U] = __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0);
+    DBN_CE(c, KT + KM) = __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0);
   };
 
   if (a.refresh) {
@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   auto stage_row = [&](int j, int buf) {
     if (j < S) {
       const double* src = crow(j);
-      double* dst = s_row + buf * NE * FAST_BLOCK + tid;
+      double* dst = s_row + buf * (2 * NP) * FAST_BLOCK + 2 * tid;
 #pragma unroll
-      for (int e = 0; e < NE; ++e) cp_async8(dst + e * FAST_BLOCK, src + (long long)e * U);
+      for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
     }
     cp_async_commit();
   };
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     const double* pl = crow(lo < 0 ? hi : lo);
     const bool has_lo = lo >= 0;
 #pragma unroll
-    for (int e = 0; e < KT; ++e) G[e] = ph[(long long)e * U] - (has_lo ? pl[(long long)e * U] : 0.0);
+    for (int e = 0; e < KT; ++e) G[e] = DBN_CE(ph, e) - (has_lo ? DBN_CE(pl, e) : 0.0);
 #pragma unroll
-    for (int i = 0; i < KM; ++i) g[i] = ph[(long long)(KT + i) * U] - (has_lo ? pl[(long long)(KT + i) * U] : 0.0);
-    s = ph[(long long)(KT + KM) * U] - (has_lo ? pl[(long long)(KT + KM) * U] : 0.0);
+    for (int i = 0; i < KM; ++i) g[i] = DBN_CE(ph, KT + i) - (has_lo ? DBN_CE(pl, KT + i) : 0.0);
+    s = DBN_CE(ph, KT + KM) - (has_lo ? DBN_CE(pl, KT + KM) : 0.0);
     form_a<KM>(G, lam, A);
     prod = ldl_factor<KM>(A, dinv);
     q = segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // The step is ~8k instructions of mostly straight-line code per thread, far more than the instruction cache
     // holds; warps that drift apart each stream it from L2 on their own (stall_no_instruction, profiles/r1_v4).
     // Block-wide barriers keep the block's warps on the same stretch of code so one fetch serves all of them.
-    if (DBN_FAST_SYNC >= 1) __syncthreads();
+    __syncthreads();
     const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * DBN_RD_STRIDE : nullptr;
     const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * DBN_RI_STRIDE : nullptr;
     double* td = (TRACE && a.td && active) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
@@ -216,13 +216,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       for (int h = 0; h < S; ++h) {
         stage_row(h + 1, (h + 1) & 1);
         cp_async_wait<1>();
-        const double* sr = s_row + (h & 1) * NE * FAST_BLOCK + tid;
+        const double* sr = s_row + (h & 1) * (2 * NP) * FAST_BLOCK + 2 * tid;
         double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
 #pragma unroll
-        for (int e = 0; e < KT; ++e) G[e] = sr[e * FAST_BLOCK];
+        for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sr, e);
 #pragma unroll
-        for (int i = 0; i < KM; ++i) g[i] = sr[(KT + i) * FAST_BLOCK];
-        s = sr[(KT + KM) * FAST_BLOCK];
+        for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, KT + i);
+        s = DBN_SE(sr, KT + KM);
         form_a<KM>(G, lam, A);
         ldl_factor<KM>(A, dinv);
         ++n_fact;
@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       }
     }
 
-    if (DBN_FAST_SYNC >= 2) __syncthreads();
     // ============================ proposals (no scoring yet) ==================================================
     // all discrete picks and both accept uniforms of the iteration come from three Philox blocks
     uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
@@ -362,13 +361,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           if (j == idx) el = pi[j];
         int w_ = 0;  // sorted(pi \ el)  (np.setdiff1d, utils.py:290, :318)
 #pragma unroll
-        for (int j = 0; j < PMAX; ++j) {
-          if (j < npi && spi[j] != el) {
+        for (int j = 0; j < PMAX; ++j) {  // selects only: a switch on w_ here becomes an indirect branch (BRX)
+          const bool keep = (j < npi) && (spi[j] != el);
 #pragma unroll
-            for (int q = 0; q < PMAX; ++q)
-              if (q == w_) star[q] = spi[j];
-            ++w_;
-          }
+          for (int q = 0; q < PMAX; ++q) star[q] = (keep && q == w_) ? spi[j] : star[q];
+          w_ += keep ? 1 : 0;
         }
         if (pmove == 1) {
           nstar = npi - 1;
@@ -520,17 +517,17 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       for (int h = 0; h < S; ++h) {
         stage_row(h + 1, (h + 1) & 1);
         cp_async_wait<1>();
-        const double* sr = s_row + (h & 1) * NE * FAST_BLOCK + tid;
+        const double* sr = s_row + (h & 1) * (2 * NP) * FAST_BLOCK + 2 * tid;
         double A[KBT], gB[KB], t1[KB], t2[KB], dinv[KB];
 #pragma unroll
-        for (int e = 0; e < KBT; ++e) A[e] = sr[eb[e] * FAST_BLOCK];
+        for (int e = 0; e < KBT; ++e) A[e] = DBN_SE(sr, eb[e]);
 #pragma unroll
         for (int p = 0; p < KB; ++p) {
-          gB[p] = sr[ezy[p] * FAST_BLOCK];
-          t1[p] = sr[et[p] * FAST_BLOCK];
+          gB[p] = DBN_SE(sr, ezy[p]);
+          t1[p] = DBN_SE(sr, et[p]);
         }
-        const double t1d = sr[ett * FAST_BLOCK], t1y = sr[ezyt * FAST_BLOCK];
-        const double s = sr[(KT + KM) * FAST_BLOCK];
+        const double t1d = DBN_SE(sr, ett), t1y = DBN_SE(sr, ezyt);
+        const double s = DBN_SE(sr, KT + KM);
         double t2d = 0.0, t2y = 0.0;
         if (has_new) {
           const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(h), h, S, N) * a.tb.row_stride;
@@ -624,40 +621,17 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     }
-    if (DBN_FAST_SYNC >= 2) __syncthreads();
-    // ---- accepted parent-set moves: the new column (zeros for a delete) takes slot `tslot` in every cached row.
-    // The warp serves one accepting lane at a time: item (j, p) = entry p of the changing column in segment row j.
-    {
-      unsigned m = __ballot_sync(FULL, p_acc);
-      while (m) {
-        const int L = __ffs(m) - 1;
-        m &= m - 1;
-        if (lane == L) {
+    // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row
+    if (p_acc) {
+      const double* __restrict__ row0 = a.tb.base;  // table row 0 is all zeros
+      for (int j = 0; j < S; ++j) {
+        const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(TAU(j), j, S, N) * a.tb.row_stride;
+        double* c = crow(j);
 #pragma unroll
-          for (int p = 0; p < KB; ++p) {
-            coop[p] = o2[p];
-            coop[8 + p] = et[p];
-          }
-          coop[KB] = o2d;
-          coop[KB + 1] = o2y;
-          coop[8 + KB] = ett;
-          coop[8 + KB + 1] = ezyt;
-        }
-        __syncwarp();
-        const int uL = __shfl_sync(FULL, u, L), SL = __shfl_sync(FULL, S, L);
-        const int tL = (tid & ~31) + L;
-        for (int idx = lane; idx < SL * (KB + 2); idx += 32) {
-          const int j = idx / (KB + 2), p = idx - j * (KB + 2);
-          const int off = coop[p], ent = coop[8 + p];
-          double v = 0.0;
-          if (off >= 0) {
-            const int bhi = DBN_SEG_END(s_tau[j * FAST_BLOCK + tL], j, SL, N);
-            v = __ldg(a.tb.base + (long long)bhi * a.tb.row_stride + off);
-            if (j > 0) v -= __ldg(a.tb.base + (long long)(s_tau[(j - 1) * FAST_BLOCK + tL] - 1) * a.tb.row_stride + off);
-          }
-          a.cache[((long long)j * NE + ent) * U + uL] = v;
-        }
-        __syncwarp();
+        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (o2[p] >= 0) ? __ldg(row + o2[p]) - __ldg(row0 + o2[p]) : 0.0;
+        DBN_CE(c, ett) = (o2d >= 0) ? __ldg(row + o2d) - __ldg(row0 + o2d) : 0.0;
+        DBN_CE(c, ezyt) = (o2y >= 0) ? __ldg(row + o2y) - __ldg(row0 + o2y) : 0.0;
+        row0 = row;
       }
     }
     // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
@@ -728,46 +702,35 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
         if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = t_acc;
       }
-      // ---- accepted changepoint moves: shift the segment rows behind the change, write the new segments' rows
-      // from the staged prefix rows.  One accepting lane at a time, the warp moves 32 entries per step.
-      {
-        unsigned m = __ballot_sync(FULL, t_acc);
-        while (m) {
-          const int L = __ffs(m) - 1;
-          m &= m - 1;
-          const int uL = __shfl_sync(FULL, u, L), SL = __shfl_sync(FULL, S, L);
-          const int mvL = __shfl_sync(FULL, tmove, L), tjL = __shfl_sync(FULL, tj, L);
-          double* cu = a.cache + uL;
-          // birth splits segment tj-1: rows tj .. S-1 move up by one; death merges tj-1 and tj: rows tj+1 .. S-1
-          // move down by one; a reallocation moves nothing
-          const int src0 = (mvL == 0) ? tjL : tjL + 1;
-          const int n_mv = (mvL == 2) ? 0 : SL - src0;
-          const int dlt_ = (mvL == 0) ? 1 : -1;
-          double v[6];
+      // ---- accepted changepoint move: a birth splits segment tj-1 (rows tj .. S-1 move up by one), a death merges
+      // segments tj-1 and tj (rows tj+1 .. S-1 move down by one), a reallocation moves nothing; the one or two new
+      // segments' rows are differences of the prefix rows staged above.  A row moves as NP 16-byte pairs.
+      if (t_acc) {
+        double2* cu = reinterpret_cast<double2*>(a.cache) + u;  // pair p of row r at cu[(r * NP + p) * U]
+        auto move_row = [&](int dst, int src) {
+          double2 t[NP];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < n_mv * NE) v[i] = cu[((long long)src0 * NE + idx) * U];
-          }
-          __syncwarp();
+          for (int p = 0; p < NP; ++p) t[p] = __ldcg(cu + ((long long)src * NP + p) * U);
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < n_mv * NE) cu[((long long)(src0 + dlt_) * NE + idx) * U] = v[i];
+          for (int p = 0; p < NP; ++p) cu[((long long)dst * NP + p) * U] = t[p];
+        };
+        if (birth) {
+          for (int r = S - 1; r >= tj; --r) move_row(r + 1, r);
+        } else if (death) {
+          for (int r = tj + 1; r < S; ++r) move_row(r - 1, r);
+        }
+        const bool has_l = tj >= 2;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const double2 xl = has_l ? __ldcg(cu + ((long long)ROW_L * NP + p) * U) : make_double2(0.0, 0.0);
+          const double2 xr = __ldcg(cu + ((long long)ROW_R * NP + p) * U);
+          if (death) {
+            cu[((long long)(tj - 1) * NP + p) * U] = make_double2(xr.x - xl.x, xr.y - xl.y);
+          } else {
+            const double2 xx = __ldcg(cu + ((long long)ROW_X * NP + p) * U);
+            cu[((long long)(tj - 1) * NP + p) * U] = make_double2(xx.x - xl.x, xx.y - xl.y);
+            cu[((long long)tj * NP + p) * U] = make_double2(xr.x - xx.x, xr.y - xx.y);
           }
-          __syncwarp();
-          if (lane < NE) {
-            const double xl = (tjL >= 2) ? cu[((long long)ROW_L * NE + lane) * U] : 0.0;
-            const double xr = cu[((long long)ROW_R * NE + lane) * U];
-            if (mvL == 1) {
-              cu[((long long)(tjL - 1) * NE + lane) * U] = xr - xl;
-            } else {
-              const double xx = cu[((long long)ROW_X * NE + lane) * U];
-              cu[((long long)(tjL - 1) * NE + lane) * U] = xx - xl;
-              cu[((long long)tjL * NE + lane) * U] = xr - xx;
-            }
-          }
-          __syncwarp();
         }
       }
       if (t_acc) {
@@ -799,16 +762,59 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
     for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
   }
-  // ---- work counters: one atomic per warp
-  unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
-                             (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
-  __syncwarp();
+  // ---- work counters: summed per block in shared memory (the staging buffers are free now), one global atomic each
+  unsigned long long* const s_cnt = reinterpret_cast<unsigned long long*>(s_dyn);
+  __syncthreads();
+  if (tid < 8) s_cnt[tid] = 0ull;
+  __syncthreads();
+  const unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
+                                   (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    unsigned long long x = v[c];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&a.counters[c], x);
+  for (int c = 0; c < 8; ++c)
+    if (v[c]) atomicAdd(&s_cnt[c], v[c]);
+  __syncthreads();
+  if (tid < 8 && s_cnt[tid]) atomicAdd(&a.counters[tid], s_cnt[tid]);
+}
+
+// Invariant check (test hook behind dbn_verify_cache): every cached segment row of every unit must equal the difference
+// of the two prefix-table rows at the segment's boundaries, restricted to the unit's column slots, bit for bit.
+// counts[0] += units with at least one differing entry, counts[1] += differing entries.
+template <int KM>
+__global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* counts) {
+  constexpr int KT = FastDims<KM>::KT, NP = FastDims<KM>::NP;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= a.U) return;
+  const long long U = a.U;
+  const int node = u / a.C, n = a.tb.n, N = a.tb.N;
+  const int nb = a.tb.zz_size + node * (n + 2);
+  const int S = a.st_S[u];
+  int cg[KM];
+  cg[0] = -1;
+  for (int s = 1; s < KM; ++s) cg[s] = a.st_cg[(s - 1) * a.U + u];
+  unsigned long long bad = 0;
+  for (int j = 0; j < S; ++j) {
+    const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N), t0 = j == 0 ? 0 : a.st_tau[(j - 1) * a.U + u] - 1;
+    const double* row = a.tb.base + (long long)t * a.tb.row_stride;
+    const double* row0 = a.tb.base + (long long)t0 * a.tb.row_stride;
+    const double* c = a.cache + 2ll * u + (long long)j * NP * (2 * U);
+    for (int i = 0; i < KM; ++i) {
+      const bool oi = (i == 0) || cg[i] >= 0;
+      const int fi = (i == 0) ? 0 : cg[i] + 1;
+      for (int jj = 0; jj <= i; ++jj) {
+        const bool oj = (jj == 0) || cg[jj] >= 0;
+        const int fj = (jj == 0) ? 0 : cg[jj] + 1;
+        const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
+        const double ex = (oi && oj) ? row[off] - row0[off] : 0.0;
+        bad += (ex != DBN_CE(c, DBN_TRI(i, jj))) ? 1 : 0;
+      }
+      const double ex = oi ? row[nb + fi] - row0[nb + fi] : 0.0;
+      bad += (ex != DBN_CE(c, KT + i)) ? 1 : 0;
+    }
+    bad += ((row[nb + n + 1] - row0[nb + n + 1]) != DBN_CE(c, KT + KM)) ? 1 : 0;
+  }
+  if (bad) {
+    atomicAdd(&counts[0], 1ull);
+    atomicAdd(&counts[1], bad);
   }
 }
 

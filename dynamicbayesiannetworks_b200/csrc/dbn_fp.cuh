@@ -1,0 +1,552 @@
+// Kernel 4 — full-parents globally coupled chain step (fp_glob_coup_nh_dbn): the regressor loop of
+// fpGlobCoupBpwLinReg.py:68-110 for design width k = n (every other gene is a parent, :27-31), any n.
+//
+// One thread block per (node, chain) unit; the k x k matrices live in shared memory when they fit (k <= ~56) and in
+// a per-block global workspace otherwise.  Per segment the block forms A_h = I + lam G_h from two prefix-table
+// rows, factorises it (Cholesky, A = L L^T) and inverts the factor (W = L^-1), after which everything the iteration
+// needs is a matrix-vector product:
+//   quadratic form   r^T C^-1 r = rho - lam |W v|^2,  v = g - G mu           (samplers.py:103-127)
+//   posterior mean   A^-1 (mu + lam g) = W^T W (mu + lam g),  cov = s2 lam W^T W  (samplers.py:189-218)
+//   draw             beta = mean + sqrt(s2 lam) W^T z
+// The changepoint move (moves.py:25-126) needs, for tau and tau*, the marginal likelihood at a mean vector and the
+// Gaussian muSampler draws from (samplers.py:307-351).  Both follow from five sums over the segments,
+//   M = sum_h (I - A_h^-1),  a = sum_h A_h^-1 g_h,  c = sum_h g_h^T A_h^-1 g_h,  s = sum_h y_h^T y_h,
+//   ld = sum_h ln det A_h,
+// because G_h A_h^-1 = (I - A_h^-1) / lam:
+//   precision  Q = I + M / (lam s2),   mean numerator  a / s2 (+ mu_in)         (samplers.py:319-337)
+//   sum_h r_h^T C_h^-1 r_h at mean mu  =  s - lam c - 2 mu.a + mu^T M mu / lam   (marginalLikelihood.py:91-150)
+// so one sweep per changepoint list scores ANY mu (the proposed mu* is only known after the sweep).
+#pragma once
+#include "dbn_chain.cuh"
+
+namespace dbn {
+
+constexpr int FP_BLOCK = 128;
+constexpr int FP_NMAT = 5;  // A/L, W, M (tau), M (tau*), Q
+constexpr int FP_NVEC = 12;
+
+struct FpArgs {
+  Table tb;
+  int num_samples, burn_in, thin, with_tau;
+  int C, U, it0, n_iter;
+  unsigned int chain_offset;
+  unsigned long long seed;
+  double T_sigma_half, a_sig, b_sig, a_lam, b_lam, log_p, log_1mp, c0, T_half_plus_a, two_b;
+  int* st_S;
+  int* st_tau;     // [SMAX][U]
+  double* st_sig;
+  double* st_lam;
+  double* st_mu;   // [k][U]
+  unsigned long long* pos;      // [n][n]  #kept mu samples with mu_j >= 0   (credible_score, scores.py:196-205)
+  unsigned long long* kept;     // [n]     #kept mu samples
+  unsigned long long* cp_hist;  // [n][N+3]
+  unsigned long long* cp_kept;  // [n]
+  unsigned long long* neg;      // [n][n]  #kept mu samples with mu_j <= 0
+  unsigned long long* counters;
+  double* ws;      // per-block workspace of FP_NMAT * ld * k doubles (null: matrices in shared memory)
+  const double* rd;
+  const int* ri;
+  double* td;
+  int* ti;
+};
+
+__host__ __device__ inline int fp_ld(int k) { return k | 1; }
+// replay / trace record strides (doubles / ints per (unit, iteration)); see include/dbn_b200.h
+__host__ __device__ inline int fp_rd_stride(int k) { return 3 + k + DBN_SMAX * k; }
+__host__ __device__ inline int fp_td_stride(int k) { return 10 + 3 * k + 3 * DBN_SMAX * k; }
+
+// ---- block-level building blocks (all threads of the block call them) -----------------------------------------------
+__device__ __forceinline__ double fp_block_sum(double x, double* red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < FP_BLOCK / 32; ++w) t += red[w];
+  return t;
+}
+
+__device__ __forceinline__ double fp_dot(const double* a, const double* b, int k, double* red) {
+  double x = 0.0;
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) x += a[i] * b[i];
+  return fp_block_sum(x, red);
+}
+
+// design column a of node `node` -> table column (0 = intercept, gene j -> j + 1); columns are sorted by gene id
+__device__ __forceinline__ int fp_col(int a, int node) { return a == 0 ? 0 : (a - 1 < node ? a : a + 1); }
+
+// A = I + lam (P[hi] - P[lo]) restricted to the node's design columns (full symmetric), g, s
+__device__ void fp_load_segment(const Table& tb, int node, int lo, int hi, double lam, double* A, int ld, int k, double* g,
+                                double* s_out) {
+  const double* __restrict__ ph = tb.base + (long long)hi * tb.row_stride;
+  const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
+  const int nb = tb.zz_size + node * (tb.n + 2);
+  for (int a = 0; a < k; ++a) {
+    const int fa = fp_col(a, node);
+    const int base = fa * (fa + 1) / 2;
+    for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
+      const int fb = fp_col(b, node);
+      const double v = lam * (__ldg(ph + base + fb) - __ldg(pl + base + fb)) + (a == b ? 1.0 : 0.0);
+      A[a * ld + b] = v;
+      A[b * ld + a] = v;
+    }
+  }
+  for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
+    const int fa = fp_col(a, node);
+    g[a] = __ldg(ph + nb + fa) - __ldg(pl + nb + fa);
+  }
+  if (threadIdx.x == 0) *s_out = __ldg(ph + nb + tb.n + 1) - __ldg(pl + nb + tb.n + 1);
+  __syncthreads();
+}
+
+// y = M x for a full symmetric (or any square) k x k matrix; thread per output row, x broadcast from shared memory
+__device__ void fp_symv(const double* M, int ld, int k, const double* x, double* y) {
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+    double acc = 0.0;
+    for (int j = 0; j < k; ++j) acc += M[j * ld + i] * x[j];  // column i of a symmetric matrix: coalesced over i
+    y[i] = acc;
+  }
+  __syncthreads();
+}
+
+// in-place lower Cholesky of the full symmetric matrix A (upper part left untouched); returns ln det A
+__device__ double fp_cholesky(double* A, int ld, int k) {
+  double logdet = 0.0;
+  for (int j = 0; j < k; ++j) {
+    __syncthreads();  // the previous column's trailing update is complete
+    const double l = sqrt(A[j * ld + j]);
+    logdet += log(l);
+    __syncthreads();  // every thread has read the pivot before it is overwritten
+    if (threadIdx.x == 0) A[j * ld + j] = l;
+    const double il = 1.0 / l;
+    for (int i = j + 1 + threadIdx.x; i < k; i += FP_BLOCK) A[i * ld + j] *= il;
+    __syncthreads();
+    // trailing update, thread per column c: A[i][c] -= A[i][j] A[c][j] for i >= c
+    for (int c = j + 1 + threadIdx.x; c < k; c += FP_BLOCK) {
+      const double lcj = A[c * ld + j];
+      for (int i = c; i < k; ++i) A[i * ld + c] -= A[i * ld + j] * lcj;
+    }
+  }
+  __syncthreads();
+  return 2.0 * logdet;
+}
+
+// W = L^-1 (lower triangular, zeros above the diagonal): forward substitution on all columns at once
+__device__ void fp_trinv(const double* L, double* W, int ld, int k) {
+  for (int c = threadIdx.x; c < k; c += FP_BLOCK) {
+    for (int i = 0; i < k; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      if (i > c)
+        for (int j = c; j < i; ++j) acc -= L[i * ld + j] * W[j * ld + c];
+      W[i * ld + c] = (i >= c) ? acc / L[i * ld + i] : 0.0;
+    }
+  }
+  __syncthreads();
+}
+
+// t = W x (lower triangular W), thread per row
+__device__ void fp_trmv(const double* W, int ld, int k, const double* x, double* t) {
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+    double acc = 0.0;
+    for (int j = 0; j <= i; ++j) acc += W[i * ld + j] * x[j];
+    t[i] = acc;
+  }
+  __syncthreads();
+}
+
+// y = W^T t (lower triangular W), thread per output entry: coalesced over a
+__device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y) {
+  for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
+    double acc = 0.0;
+    for (int i = a; i < k; ++i) acc += W[i * ld + a] * t[i];
+    y[a] = acc;
+  }
+  __syncthreads();
+}
+
+// M += I - W^T W (full symmetric)
+__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k) {
+  for (int a = 0; a < k; ++a) {
+    for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
+      double acc = 0.0;
+      for (int i = a; i < k; ++i) acc += W[i * ld + a] * W[i * ld + b];
+      const double v = ((a == b) ? 1.0 : 0.0) - acc;
+      M[a * ld + b] += v;
+      if (a != b) M[b * ld + a] += v;
+    }
+  }
+  __syncthreads();
+}
+
+// z[0..k) ~ N(0,1), Philox slots base + i/2
+__device__ void fp_normals(double* z, int k, uint32_t chain, uint32_t node, uint32_t it, uint32_t base, uint2 key) {
+  for (int p = threadIdx.x; 2 * p < k; p += FP_BLOCK) {
+    const double2 zz = normal_pair(chain, node, it, base + (uint32_t)p, key);
+    z[2 * p] = zz.x;
+    if (2 * p + 1 < k) z[2 * p + 1] = zz.y;
+  }
+  __syncthreads();
+}
+
+// the five sums of one changepoint list at lam (see the header comment); M must be zeroed by the caller
+struct FpSummary {
+  double c, s, ld;
+};
+
+template <class TauFn>
+__device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, double lam, double* A, double* W, double* M, int ld, int k,
+                              double* g, double* t, double* x, double* a_sum, double* red, double* s_tmp) {
+  FpSummary r = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] = 0.0;
+  for (int i = threadIdx.x; i < k * ld; i += FP_BLOCK) M[i] = 0.0;
+  __syncthreads();
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
+    fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
+    r.s += *s_tmp;
+    r.ld += fp_cholesky(A, ld, k);
+    fp_trinv(A, W, ld, k);
+    fp_trmv(W, ld, k, g, t);                 // t = L^-1 g
+    r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
+    fp_trmv_t(W, ld, k, t, x);               // x = A^-1 g
+    for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] += x[i];
+    fp_accumulate_i_minus_ainv(W, M, ld, k);
+    lo = hi;
+  }
+  return r;
+}
+
+// sum_h r_h^T C_h^-1 r_h at mean mu from the sums
+__device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k, const double* a_sum, const double* mu, double lam,
+                             double* tmp, double* red) {
+  fp_symv(M, ld, k, mu, tmp);
+  const double mMm = fp_dot(mu, tmp, k, red);
+  const double ma = fp_dot(mu, a_sum, k, red);
+  return sm.s - lam * sm.c - 2.0 * ma + mMm / lam;
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(FP_BLOCK) fp_glob_kernel(const FpArgs a) {
+  extern __shared__ double sm[];
+  const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
+  const int tid = threadIdx.x;
+  // shared layout: vectors | reduction scratch | ints | (matrices, when they fit)
+  double* vec = sm;
+  double* g = vec + 0 * k, *mu = vec + 1 * k, *mu_star = vec + 2 * k, *t = vec + 3 * k, *x = vec + 4 * k, *z = vec + 5 * k;
+  double* mean = vec + 6 * k, *a_cur = vec + 7 * k, *a_star = vec + 8 * k, *tmp = vec + 9 * k, *rhs = vec + 10 * k, *e = vec + 11 * k;
+  double* red = vec + FP_NVEC * k;       // [8]
+  double* sc = red + 8;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
+  int* s_tau = reinterpret_cast<int*>(sc + 8);
+  int* s_tas = s_tau + SMAX;
+  int* s_int = s_tas + SMAX;             // [8]
+  double* mats = a.ws ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
+  double* A = mats, *W = mats + (long long)ld * k, *Mc = mats + 2ll * ld * k, *Ms = mats + 3ll * ld * k, *Q = mats + 4ll * ld * k;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const bool replay = TRACE && a.rd != nullptr;
+  const int rds = fp_rd_stride(k), tds = fp_td_stride(k);
+  auto tau_cur = [&](int j) { return s_tau[j]; };
+  auto tau_star = [&](int j) { return s_tas[j]; };
+
+  for (int u = blockIdx.x; u < a.U; u += gridDim.x) {
+    const int node = u / a.C, chain = u - node * a.C;
+    const uint32_t gchain = a.chain_offset + (unsigned)chain, unode = (unsigned)node;
+    __syncthreads();
+    int S = a.st_S[u];
+    if (tid < SMAX) s_tau[tid] = a.st_tau[tid * a.U + u];
+    double sig2 = a.st_sig[u], lam = a.st_lam[u];
+    for (int i = tid; i < k; i += FP_BLOCK) mu[i] = a.st_mu[(long long)i * a.U + u];
+    __syncthreads();
+    unsigned long long n_evals = 0, n_segs = 0;
+
+    for (int li = 0; li < a.n_iter; ++li) {
+      const int it = a.it0 + li;
+      const uint32_t uit = (uint32_t)it;
+      const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * rds : nullptr;
+      const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * 4 : nullptr;
+      double* td = (TRACE && a.td) ? a.td + ((long long)u * a.n_iter + li) * tds : nullptr;
+      int* ti = (TRACE && a.ti) ? a.ti + ((long long)u * a.n_iter + li) * 16 : nullptr;
+      if (TRACE && ti && tid == 0) ti[3] = S;
+      // the initial zero vector mu_vector[0] is part of the thinned chain when burn_in == 0 (network.py:309-311)
+      if (it == 0 && a.burn_in == 0) {
+        if (tid == 0) atomicAdd(&a.kept[node], 1ull);
+        for (int j = 1 + tid; j < k; j += FP_BLOCK) {
+          const int gene = fp_col(j, node) - 1;
+          atomicAdd(&a.pos[(long long)node * n + gene], 1ull);
+          atomicAdd(&a.neg[(long long)node * n + gene], 1ull);
+        }
+      }
+
+      // ======================= Gibbs pass: sigma^2, beta_h, lambda^2 (fpGlobCoupBpwLinReg.py:70-86) ================
+      double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
+      {
+        int lo = 0;
+        for (int h = 0; h < S; ++h) {
+          const int hi = DBN_SEG_END(s_tau[h], h, S, N);
+          fp_load_segment(a.tb, node, lo, hi, lam, A, ld, k, g, sc + 3);
+          const double s = sc[3];
+          // G mu = (A mu - mu) / lam ; v = g - G mu ; rho = s - 2 mu.g + mu.G mu
+          fp_symv(A, ld, k, mu, tmp);
+          for (int i = tid; i < k; i += FP_BLOCK) {
+            const double gm = (tmp[i] - mu[i]) / lam;
+            tmp[i] = gm;
+            x[i] = g[i] - gm;              // v
+            rhs[i] = mu[i] + lam * g[i];   // numerator of the posterior mean (samplers.py:210-212)
+          }
+          __syncthreads();
+          const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
+          fp_cholesky(A, ld, k);
+          fp_trinv(A, W, ld, k);
+          fp_trmv(W, ld, k, x, t);
+          q_sum += rho - lam * fp_dot(t, t, k, red);
+          fp_trmv(W, ld, k, rhs, t);
+          fp_trmv_t(W, ld, k, t, mean);
+          ++n_segs;
+          if (!replay) {
+            fp_normals(z, k, gchain, unode, uit, (uint32_t)(h * 512), key);
+            fp_trmv_t(W, ld, k, z, e);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
+            for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = mean[i] - mu[i];
+            __syncthreads();
+            acc_dd += fp_dot(tmp, tmp, k, red);
+            acc_de += fp_dot(tmp, e, k, red);
+            acc_ee += fp_dot(e, e, k, red);
+          } else {
+            for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = rd[3 + k + h * k + i] - mu[i];  // injected beta_h
+            __syncthreads();
+            acc_dd += fp_dot(tmp, tmp, k, red);
+          }
+          if (TRACE && td) {
+            for (int i = tid; i < k; i += FP_BLOCK) {
+              td[10 + 3 * k + 2 * DBN_SMAX * k + h * k + i] = replay ? rd[3 + k + h * k + i] : e[i];  // completed below
+              td[10 + 3 * k + h * k + i] = mean[i];
+              double dg = 0.0;  // diag of A^-1 = column norms of W
+              for (int r = i; r < k; ++r) dg += W[r * ld + i] * W[r * ld + i];
+              td[10 + 3 * k + DBN_SMAX * k + h * k + i] = lam * dg;  // x sigma^2 below
+            }
+          }
+          __syncthreads();
+          lo = hi;
+        }
+      }
+      if (tid == 0) {
+        const double shape = a.a_sig + a.T_sigma_half, rate = a.b_sig + 0.5 * q_sum;
+        const double s2 = replay ? rd[0] : rate / gamma_draw(gchain, unode, uit, 20000u, key, shape);
+        const double sg = sqrt(s2 * lam);
+        const double ss = replay ? acc_dd : acc_dd + 2.0 * sg * acc_de + s2 * lam * acc_ee;
+        // samplers.py:285-289: shape a + S k / 2, rate b + sum |beta_h - mu|^2 / (2 sigma^2)
+        const double lshape = a.a_lam + 0.5 * (double)(S * k), lrate = a.b_lam + 0.5 * ss / s2;
+        const double l2 = replay ? rd[1] : lrate / gamma_draw(gchain, unode, uit, 24000u, key, lshape);
+        sc[0] = s2;
+        sc[1] = l2;
+        if (TRACE && td) {
+          td[0] = shape; td[1] = rate; td[2] = lshape; td[3] = lrate; td[4] = s2; td[5] = l2;
+          td[6] = td[7] = td[8] = td[9] = NAN;
+        }
+      }
+      __syncthreads();
+      sig2 = sc[0];
+      if (TRACE && td) {
+        const double sg = sqrt(sig2 * lam);
+        for (int i = tid; i < S * k; i += FP_BLOCK) {
+          td[10 + 3 * k + DBN_SMAX * k + i] *= sig2;
+          if (!replay) td[10 + 3 * k + 2 * DBN_SMAX * k + i] = td[10 + 3 * k + i] + sg * td[10 + 3 * k + 2 * DBN_SMAX * k + i];
+        }
+      }
+      lam = sc[1];
+
+      // ======================= changepoint move (moves.py:25-126) =================================================
+      if (a.with_tau) {
+        if (tid == 0) {
+          uint4 w = make_uint4(0, 0, 0, 0);
+          if (!replay) w = philox_block(gchain, unode, uit, 16384u, key);
+          const int move = replay ? ri[0] : (int)__umulhi(w.x, 3u);
+          const int ns = a.num_samples;
+          int valid = 1, Ss = S, hr_num = 1, hr_den = 1;
+          if (move == 0) {  // cpBirthMove (changepointMoves.py:93-124)
+            int inside = 0;
+            for (int j = 0; j < S - 1; ++j) inside += (s_tau[j] >= 2 && s_tau[j] <= ns) ? 1 : 0;
+            const int ncand = ns - 1 - inside;
+            if (ncand <= 0) {
+              valid = 0;
+            } else {
+              const int p = replay ? ri[1] : (int)__umulhi(w.y, (uint32_t)ncand);
+              int c = 2 + p;
+              for (int j = 0; j < S - 1; ++j)
+                if (s_tau[j] <= c) ++c;
+              int w_ = 0;
+              bool placed = false;
+              for (int j = 0; j < S; ++j) {
+                if (!placed && c < s_tau[j]) {
+                  s_tas[w_++] = c;
+                  placed = true;
+                }
+                s_tas[w_++] = s_tau[j];
+              }
+              Ss = S + 1;
+              if (Ss > 9) valid = 0;  // moves.py:42
+              hr_num = ns - 1 - S;    // moves.py:46
+              hr_den = Ss;
+            }
+          } else if (S < 2) {
+            valid = 0;
+          } else if (move == 1) {  // cpDeathMove (:63-91)
+            const int idx = replay ? ri[1] : (int)__umulhi(w.y, (uint32_t)(S - 1));
+            int w_ = 0;
+            for (int j = 0; j < S; ++j)
+              if (j != idx) s_tas[w_++] = s_tau[j];
+            Ss = S - 1;
+            hr_num = S;  // moves.py:55
+            hr_den = ns - 1 - Ss;
+          } else {  // cpRellocationMove (:3-61)
+            const int idx = replay ? ri[1] : (int)__umulhi(w.y, (uint32_t)(S - 1));
+            const int last = s_tau[S - 1] - 1;
+            const int left = (idx == 0) ? 1 : s_tau[idx - 1];
+            const int right = (idx + 1 == S - 1) ? last : s_tau[idx + 1];
+            const int ncand = right - left - 2;
+            if (ncand <= 0) {
+              valid = 0;
+            } else {
+              const int p = replay ? ri[2] : (int)__umulhi(w.z, (uint32_t)ncand);
+              int c = left + 1 + p;
+              if (c >= s_tau[idx]) ++c;
+              for (int j = 0; j < S; ++j) s_tas[j] = (j == idx) ? c : s_tau[j];
+            }
+          }
+          s_int[0] = move; s_int[1] = valid; s_int[2] = Ss; s_int[3] = hr_num; s_int[4] = hr_den;
+          sc[2] = replay ? rd[2] : (double)((((uint64_t)w.w << 32) | philox_block(gchain, unode, uit, 16385u, key).x) >> 11) * 0x1.0p-53;
+          if (TRACE && ti) { ti[0] = move; ti[1] = valid; ti[2] = 0; }
+        }
+        __syncthreads();
+        const int valid = s_int[1], Ss = s_int[2];
+        if (valid) {
+          const double ils = 1.0 / (lam * sig2);
+          // ---- current changepoints: log-ML at mu and the density of mu under muSampler(mu | tau) (moves.py:66-73)
+          const FpSummary sc_ = fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3);
+          n_segs += S;
+          const double q_cur = fp_quad_at(sc_, Mc, ld, k, a_cur, mu, lam, tmp, red);
+          const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + q_cur);
+          ++n_evals;
+          // Q = I + M / (lam s2); mean = Q^-1 (a / s2 + mu)   (samplers.py:324, :336: the input mu is added)
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Mc[i] * ils;
+          __syncthreads();
+          for (int i = tid; i < k; i += FP_BLOCK) {
+            Q[i * ld + i] += 1.0;
+            rhs[i] = a_cur[i] / sig2 + mu[i];
+          }
+          __syncthreads();
+          const double ldq_cur = fp_cholesky(Q, ld, k);
+          fp_trinv(Q, W, ld, k);
+          fp_trmv(W, ld, k, rhs, t);
+          fp_trmv_t(W, ld, k, t, mean);
+          if (TRACE && td)
+            for (int i = tid; i < k; i += FP_BLOCK) td[10 + k + i] = mean[i];
+          for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu[i] - mean[i];
+          __syncthreads();
+          fp_symv(Mc, ld, k, x, tmp);
+          const double dQd_cur = fp_dot(x, x, k, red) + fp_dot(x, tmp, k, red) * ils;
+          const double ld_cur = -0.5 * ((double)k * 1.8378770664093454836 - ldq_cur + dQd_cur);
+          // ---- proposed changepoints: mu* ~ muSampler(0 | tau*), its density, log-ML at mu* (moves.py:86-93)
+          const FpSummary ss_ = fp_sweep(a.tb, node, tau_star, Ss, lam, A, W, Ms, ld, k, g, t, x, a_star, red, sc + 3);
+          n_segs += Ss;
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Ms[i] * ils;
+          __syncthreads();
+          for (int i = tid; i < k; i += FP_BLOCK) {
+            Q[i * ld + i] += 1.0;
+            rhs[i] = a_star[i] / sig2;
+          }
+          __syncthreads();
+          const double ldq_star = fp_cholesky(Q, ld, k);
+          fp_trinv(Q, W, ld, k);
+          fp_trmv(W, ld, k, rhs, t);
+          fp_trmv_t(W, ld, k, t, mean);
+          if (replay) {
+            for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = rd[3 + i];
+            __syncthreads();
+          } else {
+            fp_normals(z, k, gchain, unode, uit, 8192u, key);
+            fp_trmv_t(W, ld, k, z, e);  // cov = Q^-1 = W^T W
+            for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = mean[i] + e[i];
+            __syncthreads();
+          }
+          if (TRACE && td)
+            for (int i = tid; i < k; i += FP_BLOCK) td[10 + 2 * k + i] = mean[i];
+          for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu_star[i] - mean[i];
+          __syncthreads();
+          fp_symv(Ms, ld, k, x, tmp);
+          const double dQd_star = fp_dot(x, x, k, red) + fp_dot(x, tmp, k, red) * ils;
+          const double ld_star = -0.5 * ((double)k * 1.8378770664093454836 - ldq_star + dQd_star);
+          const double q_star = fp_quad_at(ss_, Ms, ld, k, a_star, mu_star, lam, tmp, red);
+          const double ml_star = a.c0 - 0.5 * ss_.ld - a.T_half_plus_a * log(a.two_b + q_star);
+          ++n_evals;
+          const double lp_star = -0.5 * ((double)k * 1.8378770664093454836 + fp_dot(mu_star, mu_star, k, red));
+          const double lp_cur = -0.5 * ((double)k * 1.8378770664093454836 + fp_dot(mu, mu, k, red));
+          const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
+          // moves.py:112-120: u < exp(min(1, delta))
+          const double log_ratio = ml_star - ml_cur + lprior + lp_star - lp_cur + ld_cur - ld_star +
+                                   log((double)s_int[3] / (double)s_int[4]);
+          const bool acc = sc[2] < exp(fmin(1.0, log_ratio));
+          if (TRACE && td && tid == 0) {
+            td[6] = ml_cur; td[7] = ml_star; td[8] = ld_cur; td[9] = ld_star;
+          }
+          if (TRACE && ti && tid == 0) ti[2] = acc;
+          __syncthreads();
+          if (acc) {
+            S = Ss;
+            if (tid < SMAX) s_tau[tid] = s_tas[tid];
+            for (int i = tid; i < k; i += FP_BLOCK) mu[i] = mu_star[i];
+          }
+          __syncthreads();
+        }
+        // ---- counts: tau_vector[it] is kept iff it >= burn_in and (it - burn_in) % thin == 0 (network.py:321-322)
+        if (it >= a.burn_in && ((it - a.burn_in) % a.thin) == 0 && tid == 0) {
+          atomicAdd(&a.cp_kept[node], 1ull);
+          for (int j = 0; j < S - 1; ++j) atomicAdd(&a.cp_hist[(long long)node * (N + 3) + s_tau[j]], 1ull);
+        }
+      }
+      // ---- counts: mu_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin == 0 (network.py:309-311)
+      {
+        const int idx = it + 1;
+        if (idx >= a.burn_in && ((idx - a.burn_in) % a.thin) == 0) {
+          if (tid == 0) atomicAdd(&a.kept[node], 1ull);
+          for (int j = 1 + tid; j < k; j += FP_BLOCK) {
+            const int gene = fp_col(j, node) - 1;
+            if (mu[j] >= 0.0) atomicAdd(&a.pos[(long long)node * n + gene], 1ull);
+            if (mu[j] <= 0.0) atomicAdd(&a.neg[(long long)node * n + gene], 1ull);
+          }
+        }
+      }
+      if (TRACE && td)
+        for (int i = tid; i < k; i += FP_BLOCK) td[10 + i] = mu[i];
+      if (TRACE && ti && tid == 0) {
+        ti[4] = S;
+        for (int j = 0; j < SMAX; ++j) ti[5 + j] = (j < S) ? s_tau[j] : -1;
+      }
+      __syncthreads();
+    }
+
+    // ---- store state
+    if (tid == 0) {
+      a.st_S[u] = S;
+      a.st_sig[u] = sig2;
+      a.st_lam[u] = lam;
+      atomicAdd(&a.counters[0], (unsigned long long)a.n_iter);
+      atomicAdd(&a.counters[1], n_evals);
+      atomicAdd(&a.counters[2], n_segs);
+      // algorithmic bytes / flops of the executed segment factorisations (SURVEY.md 8d with k = n)
+      atomicAdd(&a.counters[3], n_segs * 16ull * (unsigned long long)(k * (k + 1) / 2 + k + 1));
+      atomicAdd(&a.counters[4], n_segs * (unsigned long long)((long long)k * k * k / 3 + 4ll * k * k + 5 * k));
+    }
+    if (tid < SMAX) a.st_tau[tid * a.U + u] = s_tau[tid];
+    for (int i = tid; i < k; i += FP_BLOCK) a.st_mu[(long long)i * a.U + u] = mu[i];
+  }
+}
+
+inline size_t fp_smem_bytes(int k, bool mats_in_smem) {
+  size_t b = (size_t)(FP_NVEC * k + 16) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
+  if (mats_in_smem) b += (size_t)FP_NMAT * fp_ld(k) * k * sizeof(double);
+  return b;
+}
+
+}  // namespace dbn

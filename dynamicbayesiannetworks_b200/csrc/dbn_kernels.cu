@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "dbn_chain_fast.cuh"
+#include "dbn_fp.cuh"
 
 namespace dbn {
 
@@ -161,6 +162,9 @@ struct dbn_handle {
   double* d_cache = nullptr;
   int *st_cg = nullptr, *st_bslot = nullptr;
   bool cache_valid = false;
+  // full-parents globally coupled chain: global mean [n][U], per-block matrix workspace (large n only)
+  double *st_mu_fp = nullptr, *d_fp_ws = nullptr;
+  int fp_grid = 0;
   unsigned long long* d_counts = nullptr;
   long long counts_elems = 0;
   unsigned long long* d_counters = nullptr;
@@ -291,6 +295,8 @@ static void free_chain(dbn_handle* h) {
   free_dev(h->d_cache);
   free_dev(h->st_cg);
   free_dev(h->st_bslot);
+  free_dev(h->st_mu_fp);
+  free_dev(h->d_fp_ws);
   h->cache_valid = false;
   free_dev(h->d_counts);
   h->have_chain = false;
@@ -521,8 +527,8 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!h || !p) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
-  if (p->method < DBN_H_DBN || p->method > DBN_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
-  if (p->fan_in < 1 || p->fan_in > PMAX) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
+  if (p->method < DBN_H_DBN || p->method > DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (p->method != DBN_FP_GLOB_DBN && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
   const long long U = (long long)h->n * h->cfg.n_chains;
@@ -549,6 +555,22 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
     CU(h, cudaMalloc(&h->st_bslot, U * SMAX * sizeof(int)));
   }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
+  if (p->method == DBN_FP_GLOB_DBN) {
+    h->counts_elems += (long long)h->n * h->n;  // neg[n][n]
+    const int k = h->n;
+    CU(h, cudaMalloc(&h->st_mu_fp, (size_t)U * k * sizeof(double)));
+    CU(h, cudaMemsetAsync(h->st_mu_fp, 0, (size_t)U * k * sizeof(double), h->stream));
+    cudaDeviceProp prop;
+    CU(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+    const bool in_smem = fp_smem_bytes(k, true) <= 160 * 1024;
+    if (12 * (size_t)k * sizeof(double) > 200 * 1024) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: n too large for the full-parents kernel");
+    h->fp_grid = (int)(in_smem ? U : (U < 2ll * prop.multiProcessorCount ? U : 2ll * prop.multiProcessorCount));
+    if (!in_smem) {
+      const size_t ws = (size_t)h->fp_grid * FP_NMAT * fp_ld(k) * k * sizeof(double);
+      cudaError_t e = cudaMalloc(&h->d_fp_ws, ws);
+      if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "full-parents workspace of %.2f GB does not fit: %s", ws / 1e9, cudaGetErrorString(e));
+    }
+  }
   CU(h, cudaMalloc(&h->d_counts, (size_t)h->counts_elems * sizeof(unsigned long long)));
   CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->counts_elems * sizeof(unsigned long long), h->stream));
   CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
@@ -562,6 +584,7 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
 int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d, int32_t* trace_i) {
   if (!h) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: call dbn_chain_init first");
+  if (h->rp.method == DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: the full-parents method runs with dbn_run_fp");
   if (n_iter < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: n_iter < 0");
   if ((replay_d == nullptr) != (replay_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay_d and replay_i must be given together");
   if ((replay_d != nullptr) && !(trace_d && trace_i)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay mode requires trace buffers");
@@ -660,6 +683,88 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   return DBN_OK;
 }
 
+int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d, int32_t* trace_i) {
+  if (!h) return DBN_ERR_INVALID;
+  if (!h->have_chain || h->rp.method != DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run_fp: call dbn_chain_init with DBN_FP_GLOB_DBN first");
+  if (n_iter < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: n_iter < 0");
+  if ((replay_d == nullptr) != (replay_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: replay_d and replay_i must be given together");
+  if ((replay_d != nullptr) && !(trace_d && trace_i)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: replay mode requires trace buffers");
+  if ((trace_d == nullptr) != (trace_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: trace_d and trace_i must be given together");
+  if (n_iter == 0) return DBN_OK;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const dbn_run_params& p = h->rp;
+  const int k = h->n;
+  FpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tb = make_table(h);
+  a.num_samples = p.num_samples; a.burn_in = p.burn_in; a.thin = p.thin; a.with_tau = p.with_tau;
+  a.C = h->cfg.n_chains; a.U = h->U; a.it0 = h->it_done; a.n_iter = n_iter;
+  a.chain_offset = (unsigned)h->cfg.chain_offset;
+  a.seed = h->cfg.seed;
+  a.T_sigma_half = p.T_sigma / 2;
+  a.a_sig = p.a_sigma; a.b_sig = p.b_sigma; a.a_lam = p.a_lambda; a.b_lam = p.b_lambda;
+  a.log_p = log(p.cp_p); a.log_1mp = log(1.0 - p.cp_p);
+  a.c0 = ml_const(p.T_ml, p.a_sigma, p.b_sigma);
+  a.T_half_plus_a = p.T_ml / 2 + p.a_sigma;
+  a.two_b = 2 * p.b_sigma;
+  a.st_S = h->st_S; a.st_tau = h->st_tau; a.st_sig = h->st_sig; a.st_lam = h->st_lam; a.st_mu = h->st_mu_fp;
+  a.pos = h->d_counts;
+  a.kept = a.pos + (long long)h->n * h->n;
+  a.cp_hist = a.kept + h->n;
+  a.cp_kept = a.cp_hist + (long long)h->n * (h->N + 3);
+  a.neg = a.cp_kept + h->n;
+  a.counters = h->d_counters;
+  a.ws = h->d_fp_ws;
+  const bool trace = trace_d != nullptr, replay = replay_d != nullptr;
+  double *d_rd = nullptr, *d_td = nullptr;
+  int *d_ri = nullptr, *d_ti = nullptr;
+  auto cleanup = [&]() { free_dev(d_rd); free_dev(d_td); free_dev(d_ri); free_dev(d_ti); };
+#define CUX(expr)                                                                \
+  do {                                                                           \
+    cudaError_t e_ = (expr);                                                     \
+    if (e_ != cudaSuccess) {                                                     \
+      cleanup();                                                                 \
+      DBN_FAIL(h, DBN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    }                                                                            \
+  } while (0)
+  const size_t rec = (size_t)h->U * n_iter;
+  const size_t rds = fp_rd_stride(k), tds = fp_td_stride(k);
+  if (trace) {
+    CUX(cudaMalloc(&d_td, rec * tds * sizeof(double)));
+    CUX(cudaMalloc(&d_ti, rec * 16 * sizeof(int)));
+    CUX(cudaMemsetAsync(d_td, 0xFF, rec * tds * sizeof(double), h->stream));
+    CUX(cudaMemsetAsync(d_ti, 0xFF, rec * 16 * sizeof(int), h->stream));
+    a.td = d_td;
+    a.ti = d_ti;
+  }
+  if (replay) {
+    CUX(cudaMalloc(&d_rd, rec * rds * sizeof(double)));
+    CUX(cudaMalloc(&d_ri, rec * 4 * sizeof(int)));
+    CUX(cudaMemcpyAsync(d_rd, replay_d, rec * rds * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMemcpyAsync(d_ri, replay_i, rec * 4 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    a.rd = d_rd;
+    a.ri = d_ri;
+  }
+  const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
+  if (trace) {
+    CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fp_glob_kernel<true><<<h->fp_grid, FP_BLOCK, smem, h->stream>>>(a);
+  } else {
+    CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fp_glob_kernel<false><<<h->fp_grid, FP_BLOCK, smem, h->stream>>>(a);
+  }
+  CUX(cudaGetLastError());
+  h->it_done += n_iter;
+  if (trace) {
+    CUX(cudaMemcpyAsync(trace_d, d_td, rec * tds * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaMemcpyAsync(trace_i, d_ti, rec * 16 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));
+  }
+  cleanup();
+#undef CUX
+  return DBN_OK;
+}
+
 int dbn_counts_size(const dbn_handle* h, int64_t* n_elems) {
   if (!h || !n_elems) return DBN_ERR_INVALID;
   if (!h->have_chain) return DBN_ERR_STATE;
@@ -724,6 +829,34 @@ int dbn_read_counters(dbn_handle* h, uint64_t out[8]) {
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaMemcpyAsync(out, h->d_counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  return DBN_OK;
+}
+
+int dbn_verify_cache(dbn_handle* h, uint64_t out[2]) {
+  if (!h || !out) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_verify_cache: call dbn_chain_init first");
+  out[0] = out[1] = 0;
+  if (!h->d_cache || !h->cache_valid) return DBN_OK;  // seq / glob methods keep no cache; nothing cached before the first dbn_run
+  CU(h, cudaSetDevice(h->cfg.device));
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tb = make_table(h);
+  a.C = h->cfg.n_chains;
+  a.U = h->U;
+  a.st_S = h->st_S; a.st_tau = h->st_tau; a.st_cg = h->st_cg; a.cache = h->d_cache;
+  unsigned long long* d = nullptr;
+  CU(h, cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->stream);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)((h->U + 127) / 128);
+    if (h->rp.fan_in <= 3) cache_verify_kernel<4><<<grid, 128, 0, h->stream>>>(a, d);
+    else cache_verify_kernel<5><<<grid, 128, 0, h->stream>>>(a, d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_CUDA, "dbn_verify_cache failed: %s", cudaGetErrorString(e));
   return DBN_OK;
 }
 

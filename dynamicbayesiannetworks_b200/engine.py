@@ -156,6 +156,40 @@ class DbnEngine:
             self._check(self._lib.dbn_run(self._h, int(n_iter), None, None, _dptr(td), _iptr(ti)), 'dbn_run')
         return unpack_trace(td, ti)
 
+    def run_fp(self, n_iter, replay=None, trace=False):
+        """dbn_run_fp: advance every unit of a full-parents globally coupled chain (method 'fp_glob_coup_nh_dbn').
+        `replay`: dict with sigma2, lambda2, u_tau [U, n_iter]; mu_tau [U, n_iter, k]; beta [U, n_iter, SMAX, k];
+        tau_move [U, n_iter]; tau_pick [U, n_iter, 2].  Returns the unpacked trace dict when requested."""
+        U, k = self.units, self.n
+        if replay is None and not trace:
+            self._check(self._lib.dbn_run_fp(self._h, int(n_iter), None, None, None, None), 'dbn_run_fp')
+            return None
+        tds = L.fp_td_stride(k)
+        td = np.empty((U, n_iter, tds))
+        ti = np.empty((U, n_iter, L.FP_TI_STRIDE), dtype=np.int32)
+        if replay is not None:
+            rd = np.full((U, n_iter, L.fp_rd_stride(k)), np.nan)
+            ri = np.full((U, n_iter, L.FP_RI_STRIDE), -1, dtype=np.int32)
+            rd[:, :, 0], rd[:, :, 1], rd[:, :, 2] = replay['sigma2'], replay['lambda2'], replay['u_tau']
+            rd[:, :, 3:3 + k] = np.asarray(replay['mu_tau'])[:, :, :k]
+            rd[:, :, 3 + k:] = np.asarray(replay['beta'])[:, :, :, :k].reshape(U, n_iter, L.SMAX * k)
+            ri[:, :, 0] = replay['tau_move']
+            ri[:, :, 1:3] = replay['tau_pick']
+            rd, ri = np.ascontiguousarray(rd), np.ascontiguousarray(ri)
+            self._check(self._lib.dbn_run_fp(self._h, int(n_iter), _dptr(rd), _iptr(ri), _dptr(td), _iptr(ti)), 'dbn_run_fp')
+        else:
+            self._check(self._lib.dbn_run_fp(self._h, int(n_iter), None, None, _dptr(td), _iptr(ti)), 'dbn_run_fp')
+        o = 10
+        return dict(
+            sig_shape=td[:, :, 0], sig_rate=td[:, :, 1], lam_shape=td[:, :, 2], lam_rate=td[:, :, 3],
+            sigma2=td[:, :, 4], lambda2=td[:, :, 5], logml=td[:, :, 6:8], mus_logdens=td[:, :, 8:10],
+            mu_after=td[:, :, o:o + k], mus_mean=td[:, :, o + k:o + 3 * k].reshape(U, n_iter, 2, k),
+            beta_mean=td[:, :, o + 3 * k:o + 3 * k + L.SMAX * k].reshape(U, n_iter, L.SMAX, k),
+            beta_cov_diag=td[:, :, o + 3 * k + L.SMAX * k:o + 3 * k + 2 * L.SMAX * k].reshape(U, n_iter, L.SMAX, k),
+            beta=td[:, :, o + 3 * k + 2 * L.SMAX * k:].reshape(U, n_iter, L.SMAX, k),
+            tau_move=ti[:, :, 0], tau_valid=ti[:, :, 1], tau_accept=ti[:, :, 2], S=ti[:, :, 3], S_after=ti[:, :, 4],
+            tau_after=ti[:, :, 5:5 + L.SMAX])
+
     def counts(self):
         ne = C.c_int64()
         self._check(self._lib.dbn_counts_size(self._h, C.byref(ne)), 'dbn_counts_size')
@@ -185,6 +219,13 @@ class DbnEngine:
                 'segment_factorisations', 'tau_accepts')
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
+    def verify_cache(self):
+        """dbn_verify_cache: (units, entries) of the h / nh kernel's segment-statistics cache that differ from what the
+        prefix table and the current (pi, tau) imply; (0, 0) when consistent."""
+        out = np.zeros(2, dtype=np.uint64)
+        self._check(self._lib.dbn_verify_cache(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))), 'dbn_verify_cache')
+        return int(out[0]), int(out[1])
+
     def reset_counters(self):
         self._check(self._lib.dbn_reset_counters(self._h), 'dbn_reset_counters')
 
@@ -200,8 +241,11 @@ def split_counts(flat, n, N):
     edge = flat[o:o + n * n].reshape(n, n); o += n * n
     nonempty = flat[o:o + n]; o += n
     cp_hist = flat[o:o + n * (N + 3)].reshape(n, N + 3); o += n * (N + 3)
-    cp_kept = flat[o:o + n]
-    return dict(edge=edge, nonempty=nonempty, cp_hist=cp_hist, cp_kept=cp_kept)
+    cp_kept = flat[o:o + n]; o += n
+    out = dict(edge=edge, nonempty=nonempty, cp_hist=cp_hist, cp_kept=cp_kept)
+    if flat.size >= o + n * n:   # full-parents method: edge = #(mu_j >= 0), nonempty = #kept, neg = #(mu_j <= 0)
+        out['neg'] = flat[o:o + n * n].reshape(n, n)
+    return out
 
 
 def pack_replay(r, U, n_iter):

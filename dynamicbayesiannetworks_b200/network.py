@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, METHOD_NAMES
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, METHOD_NAMES
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -22,6 +22,7 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'h_dbn': ('Bayesian Homogeneous', 'Varying Parents'),
     'seq_coup_nh_dbn': ('Sequentilly Coupled Non-Homogeneous', 'Varying Parents'),
     'glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Varying Parents'),
+    'fp_glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:246-247
 }
 
 
@@ -95,12 +96,13 @@ class Network():
             traces = []
             window = self.window or (n_iter if self.keep_chain else 100)
             done = 0
+            run = eng.run_fp if mid == FP_GLOB_DBN else eng.run
             while done < n_iter:
                 w = min(window, n_iter - done)
                 if self.keep_chain:
-                    traces.append(eng.run(w, trace=True))
+                    traces.append(run(w, trace=True))
                 else:
-                    eng.run(w)
+                    run(w)
                 done += w
             counts = eng.counts()
             self.counters = eng.counters()
@@ -108,6 +110,8 @@ class Network():
         return self
 
     def _finish(self, name, mid, dims, N, counts, traces):
+        if mid == FP_GLOB_DBN:
+            return self._finish_fp(dims, N, counts, traces)
         adj = parallel.edge_scores_from_counts(counts['edge'], counts['nonempty'])
         self.proposed_adj_matrix = [[float(v) for v in row] for row in adj]
         self.edge_scores = self.proposed_adj_matrix[-1]
@@ -123,6 +127,35 @@ class Network():
                 for r in self.chain_results_per_node:   # network.py:388-389
                     burned = r['tau_vector'][b:]
                     self.cps_over_response.append([burned[x] for x in range(len(burned)) if x % 10 == 0])
+
+    def _finish_fp(self, dims, N, counts, traces):
+        """network.py:303-347 for 'fp_glob_coup_nh_dbn': edge scores are credible scores of the thinned global-mean chain."""
+        adj = parallel.credible_scores_from_counts(counts['edge'], counts['neg'], counts['nonempty'])
+        self.network_args['scoring_method'] = 'fraq-score'
+        self.proposed_adj_matrix = [[float(v) for v in row] for row in adj]
+        self.edge_scores = self.proposed_adj_matrix[-1]
+        kept = np.maximum(counts['cp_kept'], 1)[:, None]
+        self.changepoint_histogram = (counts['cp_hist'] / kept)[:, :N + 1]
+        if traces:
+            cat = {k: np.concatenate([t[k] for t in traces], axis=1) for k in traces[0]}
+            C, b = self.n_chains, int(self.burn_in)
+            n_iter = cat['sigma2'].shape[1]
+            for node in range(dims):
+                u = node * C
+                pi = [j for j in range(dims) if j != node]
+                res = {   # fpGlobCoupBpwLinReg.py:112-119
+                    'lambda_sqr_vector': [1] + [float(v) for v in cat['lambda2'][u]],
+                    'sigma_sqr_vector': [1] + [float(v) for v in cat['sigma2'][u]],
+                    'pi_vector': [pi],
+                    'tau_vector': [[int(c) for c in cat['tau_after'][u, it, :cat['S_after'][u, it]]] for it in range(n_iter)],
+                    'mu_vector': [np.zeros((dims, 1))] + [np.array(cat['mu_after'][u, it]).reshape(-1, 1) for it in range(n_iter)],
+                    'betas_vector': [[np.zeros(dims)]] + [[np.array(cat['beta'][u, it, h]) for h in range(int(cat['S'][u, it]))]
+                                                          for it in range(n_iter)],
+                }
+                self.chain_results_per_node.append(res)
+                burned = res['tau_vector'][b:]
+                self.cps_over_response.append([burned[x] for x in range(len(burned)) if x % 10 == 0])
+            self.chain_results = self.chain_results_per_node[-1]
 
     @staticmethod
     def _chain_results(t, u, mid, dims, N):

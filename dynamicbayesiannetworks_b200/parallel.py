@@ -54,3 +54,14 @@ def edge_scores_from_counts(edge, nonempty):
     edge = np.asarray(edge, dtype=np.float64)
     den = np.asarray(nonempty, dtype=np.float64)[:, None]
     return np.divide(edge, den, out=np.zeros_like(edge), where=den > 0)
+
+
+def credible_scores_from_counts(pos, neg, kept):
+    """proposed_adj_matrix of the full-parents globally coupled model: max(#(mu_j >= 0), #(mu_j <= 0)) / #kept samples
+    (credible_score, scores.py:196-205, applied to the thinned mu chain by network.py:339-347); diagonal = 0."""
+    pos = np.asarray(pos, dtype=np.float64)
+    neg = np.asarray(neg, dtype=np.float64)
+    den = np.asarray(kept, dtype=np.float64)[:, None]
+    out = np.divide(np.maximum(pos, neg), den, out=np.zeros_like(pos), where=den > 0)
+    np.fill_diagonal(out, 0.0)
+    return out

@@ -43,7 +43,9 @@ typedef enum {
   DBN_H_DBN = 0,    /* 'h_dbn'            bayesianLinearRegression.py:70-155      */
   DBN_NH_DBN = 1,   /* 'varying_nh_dbn'   bayesianPwLinearRegression.py:41-141    */
   DBN_SEQ_DBN = 2,  /* 'seq_coup_nh_dbn'  seqCoupledBayesianPwLinReg.py:16-130    */
-  DBN_GLOB_DBN = 3  /* 'glob_coup_nh_dbn' globCoupBayesianPwLinReg.py:16-124      */
+  DBN_GLOB_DBN = 3, /* 'glob_coup_nh_dbn' globCoupBayesianPwLinReg.py:16-124      */
+  DBN_FP_GLOB_DBN = 4 /* 'fp_glob_coup_nh_dbn' fpGlobCoupBpwLinReg.py:16-119: every other gene is a parent (design
+                         width k = n), no parent-set move, globally coupled changepoint move; run with dbn_run_fp */
 } dbn_method;
 
 typedef struct dbn_handle dbn_handle;
@@ -191,6 +193,25 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
             int32_t* trace_i);
 
 /*
+ * dbn_run_fp: dbn_run for DBN_FP_GLOB_DBN (fpGlobCoupBpwLinReg.py:68-110): sigma^2, beta_h, lambda^2 Gibbs draws with
+ * the global mean mu as prior mean, then the globally coupled changepoint move (moves.py:25-126) with
+ * mu* ~ muSampler (samplers.py:307-351).  Records are n = k wide, so their strides depend on n:
+ *   replay_d [units, n_iter, 3 + k + DBN_SMAX*k]: sigma2, lambda2, u_tau, mu*[k], beta[DBN_SMAX][k]
+ *   replay_i [units, n_iter, 4]: tau_move, tau_pick[2], (pad)
+ *   trace_d  [units, n_iter, 10 + 3k + 3*DBN_SMAX*k]: sig_shape, sig_rate, lam_shape, lam_rate, sigma2, lambda2,
+ *            logml(tau), logml(tau*), log q(mu | tau), log q(mu* | tau*), mu after [k], muSampler mean (tau) [k],
+ *            muSampler mean (tau*) [k], beta posterior means [DBN_SMAX][k], diag of the beta covariances [DBN_SMAX][k],
+ *            drawn beta_h [DBN_SMAX][k]
+ *   trace_i  [units, n_iter, 16]: tau_move, tau_valid, tau_accept, S before, S after, tau[DBN_SMAX], (pad)
+ * Counts for this method reuse the block below with: edge[i][j] = #kept mu samples of node i with mu_j >= 0,
+ * nonempty[i] = #kept mu samples (network.py:309-311), and one more matrix appended after cp_kept:
+ * neg[n][n] = #kept samples with mu_j <= 0; the edge score is max(edge, neg) / nonempty (credible_score,
+ * scores.py:196-205 via network.py:339-347).
+ */
+int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d,
+               int32_t* trace_i);
+
+/*
  * Count matrices of the thinned chain, summed over this handle's chains (what gets all-reduced over ranks):
  *   edge[n][n]      edge[i][j] = #kept samples of node i whose parent set contains j   (scores.py:173-182)
  *   nonempty[n]     #kept samples with a non-empty parent set (the denominator, scores.py:184)
@@ -217,6 +238,11 @@ int dbn_read_state(dbn_handle* h, int32_t* pi, int32_t* pi_len, int32_t* tau, in
  * ([5]-[7] are filled by the h / nh kernel only) */
 int dbn_read_counters(dbn_handle* h, uint64_t out[8]);
 int dbn_reset_counters(dbn_handle* h);
+
+/* Test hook for the h / nh kernel's per-unit cache of segment statistics: recomputes every cached row from the prefix
+ * table and the current (pi, tau) on the device and compares bit for bit.  out[0] = units with a differing entry,
+ * out[1] = differing entries; both 0 for methods without a cache. */
+int dbn_verify_cache(dbn_handle* h, uint64_t out[2]);
 
 /* dependent-free DFMA microbenchmark: measured FP64 FMA throughput of this device in GFLOP/s */
 int dbn_measure_fp64_peak(dbn_handle* h, double* gflops);

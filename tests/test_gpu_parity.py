@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
+from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
 from oracle import dbn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -187,6 +187,7 @@ def test_free_running_edge_posteriors(eng_mod, method):
         c = e.counts()
         st = e.state()
         ctr = e.counters()
+        assert e.verify_cache() == (0, 0)   # h / nh: the per-unit segment-statistics cache still equals the table's values
     assert ctr['unit_iterations'] == n * C * n_iter
     assert np.isfinite(st['sigma2']).all() and (st['sigma2'] > 0).all()
     assert np.isfinite(st['lambda2']).all() and (st['lambda2'] > 0).all()
@@ -205,6 +206,40 @@ def test_free_running_edge_posteriors(eng_mod, method):
     # catches a wrong acceptance rule / prior / Hastings ratio (those shift frequencies by >0.2)
     assert np.abs(gpu[off] - ref[off]).max() < 0.2, (gpu, ref)
     assert np.abs(gpu[off] - ref[off]).mean() < 0.07, (gpu, ref)
+
+
+@pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn'])
+def test_plain_and_trace_builds_follow_the_same_trajectory(eng_mod, method):
+    """The TRACE instantiation of the h / nh kernel (the one the replay fixtures pin) and the plain one (the one that is
+    timed) draw the same Philox stream, so free-running chains must agree state by state: discrete state exactly,
+    sigma^2 / lambda^2 to rounding.  Many chains per warp, launches of mixed lengths, cache checked after each."""
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    data = data_list(g)
+    C = 256
+    windows = [1, 7, 40, 152, 200]
+    with eng_mod(n_chains=C, seed=77) as e:
+        e.build_stats(data)
+        e.chain_init(method, burn_in=0)
+        tr = e.run(sum(windows), trace=True)
+    with eng_mod(n_chains=C, seed=77) as e:
+        e.build_stats(data)
+        e.chain_init(method, burn_in=0)
+        done = 0
+        for w in windows:
+            e.run(w)
+            done += w
+            assert e.verify_cache() == (0, 0), done
+            st = e.state()
+            it = done - 1
+            S = tr['S_after'][:, it] if method != 'h_dbn' else st['S']
+            assert np.array_equal(st['S'], S), done
+            assert np.array_equal(st['npi'], tr['npi'][:, it]), done
+            for u in range(st['S'].size):
+                assert np.array_equal(st['pi'][u, :st['npi'][u]], tr['pi_after'][u, it, :st['npi'][u]]), (done, u)
+                if method != 'h_dbn':
+                    assert np.array_equal(st['tau'][u, :S[u]], tr['tau_after'][u, it, :S[u]]), (done, u)
+            assert np.allclose(st['sigma2'], tr['sigma2'][:, it], rtol=1e-9, atol=0), done
+            assert np.allclose(st['lambda2'], tr['lambda2'][:, it], rtol=1e-9, atol=0), done
 
 
 def test_network_dropin(eng_mod):
@@ -231,4 +266,112 @@ def test_network_dropin(eng_mod):
     big.infer_network('nh-dbn')
     assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)
     with pytest.raises(NotImplementedError):
-        Network(data, 10, 0, 1).infer_network('fp_glob_coup_nh_dbn')
+        Network(data, 10, 0, 1).infer_network('fp_var_glob_coup_nh_dbn')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel 4: full-parents globally coupled chains (design width k = n)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', FP_CHAIN_FILES, ids=ids(FP_CHAIN_FILES))
+def test_fp_glob_replay_vs_reference(eng_mod, path):
+    """fpGlobCoupBpwLinReg.py:68-110 replayed from the reference's recorded draws: changepoint lists and accept flags
+    bit-exact; log-MLs 1e-9; Gibbs parameters, muSampler means / densities as in the CPU oracle test; credible scores."""
+    from dynamicbayesiannetworks_b200 import parallel
+    g = load(path)
+    n, n_iter = g['sigma2'].shape
+    burn_in = int(g['burn_in'])
+    replay = dict(sigma2=g['sigma2'], lambda2=g['lambda2'], u_tau=g['u_tau'], mu_tau=g['mus_val'][:, :, 3, :],
+                  beta=g['beta'], tau_move=g['tau_move'], tau_pick=g['tau_pick'])
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data_list(g))
+        e.chain_init('fp_glob_coup_nh_dbn', burn_in=burn_in)
+        tr = e.run_fp(n_iter, replay=replay, trace=True)
+        counts = e.counts()
+    for key in ('S', 'tau_valid', 'tau_accept', 'tau_after'):
+        assert np.array_equal(tr[key], g[key]), key
+    assert_close(tr['sig_shape'], g['sig_shape'], 1e-12, what='sig_shape')
+    assert_close(1.0 / tr['sig_rate'], g['sig_scale'], 1e-9, what='sig_scale')
+    assert_close(tr['lam_shape'], g['lam_shape'], 1e-12, what='lam_shape')
+    assert_close(1.0 / tr['lam_rate'], g['lam_scale'], 1e-9, what='lam_scale')
+    assert_close(tr['logml'], g['logml'][:, :, 2:4], LOGML_RTOL, what='logml')
+    assert_close(tr['beta_mean'], g['beta_mean'][..., :n], 1e-7, 1e-9, what='beta_mean')
+    assert_close(tr['beta_cov_diag'], g['beta_cov_diag'][..., :n], 1e-7, 1e-13, what='beta_cov_diag')
+    ref_means = np.stack([g['mus_mean'][:, :, 2, :n], g['mus_mean'][:, :, 3, :n]], axis=2)
+    assert_close(tr['mus_mean'], ref_means, 1e-7, 1e-9, what='mus_mean')
+    ref_ld = np.stack([g['mus_logdens'][:, :, 2, 1], g['mus_logdens'][:, :, 3, 0]], axis=-1)
+    assert_close(tr['mus_logdens'], ref_ld, 1e-8, 1e-8, what='mus_logdens')
+    assert_close(tr['mu_after'], g['mu_after'][..., :n], 0, 0, what='mu_after')
+    adj = parallel.credible_scores_from_counts(counts['edge'], counts['neg'], counts['nonempty'])
+    assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
+    assert np.array_equal(counts['cp_hist'], g['cp_hist'].astype(np.int64))
+    assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
+
+
+def test_fp_glob_large_n_workspace_path(eng_mod):
+    """n = 72 does not fit the shared-memory matrices: the global-workspace path must give the same log-MLs as the
+    oracle on the same injected stream (free draws from the oracle's own chain)."""
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    data, _, _ = make_synthetic(72, 160, n_changepoints=2, max_fan_in=3, seed=5)
+    X, Y = O.lagged_matrices([data])
+    n, n_iter = 72, 6
+    # only the first 4 nodes are checked; the other units replay node 0's stream (their results are not compared).
+    # the oracle's RngDraws do not record their picks: wrap them in a recording draw source
+    class Rec(O.RngDraws):
+        def __init__(self, rng):
+            super().__init__(rng); self.log = {}
+        def move(self, it, which):
+            v = super().move(it, which); self.log[(it, 'move')] = v; return v
+        def picker(self, it, which):
+            inner = super().picker(it, which); lst = self.log.setdefault((it, 'pick'), [])
+            def f(m):
+                v = inner(m); lst.append(v); return v
+            return f
+        def uniform(self, it, which):
+            v = super().uniform(it, which); self.log[(it, 'u')] = v; return v
+        def mu_draw(self, it, slot, mean, Sigma):
+            v = super().mu_draw(it, slot, mean, Sigma); self.log[(it, 'mu', slot)] = v; return v
+    recs, trs = [], []
+    for node in range(4):
+        r = Rec(np.random.default_rng(100 + node))
+        trs.append(O.run_chain('fp_glob_coup_nh_dbn', X, Y, node, n_iter, r)); recs.append(r)
+    rp = dict(sigma2=np.ones((n, n_iter)), lambda2=np.ones((n, n_iter)), u_tau=np.full((n, n_iter), 0.5),
+              mu_tau=np.zeros((n, n_iter, n)), beta=np.zeros((n, n_iter, 10, n)),
+              tau_move=np.zeros((n, n_iter), dtype=np.int32), tau_pick=np.zeros((n, n_iter, 2), dtype=np.int32))
+    for u in range(n):
+        t, r = (trs[u], recs[u]) if u < 4 else (trs[0], recs[0])
+        rp['sigma2'][u], rp['lambda2'][u] = t['sigma2'], t['lambda2']
+        rp['beta'][u] = np.nan_to_num(t['beta'][:, :, :n])
+        for it in range(n_iter):
+            rp['tau_move'][u, it] = r.log[(it, 'move')]
+            picks = r.log.get((it, 'pick'), [])
+            rp['tau_pick'][u, it, :len(picks)] = picks
+            rp['u_tau'][u, it] = r.log.get((it, 'u'), 0.5)
+            if (it, 'mu', 3) in r.log:
+                rp['mu_tau'][u, it] = r.log[(it, 'mu', 3)]
+    with eng_mod(n_chains=1) as e:
+        e.build_stats([data])
+        e.chain_init('fp_glob_coup_nh_dbn', burn_in=0)
+        tr = e.run_fp(n_iter, replay=rp, trace=True)
+    for node in range(4):
+        assert np.array_equal(tr['tau_after'][node], trs[node]['tau_after']), node
+        assert_close(tr['logml'][node], trs[node]['logml'][:, 2:4], LOGML_RTOL, what='logml node %d' % node)
+        assert_close(1.0 / tr['sig_rate'][node], trs[node]['sig_scale'], 1e-9, what='sig_scale')
+        assert_close(tr['mu_after'][node], trs[node]['mu_after'][:, :n], 0, 0, what='mu_after')
+
+
+def test_fp_glob_network_dropin(eng_mod):
+    import pickle
+    from dynamicbayesiannetworks_b200 import Network
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    net = Network(data_list(g), 200, 50, 1)
+    net.infer_network('fp_glob_coup_nh_dbn')
+    adj = np.array(net.proposed_adj_matrix)
+    assert adj.shape == (5, 5) and (adj >= 0.5 - 1e-12)[~np.eye(5, dtype=bool)].all() and (adj <= 1).all()
+    assert np.allclose(np.diag(adj), 0)
+    r = net.chain_results
+    assert len(r['mu_vector']) == 201 and len(r['tau_vector']) == 200 and r['pi_vector'] == [[0, 1, 2, 3]]
+    assert net.network_args['type'] == 'Full Parents'
+    pickle.loads(pickle.dumps(net))
+    many = Network(data_list(g), 300, 100, 1, n_chains=32)
+    many.infer_network('fp_glob_coup_nh_dbn')
+    assert np.array(many.proposed_adj_matrix).shape == (5, 5)
