@@ -13,8 +13,10 @@
 //   * the parent-set move scores pi and pi* in ONE sweep: both column sets share a base of <= KM-1 columns, which is
 //     factorised once per segment (A_B = L D L^T); the column only pi has and the column only pi* has are two
 //     alternative last rows of that factorisation.  Only the new column (<= KM+1 values per boundary) is gathered.
-//   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new)
-//     from the <= 4 prefix-table rows involved, staged in three scratch rows of the cache.
+//   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new):
+//     the old ones are cached rows, the new ones follow from them and ONE gathered difference of two table rows
+//     (none for a death), all held in the shared-memory staging buffers (profiles/r1_v6: the 3-4 gathered rows per
+//     move and their global scratch copies were a quarter of the stall samples).
 //   * accepted moves rewrite the owner's rows: the new column in every row (parent-set move) or the rows behind an
 //     inserted / removed segment (changepoint move), as 16-byte pairs.  Only the thread that owns a unit ever writes
 //     that unit's rows: handing this work to the other lanes of the warp (v4/v5) needs votes and shuffles, and those
@@ -37,8 +39,7 @@ namespace dbn {
 #endif
 constexpr int FAST_BLOCK = DBN_FAST_BLOCK;
 constexpr int SEG_ROWS = DBN_SMAX - 1;  // <= 9 segments
-constexpr int ROW_L = SEG_ROWS, ROW_X = SEG_ROWS + 1, ROW_R = SEG_ROWS + 2;  // scratch: prefix rows left / moving / right
-constexpr int BSLOTS = SEG_ROWS + 3;    // cached rows per unit
+constexpr int BSLOTS = SEG_ROWS;        // cached rows per unit
 
 template <int KM>
 struct FastDims {
@@ -110,12 +111,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   cg[0] = -1;
 
   // prefix-table row `t` restricted to the slots' columns (zeros for empty slots), minus the same of row `t0`
-  // when t0 >= 0, -> cache row `dst`
-  auto gather_row = [&](int t, int t0, int dst) {
+  // when t0 >= 0; put(entry, value) stores it
+  auto gather = [&](int t, int t0, auto&& put) {
     const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
     const double* __restrict__ row0 = a.tb.base + (long long)(t0 < 0 ? t : t0) * a.tb.row_stride;
     const bool sub = t0 >= 0;
-    double* c = crow(dst);
 #pragma unroll
     for (int i = 0; i < KM; ++i) {
       const bool oi = (i == 0) || cg[i] >= 0;
@@ -125,11 +125,16 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         const bool oj = (j == 0) || cg[j] >= 0;
         const int fj = (j == 0) ? 0 : cg[j] + 1;
         const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
-        DBN_CE(c, DBN_TRI(i, j)) = (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0;
+        put(DBN_TRI(i, j), (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0);
       }
-      DBN_CE(c, KT + i) = oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0;
+      put(KT + i, oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0);
     }
-    DBN_CE(c, KT + KM) = __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0);
+    put(KT + KM, __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0));
+  };
+  // ... -> cache row `dst`
+  auto gather_row = [&](int t, int t0, int dst) {
+    double* c = crow(dst);
+    gather(t, t0, [&](int e, double v) { DBN_CE(c, e) = v; });
   };
 
   if (a.refresh) {
@@ -162,18 +167,15 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     }
     cp_async_commit();
   };
-  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment between two staged prefix
-  // rows: cache row `hi` minus cache row `lo` (lo < 0: table row 0 = zeros)
-  auto seg_eval = [&](int lo, int hi, double& prod, double& q) {
+  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment whose statistics are in the
+  // staging buffer `sb` (this thread's slice)
+  auto seg_eval = [&](const double* sb, double& prod, double& q) {
     double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
-    const double* ph = crow(hi);
-    const double* pl = crow(lo < 0 ? hi : lo);
-    const bool has_lo = lo >= 0;
 #pragma unroll
-    for (int e = 0; e < KT; ++e) G[e] = DBN_CE(ph, e) - (has_lo ? DBN_CE(pl, e) : 0.0);
+    for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sb, e);
 #pragma unroll
-    for (int i = 0; i < KM; ++i) g[i] = DBN_CE(ph, KT + i) - (has_lo ? DBN_CE(pl, KT + i) : 0.0);
-    s = DBN_CE(ph, KT + KM) - (has_lo ? DBN_CE(pl, KT + KM) : 0.0);
+    for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sb, KT + i);
+    s = DBN_SE(sb, KT + KM);
     form_a<KM>(G, lam, A);
     prod = ldl_factor<KM>(A, dinv);
     q = segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
@@ -653,38 +655,54 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     if (do_tau) {
       bool t_acc = false;
       const bool birth = tmove == 0, death = tmove == 1;
+      double* const b0 = s_row + 2 * tid;                   // staging buffers: free between the sweeps
+      double* const b1 = b0 + (2 * NP) * FAST_BLOCK;
+      const int ja = tj - 1;                               // first cached row the move touches
+      const int b_left = (tj >= 2) ? TAU(tj - 2) - 1 : -1;  // table row of the boundary left of the change (-1: row 0)
+      const int jr = birth ? tj - 1 : tj;                  // index in tau of the boundary right of the change
       if (tvalid) {
-        // boundaries around the change (table rows): left = b_{tj-1}, mid = b_tj (absent for a birth), right = next.
-        // They are staged in the scratch rows ROW_L, ROW_X, ROW_R (current columns); ROW_X first holds the old
-        // boundary, then the new one.  Old segments: (left, mid), (mid, right) or, for a birth, (left, right);
-        // new segments: (left, new), (new, right) or, for a death, (left, right).
-        const int b_left = (tj >= 2) ? TAU(tj - 2) - 1 : -1;
-        const int b_mid = birth ? -1 : TAU(tj - 1) - 1;
-        const int jr = birth ? tj - 1 : tj;  // index in tau of the right boundary
-        const int b_right = DBN_SEG_END(TAU(jr), jr, S, N);
-        const int rl = (b_left >= 0) ? ROW_L : -1;
+        // The span (left, right) around the change is one cached segment (birth) or two (death, reallocation).
+        //   old side: the cached rows themselves.
+        //   new side: first part A' = P[new] - P[left] from the table (the only gather); the second part, or the
+        //   merged segment of a death, follows from the cached rows by addition / subtraction.  That differs from
+        //   the table's own difference by rounding only (relative 1e-13 at worst) and is used for scoring only: the
+        //   rows written on acceptance are exact table differences again.
+        {
+          const double* src = crow(ja);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) cp_async16(b0 + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
+          if (!birth) {
+            const double* src1 = crow(ja + 1);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) cp_async16(b1 + p * (2 * FAST_BLOCK), src1 + (long long)p * (2 * U));
+          }
+          cp_async_commit();
+          cp_async_wait<0>();
+        }
         double prod_old = 1.0, q_old = 0.0, prod_new = 1.0, q_new = 0.0;
-        // steps: stage left, stage right, old side (through the old boundary, if any), new side (through the new one)
+        // steps: 0 old first (or only) segment; 1 old second segment, then b0 = whole span; 2 new first segment A'
+        // gathered into b1; 3 new second segment b0 - b1 (death: the merged span b0)
         for (int step = 0; step < 4; ++step) {
-          const int t = (step == 0) ? b_left : (step == 1) ? b_right : (step == 2) ? b_mid : (death ? -1 : trow);
-          const int dst = (step == 0) ? ROW_L : (step == 1) ? ROW_R : ROW_X;
-          if (t >= 0) gather_row(t, -1, dst);
-          if (step >= 2) {
-            const int n_e = (t >= 0) ? 2 : 1;
-            double pp = 1.0, qs = 0.0;
-            for (int e = 0; e < n_e; ++e) {
-              double pr, qq;
-              seg_eval(e == 0 ? rl : ROW_X, e == n_e - 1 ? ROW_R : ROW_X, pr, qq);
-              pp *= pr;
-              qs += qq;
-            }
-            if (step == 2) {
-              prod_old = pp;
-              q_old = qs;
+          const bool run = (step == 1) ? !birth : (step == 2) ? !death : true;
+          if (step == 2 && run) gather(trow, b_left, [&](int e, double v) { DBN_SE(b1, e) = v; });
+          if (step == 3 && !death) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) DBN_SE(b0, e) -= DBN_SE(b1, e);
+          }
+          if (run) {
+            double pr, qq;
+            seg_eval((step == 1 || step == 2) ? b1 : b0, pr, qq);
+            if (step < 2) {
+              prod_old *= pr;
+              q_old += qq;
             } else {
-              prod_new = pp;
-              q_new = qs;
+              prod_new *= pr;
+              q_new += qq;
             }
+          }
+          if (step == 1 && run) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) DBN_SE(b0, e) += DBN_SE(b1, e);
           }
         }
         const double ld_star = ld_now + dlog(prod_new / prod_old);
@@ -703,8 +721,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = t_acc;
       }
       // ---- accepted changepoint move: a birth splits segment tj-1 (rows tj .. S-1 move up by one), a death merges
-      // segments tj-1 and tj (rows tj+1 .. S-1 move down by one), a reallocation moves nothing; the one or two new
-      // segments' rows are differences of the prefix rows staged above.  A row moves as NP 16-byte pairs.
+      // segments tj-1 and tj (rows tj+1 .. S-1 move down by one), a reallocation moves nothing; the new segments'
+      // rows are exact table differences.  A row moves as NP 16-byte pairs.
       if (t_acc) {
         double2* cu = reinterpret_cast<double2*>(a.cache) + u;  // pair p of row r at cu[(r * NP + p) * U]
         auto move_row = [&](int dst, int src) {
@@ -719,18 +737,15 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         } else if (death) {
           for (int r = tj + 1; r < S; ++r) move_row(r - 1, r);
         }
-        const bool has_l = tj >= 2;
+        const int b_right = DBN_SEG_END(TAU(jr), jr, S, N);
+        if (death) {
+          gather_row(b_right, b_left, ja);
+        } else {
+          // row ja = A' (still in b1, an exact table difference); row ja + 1 = P[right] - P[new]
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          const double2 xl = has_l ? __ldcg(cu + ((long long)ROW_L * NP + p) * U) : make_double2(0.0, 0.0);
-          const double2 xr = __ldcg(cu + ((long long)ROW_R * NP + p) * U);
-          if (death) {
-            cu[((long long)(tj - 1) * NP + p) * U] = make_double2(xr.x - xl.x, xr.y - xl.y);
-          } else {
-            const double2 xx = __ldcg(cu + ((long long)ROW_X * NP + p) * U);
-            cu[((long long)(tj - 1) * NP + p) * U] = make_double2(xx.x - xl.x, xx.y - xl.y);
-            cu[((long long)tj * NP + p) * U] = make_double2(xr.x - xx.x, xr.y - xx.y);
-          }
+          for (int p = 0; p < NP; ++p)
+            cu[((long long)ja * NP + p) * U] = *reinterpret_cast<const double2*>(b1 + p * (2 * FAST_BLOCK));
+          gather_row(b_right, trow, ja + 1);
         }
       }
       if (t_acc) {
@@ -762,18 +777,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
     for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
   }
-  // ---- work counters: summed per block in shared memory (the staging buffers are free now), one global atomic each
+  // ---- work counters: summed per block through shared memory (the staging buffers are free now), one global
+  // atomic per counter and block
   unsigned long long* const s_cnt = reinterpret_cast<unsigned long long*>(s_dyn);
-  __syncthreads();
-  if (tid < 8) s_cnt[tid] = 0ull;
-  __syncthreads();
   const unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
                                    (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (v[c]) atomicAdd(&s_cnt[c], v[c]);
   __syncthreads();
-  if (tid < 8 && s_cnt[tid]) atomicAdd(&a.counters[tid], s_cnt[tid]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s_cnt[c * FAST_BLOCK + tid] = v[c];
+  __syncthreads();
+  if (tid < 8) {
+    unsigned long long t = 0;
+    for (int i = 0; i < FAST_BLOCK; ++i) t += s_cnt[tid * FAST_BLOCK + ((i + tid) & (FAST_BLOCK - 1))];
+    if (t) atomicAdd(&a.counters[tid], t);
+  }
 }
 
 // Invariant check (test hook behind dbn_verify_cache): every cached segment row of every unit must equal the difference

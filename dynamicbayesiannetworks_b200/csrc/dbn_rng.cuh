@@ -127,7 +127,9 @@ __device__ __noinline__ inline double gamma_draw(uint32_t chain, uint32_t node, 
     if (v <= 0.0) continue;
     v = v * v * v;
     const double u = 1.0 - (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
-    if (log(u) < 0.5 * z.x * z.x + d - d * v + d * log(v)) return boost * d * v;
+    const double x2 = z.x * z.x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;  // Marsaglia-Tsang squeeze: inside the exact test's region
+    if (log(u) < 0.5 * x2 + d - d * v + d * log(v)) return boost * d * v;
   }
   return boost * d;  // unreachable in practice (acceptance > 0.95 per try)
 }
