@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // e_h independent of sigma^2, so sum_h |beta_h|^2 is assembled from (|m|^2, m.e, |e|^2) after sigma^2 is drawn.
     double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
     {
+      double z_spare = 0.0;
       stage_row(0, 0);
       for (int h = 0; h < S; ++h) {
         stage_row(h + 1, (h + 1) & 1);
@@ -240,7 +241,14 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           const double sw = sqrt(lam);
 #pragma unroll
           for (int i = 0; i < KM; i += 2) {
-            const double2 z = normal_pair(gchain, unode, uit, (uint32_t)(4 * h + i / 2), key);
+            // KM odd: the last slot needs one normal of a pair; odd segments use the one an even segment left over
+            double2 z;
+            if ((KM & 1) && i == KM - 1 && (h & 1)) {
+              z = make_double2(z_spare, 0.0);
+            } else {
+              z = normal_pair(gchain, unode, uit, (uint32_t)(4 * h + i / 2), key);
+              if ((KM & 1) && i == KM - 1) z_spare = z.y;
+            }
             e[i] = ((i == 0) || cg[i] >= 0) ? sw * z.x * sqrt(dinv[i]) : 0.0;
             if (i + 1 < KM) e[i + 1] = (cg[i + 1] >= 0) ? sw * z.y * sqrt(dinv[i + 1]) : 0.0;
           }
