@@ -7,6 +7,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <cstdlib>
 
 #include "dbn_chain_fast.cuh"
 #include "dbn_fp.cuh"
@@ -37,7 +39,8 @@ __global__ void build_v_kernel(const double* __restrict__ raw, const int* __rest
   }
 }
 
-// WRITE == false: per-(chunk, column) totals.  WRITE == true: running sums from the chunk's scanned offset.
+// WRITE == false: per-(chunk, column) totals.  WRITE == true: running sums, starting from the sum of the totals of the
+// earlier chunks.
 template <bool WRITE>
 __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
                                                               const unsigned short* __restrict__ colB, int N, int W, long long R,
@@ -55,25 +58,16 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
     for (int t = 0; t < len; ++t) acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
     chunk[(long long)blockIdx.y * R + p] = acc;
   } else {
-    double acc = chunk[(long long)blockIdx.y * R + p];
+    // offset of this chunk = sum of the totals of the chunks before it, added in chunk order (coalesced, L2-resident)
+    double acc = 0.0;
+    for (int c = 0; c < (int)blockIdx.y; ++c) acc += chunk[(long long)c * R + p];
+    if (blockIdx.y == 0) __stcs(table + p, 0.0);  // row 0
     double* out = table + (long long)(t0 + 1) * R + p;
     for (int t = 0; t < len; ++t) {
       acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
       __stcs(out, acc);  // streaming store: the table is far larger than L2
       out += R;
     }
-  }
-}
-
-// exclusive scan over chunks, one thread per column
-__global__ void prefix_scan_chunks(double* __restrict__ chunk, int n_chunks, long long R) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= R) return;
-  double acc = 0.0;
-  for (int c = 0; c < n_chunks; ++c) {
-    const double v = chunk[(long long)c * R + p];
-    chunk[(long long)c * R + p] = acc;
-    acc += v;
   }
 }
 
@@ -334,9 +328,6 @@ static int launch_prefix(dbn_handle* h) {
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK - 1) / PREFIX_BLOCK), (unsigned)h->n_chunks);
   prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   CU(h, cudaGetLastError());
-  prefix_scan_chunks<<<(unsigned)((h->R + 255) / 256), 256, 0, h->stream>>>(h->d_chunk, h->n_chunks, h->R);
-  CU(h, cudaGetLastError());
-  CU(h, cudaMemsetAsync(h->d_table, 0, (size_t)h->R * sizeof(double), h->stream));  // row 0
   prefix_kernel<true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   CU(h, cudaGetLastError());
   return DBN_OK;
@@ -395,7 +386,8 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     }
     const size_t row_bytes = (size_t)h->W * sizeof(double);
     int Lc = (int)(96 * 1024 / row_bytes);
-    if (Lc > 64) Lc = 64;
+    if (Lc > 32) Lc = 32;  // measured on B200 (scripts/prefix_tune.py): 32 rows per chunk is the fastest build
+    if (const char* e = getenv("DBN_PREFIX_LC")) Lc = std::min(Lc, std::max(1, atoi(e)));  // tuning knob
     if (Lc < 1) Lc = 1;
     h->Lc = Lc;
     h->n_chunks = (int)((N + Lc - 1) / Lc);
