@@ -375,3 +375,57 @@ def test_fp_glob_network_dropin(eng_mod):
     many = Network(data_list(g), 300, 100, 1, n_chains=32)
     many.infer_network('fp_glob_coup_nh_dbn')
     assert np.array(many.proposed_adj_matrix).shape == (5, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[3] at full size (100 genes, T = 2000, 1024 chains, fan-in 4): size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_c4_full_size_properties(eng_mod):
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    n, T, C, fan = 100, 2000, 1024, 4
+    data, _, _ = make_synthetic(n, T, 3, 4, 20260119)
+    X, Y = O.lagged_matrices([data])
+    N = X.shape[0]
+    n_iter, burn, thin = 60, 20, 10
+    with eng_mod(n_chains=C, seed=5) as e:
+        e.build_stats([data])
+        e.chain_init('varying_nh_dbn', fan_in=fan, burn_in=burn, thin=thin)
+        for w in (7, 13, 40):                     # launches of different lengths carry the state and the cache on
+            e.run(w)
+            assert e.verify_cache() == (0, 0)
+        st = e.state()
+        c = e.counts()
+        ctr = e.counters()
+        # the device's log-ML of states the chains actually reached == the oracle's (the reference overflows at this T)
+        rng = np.random.default_rng(0)
+        pick = rng.choice(n * C, size=48, replace=False)
+        node = [int(u // C) for u in pick]
+        pi = [[int(v) for v in st['pi'][u, :st['npi'][u]]] for u in pick]
+        tau = [[int(v) for v in st['tau'][u, :st['S'][u]]] for u in pick]
+        lam = st['lambda2'][pick]
+        got = e.score_batch(node, pi, tau, lam, alpha=0.005, beta=0.005, T=N)
+    U = n * C
+    assert ctr['unit_iterations'] == U * n_iter
+    assert np.isfinite(st['sigma2']).all() and (st['sigma2'] > 0).all()
+    assert np.isfinite(st['lambda2']).all() and (st['lambda2'] > 0).all()
+    # structural invariants of every state: sorted distinct changepoints in [2, N] ending with N + 2, <= 9 segments,
+    # distinct parents != node, fan-in respected
+    S = st['S']
+    assert S.min() >= 1 and S.max() <= 9
+    for u in rng.choice(U, size=4000, replace=False):
+        t = st['tau'][u, :S[u]]
+        assert t[-1] == N + 2 and (np.diff(t) > 0).all() and (S[u] == 1 or (t[0] >= 2 and t[-2] <= N)), (u, t)
+        p = st['pi'][u, :st['npi'][u]]
+        assert st['npi'][u] <= fan and len(set(p.tolist())) == p.size and (u // C) not in p.tolist() and (p >= 0).all() and (p < n).all()
+    # count bookkeeping (network.py:358-359, :388-389): kept tau samples per node = C * #{it in [burn, n_iter): (it - burn) % thin == 0}
+    kept_tau = sum(1 for it in range(burn, n_iter) if (it - burn) % thin == 0)
+    assert (c['cp_kept'] == C * kept_tau).all()
+    kept_pi = sum(1 for idx in range(burn, n_iter + 1) if (idx - burn) % thin != 0)
+    assert (c['nonempty'] <= C * kept_pi).all() and (c['edge'].sum(axis=1) <= fan * c['nonempty']).all()
+    assert (np.diag(c['edge']) == 0).all()
+    assert (c['cp_hist'][:, :2] == 0).all() and (c['cp_hist'][:, N + 1:] == 0).all()
+    assert (c['cp_hist'].sum(axis=1) <= 8 * c['cp_kept']).all()
+    for b in range(len(pick)):
+        stt = O.segment_stats(X, Y[:, node[b]], pi[b], tau[b])
+        ref = O.log_ml(stt, [np.zeros(len(pi[b]) + 1)] * len(tau[b]), 0.005, 0.005, lam[b], N)
+        assert abs(got[b] - ref) <= LOGML_RTOL * abs(ref), (b, got[b], ref)
