@@ -5,24 +5,26 @@
 // Why (profiles/r1_v0): with every pass re-gathering 2 x 21 scattered doubles per segment, the v0 kernel was bound
 // by the L1 miss-request path (one 32-byte sector request per gathered double, ~1 request/cycle/SM) at 12 warps/SM.
 // Here
-//   * cache[j][entry][unit], j < 9, holds the statistics (G_h, g_h, s_h) of the unit's j-th segment in time order,
-//     restricted to the unit's design columns (15 + 5 + 1 doubles at KM = 5): the difference of the two prefix-table
-//     rows at the segment's boundaries, taken once when the state changes.  Threads of a warp read the same
-//     (j, entry) of consecutive units: fully coalesced, 21 loads per segment and sweep.  Rows are kept physically
-//     ordered, because a per-unit row indirection scatters the warp's addresses again (measured: profiles/r1_v1).
+//   * cache[j][pair][unit], j < 9, holds prefix-table row b_j (the end boundary of the unit's j-th segment, in time
+//     order) restricted to the unit's design columns (15 + 5 + 1 doubles at KM = 5, as 16-byte pairs).  Threads of a
+//     warp read the same (j, pair) of consecutive units: fully coalesced, 11 x 16 bytes per thread, segment and sweep.
+//     A segment's statistics (G_h, g_h, s_h) are the difference of two consecutive rows, taken between two
+//     shared-memory staging buffers (three buffers: current row, previous row, the one being prefetched).  Rows are
+//     kept physically ordered, because a per-unit row indirection scatters the warp's addresses again (measured:
+//     profiles/r1_v1).  Caching boundary rows rather than their differences (v6/v7) makes every update a copy: no
+//     table row has to be gathered again when a move is accepted.
 //   * the parent-set move scores pi and pi* in ONE sweep: both column sets share a base of <= KM-1 columns, which is
 //     factorised once per segment (A_B = L D L^T); the column only pi has and the column only pi* has are two
 //     alternative last rows of that factorisation.  Only the new column (<= KM+1 values per boundary) is gathered.
-//   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new):
-//     the old ones are cached rows, the new ones follow from them and ONE gathered difference of two table rows
-//     (none for a death), all held in the shared-memory staging buffers (profiles/r1_v6: the 3-4 gathered rows per
-//     move and their global scratch copies were a quarter of the stall samples).
-//   * accepted moves rewrite the owner's rows: the new column in every row (parent-set move) or the rows behind an
-//     inserted / removed segment (changepoint move), as 16-byte pairs.  Only the thread that owns a unit ever writes
-//     that unit's rows: handing this work to the other lanes of the warp (v4/v5) needs votes and shuffles, and those
+//   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new)
+//     from the <= 3 cached boundary rows around the change and ONE gathered table row, the new boundary (none for a
+//     death) (profiles/r1_v7: waiting for gathered table rows was 30 % of all stall samples).
+//   * accepted moves rewrite the owner's rows: the new column in every row (parent-set move), or one row inserted /
+//     removed / replaced (changepoint move), as 16-byte pairs.  Only the thread that owns a unit ever writes that
+//     unit's rows: handing this work to the other lanes of the warp (v4/v5) needs votes and shuffles, and those
 //     were measured to run on a split warp on rare occasions (profiles/r1_notes.md).
-// Every cached row is an exact function of (pi, tau) and the table (no running sums), so the state does not depend
-// on the history of moves.
+// Every cached row is an exact copy of table entries (no arithmetic), so the state does not depend on the history of
+// moves; dbn_verify_cache checks that bit for bit.
 // Columns are kept in cache-slot order, not sorted by gene id: for mu = 0 (h, nh) the marginal likelihood and the
 // Gibbs parameters are invariant to the column order (only rounding differs, ~1e-15 relative); traces are written
 // in the reference's sorted order.
@@ -53,14 +55,14 @@ struct FastDims {
 // entries of a pair are adjacent, so a row moves as NP 16-byte copies per thread, consecutive threads 16 bytes apart.
 __host__ __device__ inline int fast_cache_row_doubles(int km) { return 2 * ((km * (km + 1) / 2 + km + 1 + 1) / 2); }
 inline size_t fast_smem_bytes(int km) {
-  return (size_t)2 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(int);
+  return (size_t)3 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(unsigned short);
 }
 // entry e of a row whose pair 0 is at `p` (global: pair stride = 2 * U doubles; shared staging: 2 * FAST_BLOCK doubles)
 #define DBN_CE(p, e) (p)[(long long)((e) >> 1) * (2 * U) + ((e) & 1)]
 #define DBN_SE(p, e) (p)[((e) >> 1) * (2 * FAST_BLOCK) + ((e) & 1)]
 
-// 16-byte asynchronous global -> shared copy (LDGSTS): the staged row of the next segment is in flight while the
-// current one is factorised; no registers are held for it.  .cg = through L2 only (the rows are streamed, never reused
+// 16-byte asynchronous global -> shared copy (LDGSTS): the staged row of the next boundary is in flight while the
+// current segment is factorised; no registers are held for it.  .cg = through L2 only (the rows are streamed, never reused
 // from L1).
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -78,11 +80,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NE = FastDims<KM>::NE, NP = FastDims<KM>::NP;
   constexpr int KBT = KB * (KB + 1) / 2;
 
-  // dynamic shared memory: [2][NP][BLOCK][2] doubles (segment rows staged by cp.async) | tau | tau*
+  // dynamic shared memory: [3][NP][BLOCK][2] doubles (boundary rows staged by cp.async) | tau | tau* (16-bit: the host
+  // refuses series with N + 2 > 65535 for this kernel)
   extern __shared__ __align__(16) double s_dyn[];
   double* const s_row = s_dyn;
-  int* const s_tau = reinterpret_cast<int*>(s_dyn + 2 * (2 * NP) * FAST_BLOCK);
-  int* const s_tas = s_tau + SMAX * FAST_BLOCK;
+  constexpr int BUF = (2 * NP) * FAST_BLOCK;  // doubles per staging buffer
+  unsigned short* const s_tau = reinterpret_cast<unsigned short*>(s_dyn + 3 * BUF);
+  unsigned short* const s_tas = s_tau + SMAX * FAST_BLOCK;
   const int tid = threadIdx.x;
   const int u_raw = blockIdx.x * FAST_BLOCK + tid;
   const bool active = u_raw < a.U;
@@ -91,10 +95,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   const int chain = u - node * a.C;
   const int n = a.tb.n, N = a.tb.N, F = n - 1;
   const long long U = a.U;
-  auto TAU = [&](int j) -> int& { return s_tau[j * FAST_BLOCK + tid]; };
-  auto TAS = [&](int j) -> int& { return s_tas[j * FAST_BLOCK + tid]; };
-  auto tau_cur = [&](int j) { return s_tau[j * FAST_BLOCK + tid]; };
-  auto tau_star = [&](int j) { return s_tas[j * FAST_BLOCK + tid]; };
+  auto TAU = [&](int j) -> unsigned short& { return s_tau[j * FAST_BLOCK + tid]; };
+  auto TAS = [&](int j) -> unsigned short& { return s_tas[j * FAST_BLOCK + tid]; };
+  auto tau_cur = [&](int j) { return (int)s_tau[j * FAST_BLOCK + tid]; };
+  auto tau_star = [&](int j) { return (int)s_tas[j * FAST_BLOCK + tid]; };
+  double* const sbuf = s_row + 2 * tid;  // this thread's slice of staging buffer 0; buffer b at sbuf + b * BUF
   double* const cbase = a.cache + 2ll * u;
   auto crow = [&](int row) -> double* { return cbase + (long long)row * NP * (2 * U); };  // pair 0 of cached row `row`
   const int nb = a.tb.zz_size + node * (n + 2);  // table offset of this node's ZY / YY block
@@ -105,17 +110,14 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
   for (int j = 0; j < PMAX; ++j) pi[j] = a.st_pi[j * a.U + u];
   int S = active ? a.st_S[u] : 0;  // lanes past the end keep step with the warp (ballots below) on an empty state
-  for (int j = 0; j < SMAX; ++j) TAU(j) = a.st_tau[j * a.U + u];
+  for (int j = 0; j < SMAX; ++j) TAU(j) = (unsigned short)a.st_tau[j * a.U + u];
   double sig2 = a.st_sig[u], lam = a.st_lam[u];
   int cg[KM];  // gene id held by column slot s (>= 1), -1 = empty; slot 0 is the intercept
   cg[0] = -1;
 
-  // prefix-table row `t` restricted to the slots' columns (zeros for empty slots), minus the same of row `t0`
-  // when t0 >= 0; put(entry, value) stores it
-  auto gather = [&](int t, int t0, auto&& put) {
+  // prefix-table row `t` restricted to the slots' columns (zeros for empty slots); put(entry, value) stores it
+  auto gather = [&](int t, auto&& put) {
     const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
-    const double* __restrict__ row0 = a.tb.base + (long long)(t0 < 0 ? t : t0) * a.tb.row_stride;
-    const bool sub = t0 >= 0;
 #pragma unroll
     for (int i = 0; i < KM; ++i) {
       const bool oi = (i == 0) || cg[i] >= 0;
@@ -125,23 +127,21 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         const bool oj = (j == 0) || cg[j] >= 0;
         const int fj = (j == 0) ? 0 : cg[j] + 1;
         const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
-        put(DBN_TRI(i, j), (oi && oj) ? __ldg(row + off) - (sub ? __ldg(row0 + off) : 0.0) : 0.0);
+        put(DBN_TRI(i, j), (oi && oj) ? __ldg(row + off) : 0.0);
       }
-      put(KT + i, oi ? __ldg(row + nb + fi) - (sub ? __ldg(row0 + nb + fi) : 0.0) : 0.0);
+      put(KT + i, oi ? __ldg(row + nb + fi) : 0.0);
     }
-    put(KT + KM, __ldg(row + nb + n + 1) - (sub ? __ldg(row0 + nb + n + 1) : 0.0));
-  };
-  // ... -> cache row `dst`
-  auto gather_row = [&](int t, int t0, int dst) {
-    double* c = crow(dst);
-    gather(t, t0, [&](int e, double v) { DBN_CE(c, e) = v; });
+    put(KT + KM, __ldg(row + nb + n + 1));
   };
 
   if (a.refresh) {
-    // (re)build the cache from the table: canonical slots = parent positions, segment j -> row j
+    // (re)build the cache from the table: canonical slots = parent positions, end boundary of segment j -> row j
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = (s - 1 < npi) ? pi[s - 1] : -1;
-    for (int j = 0; j < S; ++j) gather_row(DBN_SEG_END(TAU(j), j, S, N), j == 0 ? -1 : TAU(j - 1) - 1, j);
+    for (int j = 0; j < S; ++j) {
+      double* c = crow(j);
+      gather(DBN_SEG_END(tau_cur(j), j, S, N), [&](int e, double v) { DBN_CE(c, e) = v; });
+    }
   } else {
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = a.st_cg[(s - 1) * a.U + u];
@@ -156,26 +156,28 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   unsigned n_pacc = 0, n_tacc = 0;  // accepted parent-set / changepoint moves
   const bool replay = TRACE && a.rd != nullptr;
 
-  // start the asynchronous copy of segment row j into staging buffer `buf` (one commit group per call, possibly
+  // start the asynchronous copy of cached row j into staging buffer `buf` (one commit group per call, possibly
   // empty, so that wait_group<1> always means "the previous call's row has landed")
   auto stage_row = [&](int j, int buf) {
     if (j < S) {
       const double* src = crow(j);
-      double* dst = s_row + buf * (2 * NP) * FAST_BLOCK + 2 * tid;
+      double* dst = sbuf + buf * BUF;
 #pragma unroll
       for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
     }
     cp_async_commit();
   };
-  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment whose statistics are in the
-  // staging buffer `sb` (this thread's slice)
-  auto seg_eval = [&](const double* sb, double& prod, double& q) {
+  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment between the boundary rows in
+  // the staging buffers `lo` (null: table row 0 = zeros) and `hi`
+  auto seg_eval = [&](const double* lo, const double* hi, double& prod, double& q) {
     double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
+    const bool hl = lo != nullptr;
+    const double* l_ = hl ? lo : hi;
 #pragma unroll
-    for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sb, e);
+    for (int e = 0; e < KT; ++e) G[e] = DBN_SE(hi, e) - (hl ? DBN_SE(l_, e) : 0.0);
 #pragma unroll
-    for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sb, KT + i);
-    s = DBN_SE(sb, KT + KM);
+    for (int i = 0; i < KM; ++i) g[i] = DBN_SE(hi, KT + i) - (hl ? DBN_SE(l_, KT + i) : 0.0);
+    s = DBN_SE(hi, KT + KM) - (hl ? DBN_SE(l_, KT + KM) : 0.0);
     form_a<KM>(G, lam, A);
     prod = ldl_factor<KM>(A, dinv);
     q = segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
@@ -216,16 +218,21 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     {
       double z_spare = 0.0;
       stage_row(0, 0);
+      int bc = 0;  // staging buffer of the current boundary row; the previous row is in (bc + 2) % 3
       for (int h = 0; h < S; ++h) {
-        stage_row(h + 1, (h + 1) & 1);
+        const int bn = (bc == 2) ? 0 : bc + 1, bp = (bc == 0) ? 2 : bc - 1;
+        stage_row(h + 1, bn);
         cp_async_wait<1>();
-        const double* sr = s_row + (h & 1) * (2 * NP) * FAST_BLOCK + 2 * tid;
+        const double* sr = sbuf + bc * BUF;
+        const double* sp = sbuf + bp * BUF;
+        const bool hp = h > 0;
+        bc = bn;
         double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
 #pragma unroll
-        for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sr, e);
+        for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sr, e) - (hp ? DBN_SE(sp, e) : 0.0);
 #pragma unroll
-        for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, KT + i);
-        s = DBN_SE(sr, KT + KM);
+        for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, KT + i) - (hp ? DBN_SE(sp, KT + i) : 0.0);
+        s = DBN_SE(sr, KT + KM) - (hp ? DBN_SE(sp, KT + KM) : 0.0);
         form_a<KM>(G, lam, A);
         ldl_factor<KM>(A, dinv);
         ++n_fact;
@@ -524,20 +531,26 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
       for (int i = 0; i < KB + 2; ++i) n_prev[i] = 0.0;
       stage_row(0, 0);
+      int bc = 0;
       for (int h = 0; h < S; ++h) {
-        stage_row(h + 1, (h + 1) & 1);
+        const int bn = (bc == 2) ? 0 : bc + 1, bp = (bc == 0) ? 2 : bc - 1;
+        stage_row(h + 1, bn);
         cp_async_wait<1>();
-        const double* sr = s_row + (h & 1) * (2 * NP) * FAST_BLOCK + 2 * tid;
+        const double* sr = sbuf + bc * BUF;
+        const double* sp = sbuf + bp * BUF;
+        const bool hp = h > 0;
+        bc = bn;
+        auto seg = [&](int e) { return DBN_SE(sr, e) - (hp ? DBN_SE(sp, e) : 0.0); };  // entry e of this segment's statistics
         double A[KBT], gB[KB], t1[KB], t2[KB], dinv[KB];
 #pragma unroll
-        for (int e = 0; e < KBT; ++e) A[e] = DBN_SE(sr, eb[e]);
+        for (int e = 0; e < KBT; ++e) A[e] = seg(eb[e]);
 #pragma unroll
         for (int p = 0; p < KB; ++p) {
-          gB[p] = DBN_SE(sr, ezy[p]);
-          t1[p] = DBN_SE(sr, et[p]);
+          gB[p] = seg(ezy[p]);
+          t1[p] = seg(et[p]);
         }
-        const double t1d = DBN_SE(sr, ett), t1y = DBN_SE(sr, ezyt);
-        const double s = DBN_SE(sr, KT + KM);
+        const double t1d = seg(ett), t1y = seg(ezyt);
+        const double s = seg(KT + KM);
         double t2d = 0.0, t2y = 0.0;
         if (has_new) {
           const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(h), h, S, N) * a.tb.row_stride;
@@ -633,15 +646,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     }
     // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row
     if (p_acc) {
-      const double* __restrict__ row0 = a.tb.base;  // table row 0 is all zeros
       for (int j = 0; j < S; ++j) {
-        const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(TAU(j), j, S, N) * a.tb.row_stride;
+        const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
         double* c = crow(j);
 #pragma unroll
-        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (o2[p] >= 0) ? __ldg(row + o2[p]) - __ldg(row0 + o2[p]) : 0.0;
-        DBN_CE(c, ett) = (o2d >= 0) ? __ldg(row + o2d) - __ldg(row0 + o2d) : 0.0;
-        DBN_CE(c, ezyt) = (o2y >= 0) ? __ldg(row + o2y) - __ldg(row0 + o2y) : 0.0;
-        row0 = row;
+        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (o2[p] >= 0) ? __ldg(row + o2[p]) : 0.0;
+        DBN_CE(c, ett) = (o2d >= 0) ? __ldg(row + o2d) : 0.0;
+        DBN_CE(c, ezyt) = (o2y >= 0) ? __ldg(row + o2y) : 0.0;
       }
     }
     // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
@@ -663,54 +674,46 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     if (do_tau) {
       bool t_acc = false;
       const bool birth = tmove == 0, death = tmove == 1;
-      double* const b0 = s_row + 2 * tid;                   // staging buffers: free between the sweeps
-      double* const b1 = b0 + (2 * NP) * FAST_BLOCK;
-      const int ja = tj - 1;                               // first cached row the move touches
-      const int b_left = (tj >= 2) ? TAU(tj - 2) - 1 : -1;  // table row of the boundary left of the change (-1: row 0)
-      const int jr = birth ? tj - 1 : tj;                  // index in tau of the boundary right of the change
+      double* const b0 = sbuf;                             // staging buffers: free between the sweeps
+      double* const b1 = sbuf + BUF;
+      double* const b2 = sbuf + 2 * BUF;
+      const int ja = tj - 1;  // cached row the move inserts before (birth), removes (death) or replaces (reallocation)
       if (tvalid) {
-        // The span (left, right) around the change is one cached segment (birth) or two (death, reallocation).
-        //   old side: the cached rows themselves.
-        //   new side: first part A' = P[new] - P[left] from the table (the only gather); the second part, or the
-        //   merged segment of a death, follows from the cached rows by addition / subtraction.  That differs from
-        //   the table's own difference by rounding only (relative 1e-13 at worst) and is used for scoring only: the
-        //   rows written on acceptance are exact table differences again.
+        // The boundaries around the change: left = row ja-1 (table row 0 when ja == 0), mid = row ja (death,
+        // reallocation), right = row ja (birth) or ja+1; they are cached rows.  The new boundary (birth,
+        // reallocation) is the only table row that has to be gathered; it replaces mid in b1.
+        //   old segments: (left, mid), (mid, right)   or, for a birth, (left, right)
+        //   new segments: (left, new), (new, right)   or, for a death, (left, right)
+        const bool has_l = ja >= 1;
         {
-          const double* src = crow(ja);
+          auto stage = [&](int row, double* dst) {
+            const double* src = crow(row);
 #pragma unroll
-          for (int p = 0; p < NP; ++p) cp_async16(b0 + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
-          if (!birth) {
-            const double* src1 = crow(ja + 1);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) cp_async16(b1 + p * (2 * FAST_BLOCK), src1 + (long long)p * (2 * U));
-          }
+            for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
+          };
+          if (has_l) stage(ja - 1, b0);
+          if (!birth) stage(ja, b1);
+          stage(birth ? ja : ja + 1, b2);
           cp_async_commit();
           cp_async_wait<0>();
         }
+        const double* lo0 = has_l ? b0 : nullptr;
         double prod_old = 1.0, q_old = 0.0, prod_new = 1.0, q_new = 0.0;
-        // steps: 0 old first (or only) segment; 1 old second segment, then b0 = whole span; 2 new first segment A'
-        // gathered into b1; 3 new second segment b0 - b1 (death: the merged span b0)
+        // steps 0, 1: the old segments; 2, 3: the new ones (b1 holds the new boundary from step 2 on)
         for (int step = 0; step < 4; ++step) {
-          const bool run = (step == 1) ? !birth : (step == 2) ? !death : true;
-          if (step == 2 && run) gather(trow, b_left, [&](int e, double v) { DBN_SE(b1, e) = v; });
-          if (step == 3 && !death) {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) DBN_SE(b0, e) -= DBN_SE(b1, e);
-          }
-          if (run) {
-            double pr, qq;
-            seg_eval((step == 1 || step == 2) ? b1 : b0, pr, qq);
-            if (step < 2) {
-              prod_old *= pr;
-              q_old += qq;
-            } else {
-              prod_new *= pr;
-              q_new += qq;
-            }
-          }
-          if (step == 1 && run) {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) DBN_SE(b0, e) += DBN_SE(b1, e);
+          const bool two = (step < 2) ? !birth : !death;  // does this side have two segments?
+          if (step == 2 && two) gather(trow, [&](int e, double v) { DBN_SE(b1, e) = v; });
+          if ((step & 1) && !two) continue;
+          const double* lo = (step & 1) ? b1 : lo0;
+          const double* hi = ((step & 1) || !two) ? b2 : b1;
+          double pr, qq;
+          seg_eval(lo, hi, pr, qq);
+          if (step < 2) {
+            prod_old *= pr;
+            q_old += qq;
+          } else {
+            prod_new *= pr;
+            q_new += qq;
           }
         }
         const double ld_star = ld_now + dlog(prod_new / prod_old);
@@ -728,9 +731,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
         if (TRACE && ti) ti[DBN_TI_TAU_ACCEPT] = t_acc;
       }
-      // ---- accepted changepoint move: a birth splits segment tj-1 (rows tj .. S-1 move up by one), a death merges
-      // segments tj-1 and tj (rows tj+1 .. S-1 move down by one), a reallocation moves nothing; the new segments'
-      // rows are exact table differences.  A row moves as NP 16-byte pairs.
+      // ---- accepted changepoint move: a birth inserts the new boundary's row before row ja (rows ja .. S-1 move up by
+      // one), a death removes row ja (rows ja+1 .. S-1 move down by one), a reallocation replaces row ja.  The new
+      // boundary's row is still in b1.  A row moves as NP 16-byte pairs.
       if (t_acc) {
         double2* cu = reinterpret_cast<double2*>(a.cache) + u;  // pair p of row r at cu[(r * NP + p) * U]
         auto move_row = [&](int dst, int src) {
@@ -741,19 +744,14 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           for (int p = 0; p < NP; ++p) cu[((long long)dst * NP + p) * U] = t[p];
         };
         if (birth) {
-          for (int r = S - 1; r >= tj; --r) move_row(r + 1, r);
+          for (int r = S - 1; r >= ja; --r) move_row(r + 1, r);
         } else if (death) {
-          for (int r = tj + 1; r < S; ++r) move_row(r - 1, r);
+          for (int r = ja + 1; r < S; ++r) move_row(r - 1, r);
         }
-        const int b_right = DBN_SEG_END(TAU(jr), jr, S, N);
-        if (death) {
-          gather_row(b_right, b_left, ja);
-        } else {
-          // row ja = A' (still in b1, an exact table difference); row ja + 1 = P[right] - P[new]
+        if (!death) {
 #pragma unroll
           for (int p = 0; p < NP; ++p)
             cu[((long long)ja * NP + p) * U] = *reinterpret_cast<const double2*>(b1 + p * (2 * FAST_BLOCK));
-          gather_row(b_right, trow, ja + 1);
         }
       }
       if (t_acc) {
@@ -801,8 +799,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   }
 }
 
-// Invariant check (test hook behind dbn_verify_cache): every cached segment row of every unit must equal the difference
-// of the two prefix-table rows at the segment's boundaries, restricted to the unit's column slots, bit for bit.
+// Invariant check (test hook behind dbn_verify_cache): every cached row of every unit must equal the prefix-table row
+// at the end boundary of the corresponding segment, restricted to the unit's column slots, bit for bit.
 // counts[0] += units with at least one differing entry, counts[1] += differing entries.
 template <int KM>
 __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* counts) {
@@ -818,9 +816,8 @@ __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* count
   for (int s = 1; s < KM; ++s) cg[s] = a.st_cg[(s - 1) * a.U + u];
   unsigned long long bad = 0;
   for (int j = 0; j < S; ++j) {
-    const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N), t0 = j == 0 ? 0 : a.st_tau[(j - 1) * a.U + u] - 1;
+    const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N);
     const double* row = a.tb.base + (long long)t * a.tb.row_stride;
-    const double* row0 = a.tb.base + (long long)t0 * a.tb.row_stride;
     const double* c = a.cache + 2ll * u + (long long)j * NP * (2 * U);
     for (int i = 0; i < KM; ++i) {
       const bool oi = (i == 0) || cg[i] >= 0;
@@ -829,13 +826,13 @@ __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* count
         const bool oj = (jj == 0) || cg[jj] >= 0;
         const int fj = (jj == 0) ? 0 : cg[jj] + 1;
         const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
-        const double ex = (oi && oj) ? row[off] - row0[off] : 0.0;
+        const double ex = (oi && oj) ? row[off] : 0.0;
         bad += (ex != DBN_CE(c, DBN_TRI(i, jj))) ? 1 : 0;
       }
-      const double ex = oi ? row[nb + fi] - row0[nb + fi] : 0.0;
+      const double ex = oi ? row[nb + fi] : 0.0;
       bad += (ex != DBN_CE(c, KT + i)) ? 1 : 0;
     }
-    bad += ((row[nb + n + 1] - row0[nb + n + 1]) != DBN_CE(c, KT + KM)) ? 1 : 0;
+    bad += (row[nb + n + 1] != DBN_CE(c, KT + KM)) ? 1 : 0;
   }
   if (bad) {
     atomicAdd(&counts[0], 1ull);

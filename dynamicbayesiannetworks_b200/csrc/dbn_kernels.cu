@@ -539,6 +539,7 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   CU(h, cudaMalloc(&h->st_del, U * sizeof(double)));
   CU(h, cudaMalloc(&h->st_mu, U * KMAX * sizeof(double)));
   if (p->method == DBN_H_DBN || p->method == DBN_NH_DBN) {
+    if (h->N + 2 > 65535) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: the h / nh kernel keeps changepoints as 16-bit values (N + 2 <= 65535), N = %d", h->N);
     const int km = p->fan_in <= 3 ? 4 : 5;
     const size_t cache_bytes = (size_t)BSLOTS * fast_cache_row_doubles(km) * U * sizeof(double);
     cudaError_t e = cudaMalloc(&h->d_cache, cache_bytes);
