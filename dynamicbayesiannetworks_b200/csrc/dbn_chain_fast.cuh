@@ -68,6 +68,11 @@ __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+// 8-byte variant (through L1: used for single prefix-table entries, which are read-only)
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -514,8 +519,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         for (int q = 0; q <= p; ++q) eb[DBN_TRI(p, q)] = DBN_TRI(perm[p], perm[q]);  // perm is increasing on the base
         et[p] = (tslot > perm[p]) ? DBN_TRI(tslot, perm[p]) : DBN_TRI(perm[p], tslot);
         ezy[p] = KT + perm[p];
-        const int fp = (p == 0) ? 0 : cg[perm[p]] + 1;  // 0 when the slot is empty; masked by o2 < 0
-        const bool occ = (p == 0) || cg[perm[p]] >= 0;
+        // perm[p] is p or p + 1: selects keep cg in registers (a run-time index sends the array to local memory)
+        const int cgp = (p == 0) ? -1 : ((p < tslot) ? cg[p] : cg[p + 1 < KM ? p + 1 : p]);
+        const int fp = (p == 0) ? 0 : cgp + 1;  // 0 when the slot is empty; masked by o2 < 0
+        const bool occ = (p == 0) || cgp >= 0;
         const int hi = max(cf, fp), lo = min(cf, fp);
         o2[p] = (has_new && occ) ? hi * (hi + 1) / 2 + lo : -1;
       }
@@ -644,15 +651,37 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     }
-    // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row
+    // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row.
+    // Its table entries at all S boundaries (<= 9 x (KM + 1) values) are fetched in ONE round trip, by cp.async into
+    // the staging buffers (free between the sweeps), instead of one dependent round trip per boundary.
     if (p_acc) {
+      // value v = j * (KB + 2) + p lives in this thread's own slices of the three buffers (2 NP doubles each)
+      static_assert(SEG_ROWS * (KB + 2) <= 3 * 2 * NP, "the staging buffers hold the new column at every boundary");
+      auto stash = [&](int v) -> double* {
+        const int b_ = v / (2 * NP), w_ = v - b_ * (2 * NP);
+        return sbuf + b_ * BUF + (w_ >> 1) * (2 * FAST_BLOCK) + (w_ & 1);
+      };
+      const bool fetch = o2d >= 0;
+      if (fetch) {
+        for (int j = 0; j < S; ++j) {
+          const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
+          const int v0 = j * (KB + 2);
+#pragma unroll
+          for (int p = 0; p < KB; ++p)
+            if (o2[p] >= 0) cp_async8(stash(v0 + p), row + o2[p]);
+          cp_async8(stash(v0 + KB), row + o2d);
+          cp_async8(stash(v0 + KB + 1), row + o2y);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
       for (int j = 0; j < S; ++j) {
-        const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
+        const int v0 = j * (KB + 2);
         double* c = crow(j);
 #pragma unroll
-        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (o2[p] >= 0) ? __ldg(row + o2[p]) : 0.0;
-        DBN_CE(c, ett) = (o2d >= 0) ? __ldg(row + o2d) : 0.0;
-        DBN_CE(c, ezyt) = (o2y >= 0) ? __ldg(row + o2y) : 0.0;
+        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (fetch && o2[p] >= 0) ? *stash(v0 + p) : 0.0;
+        DBN_CE(c, ett) = fetch ? *stash(v0 + KB) : 0.0;
+        DBN_CE(c, ezyt) = fetch ? *stash(v0 + KB + 1) : 0.0;
       }
     }
     // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
@@ -743,10 +772,26 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
           for (int p = 0; p < NP; ++p) cu[((long long)dst * NP + p) * U] = t[p];
         };
+        // two rows per round trip (both loaded before either is stored; a pair never overlaps its own targets)
+        auto move_two = [&](int src_a, int src_b, int dlt_) {
+          double2 ta[NP], tb_[NP];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) ta[p] = __ldcg(cu + ((long long)src_a * NP + p) * U);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) tb_[p] = __ldcg(cu + ((long long)src_b * NP + p) * U);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) cu[((long long)(src_a + dlt_) * NP + p) * U] = ta[p];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) cu[((long long)(src_b + dlt_) * NP + p) * U] = tb_[p];
+        };
         if (birth) {
-          for (int r = S - 1; r >= ja; --r) move_row(r + 1, r);
+          int r = S - 1;
+          for (; r - 1 >= ja; r -= 2) move_two(r, r - 1, 1);
+          if (r >= ja) move_row(r + 1, r);
         } else if (death) {
-          for (int r = ja + 1; r < S; ++r) move_row(r - 1, r);
+          int r = ja + 1;
+          for (; r + 1 < S; r += 2) move_two(r, r + 1, -1);
+          if (r < S) move_row(r - 1, r);
         }
         if (!death) {
 #pragma unroll
