@@ -178,6 +178,17 @@ __global__ void init_state_kernel(int U, int N, int* npi, int* pi, int* S, int* 
 }
 
 
+struct TauList {
+  int len;
+  int c[DBN_SMAX];
+};
+__global__ void set_tau_kernel(int U, TauList t, int* S, int* tau) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  S[u] = t.len;
+  for (int j = 0; j < DBN_SMAX; ++j) tau[j * U + u] = (j < t.len) ? t.c[j] : 0;
+}
+
 typedef void (*chain_fn)(const ChainArgs);
 
 template <int KM, bool TRACE>
@@ -571,6 +582,26 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
                                                                        h->st_lam, h->st_del, h->st_mu);
   CU(h, cudaGetLastError());
   h->have_chain = true;
+  return DBN_OK;
+}
+
+int dbn_set_changepoints(dbn_handle* h, const int32_t* tau, int32_t len) {
+  if (!h || !tau) return DBN_ERR_INVALID;
+  if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_set_changepoints: call dbn_chain_init first");
+  if (h->it_done != 0) DBN_FAIL(h, DBN_ERR_STATE, "dbn_set_changepoints: the chain has already been advanced");
+  if (h->rp.method == DBN_H_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_set_changepoints: the homogeneous model has no changepoints");
+  if (len < 1 || len > DBN_SMAX - 1) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_set_changepoints: 1..%d changepoints (with the pseudo changepoint)", DBN_SMAX - 1);
+  if (tau[len - 1] != h->N + 2) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_set_changepoints: the last entry must be the pseudo changepoint N + 2 = %d (network.py:162)", h->N + 2);
+  for (int j = 0; j + 1 < len; ++j)
+    if (tau[j] < 2 || tau[j] > h->N || (j > 0 && tau[j] <= tau[j - 1]))
+      DBN_FAIL(h, DBN_ERR_INVALID, "dbn_set_changepoints: changepoints must be increasing values in 2..N");
+  CU(h, cudaSetDevice(h->cfg.device));
+  TauList t;
+  t.len = len;
+  for (int j = 0; j < DBN_SMAX; ++j) t.c[j] = (j < len) ? tau[j] : 0;
+  set_tau_kernel<<<(unsigned)((h->U + 255) / 256), 256, 0, h->stream>>>(h->U, t, h->st_S, h->st_tau);
+  CU(h, cudaGetLastError());
+  h->cache_valid = false;
   return DBN_OK;
 }
 

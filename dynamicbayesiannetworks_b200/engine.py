@@ -140,6 +140,12 @@ class DbnEngine:
         self.units = self.n * self.n_chains
         return self
 
+    def set_changepoints(self, tau):
+        """dbn_set_changepoints: start every unit from the changepoint list `tau` (ends with the pseudo changepoint N + 2)."""
+        t = np.ascontiguousarray(np.asarray(tau, dtype=np.int32).ravel())
+        self._check(self._lib.dbn_set_changepoints(self._h, _iptr(t), int(t.size)), 'dbn_set_changepoints')
+        return self
+
     def run(self, n_iter, replay=None, trace=False):
         """Advance every unit by n_iter iterations.  `replay`: dict of recorded draws (see pack_replay);
         returns the unpacked trace dict when trace (or replay) is requested, else None (asynchronous)."""

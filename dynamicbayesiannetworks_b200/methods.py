@@ -14,10 +14,12 @@ METHOD_IDS = {
     'seq_coup_nh_dbn': SEQ_DBN, 'seq-dbn': SEQ_DBN,
     'glob_coup_nh_dbn': GLOB_DBN, 'glob-dbn': GLOB_DBN,
     'fp_glob_coup_nh_dbn': FP_GLOB_DBN,   # network.py:245-257; CLI 'glob-dbn' of examples/full_parents_test.py:165-179
+    'fixed_nh_dbn': NH_DBN,               # network.py:178-189: the nh regressor on predefined changepoints (FIXED_CP below)
 }
+FIXED_CP = ('fixed_nh_dbn',)              # no changepoint move (bayesianPwLinearRegression.py:117), num_samples - 1
 METHOD_NAMES = {H_DBN: 'h_dbn', NH_DBN: 'varying_nh_dbn', SEQ_DBN: 'seq_coup_nh_dbn', GLOB_DBN: 'glob_coup_nh_dbn',
                 FP_GLOB_DBN: 'fp_glob_coup_nh_dbn'}
-NOT_YET = ('fixed_nh_dbn', 'var_glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_h_dbn', 'fp_seq_coup_nh_dbn',
+NOT_YET = ('var_glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_h_dbn', 'fp_seq_coup_nh_dbn',
            'fp_var_glob_coup_nh_dbn')
 
 
@@ -36,16 +38,19 @@ def run_params(method, N, fan_in=3, burn_in=0, thin=10, with_tau=True, **over):
     """dbn_run_params for `method` on N regression rows.
 
     num_samples / T: network.py:160 (nh: N), :195 (h: N+1; its ML gets N, bayesianLinearRegression.py:134-135),
-    :216 (seq: N-1), :240 (glob: N).  sigma^2 ~ IG(0.005, 0.005) for nh and seq
+    :216 (seq: N-1), :240 (glob: N), :185 (fixed nh: N-1).  sigma^2 ~ IG(0.005, 0.005) for nh and seq
     (bayesianPwLinearRegression.py:69-70, seqCoupledBayesianPwLinReg.py:44-45), IG(0.01, 0.01) for h and glob
     (bayesianLinearRegression.py:110-111, globCoupBayesianPwLinReg.py:43-44); lambda^2, delta^2 ~ IG(2, 0.2);
     changepoint prior p = 0.125 (priors.py:20); thinning 10 (network.py:359).
     """
     m = method_id(method)
-    p = dict(method=m, fan_in=fan_in, with_tau=int(bool(with_tau) and m != H_DBN), burn_in=burn_in, thin=thin,
+    fixed = method in FIXED_CP
+    p = dict(method=m, fan_in=fan_in, with_tau=int(bool(with_tau) and m != H_DBN and not fixed), burn_in=burn_in, thin=thin,
              a_lambda=2.0, b_lambda=0.2, a_delta=2.0, b_delta=0.2, cp_p=0.125)
     if m == H_DBN:
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N + 1), a_sigma=0.01, b_sigma=0.01)
+    elif m == NH_DBN and fixed:   # network.py:182-188 passes num_samples - 1
+        p.update(num_samples=N - 1, T_ml=float(N - 1), T_sigma=float(N - 1), a_sigma=0.005, b_sigma=0.005)
     elif m == NH_DBN:
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N), a_sigma=0.005, b_sigma=0.005)
     elif m == SEQ_DBN:

@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, METHOD_NAMES
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, METHOD_NAMES, FIXED_CP
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -23,6 +23,7 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'seq_coup_nh_dbn': ('Sequentilly Coupled Non-Homogeneous', 'Varying Parents'),
     'glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Varying Parents'),
     'fp_glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:246-247
+    'fixed_nh_dbn': ('Bayesian Non-Homogeneous', 'Varying Parents-Fixed changepoints'),   # network.py:179-180
 }
 
 
@@ -80,7 +81,7 @@ class Network():
         """network.py:398-416: all nodes (and all chains) advance together on the device instead of one regressor per
         node in a Python loop; edge scores are the thinned-chain frequencies of scores.py:155-194."""
         mid = method_id(method)
-        name = METHOD_NAMES[mid]
+        name = method if method in FIXED_CP else METHOD_NAMES[mid]
         if self.lag != 1:
             raise NotImplementedError('lag > 1 (network.py:92-122) is a later row of the scope table')
         dims = self.data[0].shape[1]
@@ -92,6 +93,8 @@ class Network():
         with DbnEngine(n_chains=self.n_chains, device=self.device, seed=self.seed) as eng:
             eng.build_stats(self.data, lag=self.lag)
             eng.chain_init(name, fan_in=self.fan_in, burn_in=int(self.burn_in), thin=self.thin)
+            if name in FIXED_CP:   # network.py:178-189: the predefined change points, pseudo changepoint included
+                eng.set_changepoints(self.change_points)
             N = eng.N
             traces = []
             window = self.window or (n_iter if self.keep_chain else 100)

@@ -189,6 +189,14 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p);
  *   trace_d/trace_i   : NULL, or host arrays [units, n_iter, DBN_TD_STRIDE] / [.., DBN_TI_STRIDE] to fill.
  * Without replay/trace the call is asynchronous on the handle's stream.
  */
+/*
+ * Start every unit from the changepoint list `tau` (1-based cut positions, increasing, the last one the pseudo
+ * changepoint N + 2) instead of [N + 2].  Call between dbn_chain_init and the first dbn_run.  With
+ * dbn_run_params.with_tau == 0 this is 'fixed_nh_dbn' (network.py:178-189: BayesianPieceWiseLinearRegression with
+ * predefined change points, bayesianPwLinearRegression.py:117 skips the changepoint move).
+ */
+int dbn_set_changepoints(dbn_handle* h, const int32_t* tau, int32_t len);
+
 int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d,
             int32_t* trace_i);
 

@@ -32,11 +32,12 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN = 0, 1, 2, 3, 4
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN = 0, 1, 2, 3, 4, 5
 METHOD_IDS = {
     'fp_glob_coup_nh_dbn': FP_GLOB_DBN, 'fp-glob-dbn': FP_GLOB_DBN,
     'h_dbn': H_DBN, 'h-dbn': H_DBN,
     'varying_nh_dbn': NH_DBN, 'nh-dbn': NH_DBN,
+    'fixed_nh_dbn': FIXED_NH_DBN,      # network.py:178-189: nh regressor, predefined changepoints, no changepoint move
     'seq_coup_nh_dbn': SEQ_DBN, 'seq-dbn': SEQ_DBN,
     'glob_coup_nh_dbn': GLOB_DBN, 'glob-dbn': GLOB_DBN,
 }
@@ -58,7 +59,8 @@ def method_constants(method, N):
         c.update(T_ml=N, T_sigma=N + 1, num_samples=N, a_sig=0.01, b_sig=0.01)
     elif m == NH_DBN:
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.005, b_sig=0.005)
-    elif m == SEQ_DBN:
+    elif m in (SEQ_DBN, FIXED_NH_DBN):
+        # seq: network.py:213-219; fixed nh: network.py:182-188 also passes num_samples - 1
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
     elif m in (GLOB_DBN, FP_GLOB_DBN):
         # network.py:237-243, :249-255 (num_samples = N for both); fpGlobCoupBpwLinReg.py:49-50 (IG(0.01, 0.01))
@@ -481,7 +483,7 @@ def _accept_glob(log_ratio, u):
     return u < math.exp(min(1.0, log_ratio))
 
 
-def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
+def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_tau=None):
     """One (node, chain) unit for `n_iter` iterations; returns a trace dict shaped like the golden files.
 
     Order of updates per iteration follows bayesianLinearRegression.py:114-147 (h),
@@ -498,10 +500,10 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True):
     c = method_constants(m, N)
     fp = m == FP_GLOB_DBN
     seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN)
-    has_tau = with_tau and m != H_DBN
+    has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
     KM, SM = (max(5, n) if fp else 5), 10
 
-    pi, tau = (list(features) if fp else []), [N + 2]
+    pi, tau = (list(features) if fp else []), ([int(c) for c in init_tau] if init_tau is not None else [N + 2])
     lam = sig = dlt = 1.0
     mu = np.zeros(len(pi) + 1)                                      # glob: current global mean (k entries)
     tr = {k_: np.full(n_iter, np.nan) for k_ in (

@@ -164,10 +164,13 @@ def _parse_move(ev, pos, end):
     return rec, pos
 
 
-def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
-    """Run Network.infer_network(method) with recording and write chain_<name>_<method>.npz."""
+def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_points=None):
+    """Run Network.infer_network(method) with recording and write chain_<name>_<method>.npz.
+    `change_points`: the predefined list of 'fixed_nh_dbn' (network.py:178-189), ending with the pseudo changepoint."""
     n = data_list[0].shape[1]
-    has_tau = method != 'h_dbn'
+    is_fixed = method == 'fixed_nh_dbn'              # segments but no changepoint move
+    has_tau = method not in ('h_dbn', 'fixed_nh_dbn')
+    multi_seg = method != 'h_dbn'
     is_seq = method == 'seq_coup_nh_dbn'
     is_fp = method == 'fp_glob_coup_nh_dbn'       # full parents: no parent-set move, design width = n
     is_glob = method == 'glob_coup_nh_dbn' or is_fp
@@ -177,7 +180,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
     random.seed(seed)
     _install_hooks()
     try:
-        net = Network([d.copy() for d in data_list], n_iter, burn_in, 1)
+        net = Network([d.copy() for d in data_list], n_iter, burn_in, 1, list(change_points) if is_fixed else [])
         per_node = []
         with contextlib.redirect_stdout(io.StringIO()):
             for i in range(n):
@@ -241,7 +244,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
         pos = start
         pi_vec = res['pi_vector']
         tau_vec = res['tau_vector']
-        cur_tau = [N + 2]
+        cur_tau = [int(c) for c in change_points] if is_fixed else [N + 2]
         cur_pi = [j for j in range(n) if j != i] if is_fp else []
         cur_mu = np.zeros(len(cur_pi) + 1)
         for it in range(n_iter):
@@ -250,7 +253,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
             e = ev[pos]; assert e[0] == 'gamma', (i, it, e)
             g['sig_shape'][i, it], g['sig_scale'][i, it], g['sigma2'][i, it] = e[1], e[2], 1.0 / e[3]
             pos += 1
-            for h in range(S if has_tau else 1):
+            for h in range(S if multi_seg else 1):
                 e = ev[pos]; assert e[0] == 'mvn', (i, it, h, e)
                 g['beta_mean'][i, it, h] = _pad_vec(e[1], KM)
                 g['beta_cov'][i, it, h] = _pad_mat(e[2], KM)
@@ -337,6 +340,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed):
         out['beta_cov_diag'] = np.diagonal(out.pop('beta_cov'), axis1=-2, axis2=-1).copy()
         out['mus_cov_diag'] = np.diagonal(out.pop('mus_cov'), axis1=-2, axis2=-1).copy()
     out['method'] = np.array(method)
+    if is_fixed:
+        out['change_points'] = np.array([int(c) for c in change_points], dtype=np.int32)
     out['n_iter'] = np.array(n_iter)
     out['burn_in'] = np.array(burn_in)
     out['seed'] = np.array(seed)
@@ -474,6 +479,10 @@ def main():
     syn, _, _ = make_synthetic(8, 200, n_changepoints=3, max_fan_in=3, seed=7)
     syn_long, _, _ = make_synthetic(6, 341, n_changepoints=2, max_fan_in=3, seed=11)
 
+    if 'fixed-only' in sys.argv:    # add the fixed-changepoint fixtures without re-minting the others
+        run_chain_golden('yeast', yeast, 'fixed_nh_dbn', n_iter=240, burn_in=40, seed=1, change_points=[12, 23, 35])
+        run_chain_golden('synth200', [syn], 'fixed_nh_dbn', n_iter=120, burn_in=20, seed=3, change_points=[51, 101, 151, 201])
+        return
     if 'fp-only' in sys.argv:       # add the full-parents fixtures without re-minting the others
         run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
         run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
@@ -494,6 +503,8 @@ def main():
     run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
     run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
     run_chain_golden('synth200', [syn], 'fp_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
+    run_chain_golden('yeast', yeast, 'fixed_nh_dbn', n_iter=240, burn_in=40, seed=1, change_points=[12, 23, 35])
+    run_chain_golden('synth200', [syn], 'fixed_nh_dbn', n_iter=120, burn_in=20, seed=3, change_points=[51, 101, 151, 201])
 
 
 if __name__ == '__main__':

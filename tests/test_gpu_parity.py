@@ -117,12 +117,14 @@ def test_chain_replay_vs_reference(eng_mod, path):
     with eng_mod(n_chains=1) as e:
         e.build_stats(data_list(g))
         e.chain_init(method, burn_in=burn_in)
+        if 'change_points' in g:            # 'fixed_nh_dbn' (network.py:178-189)
+            e.set_changepoints(g['change_points'])
         tr = e.run(n_iter, replay=golden_replay(g), trace=True)
         counts = e.counts()
     for key in ('pi_valid', 'pi_accept', 'npi', 'S'):
         assert np.array_equal(tr[key], g[key]), key
     assert np.array_equal(tr['pi_after'], g['pi_after']), 'pi_after'
-    if method != 'h_dbn':
+    if method not in ('h_dbn', 'fixed_nh_dbn'):
         for key in ('tau_valid', 'tau_accept'):
             assert np.array_equal(tr[key], g[key]), key
     assert np.array_equal(tr['tau_after'], g['tau_after']), 'tau_after'
@@ -262,6 +264,13 @@ def test_network_dropin(eng_mod):
         if method == 'seq_coup_nh_dbn':
             assert len(r['delta_sqr_vector']) == 301
         pickle.loads(pickle.dumps(net))
+    fixed = Network(data, 300, 100, 1, [12, 23, 35])          # network.py:178-189: predefined change points
+    fixed.infer_network('fixed_nh_dbn')
+    assert all(t == [12, 23, 35] for t in fixed.chain_results['tau_vector'])
+    assert np.isfinite(np.array(fixed.proposed_adj_matrix)).all()
+    assert fixed.network_args['type'] == 'Varying Parents-Fixed changepoints'
+    with pytest.raises(RuntimeError):                          # the list must end with the pseudo changepoint N + 2
+        Network(data, 10, 0, 1, [12, 23]).infer_network('fixed_nh_dbn')
     big = Network(data, 400, 100, 1, n_chains=128)
     big.infer_network('nh-dbn')
     assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)

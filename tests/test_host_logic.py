@@ -11,11 +11,14 @@ from oracle import dbn_oracle as O
 
 def test_method_table_matches_oracle():
     from dynamicbayesiannetworks_b200.methods import run_params, METHOD_IDS
-    for name in ('h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'h-dbn', 'nh-dbn', 'seq-dbn', 'glob-dbn'):
+    for name in ('h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'h-dbn', 'nh-dbn', 'seq-dbn', 'glob-dbn', 'fixed_nh_dbn'):
         for N in (33, 119, 1999):
             p = run_params(name, N)
             c = O.method_constants(name, N)
-            assert METHOD_IDS[name] == O.METHOD_IDS[name]
+            if name == 'fixed_nh_dbn':      # same device kernel as nh, without the changepoint move
+                assert METHOD_IDS[name] == O.NH_DBN and p['with_tau'] == 0
+            else:
+                assert METHOD_IDS[name] == O.METHOD_IDS[name]
             assert (p['T_ml'], p['T_sigma'], p['num_samples']) == (c['T_ml'], c['T_sigma'], c['num_samples'])
             assert (p['a_sigma'], p['b_sigma'], p['a_lambda'], p['b_lambda'], p['a_delta'], p['b_delta']) == (
                 c['a_sig'], c['b_sig'], c['a_lam'], c['b_lam'], c['a_del'], c['b_del'])

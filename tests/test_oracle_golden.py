@@ -69,7 +69,7 @@ def test_chain_replay(path):
     edge = np.zeros((n, n)); nonempty = np.zeros(n)
     cp_hist = np.zeros((n, N + 3)); cp_kept = np.zeros(n)
     for node in range(n):
-        tr = O.run_chain(method, X, Y, node, n_iter, O.ReplayDraws(g, node))
+        tr = O.run_chain(method, X, Y, node, n_iter, O.ReplayDraws(g, node), init_tau=g.get('change_points'))
         for key in ('pi_valid', 'pi_accept', 'npi', 'pi_after', 'S', 'tau_after'):
             assert np.array_equal(tr[key], g[key][node]), (key, node)
         if method != 'h_dbn':
