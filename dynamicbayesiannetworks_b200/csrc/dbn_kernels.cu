@@ -40,7 +40,12 @@ __global__ void build_v_kernel(const double* __restrict__ raw, const int* __rest
 }
 
 // WRITE == false: per-(chunk, column) totals.  WRITE == true: running sums, starting from the sum of the totals of the
-// earlier chunks.
+// earlier chunks.  Every thread serves PREFIX_CPT columns (PREFIX_BLOCK apart, so each store instruction is coalesced):
+// the chunk's `v` rows are staged once per PREFIX_BLOCK * PREFIX_CPT columns instead of once per PREFIX_BLOCK.
+#ifndef DBN_PREFIX_CPT
+#define DBN_PREFIX_CPT 4
+#endif
+constexpr int PREFIX_CPT = DBN_PREFIX_CPT;
 template <bool WRITE>
 __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
                                                               const unsigned short* __restrict__ colB, int N, int W, long long R,
@@ -50,22 +55,45 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
   const int len = min(Lc, N - t0);
   for (int i = threadIdx.x; i < len * W; i += PREFIX_BLOCK) sv[i] = V[(long long)t0 * W + i];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * PREFIX_BLOCK + threadIdx.x;
-  if (p >= R) return;
-  const int ca = colA[p], cb = colB[p];
+  const long long p0 = (long long)blockIdx.x * (PREFIX_BLOCK * PREFIX_CPT) + threadIdx.x;
+  int ca[PREFIX_CPT], cb[PREFIX_CPT];
+  bool live[PREFIX_CPT];
+  double acc[PREFIX_CPT];
+#pragma unroll
+  for (int j = 0; j < PREFIX_CPT; ++j) {
+    const long long p = p0 + (long long)j * PREFIX_BLOCK;
+    live[j] = p < R;
+    ca[j] = live[j] ? colA[p] : 0;
+    cb[j] = live[j] ? colB[p] : 0;
+    acc[j] = 0.0;
+  }
   if (!WRITE) {
-    double acc = 0.0;
-    for (int t = 0; t < len; ++t) acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
-    chunk[(long long)blockIdx.y * R + p] = acc;
+    for (int t = 0; t < len; ++t) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j) acc[j] = fma(sv[t * W + ca[j]], sv[t * W + cb[j]], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < PREFIX_CPT; ++j)
+      if (live[j]) chunk[(long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK] = acc[j];
   } else {
     // offset of this chunk = sum of the totals of the chunks before it, added in chunk order (coalesced, L2-resident)
-    double acc = 0.0;
-    for (int c = 0; c < (int)blockIdx.y; ++c) acc += chunk[(long long)c * R + p];
-    if (blockIdx.y == 0) __stcs(table + p, 0.0);  // row 0
-    double* out = table + (long long)(t0 + 1) * R + p;
+    for (int c = 0; c < (int)blockIdx.y; ++c) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j)
+        if (live[j]) acc[j] += chunk[(long long)c * R + p0 + (long long)j * PREFIX_BLOCK];
+    }
+    if (blockIdx.y == 0) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j)
+        if (live[j]) __stcs(table + p0 + (long long)j * PREFIX_BLOCK, 0.0);  // row 0
+    }
+    double* out = table + (long long)(t0 + 1) * R + p0;
     for (int t = 0; t < len; ++t) {
-      acc = fma(sv[t * W + ca], sv[t * W + cb], acc);
-      __stcs(out, acc);  // streaming store: the table is far larger than L2
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j) {
+        acc[j] = fma(sv[t * W + ca[j]], sv[t * W + cb[j]], acc[j]);
+        if (live[j]) __stcs(out + (long long)j * PREFIX_BLOCK, acc[j]);  // streaming store: the table is far larger than L2
+      }
       out += R;
     }
   }
@@ -336,7 +364,7 @@ static int launch_prefix(dbn_handle* h) {
   build_v_kernel<<<296, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, N, n, h->d_V);
   CU(h, cudaGetLastError());
   const size_t smem = (size_t)h->Lc * W * sizeof(double);
-  dim3 grid((unsigned)((h->R + PREFIX_BLOCK - 1) / PREFIX_BLOCK), (unsigned)h->n_chunks);
+  dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
   prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   CU(h, cudaGetLastError());
   prefix_kernel<true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
@@ -397,8 +425,9 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     }
     const size_t row_bytes = (size_t)h->W * sizeof(double);
     int Lc = (int)(96 * 1024 / row_bytes);
-    if (Lc > 32) Lc = 32;  // measured on B200 (scripts/prefix_tune.py): 32 rows per chunk is the fastest build
-    if (const char* e = getenv("DBN_PREFIX_LC")) Lc = std::min(Lc, std::max(1, atoi(e)));  // tuning knob
+    const int Lmax = Lc;
+    if (Lc > 32) Lc = 32;  // measured on B200 (scripts/prefix_tune.py)
+    if (const char* e = getenv("DBN_PREFIX_LC")) Lc = std::min(Lmax, std::max(1, atoi(e)));  // tuning knob
     if (Lc < 1) Lc = 1;
     h->Lc = Lc;
     h->n_chunks = (int)((N + Lc - 1) / Lc);
