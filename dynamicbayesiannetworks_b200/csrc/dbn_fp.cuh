@@ -21,7 +21,11 @@
 
 namespace dbn {
 
-constexpr int FP_BLOCK = 128;
+constexpr int FP_BLOCK_MAX = 128;
+// threads per block: one warp while a matrix row fits it (k <= 32: the block barriers are then warp-local and the idle
+// warps of a wider block no longer wait in them — 54 % of all stall samples at k = 11, profiles/r1_v9), else 64 / 128
+inline int fp_block_threads(int k) { return k <= 32 ? 32 : (k <= 64 ? 64 : 128); }
+#define FP_BLOCK ((int)blockDim.x)
 constexpr int FP_NMAT = 5;  // A/L, W, M (tau), M (tau*), Q
 constexpr int FP_NVEC = 12;
 
@@ -64,7 +68,7 @@ __device__ __forceinline__ double fp_block_sum(double x, double* red) {
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < FP_BLOCK / 32; ++w) t += red[w];
+  for (int w = 0; w < (FP_BLOCK >> 5); ++w) t += red[w];
   return t;
 }
 
@@ -83,15 +87,16 @@ __device__ void fp_load_segment(const Table& tb, int node, int lo, int hi, doubl
   const double* __restrict__ ph = tb.base + (long long)hi * tb.row_stride;
   const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
   const int nb = tb.zz_size + node * (tb.n + 2);
-  for (int a = 0; a < k; ++a) {
-    const int fa = fp_col(a, node);
-    const int base = fa * (fa + 1) / 2;
-    for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
-      const int fb = fp_col(b, node);
-      const double v = lam * (__ldg(ph + base + fb) - __ldg(pl + base + fb)) + (a == b ? 1.0 : 0.0);
-      A[a * ld + b] = v;
-      A[b * ld + a] = v;
-    }
+  for (int e = threadIdx.x; e < k * (k + 1) / 2; e += FP_BLOCK) {
+    int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);  // row of packed entry e; corrected for rounding below
+    while (a * (a + 1) / 2 > e) --a;
+    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+    const int b = e - a * (a + 1) / 2;
+    const int fa = fp_col(a, node), fb = fp_col(b, node);
+    const int off = fa * (fa + 1) / 2 + fb;
+    const double v = lam * (__ldg(ph + off) - __ldg(pl + off)) + (a == b ? 1.0 : 0.0);
+    A[a * ld + b] = v;
+    A[b * ld + a] = v;
   }
   for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
     const int fa = fp_col(a, node);
@@ -112,15 +117,23 @@ __device__ void fp_symv(const double* M, int ld, int k, const double* x, double*
 }
 
 // in-place lower Cholesky of the full symmetric matrix A (upper part left untouched); returns ln det A
-__device__ double fp_cholesky(double* A, int ld, int k) {
-  double logdet = 0.0;
+__device__ double fp_cholesky(double* A, int ld, int k, double* idiag) {  // idiag[j] = 1 / L[j][j]
+  double mant = 1.0;  // product of the pivots l_j = sqrt(d_j) as mantissa x 2^expo: one log per factorisation
+  int expo = 0;
   for (int j = 0; j < k; ++j) {
     __syncthreads();  // the previous column's trailing update is complete
     const double l = sqrt(A[j * ld + j]);
-    logdet += log(l);
+    {
+      int ex;
+      mant = frexp(mant * l, &ex);
+      expo += ex;
+    }
     __syncthreads();  // every thread has read the pivot before it is overwritten
-    if (threadIdx.x == 0) A[j * ld + j] = l;
     const double il = 1.0 / l;
+    if (threadIdx.x == 0) {
+      A[j * ld + j] = l;
+      idiag[j] = il;
+    }
     for (int i = j + 1 + threadIdx.x; i < k; i += FP_BLOCK) A[i * ld + j] *= il;
     __syncthreads();
     // trailing update, thread per column c: A[i][c] -= A[i][j] A[c][j] for i >= c
@@ -130,17 +143,17 @@ __device__ double fp_cholesky(double* A, int ld, int k) {
     }
   }
   __syncthreads();
-  return 2.0 * logdet;
+  return 2.0 * (log(mant) + (double)expo * 0.69314718055994530942);
 }
 
 // W = L^-1 (lower triangular, zeros above the diagonal): forward substitution on all columns at once
-__device__ void fp_trinv(const double* L, double* W, int ld, int k) {
+__device__ void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag) {
   for (int c = threadIdx.x; c < k; c += FP_BLOCK) {
-    for (int i = 0; i < k; ++i) {
+    for (int i = 0; i < c; ++i) W[i * ld + c] = 0.0;
+    for (int i = c; i < k; ++i) {
       double acc = (i == c) ? 1.0 : 0.0;
-      if (i > c)
-        for (int j = c; j < i; ++j) acc -= L[i * ld + j] * W[j * ld + c];
-      W[i * ld + c] = (i >= c) ? acc / L[i * ld + i] : 0.0;
+      for (int j = c; j < i; ++j) acc -= L[i * ld + j] * W[j * ld + c];
+      W[i * ld + c] = acc * idiag[i];
     }
   }
   __syncthreads();
@@ -207,8 +220,8 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
     const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
     fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
     r.s += *s_tmp;
-    r.ld += fp_cholesky(A, ld, k);
-    fp_trinv(A, W, ld, k);
+    r.ld += fp_cholesky(A, ld, k, t);
+    fp_trinv(A, W, ld, k, t);
     fp_trmv(W, ld, k, g, t);                 // t = L^-1 g
     r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
     fp_trmv_t(W, ld, k, t, x);               // x = A^-1 g
@@ -229,7 +242,7 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
 }
 
 template <bool TRACE>
-__global__ void __launch_bounds__(FP_BLOCK) fp_glob_kernel(const FpArgs a) {
+__global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
   extern __shared__ double sm[];
   const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
   const int tid = threadIdx.x;
@@ -297,8 +310,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_glob_kernel(const FpArgs a) {
           }
           __syncthreads();
           const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
-          fp_cholesky(A, ld, k);
-          fp_trinv(A, W, ld, k);
+          fp_cholesky(A, ld, k, t);
+          fp_trinv(A, W, ld, k, t);
           fp_trmv(W, ld, k, x, t);
           q_sum += rho - lam * fp_dot(t, t, k, red);
           fp_trmv(W, ld, k, rhs, t);
@@ -436,8 +449,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_glob_kernel(const FpArgs a) {
             rhs[i] = a_cur[i] / sig2 + mu[i];
           }
           __syncthreads();
-          const double ldq_cur = fp_cholesky(Q, ld, k);
-          fp_trinv(Q, W, ld, k);
+          const double ldq_cur = fp_cholesky(Q, ld, k, t);
+          fp_trinv(Q, W, ld, k, t);
           fp_trmv(W, ld, k, rhs, t);
           fp_trmv_t(W, ld, k, t, mean);
           if (TRACE && td)
@@ -457,8 +470,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_glob_kernel(const FpArgs a) {
             rhs[i] = a_star[i] / sig2;
           }
           __syncthreads();
-          const double ldq_star = fp_cholesky(Q, ld, k);
-          fp_trinv(Q, W, ld, k);
+          const double ldq_star = fp_cholesky(Q, ld, k, t);
+          fp_trinv(Q, W, ld, k, t);
           fp_trmv(W, ld, k, rhs, t);
           fp_trmv_t(W, ld, k, t, mean);
           if (replay) {

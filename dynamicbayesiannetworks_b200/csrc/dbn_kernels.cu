@@ -801,10 +801,10 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
   if (trace) {
     CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fp_glob_kernel<true><<<h->fp_grid, FP_BLOCK, smem, h->stream>>>(a);
+    fp_glob_kernel<true><<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
   } else {
     CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fp_glob_kernel<false><<<h->fp_grid, FP_BLOCK, smem, h->stream>>>(a);
+    fp_glob_kernel<false><<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
   }
   CUX(cudaGetLastError());
   h->it_done += n_iter;
