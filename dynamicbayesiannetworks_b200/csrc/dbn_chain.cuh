@@ -164,8 +164,11 @@ __device__ __forceinline__ double sqnorm_k(const double (&x)[KM]) {
   return dot<KM>(x, x);
 }
 
+#ifndef DBN_CHAIN_MINB
+#define DBN_CHAIN_MINB 1
+#endif
 template <int METHOD, int KM, bool TRACE>
-__global__ void __launch_bounds__(CHAIN_BLOCK) chain_kernel(const ChainArgs a) {
+__global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(const ChainArgs a) {
   constexpr bool SEQ = METHOD == DBN_SEQ_DBN;
   constexpr bool GLOB = METHOD == DBN_GLOB_DBN;
   constexpr bool HOMOG = METHOD == DBN_H_DBN;
