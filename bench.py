@@ -212,13 +212,28 @@ def main():
     eng.build_stats([data])
     eng.chain_init(METHOD, fan_in=FAN_IN, burn_in=0)
     local_counts = parallel.counts_tensor(eng)
-    global_counts = torch.empty_like(local_counts)
+    global_counts = [torch.empty_like(local_counts), torch.empty_like(local_counts)]
+    pending = [None, None]
     units = N_GENES * CHAINS_PER_GPU
+    step_no = [0]
 
     def step():
+        """One thinning window on every unit, then the all-reduce of the count block over the ranks.  The block is
+        snapshotted on the kernel's stream and reduced on NCCL's stream (async_op), so the next window's kernel does
+        not wait for the collective; a snapshot buffer is reused only after its reduction has finished."""
         eng.run(WINDOW)
         if world > 1:
-            parallel.allreduce_counts(local_counts, out=global_counts)
+            j = step_no[0] & 1
+            step_no[0] += 1
+            if pending[j] is not None:
+                pending[j].wait()
+            _, pending[j] = parallel.allreduce_counts(local_counts, out=global_counts[j], async_op=True)
+
+    def drain():
+        for j in (0, 1):
+            if pending[j] is not None:
+                pending[j].wait()
+                pending[j] = None
 
     def barrier():
         if world > 1:
@@ -227,6 +242,7 @@ def main():
 
     for _ in range(W):
         step()
+    drain()
     barrier()
     eng.reset_counters()
     sampler = ClockSampler(local_rank)
@@ -237,6 +253,7 @@ def main():
     ev0.record()
     for _ in range(K):
         step()
+    drain()          # the last reductions are inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -263,10 +280,15 @@ def main():
     for _ in range(Ke):
         eng.build_stats([data])
         eng.run(WINDOW)
-        cnt = eng.counts()
+        if world > 1:       # the caller reads the counts of ALL chains: reduce over the ranks, then device -> host
+            g = parallel.allreduce_counts(local_counts, out=global_counts[0])
+            host_counts = g.cpu().numpy()
+            d2h = host_counts.nbytes
+        else:
+            cnt = eng.counts()
+            d2h = sum(v.nbytes for v in cnt.values())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    d2h = sum(v.nbytes for v in cnt.values())
     if world > 1:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,7 +328,7 @@ def main():
                      'fp64': {'achieved_gflops': ctr['algorithmic_flops'] / K / avg_launch_s / 1e9,
                               'peak_gflops_measured_dfma': fp64_peak}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'steps': Ke, 'what': 'dbn_build_stats(host series) + dbn_run(10 iterations) + dbn_read_counts(host) per step'},
+                'steps': Ke, 'what': 'dbn_build_stats(host series) + dbn_run(10 iterations) + (N > 1: all-reduce of the counts) + counts to host, per step'},
         'gpu_launches': K * (1 if world == 1 else 1),
         'clocks': clocks,
     }
