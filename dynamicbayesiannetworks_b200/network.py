@@ -90,7 +90,15 @@ class Network():
         for i in range(dims):
             self.set_network_configuration(i)
         n_iter = int(self.chain_length)
-        with DbnEngine(n_chains=self.n_chains, device=self.device, seed=self.seed) as eng:
+        # under torch.distributed (one process per GPU) the chains are sharded over the ranks and the count matrices
+        # all-reduced at the end: every rank returns the scores of ALL chains
+        rank, world = parallel.dist_rank_world()
+        chain_offset, n_local = parallel.shard_chains(self.n_chains, rank, world)
+        if n_local < 1:
+            raise ValueError('n_chains = %d is fewer than the %d ranks' % (self.n_chains, world))
+        if world > 1 and self.keep_chain:
+            raise ValueError('keep_chain (per-iteration histories) is a single-process feature')
+        with DbnEngine(n_chains=n_local, device=self.device, seed=self.seed, chain_offset=chain_offset) as eng:
             eng.build_stats(self.data, lag=self.lag)
             eng.chain_init(name, fan_in=self.fan_in, burn_in=int(self.burn_in), thin=self.thin)
             if name in FIXED_CP:   # network.py:178-189: the predefined change points, pseudo changepoint included
@@ -107,7 +115,7 @@ class Network():
                 else:
                     run(w)
                 done += w
-            counts = eng.counts()
+            counts = eng.counts() if world == 1 else parallel.global_counts(eng)
             self.counters = eng.counters()
         self._finish(name, mid, dims, N, counts, traces)
         return self

@@ -48,6 +48,26 @@ def allreduce_counts(local, out=None, async_op=False):
     return (out, None) if async_op else out
 
 
+def dist_rank_world():
+    """(rank, world_size) of the default process group, (0, 1) without one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def global_counts(engine):
+    """All-reduce the engine's count block over the ranks (NCCL, on device memory) and return it split into the named
+    matrices, like DbnEngine.counts()."""
+    from .engine import split_counts
+    engine.sync()                 # the chain kernels ran on the engine's own stream
+    total = allreduce_counts(counts_tensor(engine))
+    return split_counts(total.cpu().numpy().astype(np.int64), engine.n, engine.N)
+
+
 def edge_scores_from_counts(edge, nonempty):
     """proposed_adj_matrix: edge[i][j] / #kept non-empty parent sets of node i (scores.py:184-192).  A node whose
     every kept sample had an empty parent set makes the reference divide by zero; 0.0 is returned here."""

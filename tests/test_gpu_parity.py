@@ -438,3 +438,21 @@ def test_c4_full_size_properties(eng_mod):
         stt = O.segment_stats(X, Y[:, node[b]], pi[b], tau[b])
         ref = O.log_ml(stt, [np.zeros(len(pi[b]) + 1)] * len(tau[b]), 0.005, 0.005, lam[b], N)
         assert abs(got[b] - ref) <= LOGML_RTOL * abs(ref), (b, got[b], ref)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU: chains sharded over two ranks + NCCL all-reduce of the counts == the unsharded run (needs 2 GPUs)
+# ---------------------------------------------------------------------------------------------------------
+def test_network_sharded_over_two_gpus_matches_unsharded():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from helpers import ROOT
+    import os
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29571', os.path.join(ROOT, 'scripts', 'dist_network_check.py')]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert res.stdout.count('sharded == unsharded: True') == 8, res.stdout[-3000:]
