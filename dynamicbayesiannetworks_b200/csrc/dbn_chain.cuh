@@ -804,15 +804,19 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
     for (int i = 0; i < KM; ++i) a.st_mu[i * a.U + u] = mu[i];
   }
   }
-  // ---- work counters: one atomic per warp
-  unsigned long long v[5] = {(unsigned long long)n_it, wk.evals, wk.segs, wk.bytes, wk.flops};
-  __syncwarp();
+  // ---- work counters: summed per block through shared memory (no warp shuffles: see profiles/r1_notes.md), one
+  // global atomic per counter and block
+  const unsigned long long v[5] = {(unsigned long long)n_it, wk.evals, wk.segs, wk.bytes, wk.flops};
+  unsigned long long* const s_cnt = reinterpret_cast<unsigned long long*>(s_tau);  // 5 x CHAIN_BLOCK x 8 B <= s_tau
+  static_assert(5 * CHAIN_BLOCK * sizeof(unsigned long long) <= SMAX * CHAIN_BLOCK * sizeof(int), "counter scratch fits s_tau");
+  __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    unsigned long long x = v[c];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&a.counters[c], x);
+  for (int c = 0; c < 5; ++c) s_cnt[c * CHAIN_BLOCK + tid] = v[c];
+  __syncthreads();
+  if (tid < 5) {
+    unsigned long long t = 0;
+    for (int i = 0; i < CHAIN_BLOCK; ++i) t += s_cnt[tid * CHAIN_BLOCK + i];
+    if (t) atomicAdd(&a.counters[tid], t);
   }
 }
 

@@ -60,15 +60,15 @@ __host__ __device__ inline int fp_rd_stride(int k) { return 3 + k + DBN_SMAX * k
 __host__ __device__ inline int fp_td_stride(int k) { return 10 + 3 * k + 3 * DBN_SMAX * k; }
 
 // ---- block-level building blocks (all threads of the block call them) -----------------------------------------------
+// sum of x over the block, the same value (same order of additions) in every thread.  Through shared memory and block
+// barriers only: warp shuffles are emitted without a warp barrier where ptxas considers the warp convergent, which is
+// not safe after divergent loops (profiles/r1_notes.md).
 __device__ __forceinline__ double fp_block_sum(double x, double* red) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();  // red is free (every thread has read the previous sum)
+  red[threadIdx.x] = x;
   __syncthreads();
   double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < (FP_BLOCK >> 5); ++w) t += red[w];
+  for (int w = 0; w < FP_BLOCK; ++w) t += red[w];
   return t;
 }
 
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
   double* vec = sm;
   double* g = vec + 0 * k, *mu = vec + 1 * k, *mu_star = vec + 2 * k, *t = vec + 3 * k, *x = vec + 4 * k, *z = vec + 5 * k;
   double* mean = vec + 6 * k, *a_cur = vec + 7 * k, *a_star = vec + 8 * k, *tmp = vec + 9 * k, *rhs = vec + 10 * k, *e = vec + 11 * k;
-  double* red = vec + FP_NVEC * k;       // [8]
-  double* sc = red + 8;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
+  double* red = vec + FP_NVEC * k;       // [FP_BLOCK_MAX]
+  double* sc = red + FP_BLOCK_MAX;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
   int* s_tau = reinterpret_cast<int*>(sc + 8);
   int* s_tas = s_tau + SMAX;
   int* s_int = s_tas + SMAX;             // [8]
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
 }
 
 inline size_t fp_smem_bytes(int k, bool mats_in_smem) {
-  size_t b = (size_t)(FP_NVEC * k + 16) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
+  size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 8) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
   if (mats_in_smem) b += (size_t)FP_NMAT * fp_ld(k) * k * sizeof(double);
   return b;
 }
