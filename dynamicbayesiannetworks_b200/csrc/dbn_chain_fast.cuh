@@ -34,10 +34,10 @@
 namespace dbn {
 
 #ifndef DBN_FAST_BLOCK
-#define DBN_FAST_BLOCK 128
+#define DBN_FAST_BLOCK 192   // 2 blocks of 6 warps per SM measured 2.4 % faster than 3 of 4 (same 12 warps; 168 registers)
 #endif
 #ifndef DBN_FAST_MINB
-#define DBN_FAST_MINB 3
+#define DBN_FAST_MINB 2
 #endif
 constexpr int FAST_BLOCK = DBN_FAST_BLOCK;
 constexpr int SEG_ROWS = DBN_SMAX - 1;  // <= 9 segments
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   __syncthreads();
   if (tid < 8) {
     unsigned long long t = 0;
-    for (int i = 0; i < FAST_BLOCK; ++i) t += s_cnt[tid * FAST_BLOCK + ((i + tid) & (FAST_BLOCK - 1))];
+    for (int i = 0; i < FAST_BLOCK; ++i) t += s_cnt[tid * FAST_BLOCK + i];
     if (t) atomicAdd(&a.counters[tid], t);
   }
 }
