@@ -143,9 +143,46 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // (re)build the cache from the table: canonical slots = parent positions, end boundary of segment j -> row j
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = (s - 1 < npi) ? pi[s - 1] : -1;
-    for (int j = 0; j < S; ++j) {
-      double* c = crow(j);
-      gather(DBN_SEG_END(tau_cur(j), j, S, N), [&](int e, double v) { DBN_CE(c, e) = v; });
+    // three rows per round trip: their table entries are requested with 8-byte cp.async into the three staging
+    // buffers, then each buffer is written out as the row's 16-byte pairs
+    for (int j0 = 0; j0 < S; j0 += 3) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int j = j0 + b;
+        if (j < S) {
+          const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
+          double* dst = sbuf + b * BUF;
+#pragma unroll
+          for (int i = 0; i < KM; ++i) {
+            const bool oi = (i == 0) || cg[i] >= 0;
+            const int fi = (i == 0) ? 0 : cg[i] + 1;
+#pragma unroll
+            for (int jj = 0; jj <= i; ++jj) {
+              const bool oj = (jj == 0) || cg[jj] >= 0;
+              const int fj = (jj == 0) ? 0 : cg[jj] + 1;
+              const int hi = max(fi, fj), lo = min(fi, fj);
+              if (oi && oj) cp_async8(&DBN_SE(dst, DBN_TRI(i, jj)), row + hi * (hi + 1) / 2 + lo);
+              else DBN_SE(dst, DBN_TRI(i, jj)) = 0.0;
+            }
+            if (oi) cp_async8(&DBN_SE(dst, KT + i), row + nb + fi);
+            else DBN_SE(dst, KT + i) = 0.0;
+          }
+          cp_async8(&DBN_SE(dst, KT + KM), row + nb + n + 1);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int j = j0 + b;
+        if (j < S) {
+          double2* cu = reinterpret_cast<double2*>(a.cache) + u;
+          const double* src = sbuf + b * BUF;
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            cu[((long long)j * NP + p) * U] = *reinterpret_cast<const double2*>(src + p * (2 * FAST_BLOCK));
+        }
+      }
     }
   } else {
 #pragma unroll

@@ -168,11 +168,14 @@ struct dbn_handle {
   int zz_size = 0;
   double* d_raw = nullptr;
   int* d_xrow = nullptr;
+  std::vector<int> seg_len;  // series-segment lengths the row map on the device was built for
   double* d_V = nullptr;
   unsigned short *d_colA = nullptr, *d_colB = nullptr;
   double* d_chunk = nullptr;
   double* d_table = nullptr;
   bool have_stats = false;
+  void* pinned = nullptr;  // host bounce buffer of dbn_read_counts
+  size_t pinned_bytes = 0;
   // chain
   bool have_chain = false;
   dbn_run_params rp;
@@ -342,6 +345,7 @@ void dbn_destroy(dbn_handle* h) {
   free_stats(h);
   free_chain(h);
   free_dev(h->d_counters);
+  if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -447,10 +451,13 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
   }
   // same geometry: the table is rebuilt in place and the chain state (if any) carries on over the new data
   CU(h, cudaMemcpyAsync(h->d_raw, data, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  int rc = launch_prefix(h);
+  if (!same_geometry || h->seg_len != std::vector<int>(seg_len, seg_len + n_seg)) {
+    CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->seg_len.assign(seg_len, seg_len + n_seg);
+  }
+  CU(h, cudaStreamSynchronize(h->stream));  // the caller's buffer and the staging vector are free again
+  int rc = launch_prefix(h);                 // asynchronous: overlaps whatever the host does next
   if (rc != DBN_OK) return rc;
-  CU(h, cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
   h->have_stats = true;
   h->cache_valid = false;  // the chain (if any) re-gathers its boundary rows from the new table
   return DBN_OK;
@@ -829,8 +836,23 @@ int dbn_read_counts(dbn_handle* h, int64_t* out) {
   if (!h || !out) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_read_counts: call dbn_chain_init first");
   CU(h, cudaSetDevice(h->cfg.device));
-  CU(h, cudaMemcpyAsync(out, h->d_counts, (size_t)h->counts_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  // through a pinned bounce buffer owned by the handle: a device -> pageable copy runs at a fraction of the link rate
+  const size_t bytes = (size_t)h->counts_elems * sizeof(int64_t);
+  if (h->pinned_bytes < bytes) {
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinned_bytes = 0;
+    if (cudaMallocHost(&h->pinned, bytes) == cudaSuccess) h->pinned_bytes = bytes;
+    else cudaGetLastError();  // no pinned memory: fall back to the direct copy below
+  }
+  if (h->pinned_bytes >= bytes) {
+    CU(h, cudaMemcpyAsync(h->pinned, h->d_counts, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, h->pinned, bytes);
+  } else {
+    CU(h, cudaMemcpyAsync(out, h->d_counts, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
   return DBN_OK;
 }
 

@@ -72,7 +72,8 @@ class DbnEngine:
         n = segs[0].shape[1]
         if any(s.ndim != 2 or s.shape[1] != n for s in segs):
             raise ValueError('all data segments must be [len, n] with the same n')
-        flat = np.ascontiguousarray(np.concatenate(segs, axis=0))
+        # a single series is passed as it is (no host copy: a pinned caller buffer stays pinned for the H2D copy)
+        flat = segs[0] if len(segs) == 1 else np.ascontiguousarray(np.concatenate(segs, axis=0))
         seg_len = np.array([s.shape[0] for s in segs], dtype=np.int32)
         self._check(self._lib.dbn_build_stats(self._h, _dptr(flat), _iptr(seg_len), len(segs), n, int(lag)), 'dbn_build_stats')
         self.n = n
