@@ -35,9 +35,8 @@ struct ChainArgs {
   double* st_del;
   double* st_mu;  // [KMAX][U]
   // h / nh fast path (dbn_chain_fast.cuh): per-unit cache of the current state's boundary rows
-  double* cache;  // [BSLOTS][NE][U]
+  double* cache;  // [BSLOTS][NP][U] pairs of doubles: prefix-table rows at the segment boundaries (dbn_chain_fast.cuh)
   int* st_cg;     // [PMAX][U] gene id held by column slot s+1, -1 = empty
-  int* st_bslot;  // [SMAX][U] cache slot of boundary j+1
   int refresh;    // 1: rebuild the cache from the table at kernel start
   // counts (contiguous block): edge[n][n], nonempty[n], cp_hist[n][N+3], cp_kept[n]
   unsigned long long* edge;

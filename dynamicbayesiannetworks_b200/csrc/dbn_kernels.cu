@@ -185,7 +185,7 @@ struct dbn_handle {
   double *st_sig = nullptr, *st_lam = nullptr, *st_del = nullptr, *st_mu = nullptr;
   // h / nh fast path: boundary-row cache, column slots, boundary slots
   double* d_cache = nullptr;
-  int *st_cg = nullptr, *st_bslot = nullptr;
+  int* st_cg = nullptr;
   bool cache_valid = false;
   // full-parents globally coupled chain: global mean [n][U], per-block matrix workspace (large n only)
   double *st_mu_fp = nullptr, *d_fp_ws = nullptr;
@@ -330,7 +330,6 @@ static void free_chain(dbn_handle* h) {
   free_dev(h->st_mu);
   free_dev(h->d_cache);
   free_dev(h->st_cg);
-  free_dev(h->st_bslot);
   free_dev(h->st_mu_fp);
   free_dev(h->d_fp_ws);
   h->cache_valid = false;
@@ -592,7 +591,6 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
     cudaError_t e = cudaMalloc(&h->d_cache, cache_bytes);
     if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "boundary-row cache of %.2f GB does not fit: %s", cache_bytes / 1e9, cudaGetErrorString(e));
     CU(h, cudaMalloc(&h->st_cg, U * PMAX * sizeof(int)));
-    CU(h, cudaMalloc(&h->st_bslot, U * SMAX * sizeof(int)));
   }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
   if (p->method == DBN_FP_GLOB_DBN) {
@@ -685,7 +683,6 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   a.counters = h->d_counters;
   a.cache = h->d_cache;
   a.st_cg = h->st_cg;
-  a.st_bslot = h->st_bslot;
   a.refresh = h->cache_valid ? 0 : 1;
 
   const bool trace = trace_d != nullptr;
