@@ -32,8 +32,9 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN = 0, 1, 2, 3, 4, 5
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN = 0, 1, 2, 3, 4, 5, 6
 METHOD_IDS = {
+    'var_glob_coup_nh_dbn': VV_GLOB_DBN, 'var-glob-dbn': VV_GLOB_DBN,   # network.py:258-269, vvglobCoup.py
     'fp_glob_coup_nh_dbn': FP_GLOB_DBN, 'fp-glob-dbn': FP_GLOB_DBN,
     'h_dbn': H_DBN, 'h-dbn': H_DBN,
     'varying_nh_dbn': NH_DBN, 'nh-dbn': NH_DBN,
@@ -62,8 +63,9 @@ def method_constants(method, N):
     elif m in (SEQ_DBN, FIXED_NH_DBN):
         # seq: network.py:213-219; fixed nh: network.py:182-188 also passes num_samples - 1
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
-    elif m in (GLOB_DBN, FP_GLOB_DBN):
-        # network.py:237-243, :249-255 (num_samples = N for both); fpGlobCoupBpwLinReg.py:49-50 (IG(0.01, 0.01))
+    elif m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN):
+        # network.py:237-243, :249-255, :261-267 (num_samples = N); fpGlobCoupBpwLinReg.py:49-50, vvglobCoup.py:42-43
+        # (IG(0.01, 0.01)); the segment-specific-variance model uses T_h per segment instead of T (log_ml_vv)
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.01, b_sig=0.01)
     else:
         raise ValueError(method)
@@ -186,6 +188,18 @@ def log_ml_h(stats, alpha, beta, lam, T):
     return log_ml(stats[:1], [np.zeros(k)], alpha, beta, lam, T)
 
 
+def log_ml_vv(stats, mu, alpha, beta, lam):
+    """vvLogMargLikelihood (marginalLikelihood.py:5-43): segments with their own variance, i.e. the sum over segments
+    of single-segment log marginal likelihoods, each with its own length T_h in the Gamma / pi / exponent terms
+    (:29-30, :39), all with lambda^2 and the same prior mean mu (:32)."""
+    acc = 0.0
+    for G, g, s, T_h in stats:
+        ld, q = seg_quadratic(G, g, s, mu, lam)
+        acc += (math.lgamma(T_h / 2 + alpha) - math.lgamma(alpha) - (T_h / 2) * math.log(math.pi)
+                + alpha * math.log(2 * beta) - 0.5 * ld - (T_h / 2 + alpha) * math.log(2 * beta + q))
+    return acc
+
+
 # ------------------------------------------------------------------------------------------------
 # a7 — priors
 # ------------------------------------------------------------------------------------------------
@@ -246,11 +260,14 @@ def mu_posterior(stats, mu_in, sigma2, lam):
     """
     k = stats[0][0].shape[0]
     Q = np.eye(k)
-    m = np.asarray(mu_in, dtype=float).ravel().copy()
-    for G, g, _, _ in stats:
+    # vvMuSampler (samplers.py:353-394): segment-specific sigma^2_h (:362) and NO mu_in term in the mean (:379)
+    per_seg = isinstance(sigma2, (list, tuple, np.ndarray))
+    m = np.zeros(k) if mu_in is None else np.asarray(mu_in, dtype=float).ravel().copy()
+    for h, (G, g, _, _) in enumerate(stats):
         A = np.eye(k) + lam * G
-        Q = Q + np.linalg.solve(A, G) / sigma2
-        m = m + np.linalg.solve(A, g) / sigma2
+        s2 = sigma2[h] if per_seg else sigma2
+        Q = Q + np.linalg.solve(A, G) / s2
+        m = m + np.linalg.solve(A, g) / s2
     Sigma = np.linalg.inv(Q)
     return Sigma @ m, Sigma, Q
 
@@ -297,7 +314,8 @@ def beta_params(stats, mus, lam, sigma2, seq=False, dlt=None):
         k = G.shape[0]
         P = np.eye(k) / w + G
         Pinv = np.linalg.inv(P)
-        out.append((Pinv @ (np.asarray(mus[h], dtype=float).ravel() / w + g), sigma2 * Pinv))
+        s2 = sigma2[h] if isinstance(sigma2, (list, tuple, np.ndarray)) else sigma2   # vvBetaSamplerWithChangepoints (samplers.py:169-187)
+        out.append((Pinv @ (np.asarray(mus[h], dtype=float).ravel() / w + g), s2 * Pinv))
     return out
 
 
@@ -316,9 +334,10 @@ def lambda2_params(method, betas, mu, sigma2, a_lam, b_lam):
     if method == SEQ_DBN:
         return a_lam + (k + 1) / 2, b_lam + 0.5 * float(betas[0] @ betas[0]) / sigma2
     acc = 0.0
-    for b in betas:
+    for h, b in enumerate(betas):
         d = b - mu
-        acc += float(d @ d) / sigma2
+        # segment-specific variances when sigma2 is a list (samplers.py:275-282)
+        acc += float(d @ d) / (sigma2[h] if isinstance(sigma2, (list, tuple, np.ndarray)) else sigma2)
     return a_lam + len(betas) * k / 2, b_lam + 0.5 * acc
 
 
@@ -424,6 +443,9 @@ class ReplayDraws:
     def inv_gamma(self, it, which, shape, rate):
         return float(self.g[{'sigma': 'sigma2', 'lambda': 'lambda2', 'delta': 'delta2'}[which]][self.i, it])
 
+    def inv_gamma_seg(self, it, h, shape, rate):
+        return float(self.g['sigma2v'][self.i, it, h])
+
     def beta(self, it, h, mean, cov):
         k = len(mean)
         return np.array(self.g['beta'][self.i, it, h, :k])
@@ -450,6 +472,9 @@ class RngDraws:
         self.rng = rng
 
     def inv_gamma(self, it, which, shape, rate):
+        return 1.0 / self.rng.gamma(shape, 1.0 / rate)
+
+    def inv_gamma_seg(self, it, h, shape, rate):
         return 1.0 / self.rng.gamma(shape, 1.0 / rate)
 
     def beta(self, it, h, mean, cov):
@@ -499,7 +524,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     F = len(features)
     c = method_constants(m, N)
     fp = m == FP_GLOB_DBN
-    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN)
+    vv = m == VV_GLOB_DBN          # vvglobCoup.py:66-123: segment-specific sigma^2_h, mu* drawn in the parent-set move only
+    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN)
     has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
     KM, SM = (max(5, n) if fp else 5), 10
 
@@ -519,6 +545,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     tr['mus_cov'] = np.full((n_iter, 4, KM, KM), np.nan)
     tr['mus_logdens'] = np.full((n_iter, 4, 2), np.nan)
     tr['mu_after'] = np.full((n_iter, KM), np.nan)
+    for k_ in ('sigma2v', 'sig_shape_v', 'sig_scale_v'):
+        tr[k_] = np.full((n_iter, SM), np.nan)
     tr['n_evals'] = 0
 
     def prior_means(stats, lam_, dlt_, mu_):
@@ -529,6 +557,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
 
     def score(stats, lam_, dlt_, mu_):
         tr['n_evals'] += 1
+        if vv:
+            return log_ml_vv(stats, mu_, c['a_sig'], c['b_sig'], lam_)
         return log_ml(stats, prior_means(stats, lam_, dlt_, mu_), c['a_sig'], c['b_sig'], lam_, c['T_ml'], seq, dlt_)
 
     for it in range(n_iter):
@@ -537,10 +567,20 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
         tr['S'][it] = S
         # ---- sigma^2
         mus = prior_means(stats, lam, dlt, mu)
-        shape, rate = sigma2_params(stats, mus, lam, c['a_sig'], c['b_sig'], c['T_sigma'], seq, dlt)
-        tr['sig_shape'][it], tr['sig_scale'][it] = shape, 1.0 / rate
-        sig = draws.inv_gamma(it, 'sigma', shape, rate)
-        tr['sigma2'][it] = sig
+        if vv:
+            # segmentSigmaSampler (samplers.py:90-101): sigmaSqrSampler per segment with numSamples = T = T_h
+            sig = []
+            for h, (G, g_, s_, T_h) in enumerate(stats):
+                shape, rate = c['a_sig'] + T_h / 2, c['b_sig'] + 0.5 * seg_quadratic(G, g_, s_, mu, lam)[1]
+                sig.append(draws.inv_gamma_seg(it, h, shape, rate))
+                tr['sig_shape_v'][it, h], tr['sig_scale_v'][it, h], tr['sigma2v'][it, h] = shape, 1.0 / rate, sig[-1]
+            tr['sig_shape'][it], tr['sig_scale'][it], tr['sigma2'][it] = (
+                tr['sig_shape_v'][it, 0], tr['sig_scale_v'][it, 0], sig[0])
+        else:
+            shape, rate = sigma2_params(stats, mus, lam, c['a_sig'], c['b_sig'], c['T_sigma'], seq, dlt)
+            tr['sig_shape'][it], tr['sig_scale'][it] = shape, 1.0 / rate
+            sig = draws.inv_gamma(it, 'sigma', shape, rate)
+            tr['sigma2'][it] = sig
         # ---- beta
         betas = []
         for h, (mean, cov) in enumerate(beta_params(stats, mus, lam, sig, seq, dlt)):
@@ -576,11 +616,12 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
             lp = math.log(pi_prior(star, F, fan_in)) - math.log(pi_prior(pi, F, fan_in))
             if glob:
                 # moves.py:476-491: mu* ~ q(.|pi*, mu_in = 0); reverse density with mu_in = current mu
-                mean_s, Sig_s, Q_s = mu_posterior(stats_star, np.zeros(len(star) + 1), sig, lam)
+                # (vv: moves.py:361-375, vvMuSampler has no mu_in term in its mean, samplers.py:379)
+                mean_s, Sig_s, Q_s = mu_posterior(stats_star, None if vv else np.zeros(len(star) + 1), sig, lam)
                 mu_star = draws.mu_draw(it, 0, mean_s, Sig_s)
                 ml_star = score(stats_star, lam, dlt, mu_star)
                 ml_cur = score(stats, lam, dlt, mu)
-                mean_c, Sig_c, Q_c = mu_posterior(stats, mu, sig, lam)
+                mean_c, Sig_c, Q_c = mu_posterior(stats, None if vv else mu, sig, lam)
                 ld_star = mvn_logpdf_prec(mu_star, mean_s, Q_s)
                 ld_cur = mvn_logpdf_prec(mu, mean_c, Q_c)
                 tr['mus_mean'][it, 0, :len(mean_s)] = mean_s
@@ -619,7 +660,12 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
                 stats_star = segment_stats(X, y, pi, star)
                 lp = log_cp_prior(star) - log_cp_prior(tau)
                 k = len(pi) + 1
-                if glob:
+                if vv:
+                    # vvGlobCoupTauMove (moves.py:238-307): mu is kept, no proposal densities; glob-style hr and accept
+                    ml_cur = score(stats, lam, dlt, mu)
+                    ml_star = score(stats_star, lam, dlt, mu)
+                    acc = _accept_glob(ml_star - ml_cur + lp + math.log(hr), draws.uniform(it, 'tau'))
+                elif glob:
                     # moves.py:66-93: current density first (mu_in = mu), then mu* ~ q(.|tau*, mu_in = 0)
                     ml_cur = score(stats, lam, dlt, mu)
                     mean_c, Sig_c, Q_c = mu_posterior(stats, mu, sig, lam)
@@ -645,7 +691,7 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
                 tr['tau_accept'][it] = int(acc)
                 if acc:
                     tau = star
-                    if glob:
+                    if glob and not vv:
                         mu = mu_star
         tr['tau_after'][it, :len(tau)] = tau
         if glob:

@@ -56,6 +56,8 @@ def _install_hooks():
     _orig['logml_h'] = ref_moves.calculateMarginalLikelihood
     _orig['musampler'] = ref_moves.muSampler
     _orig['betatilde'] = ref_samplers.betaTildeSampler
+    _orig['logml_vv'] = ref_moves.vvLogMargLikelihood
+    _orig['vvmusampler'] = ref_moves.vvMuSampler
 
     def gamma(shape, scale=1.0, size=None):
         v = _orig['gamma'](shape, scale=scale, size=size)
@@ -101,6 +103,16 @@ def _install_hooks():
         EVENTS.append(('musampler', float(d), float(db)))
         return s, d, db
 
+    def logml_vv(*a, **k):
+        v = _orig['logml_vv'](*a, **k)
+        EVENTS.append(('logml', float(np.asarray(v).item())))
+        return v
+
+    def vvmusampler(*a, **k):
+        s, d, db = _orig['vvmusampler'](*a, **k)
+        EVENTS.append(('musampler', float(d), float(db)))
+        return s, d, db
+
     np.random.gamma = gamma
     np.random.multivariate_normal = mvn
     np.random.choice = choice
@@ -109,6 +121,8 @@ def _install_hooks():
     ref_moves.calculateMarginalLikelihoodWithChangepoints = logml_cp
     ref_moves.calculateMarginalLikelihood = logml_h
     ref_moves.muSampler = musampler
+    ref_moves.vvLogMargLikelihood = logml_vv
+    ref_moves.vvMuSampler = vvmusampler
 
 
 def _remove_hooks():
@@ -120,6 +134,8 @@ def _remove_hooks():
     ref_moves.calculateMarginalLikelihoodWithChangepoints = _orig['logml_cp']
     ref_moves.calculateMarginalLikelihood = _orig['logml_h']
     ref_moves.muSampler = _orig['musampler']
+    ref_moves.vvLogMargLikelihood = _orig['logml_vv']
+    ref_moves.vvMuSampler = _orig['vvmusampler']
 
 
 # ----------------------------------------------------------------------------------------------
@@ -173,7 +189,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     multi_seg = method != 'h_dbn'
     is_seq = method == 'seq_coup_nh_dbn'
     is_fp = method == 'fp_glob_coup_nh_dbn'       # full parents: no parent-set move, design width = n
-    is_glob = method == 'glob_coup_nh_dbn' or is_fp
+    is_vv = method == 'var_glob_coup_nh_dbn'      # vvglobCoup.py: segment-specific sigma^2_h, mu* drawn in the pi move only
+    is_glob = method == 'glob_coup_nh_dbn' or is_fp or is_vv
     KM = globals()['KM'] if not is_fp else max(globals()['KM'], n)
     EVENTS.clear()
     np.random.seed(seed)
@@ -219,6 +236,9 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     for key in ('sigma2', 'lambda2', 'delta2', 'u_pi', 'u_tau', 'sig_shape', 'sig_scale', 'lam_shape', 'lam_scale',
                 'del_shape', 'del_scale'):
         g[key] = np.full(shp, NAN)
+    if is_vv:
+        for key in ('sigma2v', 'sig_shape_v', 'sig_scale_v'):
+            g[key] = np.full(shp + (SM,), NAN)
     g['beta'] = np.full(shp + (SM, KM), NAN)
     g['beta_mean'] = np.full(shp + (SM, KM), NAN)
     g['beta_cov'] = np.full(shp + (SM, KM, KM), NAN)
@@ -250,9 +270,13 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
         for it in range(n_iter):
             S = len(cur_tau)
             g['S'][i, it] = S
-            e = ev[pos]; assert e[0] == 'gamma', (i, it, e)
-            g['sig_shape'][i, it], g['sig_scale'][i, it], g['sigma2'][i, it] = e[1], e[2], 1.0 / e[3]
-            pos += 1
+            for h in range(S if is_vv else 1):      # segmentSigmaSampler (samplers.py:90-101): one draw per segment
+                e = ev[pos]; assert e[0] == 'gamma', (i, it, e)
+                if h == 0:
+                    g['sig_shape'][i, it], g['sig_scale'][i, it], g['sigma2'][i, it] = e[1], e[2], 1.0 / e[3]
+                if is_vv:
+                    g['sig_shape_v'][i, it, h], g['sig_scale_v'][i, it, h], g['sigma2v'][i, it, h] = e[1], e[2], 1.0 / e[3]
+                pos += 1
             for h in range(S if multi_seg else 1):
                 e = ev[pos]; assert e[0] == 'mvn', (i, it, h, e)
                 g['beta_mean'][i, it, h] = _pad_vec(e[1], KM)
@@ -314,7 +338,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
                 if rec['valid']:
                     g['logml'][i, it, 2] = rec['logml'][0]
                     g['logml'][i, it, 3] = rec['logml'][1]
-                if is_glob and rec['valid']:
+                if is_glob and not is_vv and rec['valid']:
                     for j, m in enumerate(rec['mvn']):
                         g['mus_mean'][i, it, 2 + j] = _pad_vec(m[1], KM)
                         g['mus_cov'][i, it, 2 + j] = _pad_mat(m[2], KM)
@@ -328,7 +352,10 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
             if is_glob:
                 g['mu_after'][i, it] = _pad_vec(cur_mu, KM)
             # cross-check the recorded Gibbs outputs against the reference's own history
-            assert abs(res['sigma_sqr_vector'][it + 1] - g['sigma2'][i, it]) <= 1e-12 * abs(g['sigma2'][i, it])
+            if is_vv:
+                assert np.allclose(res['sigma_sqr_vector'][it + 1], g['sigma2v'][i, it, :S], rtol=1e-12, atol=0)
+            else:
+                assert abs(res['sigma_sqr_vector'][it + 1] - g['sigma2'][i, it]) <= 1e-12 * abs(g['sigma2'][i, it])
             assert abs(float(np.asarray(res['lambda_sqr_vector'][it + 1]).item()) - g['lambda2'][i, it]) \
                 <= 1e-12 * abs(g['lambda2'][i, it])
         assert pos == end, (i, pos, end, ev[pos] if pos < end else None)
@@ -483,6 +510,11 @@ def main():
         run_chain_golden('yeast', yeast, 'fixed_nh_dbn', n_iter=240, burn_in=40, seed=1, change_points=[12, 23, 35])
         run_chain_golden('synth200', [syn], 'fixed_nh_dbn', n_iter=120, burn_in=20, seed=3, change_points=[51, 101, 151, 201])
         return
+    if 'vv-only' in sys.argv:       # add the segment-specific-variance fixtures without re-minting the others
+        run_chain_golden('yeast', yeast, 'var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
+        run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
+        return
     if 'fp-only' in sys.argv:       # add the full-parents fixtures without re-minting the others
         run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
         run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
@@ -505,6 +537,9 @@ def main():
     run_chain_golden('synth200', [syn], 'fp_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
     run_chain_golden('yeast', yeast, 'fixed_nh_dbn', n_iter=240, burn_in=40, seed=1, change_points=[12, 23, 35])
     run_chain_golden('synth200', [syn], 'fixed_nh_dbn', n_iter=120, burn_in=20, seed=3, change_points=[51, 101, 151, 201])
+    run_chain_golden('yeast', yeast, 'var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
+    run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
 
 
 if __name__ == '__main__':

@@ -79,7 +79,10 @@ def test_chain_replay(path):
             assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
         assert_close(tr['beta_cov'], g['beta_cov'][node], 1e-9, 1e-13, what='beta_cov node %d' % node)
         assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
-        if method == 'glob_coup_nh_dbn':
+        if method == 'var_glob_coup_nh_dbn':
+            for key in ('sig_shape_v', 'sig_scale_v'):
+                assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+        if method in ('glob_coup_nh_dbn', 'var_glob_coup_nh_dbn'):
             assert_close(tr['mus_mean'], g['mus_mean'][node], 1e-8, 1e-11, what='mus_mean node %d' % node)
             assert_close(tr['mus_cov'], g['mus_cov'][node], 1e-8, 1e-12, what='mus_cov node %d' % node)
             ref = g['mus_logdens'][node].copy()
