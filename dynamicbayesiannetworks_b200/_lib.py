@@ -18,7 +18,8 @@ RD_SIGMA2, RD_LAMBDA2, RD_DELTA2, RD_U_PI, RD_U_TAU = 0, 1, 2, 3, 4
 RD_MU_PI = 5
 RD_MU_TAU = 5 + KMAX
 RD_BETA = 5 + 2 * KMAX
-RD_STRIDE = 5 + 2 * KMAX + SMAX * KMAX
+RD_SIGMA2V = 5 + 2 * KMAX + SMAX * KMAX
+RD_STRIDE = RD_SIGMA2V + SMAX
 RI_PI_MOVE, RI_PI_PICK, RI_TAU_MOVE, RI_TAU_PICK, RI_STRIDE = 0, 1, 3, 4, 8
 TD_SIG_SHAPE, TD_SIG_RATE, TD_LAM_SHAPE, TD_LAM_RATE, TD_DEL_SHAPE, TD_DEL_RATE = 0, 1, 2, 3, 4, 5
 TD_LOGML, TD_SIGMA2, TD_LAMBDA2, TD_DELTA2, TD_MU, TD_MUS_LOGDENS, TD_MUS_MEAN = 6, 10, 11, 12, 13, 18, 22
@@ -26,7 +27,10 @@ TD_MUS_COV = 22 + 4 * KMAX
 TD_BETA_MEAN = TD_MUS_COV + 4 * KTRI
 TD_BETA_COV = TD_BETA_MEAN + SMAX * KMAX
 TD_BETA = TD_BETA_COV + SMAX * KTRI
-TD_STRIDE = TD_BETA + SMAX * KMAX
+TD_SIGV_SHAPE = TD_BETA + SMAX * KMAX
+TD_SIGV_RATE = TD_SIGV_SHAPE + SMAX
+TD_SIGMA2V = TD_SIGV_RATE + SMAX
+TD_STRIDE = TD_SIGMA2V + SMAX
 TI_PI_VALID, TI_PI_ACCEPT, TI_TAU_VALID, TI_TAU_ACCEPT, TI_NPI, TI_PI, TI_S, TI_TAU = 0, 1, 2, 3, 4, 5, 9, 10
 TI_PI_MOVE, TI_TAU_MOVE, TI_S_BEFORE, TI_STRIDE = 20, 21, 22, 24
 

@@ -169,13 +169,15 @@ __device__ __forceinline__ double sqnorm_k(const double (&x)[KM]) {
 template <int METHOD, int KM, bool TRACE>
 __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(const ChainArgs a) {
   constexpr bool SEQ = METHOD == DBN_SEQ_DBN;
-  constexpr bool GLOB = METHOD == DBN_GLOB_DBN;
+  constexpr bool VV = METHOD == DBN_VV_GLOB_DBN;   // globally coupled, segment-specific variances (vvglobCoup.py:66-123)
+  constexpr bool GLOB = METHOD == DBN_GLOB_DBN || VV;
   constexpr bool HOMOG = METHOD == DBN_H_DBN;
   constexpr int KT = KM * (KM + 1) / 2;
   constexpr int NB = (TRACE || SEQ) ? SMAX : 1;
 
   __shared__ int s_tau[SMAX * CHAIN_BLOCK];
   __shared__ int s_tas[SMAX * CHAIN_BLOCK];
+  __shared__ double s_sigv[VV ? SMAX * CHAIN_BLOCK : 1];   // VV: sigma^2_h of the current iteration
   const int tid = threadIdx.x;
   const int u_raw = blockIdx.x * CHAIN_BLOCK + tid;
   const bool active = u_raw < a.U;   // lanes past the end run zero iterations so warp-wide reductions stay full
@@ -188,6 +190,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
   auto TAS = [&](int j) -> int& { return s_tas[j * CHAIN_BLOCK + tid]; };
   auto tau_cur = [&](int j) { return s_tau[j * CHAIN_BLOCK + tid]; };
   auto tau_star = [&](int j) { return s_tas[j * CHAIN_BLOCK + tid]; };
+  auto SIGV = [&](int h) -> double& { return s_sigv[VV ? h * CHAIN_BLOCK + tid : 0]; };
+  const double vv_c = VV ? a.a_sig * log(a.two_b) - lgamma(a.a_sig) : 0.0;
 
   // ---- load state
   int npi = a.st_npi[u];
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
     // e_h = sqrt(w) L^-T D^-1/2 z_h independent of sigma^2, so sum_h |beta_h - c_h|^2 is assembled from
     // (|d|^2, d.e, |e|^2) after sigma^2 has been drawn: no second sweep, no per-segment storage (nh/glob/h).
     double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
+    double acc_ss = 0.0;  // VV: sum_h |beta_h - mu|^2 / sigma^2_h (samplers.py:275-282)
     double bm[NB][KM], be[NB][KM];  // seq / trace: per-segment mean and e (or injected beta in replay)
     {
       double bt_cur[KM], bt_prev[KM];
@@ -255,11 +260,32 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         double pm[KM];  // prior mean of this segment
 #pragma unroll
         for (int i = 0; i < KM; ++i) pm[i] = SEQ ? bt_cur[i] : mu[i];
+        double q_h;
         if constexpr (SEQ || GLOB)
-          q_sum += segment_q<KM, true>(G, g, s, pm, w, A, dinv, wv);
+          q_h = segment_q<KM, true>(G, g, s, pm, w, A, dinv, wv);
         else
-          q_sum += segment_q<KM, false>(G, g, s, pm, w, A, dinv, wv);
+          q_h = segment_q<KM, false>(G, g, s, pm, w, A, dinv, wv);
+        q_sum += q_h;
         wk.segment(k, SEQ || GLOB);
+        double sig_h = 1.0;
+        if constexpr (VV) {
+          // segmentSigmaSampler (samplers.py:90-101): sigmaSqrSampler on segment h alone, numSamples = T = T_h
+          const double shape = a.a_sig + 0.5 * (double)(hi - lo);
+          const double rate = a.b_sig + 0.5 * q_h;
+          sig_h = replay ? rd[DBN_RD_SIGMA2V + h] : rate / rng.gamma(shape);
+          SIGV(h) = sig_h;
+          if (TRACE && td) {
+            td[DBN_TD_SIGV_SHAPE + h] = shape;
+            td[DBN_TD_SIGV_RATE + h] = rate;
+            td[DBN_TD_SIGMA2V + h] = sig_h;
+            if (h == 0) {
+              td[DBN_TD_SIG_SHAPE] = shape;
+              td[DBN_TD_SIG_RATE] = rate;
+              td[DBN_TD_SIGMA2] = sig_h;
+            }
+          }
+          if (h == 0) sig2 = sig_h;
+        }
         // posterior mean of beta_h: (I/w + G)^-1 (pm/w + g) = A^-1 (pm + w g)   (samplers.py:210-212)
         double mean[KM];
 #pragma unroll
@@ -310,14 +336,21 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             double d[KM];
 #pragma unroll
             for (int i = 0; i < KM; ++i) d[i] = mean[i] - pm[i];
-            acc_dd += dot<KM>(d, d);
-            acc_de += dot<KM>(d, e);
-            acc_ee += dot<KM>(e, e);
+            if constexpr (VV) {
+              acc_ss += (dot<KM>(d, d) + 2.0 * sqrt(sig_h) * dot<KM>(d, e)) / sig_h + dot<KM>(e, e);
+            } else {
+              acc_dd += dot<KM>(d, d);
+              acc_de += dot<KM>(d, e);
+              acc_ee += dot<KM>(e, e);
+            }
           } else {
             double d[KM];
 #pragma unroll
             for (int i = 0; i < KM; ++i) d[i] = (i < k) ? e[i] - pm[i] : 0.0;
-            acc_dd += dot<KM>(d, d);
+            if constexpr (VV)
+              acc_ss += dot<KM>(d, d) / sig_h;
+            else
+              acc_dd += dot<KM>(d, d);
           }
         }
         if (SEQ && h >= 1) {
@@ -335,7 +368,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       }
     }
     // ---- sigma^2 ~ IG: shape a + T/2, rate b + q/2 (samplers.py:118-125, :81-86, :135-141)
-    {
+    if constexpr (!VV) {
       const double shape = a.a_sig + a.T_sigma_half;
       const double rate = a.b_sig + 0.5 * q_sum;
       sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / rng.gamma(shape);
@@ -346,13 +379,15 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       }
     }
     const double sg = sqrt(sig2);
+    auto sig_of = [&](int h) -> double { return VV ? SIGV(h) : sig2; };   // variance of segment h
     if (TRACE && td) {
       for (int h = 0; h < S; ++h) {
+        const double s2h = sig_of(h), sgh = sqrt(s2h);
         for (int i = 0; i < KM; ++i) {
-          const double b = replay ? be[h < NB ? h : 0][i] : bm[h < NB ? h : 0][i] + sg * be[h < NB ? h : 0][i];
+          const double b = replay ? be[h < NB ? h : 0][i] : bm[h < NB ? h : 0][i] + sgh * be[h < NB ? h : 0][i];
           td[DBN_TD_BETA + h * KMAX + i] = (i < k) ? b : NAN;
         }
-        for (int e = 0; e < DBN_KTRI; ++e) td[DBN_TD_BETA_COV + h * DBN_KTRI + e] *= sig2;
+        for (int e = 0; e < DBN_KTRI; ++e) td[DBN_TD_BETA_COV + h * DBN_KTRI + e] *= s2h;
       }
     }
     // ---- lambda^2
@@ -365,6 +400,10 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         for (int i = 0; i < KM; ++i) b0[i] = replay ? be[0][i] : bm[0][i] + sg * be[0][i];
         shape = a.a_lam + 0.5 * (double)(k + 1);
         rate = a.b_lam + 0.5 * dot<KM>(b0, b0) / sig2;
+      } else if constexpr (VV) {
+        // samplers.py:265-294 with the list of sigma^2_h: shape a + S k / 2, rate b + sum_h |beta_h - mu|^2 / (2 sigma^2_h)
+        shape = a.a_lam + 0.5 * (double)(S * k);
+        rate = a.b_lam + 0.5 * acc_ss;
       } else {
         const double ss = replay ? acc_dd : (acc_dd + 2.0 * sg * acc_de + sig2 * acc_ee);
         // nh/glob: samplers.py:285-289 shape a + S k/2 ; h: :301 shape a + k/2 ; rate b + ss / (2 sigma^2)
@@ -439,6 +478,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
     auto score = [&](const Cols<KM>& c, auto tau_fn, int S_, const double(&mu_)[KM]) -> double {
       if constexpr (SEQ)
         return score_seq<KM>(a.tb, c, tau_fn, S_, lam, dlt, a.c0, a.T_half_plus_a, a.two_b, wk);
+      else if constexpr (VV)
+        return score_vv<KM>(a.tb, c, tau_fn, S_, lam, mu_, a.a_sig, vv_c, a.two_b, wk);
       else if constexpr (GLOB)
         return score_plain<KM, true>(a.tb, c, tau_fn, S_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
       else
@@ -543,7 +584,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         double Qs[KT], m0s[KM];
         if constexpr (GLOB) {
           // moves.py:476-491: mu* ~ muSampler(0 | pi*), reverse density muSampler(mu | pi) at the current mu
-          mu_posterior<KM>(a.tb, cstar, tau_cur, S, lam, sig2, Qs, m0s, wk);
+          // (VV: moves.py:361-375; vvMuSampler has segment-specific variances and no mu_in term, samplers.py:353-394)
+          mu_posterior<KM>(a.tb, cstar, tau_cur, S, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {
@@ -563,11 +605,11 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           const double ld_star = gs.logpdf(mu_star, Qs, ks);
           ml_star = score(cstar, tau_cur, S, mu_star);
           ml_cur = score(cols, tau_cur, S, mu);
-          mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig2, Qc, m0c, wk);
+          mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig_of, Qc, m0c, wk);
           have_qc = true;
           double mc[KM];
 #pragma unroll
-          for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + mu[i];  // samplers.py:336: the input mu is the prior mean term
+          for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + (VV ? 0.0 : mu[i]);  // samplers.py:336: the input mu is the prior mean term
           GaussQ<KM> gc;
           gc.setup(Qc, mc);
           const double ld_cur = gc.logpdf(mu, Qc, k);
@@ -705,9 +747,15 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         double mu_star[KM];
 #pragma unroll
         for (int i = 0; i < KM; ++i) mu_star[i] = 0.0;
-        if constexpr (GLOB) {
+        if constexpr (VV) {
+          // vvGlobCoupTauMove (moves.py:238-307): mu is kept, so only the two marginal likelihoods enter
+#pragma unroll
+          for (int i = 0; i < KM; ++i) mu_star[i] = mu[i];
+          ml_star = score(cols, tau_star, Ss, mu);        // :283-284
+          log_ratio = ml_star - ml_cur + lprior + log_hr;  // :291-295
+        } else if constexpr (GLOB) {
           // moves.py:72-93: density of the current mu under muSampler(mu | tau), then mu* ~ muSampler(0 | tau*)
-          if (!have_qc) mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig2, Qc, m0c, wk);
+          if (!have_qc) mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig_of, Qc, m0c, wk);
           double mc[KM];
 #pragma unroll
           for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + mu[i];
@@ -715,7 +763,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           gc.setup(Qc, mc);
           const double ld_cur = gc.logpdf(mu, Qc, k);
           double Qs[KT], m0s[KM];
-          mu_posterior<KM>(a.tb, cols, tau_star, Ss, lam, sig2, Qs, m0s, wk);
+          mu_posterior<KM>(a.tb, cols, tau_star, Ss, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {

@@ -228,6 +228,7 @@ static chain_fn pick_method(int method) {
     case DBN_H_DBN: return chain_fast_kernel<DBN_H_DBN, KM, TRACE>;
     case DBN_NH_DBN: return chain_fast_kernel<DBN_NH_DBN, KM, TRACE>;
     case DBN_SEQ_DBN: return chain_kernel<DBN_SEQ_DBN, KM, TRACE>;
+    case DBN_VV_GLOB_DBN: return chain_kernel<DBN_VV_GLOB_DBN, KM, TRACE>;
     default: return chain_kernel<DBN_GLOB_DBN, KM, TRACE>;
   }
 }
@@ -565,7 +566,7 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!h || !p) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
-  if (p->method < DBN_H_DBN || p->method > DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (p->method < DBN_H_DBN || p->method > DBN_VV_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
   if (p->method != DBN_FP_GLOB_DBN && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");

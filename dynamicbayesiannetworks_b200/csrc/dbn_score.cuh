@@ -224,6 +224,31 @@ __device__ __forceinline__ double score_plain(const Table& t, const Cols<KM>& c,
   return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
 }
 
+// ----- vvLogMargLikelihood (marginalLikelihood.py:5-43): segment-specific variances ---------------------------
+// The sum over the segments of single-segment log marginal likelihoods, each with its own length T_h in the Gamma, pi
+// and exponent terms (:29-30, :39), lambda^2 and the prior mean mu shared (:13, :32).
+// c_seg = a ln(2b) - lgamma(a); ln(pi) = 1.1447298858494002.
+template <int KM, class TauFn>
+__device__ __forceinline__ double score_vv(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam,
+                                           const double (&mu)[KM], double a_sig, double c_seg, double two_b, Work& wk) {
+  double acc = 0.0;
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
+    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
+    load_segment<KM>(t, c, lo, hi, G, g, s);
+    form_a<KM>(G, lam, A);
+    const double ld = log(ldl_factor<KM>(A, dinv));
+    const double q = segment_q<KM, true>(G, g, s, mu, lam, A, dinv, wv);
+    const double Th_half = 0.5 * (double)(hi - lo);
+    acc += lgamma(Th_half + a_sig) + c_seg - Th_half * 1.1447298858494002 - 0.5 * ld - (Th_half + a_sig) * log(two_b + q);
+    wk.segment(c.k, true);
+    wk.flops += 12;
+    lo = hi;
+  }
+  wk.eval();
+  return acc;
+}
 // ----- a2 + a8: sequentially coupled log marginal likelihood ------------------------------------------------
 // Prior means are betaTildeSampler's (samplers.py:4-54): bt[0] = 0, bt[1] = (I/lam + G_1)^-1 g_1,
 // bt[h] = (I/dlt + G_{h-1})^-1 (bt[h-2]/dlt + g_{h-1}); C_h uses dlt for h > 0 (marginalLikelihood.py:104-107).
@@ -271,10 +296,11 @@ __device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, T
 
 // ----- a9: muSampler's Gaussian (samplers.py:307-351) on sufficient statistics ----------------------------
 // Q = I + sum_h A_h^-1 G_h / s2 (precision), m0 = sum_h A_h^-1 g_h / s2 (mean numerator WITHOUT the mu_in term).
-template <int KM, class TauFn>
-__device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, double sig2,
+// sig2(h) is a callable: the same sigma^2 for every segment (glob), or the segment-specific sigma^2_h of vvMuSampler
+// (samplers.py:353-394).
+template <int KM, class TauFn, class SigFn>
+__device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, SigFn sig2,
                                              double (&Q)[KM * (KM + 1) / 2], double (&m0)[KM], Work& wk) {
-  const double is2 = 1.0 / sig2;
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
     m0[i] = 0.0;
@@ -288,6 +314,7 @@ __device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, 
     load_segment<KM>(t, c, lo, hi, G, g, s);
     form_a<KM>(G, lam, A);
     ldl_factor<KM>(A, dinv);
+    const double is2 = 1.0 / sig2(h);
     double x[KM];
 #pragma unroll
     for (int i = 0; i < KM; ++i) x[i] = g[i];

@@ -270,6 +270,8 @@ def pack_replay(r, U, n_iter):
         rd[:, :, L.RD_MU_PI:L.RD_MU_PI + L.KMAX] = r['mu_pi']
         rd[:, :, L.RD_MU_TAU:L.RD_MU_TAU + L.KMAX] = r['mu_tau']
     rd[:, :, L.RD_BETA:L.RD_BETA + L.SMAX * L.KMAX] = np.asarray(r['beta']).reshape(U, n_iter, L.SMAX * L.KMAX)
+    if 'sigma2v' in r:      # segment-specific variances of 'var_glob_coup_nh_dbn'
+        rd[:, :, L.RD_SIGMA2V:L.RD_SIGMA2V + L.SMAX] = r['sigma2v']
     ri[:, :, L.RI_PI_MOVE] = r['pi_move']
     ri[:, :, L.RI_PI_PICK:L.RI_PI_PICK + 2] = r['pi_pick']
     if 'tau_move' in r:
@@ -302,6 +304,8 @@ def unpack_trace(td, ti):
         beta_mean=td[:, :, L.TD_BETA_MEAN:L.TD_BETA_MEAN + L.SMAX * L.KMAX].reshape(U, n_iter, L.SMAX, L.KMAX),
         beta_cov=_unpack_tri(td[:, :, L.TD_BETA_COV:L.TD_BETA_COV + L.SMAX * L.KTRI].reshape(U, n_iter, L.SMAX, L.KTRI)),
         beta=td[:, :, L.TD_BETA:L.TD_BETA + L.SMAX * L.KMAX].reshape(U, n_iter, L.SMAX, L.KMAX),
+        sig_shape_v=td[:, :, L.TD_SIGV_SHAPE:L.TD_SIGV_SHAPE + L.SMAX], sig_rate_v=td[:, :, L.TD_SIGV_RATE:L.TD_SIGV_RATE + L.SMAX],
+        sigma2v=td[:, :, L.TD_SIGMA2V:L.TD_SIGMA2V + L.SMAX],
         pi_valid=ti[:, :, L.TI_PI_VALID], pi_accept=ti[:, :, L.TI_PI_ACCEPT],
         tau_valid=ti[:, :, L.TI_TAU_VALID], tau_accept=ti[:, :, L.TI_TAU_ACCEPT],
         npi=ti[:, :, L.TI_NPI], pi_after=ti[:, :, L.TI_PI:L.TI_PI + L.PMAX],

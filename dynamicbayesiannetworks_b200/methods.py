@@ -5,7 +5,7 @@ every hyper-parameter is a literal inside that regressor's `fit()` (SURVEY.md se
 reproduces them so that the CUDA path is a drop-in; keyword arguments of `Network` / `DbnEngine.chain_init` may
 override any of them (BASELINE config 4 needs fan-in 4).
 """
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN = 0, 1, 2, 3, 4
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN = 0, 1, 2, 3, 4, 5
 
 # method strings of network.py:154-281 and the CLI aliases of examples/yeast_tests.py:179-187
 METHOD_IDS = {
@@ -14,12 +14,14 @@ METHOD_IDS = {
     'seq_coup_nh_dbn': SEQ_DBN, 'seq-dbn': SEQ_DBN,
     'glob_coup_nh_dbn': GLOB_DBN, 'glob-dbn': GLOB_DBN,
     'fp_glob_coup_nh_dbn': FP_GLOB_DBN,   # network.py:245-257; CLI 'glob-dbn' of examples/full_parents_test.py:165-179
+    'var_glob_coup_nh_dbn': VV_GLOB_DBN,  # network.py:258-269 (vvglobCoup.py); CLI 'var-glob-dbn' of examples/yeast_tests.py:188-189
+    'var-glob-dbn': VV_GLOB_DBN,
     'fixed_nh_dbn': NH_DBN,               # network.py:178-189: the nh regressor on predefined changepoints (FIXED_CP below)
 }
 FIXED_CP = ('fixed_nh_dbn',)              # no changepoint move (bayesianPwLinearRegression.py:117), num_samples - 1
 METHOD_NAMES = {H_DBN: 'h_dbn', NH_DBN: 'varying_nh_dbn', SEQ_DBN: 'seq_coup_nh_dbn', GLOB_DBN: 'glob_coup_nh_dbn',
-                FP_GLOB_DBN: 'fp_glob_coup_nh_dbn'}
-NOT_YET = ('var_glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_h_dbn', 'fp_seq_coup_nh_dbn',
+                FP_GLOB_DBN: 'fp_glob_coup_nh_dbn', VV_GLOB_DBN: 'var_glob_coup_nh_dbn'}
+NOT_YET = ('fp_varying_nh_dbn', 'fp_h_dbn', 'fp_seq_coup_nh_dbn',
            'fp_var_glob_coup_nh_dbn')
 
 
@@ -55,7 +57,8 @@ def run_params(method, N, fan_in=3, burn_in=0, thin=10, with_tau=True, **over):
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N), a_sigma=0.005, b_sigma=0.005)
     elif m == SEQ_DBN:
         p.update(num_samples=N - 1, T_ml=float(N - 1), T_sigma=float(N - 1), a_sigma=0.005, b_sigma=0.005)
-    else:  # glob and fp-glob: network.py:237-243, :249-255; IG(0.01, 0.01) in both (fpGlobCoupBpwLinReg.py:49-50)
+    else:  # glob, fp-glob, var-glob: network.py:237-243, :249-255, :261-267; IG(0.01, 0.01) in all three
+        # (fpGlobCoupBpwLinReg.py:49-50, vvglobCoup.py:42-43); var-glob uses the segment lengths T_h instead of T
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N), a_sigma=0.01, b_sigma=0.01)
     for k, v in over.items():
         if k not in p:

@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, METHOD_NAMES, FIXED_CP
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, METHOD_NAMES, FIXED_CP
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -24,6 +24,7 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Varying Parents'),
     'fp_glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:246-247
     'fixed_nh_dbn': ('Bayesian Non-Homogeneous', 'Varying Parents-Fixed changepoints'),   # network.py:179-180
+    'var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Varying Parents'),   # network.py:259-260
 }
 
 
@@ -188,6 +189,8 @@ class Network():
         res['betas_vector'] = betas
         if mid == SEQ_DBN:
             res['delta_sqr_vector'] = [1] + [float(v) for v in t['delta2'][u]]
-        if mid == GLOB_DBN:
+        if mid == VV_GLOB_DBN:   # vvglobCoup.py:59,70-72,125: one variance per segment and iteration
+            res['sigma_sqr_vector'] = [[1]] + [[float(v) for v in t['sigma2v'][u, it, :int(t['S'][u, it])]] for it in range(n_iter)]
+        if mid in (GLOB_DBN, VV_GLOB_DBN):
             res['mu_vector'] = [np.zeros((1, 1))] + [np.array(t['mu_after'][u, it, :t['npi'][u, it] + 1]).reshape(-1, 1) for it in range(n_iter)]
         return res

@@ -44,8 +44,12 @@ typedef enum {
   DBN_NH_DBN = 1,   /* 'varying_nh_dbn'   bayesianPwLinearRegression.py:41-141    */
   DBN_SEQ_DBN = 2,  /* 'seq_coup_nh_dbn'  seqCoupledBayesianPwLinReg.py:16-130    */
   DBN_GLOB_DBN = 3, /* 'glob_coup_nh_dbn' globCoupBayesianPwLinReg.py:16-124      */
-  DBN_FP_GLOB_DBN = 4 /* 'fp_glob_coup_nh_dbn' fpGlobCoupBpwLinReg.py:16-119: every other gene is a parent (design
+  DBN_FP_GLOB_DBN = 4, /* 'fp_glob_coup_nh_dbn' fpGlobCoupBpwLinReg.py:16-119: every other gene is a parent (design
                          width k = n), no parent-set move, globally coupled changepoint move; run with dbn_run_fp */
+  DBN_VV_GLOB_DBN = 5  /* 'var_glob_coup_nh_dbn' vvglobCoup.py:16-123: globally coupled with a segment-specific
+                         variance sigma^2_h (segmentSigmaSampler samplers.py:90-101), vvLogMargLikelihood
+                         (marginalLikelihood.py:5-43), vvMuSampler (samplers.py:353-394), vvGlobCoupPiMove /
+                         vvGlobCoupTauMove (moves.py:238-415)                                                  */
 } dbn_method;
 
 typedef struct dbn_handle dbn_handle;
@@ -139,7 +143,8 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p);
 #define DBN_RD_MU_PI 5                     /* [DBN_KMAX] mu* drawn in the parent-set move (glob)  */
 #define DBN_RD_MU_TAU (5 + DBN_KMAX)       /* [DBN_KMAX] mu* drawn in the changepoint move (glob) */
 #define DBN_RD_BETA (5 + 2 * DBN_KMAX)     /* [DBN_SMAX][DBN_KMAX] beta_h                         */
-#define DBN_RD_STRIDE (5 + 2 * DBN_KMAX + DBN_SMAX * DBN_KMAX)
+#define DBN_RD_SIGMA2V (5 + 2 * DBN_KMAX + DBN_SMAX * DBN_KMAX) /* [DBN_SMAX] sigma^2_h (DBN_VV_GLOB_DBN) */
+#define DBN_RD_STRIDE (5 + 2 * DBN_KMAX + DBN_SMAX * DBN_KMAX + DBN_SMAX)
 #define DBN_RI_PI_MOVE 0
 #define DBN_RI_PI_PICK 1                   /* [2] index into the candidate list of each np.random.choice */
 #define DBN_RI_TAU_MOVE 3
@@ -165,7 +170,11 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p);
 #define DBN_TD_BETA_MEAN (DBN_TD_MUS_COV + 4 * DBN_KTRI)            /* [DBN_SMAX][DBN_KMAX]              */
 #define DBN_TD_BETA_COV (DBN_TD_BETA_MEAN + DBN_SMAX * DBN_KMAX)    /* [DBN_SMAX][DBN_KTRI]              */
 #define DBN_TD_BETA (DBN_TD_BETA_COV + DBN_SMAX * DBN_KTRI)         /* [DBN_SMAX][DBN_KMAX] drawn beta_h */
-#define DBN_TD_STRIDE (DBN_TD_BETA + DBN_SMAX * DBN_KMAX)
+/* DBN_VV_GLOB_DBN: per-segment sigma^2_h Gibbs shape / rate / draw; the scalar slots above hold segment 0's */
+#define DBN_TD_SIGV_SHAPE (DBN_TD_BETA + DBN_SMAX * DBN_KMAX)       /* [DBN_SMAX] */
+#define DBN_TD_SIGV_RATE (DBN_TD_SIGV_SHAPE + DBN_SMAX)             /* [DBN_SMAX] */
+#define DBN_TD_SIGMA2V (DBN_TD_SIGV_RATE + DBN_SMAX)                /* [DBN_SMAX] */
+#define DBN_TD_STRIDE (DBN_TD_SIGMA2V + DBN_SMAX)
 #define DBN_TI_PI_VALID 0
 #define DBN_TI_PI_ACCEPT 1
 #define DBN_TI_TAU_VALID 2

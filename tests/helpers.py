@@ -52,6 +52,8 @@ def golden_replay(g):
     if 'mus_val' in g:
         r['mu_pi'] = g['mus_val'][:, :, 0, :]
         r['mu_tau'] = g['mus_val'][:, :, 3, :]
+    if 'sigma2v' in g:      # var_glob_coup_nh_dbn: one variance per segment
+        r['sigma2v'] = g['sigma2v']
     return r
 
 

@@ -138,7 +138,10 @@ def test_chain_replay_vs_reference(eng_mod, path):
     assert_close(tr['logml'], g['logml'], LOGML_RTOL, what='logml')
     assert_close(tr['beta_mean'], g['beta_mean'], 1e-8, 1e-11, what='beta_mean')
     assert_close_mat(tr['beta_cov'], g['beta_cov'], 1e-9, what='beta_cov')
-    if method == 'glob_coup_nh_dbn':
+    if method == 'var_glob_coup_nh_dbn':
+        assert_close(tr['sig_shape_v'], g['sig_shape_v'], 1e-12, what='sig_shape_v')
+        assert_close(1.0 / tr['sig_rate_v'], g['sig_scale_v'], 1e-9, what='sig_scale_v')
+    if method in ('glob_coup_nh_dbn', 'var_glob_coup_nh_dbn'):
         assert_close(tr['mus_mean'], g['mus_mean'], 1e-8, 1e-11, what='mus_mean')
         assert_close_mat(tr['mus_cov'], g['mus_cov'], 1e-9, what='mus_cov')
         ref = np.stack([g['mus_logdens'][:, :, 0, 0], g['mus_logdens'][:, :, 1, 1], g['mus_logdens'][:, :, 2, 1],
@@ -173,7 +176,7 @@ def test_chain_replay_split_launches(eng_mod):
 # ---------------------------------------------------------------------------------------------------------
 # free-running Philox chains: statistical agreement with the oracle's free-running chains
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn'])
+@pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'var_glob_coup_nh_dbn'])
 def test_free_running_edge_posteriors(eng_mod, method):
     g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
     data = data_list(g)
@@ -250,7 +253,7 @@ def test_network_dropin(eng_mod):
     from dynamicbayesiannetworks_b200 import Network
     g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
     data = data_list(g)
-    for method in ('h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn'):
+    for method in ('h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'var_glob_coup_nh_dbn'):
         net = Network(data, 300, 100, 1)
         net.infer_network(method)
         adj = np.array(net.proposed_adj_matrix)
@@ -263,6 +266,9 @@ def test_network_dropin(eng_mod):
             assert len(net.cps_over_response) == 5 and len(net.cps_over_response[0]) == 20
         if method == 'seq_coup_nh_dbn':
             assert len(r['delta_sqr_vector']) == 301
+        if method == 'var_glob_coup_nh_dbn':   # vvglobCoup.py:70-72: one variance per segment of the iteration's tau
+            assert all(len(r['sigma_sqr_vector'][it + 1]) == (1 if it == 0 else len(r['tau_vector'][it - 1])) for it in range(300))
+            assert len(r['mu_vector']) == 301
         pickle.loads(pickle.dumps(net))
     fixed = Network(data, 300, 100, 1, [12, 23, 35])          # network.py:178-189: predefined change points
     fixed.infer_network('fixed_nh_dbn')
