@@ -46,7 +46,22 @@ __global__ void build_v_kernel(const double* __restrict__ raw, const int* __rest
 #define DBN_PREFIX_CPT 4
 #endif
 constexpr int PREFIX_CPT = DBN_PREFIX_CPT;
-template <bool WRITE>
+// With many chunks (long series, wide rows: BASELINE config 5 has 910) summing the earlier chunks' totals inside the write
+// pass is quadratic in the chunk count; chunk_scan_kernel turns the totals into exclusive running sums once
+// (thread per column, coalesced over columns) and the write pass reads a single offset row (SCANNED).
+constexpr int PREFIX_SCAN_CHUNKS = 96;  // up to here the in-pass sum is cheaper than one more launch (config 4: 63 chunks)
+__global__ void __launch_bounds__(256) chunk_scan_kernel(double* __restrict__ chunk, long long R, int n_chunks) {
+  const long long p = blockIdx.x * 256ll + threadIdx.x;
+  if (p >= R) return;
+  double acc = 0.0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const double v = chunk[(long long)c * R + p];
+    chunk[(long long)c * R + p] = acc;
+    acc += v;
+  }
+}
+
+template <bool WRITE, bool SCANNED = false>
 __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
                                                               const unsigned short* __restrict__ colB, int N, int W, long long R,
                                                               int Lc, double* __restrict__ chunk, double* __restrict__ table) {
@@ -77,10 +92,16 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
       if (live[j]) chunk[(long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK] = acc[j];
   } else {
     // offset of this chunk = sum of the totals of the chunks before it, added in chunk order (coalesced, L2-resident)
-    for (int c = 0; c < (int)blockIdx.y; ++c) {
+    if constexpr (SCANNED) {
 #pragma unroll
       for (int j = 0; j < PREFIX_CPT; ++j)
-        if (live[j]) acc[j] += chunk[(long long)c * R + p0 + (long long)j * PREFIX_BLOCK];
+        if (live[j]) acc[j] = chunk[(long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK];
+    } else {
+      for (int c = 0; c < (int)blockIdx.y; ++c) {
+#pragma unroll
+        for (int j = 0; j < PREFIX_CPT; ++j)
+          if (live[j]) acc[j] += chunk[(long long)c * R + p0 + (long long)j * PREFIX_BLOCK];
+      }
     }
     if (blockIdx.y == 0) {
 #pragma unroll
@@ -371,7 +392,13 @@ static int launch_prefix(dbn_handle* h) {
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
   prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   CU(h, cudaGetLastError());
-  prefix_kernel<true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  if (h->n_chunks > PREFIX_SCAN_CHUNKS) {
+    chunk_scan_kernel<<<(unsigned)((h->R + 255) / 256), 256, 0, h->stream>>>(h->d_chunk, h->R, h->n_chunks);
+    CU(h, cudaGetLastError());
+    prefix_kernel<true, true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  } else {
+    prefix_kernel<true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  }
   CU(h, cudaGetLastError());
   return DBN_OK;
 }
@@ -437,6 +464,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     h->n_chunks = (int)((N + Lc - 1) / Lc);
     CU(h, cudaFuncSetAttribute(prefix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+    CU(h, cudaFuncSetAttribute(prefix_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
     CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));

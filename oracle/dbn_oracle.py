@@ -32,8 +32,10 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN = 0, 1, 2, 3, 4, 5, 6
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8
 METHOD_IDS = {
+    'fp_varying_nh_dbn': FP_NH_DBN,    # network.py:165-177, fullParentsBpwLinReg.py
+    'fp_h_dbn': FP_H_DBN,              # network.py:200-209, fpBayesianLinearRegression.py
     'var_glob_coup_nh_dbn': VV_GLOB_DBN, 'var-glob-dbn': VV_GLOB_DBN,   # network.py:258-269, vvglobCoup.py
     'fp_glob_coup_nh_dbn': FP_GLOB_DBN, 'fp-glob-dbn': FP_GLOB_DBN,
     'h_dbn': H_DBN, 'h-dbn': H_DBN,
@@ -58,8 +60,12 @@ def method_constants(method, N):
     if m == H_DBN:
         # fit(): T = self.num_samples = N+1 (bayesianLinearRegression.py:96); ML gets num_samples-1 = N (:134-135)
         c.update(T_ml=N, T_sigma=N + 1, num_samples=N, a_sig=0.01, b_sig=0.01)
-    elif m == NH_DBN:
+    elif m in (NH_DBN, FP_NH_DBN):
+        # fp: network.py:168-174 (num_samples = N), fullParentsBpwLinReg.py:73-74 (IG(0.005, 0.005))
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.005, b_sig=0.005)
+    elif m == FP_H_DBN:
+        # network.py:203-207 (num_samples + 1), fpBayesianLinearRegression.py:70,84-85,90-91: shape a + (N+1)/2, no moves
+        c.update(T_ml=N, T_sigma=N + 1, num_samples=N, a_sig=0.01, b_sig=0.01)
     elif m in (SEQ_DBN, FIXED_NH_DBN):
         # seq: network.py:213-219; fixed nh: network.py:182-188 also passes num_samples - 1
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
@@ -523,10 +529,10 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     features = [j for j in range(n) if j != node]
     F = len(features)
     c = method_constants(m, N)
-    fp = m == FP_GLOB_DBN
+    fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN)    # full parents: pi = every other gene, no parent-set move
     vv = m == VV_GLOB_DBN          # vvglobCoup.py:66-123: segment-specific sigma^2_h, mu* drawn in the parent-set move only
     seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN)
-    has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
+    has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN, FP_H_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
     KM, SM = (max(5, n) if fp else 5), 10
 
     pi, tau = (list(features) if fp else []), ([int(c) for c in init_tau] if init_tau is not None else [N + 2])
@@ -591,6 +597,7 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
         tr.setdefault('beta', np.full((n_iter, SM, KM), np.nan))
         for h, b_ in enumerate(betas):
             tr['beta'][it, h, :k] = b_
+        # (fp-h: S = 1, so the nh / glob shape a + S k / 2 is samplers.py:296-305's a + k / 2)
         shape, rate = lambda2_params(GLOB_DBN if fp else m, betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
         tr['lam_shape'][it], tr['lam_scale'][it] = shape, 1.0 / rate
         lam_new = draws.inv_gamma(it, 'lambda', shape, rate)
@@ -744,6 +751,13 @@ def credible_scores(mu_samples, features, n):
         col = mu_samples[:, j + 1]
         row[f] = max(np.mean(col >= 0), np.mean(col <= 0))
     return row
+
+
+def beta_kept(it, burn_in):
+    """Full-parents methods scored from the beta chain (network.py:316-320): betas_vector[2:][burn_in:][x], x % 10 == 0,
+    i.e. betas_vector[it + 1] (the draw of iteration it) is kept iff it - 1 >= burn_in and (it - 1 - burn_in) % 10 == 0;
+    every segment's vector of a kept iteration is one posterior sample (beta_post_matrix, scores.py:139-153)."""
+    return it - 1 >= burn_in and (it - 1 - burn_in) % THIN == 0
 
 
 def mu_kept(idx, burn_in):

@@ -65,9 +65,11 @@ def main():
     run('yeast fixed nh-dbn, 64 chains', yeast, 'fixed_nh_dbn', 64, 100, 20)
     run('c3 mTOR seq-dbn, 256 chains', mtor, 'seq_coup_nh_dbn', 256, 50, 10)
     run('c3 mTOR glob-dbn, 256 chains', mtor, 'glob_coup_nh_dbn', 256, 50, 10)
+    run('mTOR var-glob-dbn, 256 chains', mtor, 'var_glob_coup_nh_dbn', 256, 50, 10)
     run('mTOR nh-dbn, 4096 chains (device filled)', mtor, 'varying_nh_dbn', 4096, 50, 10)
     run('mTOR seq-dbn, 4096 chains (device filled)', mtor, 'seq_coup_nh_dbn', 4096, 50, 10)
     run('mTOR glob-dbn, 4096 chains (device filled)', mtor, 'glob_coup_nh_dbn', 4096, 50, 10)
+    run('mTOR var-glob-dbn, 4096 chains (device filled)', mtor, 'var_glob_coup_nh_dbn', 4096, 50, 10)
     run('yeast fp-glob-dbn, 64 chains', yeast, 'fp_glob_coup_nh_dbn', 64, 20, 5)
     run('mTOR fp-glob-dbn, 256 chains', mtor, 'fp_glob_coup_nh_dbn', 256, 10, 3)
     run('synthetic 40 genes T=400 fp-glob-dbn, 64 chains', [syn40], 'fp_glob_coup_nh_dbn', 64, 5, 2)

@@ -185,12 +185,13 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     `change_points`: the predefined list of 'fixed_nh_dbn' (network.py:178-189), ending with the pseudo changepoint."""
     n = data_list[0].shape[1]
     is_fixed = method == 'fixed_nh_dbn'              # segments but no changepoint move
-    has_tau = method not in ('h_dbn', 'fixed_nh_dbn')
+    has_tau = method not in ('h_dbn', 'fixed_nh_dbn', 'fp_h_dbn')
     multi_seg = method != 'h_dbn'
     is_seq = method == 'seq_coup_nh_dbn'
-    is_fp = method == 'fp_glob_coup_nh_dbn'       # full parents: no parent-set move, design width = n
+    is_fp = method.startswith('fp_')              # full parents: no parent-set move, design width = n
+    is_fp_glob = method == 'fp_glob_coup_nh_dbn'
     is_vv = method == 'var_glob_coup_nh_dbn'      # vvglobCoup.py: segment-specific sigma^2_h, mu* drawn in the pi move only
-    is_glob = method == 'glob_coup_nh_dbn' or is_fp or is_vv
+    is_glob = method == 'glob_coup_nh_dbn' or is_fp_glob or is_vv
     KM = globals()['KM'] if not is_fp else max(globals()['KM'], n)
     EVENTS.clear()
     np.random.seed(seed)
@@ -211,14 +212,18 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
                     # histogram): thin the mu chain, stack it, credible_score per feature (scores.py:196-205,:245-246)
                     import dyban.scores as ref_scores
                     feats = [int(s_[1:]) for s_ in list(net.network_configuration['features'])]
-                    burned = res['mu_vector'][burn_in:]
-                    thinned = [[burned[x]] for x in range(len(burned)) if x % 10 == 0]
+                    if is_fp_glob:
+                        burned = res['mu_vector'][burn_in:]
+                        thinned = [[burned[x]] for x in range(len(burned)) if x % 10 == 0]
+                    else:   # network.py:316-320: the beta chain shifted by 2, every segment's vector is a sample
+                        burned = res['betas_vector'][2:][burn_in:]
+                        thinned = [burned[x] for x in range(len(burned)) if x % 10 == 0]
                     bm = ref_scores.beta_post_matrix(thinned)
                     row = [0.0] * n
                     for j, f in enumerate(feats):
                         row[f] = ref_scores.credible_score(bm[:, j + 1])
                     net.proposed_adj_matrix.append(row)
-                    burned_cps = res['tau_vector'][burn_in:]
+                    burned_cps = res['tau_vector'][burn_in:] if has_tau else []
                     net.cps_over_response.append([burned_cps[x] for x in range(len(burned_cps)) if x % 10 == 0])
                     continue
                 try:
@@ -262,8 +267,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     for i, (start, end, res) in enumerate(per_node):
         ev = EVENTS
         pos = start
-        pi_vec = res['pi_vector']
-        tau_vec = res['tau_vector']
+        pi_vec = res.get('pi_vector', [])
+        tau_vec = res.get('tau_vector', [])
         cur_tau = [int(c) for c in change_points] if is_fixed else [N + 2]
         cur_pi = [j for j in range(n) if j != i] if is_fp else []
         cur_mu = np.zeros(len(cur_pi) + 1)
@@ -365,7 +370,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
         # n-wide covariances would make the fixture several MB: keep their diagonals (the means, log-densities and
         # log-MLs recorded beside them pin the same matrices through Q^-1 and ln det Q)
         out['beta_cov_diag'] = np.diagonal(out.pop('beta_cov'), axis1=-2, axis2=-1).copy()
-        out['mus_cov_diag'] = np.diagonal(out.pop('mus_cov'), axis1=-2, axis2=-1).copy()
+        if 'mus_cov' in out:
+            out['mus_cov_diag'] = np.diagonal(out.pop('mus_cov'), axis1=-2, axis2=-1).copy()
     out['method'] = np.array(method)
     if is_fixed:
         out['change_points'] = np.array([int(c) for c in change_points], dtype=np.int32)
@@ -515,6 +521,13 @@ def main():
         run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
         run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
         return
+    if 'fp2-only' in sys.argv:      # full-parents nh / h fixtures
+        run_chain_golden('yeast', yeast, 'fp_varying_nh_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'fp_varying_nh_dbn', n_iter=60, burn_in=20, seed=2)
+        run_chain_golden('synth200', [syn], 'fp_varying_nh_dbn', n_iter=100, burn_in=20, seed=3)
+        run_chain_golden('yeast', yeast, 'fp_h_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'fp_h_dbn', n_iter=60, burn_in=20, seed=2)
+        return
     if 'fp-only' in sys.argv:       # add the full-parents fixtures without re-minting the others
         run_chain_golden('yeast', yeast, 'fp_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
         run_chain_golden('mtor', mtor, 'fp_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
@@ -540,6 +553,11 @@ def main():
     run_chain_golden('yeast', yeast, 'var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
     run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
     run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
+    run_chain_golden('yeast', yeast, 'fp_varying_nh_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'fp_varying_nh_dbn', n_iter=60, burn_in=20, seed=2)
+    run_chain_golden('synth200', [syn], 'fp_varying_nh_dbn', n_iter=100, burn_in=20, seed=3)
+    run_chain_golden('yeast', yeast, 'fp_h_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'fp_h_dbn', n_iter=60, burn_in=20, seed=2)
 
 
 if __name__ == '__main__':

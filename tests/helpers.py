@@ -12,8 +12,10 @@ LOGML_RTOL = 1e-9
 
 KAT_FILES = sorted(glob.glob(os.path.join(GOLDEN, 'kat_logml_*.npz')))
 _ALL_CHAINS = sorted(glob.glob(os.path.join(GOLDEN, 'chain_*.npz')))
-FP_CHAIN_FILES = [p for p in _ALL_CHAINS if '_fp_' in os.path.basename(p)]      # full-parents glob-coupled (n-wide)
-CHAIN_FILES = [p for p in _ALL_CHAINS if p not in FP_CHAIN_FILES]
+_FP_ALL = [p for p in _ALL_CHAINS if '_fp_' in os.path.basename(p)]              # full-parents methods (n-wide records)
+FP_CHAIN_FILES = [p for p in _FP_ALL if 'fp_glob' in os.path.basename(p)]        # globally coupled: scored from the mu chain
+FP_PLAIN_FILES = [p for p in _FP_ALL if p not in FP_CHAIN_FILES]                 # fp_varying_nh / fp_h: scored from the beta chain
+CHAIN_FILES = [p for p in _ALL_CHAINS if p not in _FP_ALL]
 
 
 def load(path):

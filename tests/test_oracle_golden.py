@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from helpers import FP_PLAIN_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
 from oracle import dbn_oracle as O
 
 
@@ -133,3 +133,38 @@ def test_fp_glob_chain_replay(path):
         kept = [mu_vec[i] for i in range(len(mu_vec)) if O.mu_kept(i, burn_in)]
         adj[node] = O.credible_scores(np.array(kept), [j for j in range(n) if j != node], n)
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
+
+
+@pytest.mark.parametrize('path', FP_PLAIN_FILES, ids=ids(FP_PLAIN_FILES))
+def test_fp_plain_chain_replay(path):
+    """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) and fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
+    the reference's recorded draws: changepoint lists / accept flags bit-exact, Gibbs parameters and log-MLs, and the
+    credible-score row of network.py:316-347 from the thinned beta chain (every segment's vector is a sample)."""
+    g = load(path)
+    method = str(g['method'])
+    X, Y = O.lagged_matrices(data_list(g))
+    n = X.shape[1]
+    n_iter, burn_in, N = int(g['n_iter']), int(g['burn_in']), int(g['N'])
+    adj = np.zeros((n, n))
+    cp_hist = np.zeros((n, N + 3)); cp_kept = np.zeros(n)
+    for node in range(n):
+        tr = O.run_chain(method, X, Y, node, n_iter, O.ReplayDraws(g, node))
+        assert np.array_equal(tr['S'], g['S'][node]) and np.array_equal(tr['tau_after'], g['tau_after'][node]), node
+        if method != 'fp_h_dbn':
+            for key in ('tau_valid', 'tau_accept'):
+                assert np.array_equal(tr[key], g[key][node]), (key, node)
+        for key in ('sig_shape', 'sig_scale', 'lam_shape', 'lam_scale'):
+            assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+        assert_close(tr['beta_mean'], g['beta_mean'][node], 1e-7, 1e-9, what='beta_mean node %d' % node)
+        assert_close(np.diagonal(tr['beta_cov'], axis1=-2, axis2=-1), g['beta_cov_diag'][node], 1e-7, 1e-13, what='beta_cov')
+        assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
+        samples = [tr['beta'][it, h, :n] for it in range(n_iter) if O.beta_kept(it, burn_in) for h in range(tr['S'][it])]
+        adj[node] = O.credible_scores(np.array(samples), [j for j in range(n) if j != node], n)
+        for it in range(n_iter):
+            if O.tau_kept(it, burn_in) and method != 'fp_h_dbn':
+                cp_kept[node] += 1
+                for c in [c for c in tr['tau_after'][it] if c >= 0][:-1]:
+                    cp_hist[node, c] += 1
+    assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores of the beta chain)')
+    if 'cp_hist' in g:
+        assert np.array_equal(cp_hist, g['cp_hist']) and np.array_equal(cp_kept, g['cp_kept'])
