@@ -48,6 +48,7 @@ struct FpArgs {
   unsigned long long* neg;      // [n][n]  #kept mu samples with mu_j <= 0
   unsigned long long* counters;
   double* ws;      // per-block workspace of FP_NMAT * ld * k doubles (null: matrices in shared memory)
+  double* bsc;     // plain full-parents methods: per-block [SMAX][2][k] posterior mean and direction of every beta_h
   const double* rd;
   const int* ri;
   double* td;
@@ -232,6 +233,38 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
   return r;
 }
 
+// t = L^-1 g by forward substitution on the Cholesky factor (idiag[j] = 1 / L[j][j]); column-oriented, k block steps
+__device__ void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t) {
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) t[i] = g[i];
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (threadIdx.x == 0) t[j] *= idiag[j];
+    __syncthreads();
+    const double tj = t[j];
+    for (int i = j + 1 + threadIdx.x; i < k; i += FP_BLOCK) t[i] -= L[i * ld + j] * tj;
+    __syncthreads();
+  }
+}
+
+// plain (mu = 0) marginal likelihood of one changepoint list (marginalLikelihood.py:91-150): only
+// s = sum y_h^T y_h, c = sum g_h^T A_h^-1 g_h and ld = sum ln det A_h are needed, so no inverse is formed
+template <class TauFn>
+__device__ FpSummary fp_sweep_plain(const Table& tb, int node, TauFn tau, int S, double lam, double* A, int ld, int k, double* g,
+                                    double* t, double* idiag, double* red, double* s_tmp) {
+  FpSummary r = {0.0, 0.0, 0.0};
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
+    fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
+    r.s += *s_tmp;
+    r.ld += fp_cholesky(A, ld, k, idiag);
+    fp_trsv(A, ld, k, idiag, g, t);
+    r.c += fp_dot(t, t, k, red);
+    lo = hi;
+  }
+  return r;
+}
+
 // sum_h r_h^T C_h^-1 r_h at mean mu from the sums
 __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k, const double* a_sum, const double* mu, double lam,
                              double* tmp, double* red) {
@@ -241,7 +274,10 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
   return sm.s - lam * sm.c - 2.0 * ma + mMm / lam;
 }
 
-template <bool TRACE>
+// GLOBM: the globally coupled model (fpGlobCoupBpwLinReg.py).  !GLOBM: the plain full-parents models, prior mean 0 —
+// fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140: nh changepoint move of moves.py:129-236) and, with with_tau == 0,
+// fp_h_dbn (fpBayesianLinearRegression.py:40-125: Gibbs draws only); their edge scores come from the thinned beta chain.
+template <bool TRACE, bool GLOBM = true>
 __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
   extern __shared__ double sm[];
   const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
@@ -257,6 +293,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
   int* s_int = s_tas + SMAX;             // [8]
   double* mats = a.ws ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
   double* A = mats, *W = mats + (long long)ld * k, *Mc = mats + 2ll * ld * k, *Ms = mats + 3ll * ld * k, *Q = mats + 4ll * ld * k;
+  double* bsc = a.bsc ? a.bsc + (long long)blockIdx.x * (2 * SMAX) * k : nullptr;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   const bool replay = TRACE && a.rd != nullptr;
   const int rds = fp_rd_stride(k), tds = fp_td_stride(k);
@@ -283,7 +320,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
       int* ti = (TRACE && a.ti) ? a.ti + ((long long)u * a.n_iter + li) * 16 : nullptr;
       if (TRACE && ti && tid == 0) ti[3] = S;
       // the initial zero vector mu_vector[0] is part of the thinned chain when burn_in == 0 (network.py:309-311)
-      if (it == 0 && a.burn_in == 0) {
+      if (GLOBM && it == 0 && a.burn_in == 0) {
         if (tid == 0) atomicAdd(&a.kept[node], 1ull);
         for (int j = 1 + tid; j < k; j += FP_BLOCK) {
           const int gene = fp_col(j, node) - 1;
@@ -325,6 +362,12 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
             acc_dd += fp_dot(tmp, tmp, k, red);
             acc_de += fp_dot(tmp, e, k, red);
             acc_ee += fp_dot(e, e, k, red);
+            if constexpr (!GLOBM) {   // kept for the sign counts below (read back by the thread that writes it)
+              for (int i = tid; i < k; i += FP_BLOCK) {
+                bsc[(2 * h) * k + i] = mean[i];
+                bsc[(2 * h + 1) * k + i] = e[i];
+              }
+            }
           } else {
             for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = rd[3 + k + h * k + i] - mu[i];  // injected beta_h
             __syncthreads();
@@ -367,6 +410,26 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
           if (!replay) td[10 + 3 * k + 2 * DBN_SMAX * k + i] = td[10 + 3 * k + i] + sg * td[10 + 3 * k + 2 * DBN_SMAX * k + i];
         }
       }
+      if constexpr (!GLOBM) {
+        // ---- counts: betas_vector[2:][burn_in:][x % 10 == 0] (network.py:316-320) keeps the draw of iteration it iff
+        // it - 1 >= burn_in and (it - 1 - burn_in) % thin == 0; every segment's beta_h is one posterior sample
+        // (beta_post_matrix, scores.py:139-153); pos / neg feed credible_score (scores.py:196-205)
+        if (it - 1 >= a.burn_in && ((it - 1 - a.burn_in) % a.thin) == 0) {
+          const double sgb = sqrt(sig2 * lam);
+          if (tid == 0) atomicAdd(&a.kept[node], (unsigned long long)S);
+          for (int j = 1 + tid; j < k; j += FP_BLOCK) {
+            unsigned long long npos = 0, nneg = 0;
+            for (int h = 0; h < S; ++h) {
+              const double b = replay ? rd[3 + k + h * k + j] : bsc[(2 * h) * k + j] + sgb * bsc[(2 * h + 1) * k + j];
+              npos += (b >= 0.0) ? 1 : 0;
+              nneg += (b <= 0.0) ? 1 : 0;
+            }
+            const int gene = fp_col(j, node) - 1;
+            if (npos) atomicAdd(&a.pos[(long long)node * n + gene], npos);
+            if (nneg) atomicAdd(&a.neg[(long long)node * n + gene], nneg);
+          }
+        }
+      }
       lam = sc[1];
 
       // ======================= changepoint move (moves.py:25-126) =================================================
@@ -398,9 +461,9 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
                 s_tas[w_++] = s_tau[j];
               }
               Ss = S + 1;
-              if (Ss > 9) valid = 0;  // moves.py:42
-              hr_num = ns - 1 - S;    // moves.py:46
-              hr_den = Ss;
+              if (Ss > 9) valid = 0;  // moves.py:42 (glob) / :156 (nh: == 10)
+              hr_num = GLOBM ? ns - 1 - S : ns - S;    // moves.py:46 / :159
+              hr_den = GLOBM ? Ss : Ss - 1;
             }
           } else if (S < 2) {
             valid = 0;
@@ -410,8 +473,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
             for (int j = 0; j < S; ++j)
               if (j != idx) s_tas[w_++] = s_tau[j];
             Ss = S - 1;
-            hr_num = S;  // moves.py:55
-            hr_den = ns - 1 - Ss;
+            hr_num = GLOBM ? S : S - 1;  // moves.py:55 / :163
+            hr_den = GLOBM ? ns - 1 - Ss : ns - Ss;
           } else {  // cpRellocationMove (:3-61)
             const int idx = replay ? ri[1] : (int)__umulhi(w.y, (uint32_t)(S - 1));
             const int last = s_tau[S - 1] - 1;
@@ -433,7 +496,29 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
         }
         __syncthreads();
         const int valid = s_int[1], Ss = s_int[2];
-        if (valid) {
+        if (!GLOBM && valid) {
+          // moves.py:184-232: two plain marginal likelihoods (prior mean 0), u < min(1, exp(delta))
+          const FpSummary sc_ = fp_sweep_plain(a.tb, node, tau_cur, S, lam, A, ld, k, g, t, x, red, sc + 3);
+          const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + sc_.s - lam * sc_.c);
+          const FpSummary ss_ = fp_sweep_plain(a.tb, node, tau_star, Ss, lam, A, ld, k, g, t, x, red, sc + 3);
+          const double ml_star = a.c0 - 0.5 * ss_.ld - a.T_half_plus_a * log(a.two_b + ss_.s - lam * ss_.c);
+          n_segs += S + Ss;
+          n_evals += 2;
+          const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
+          const double log_ratio = ml_star - ml_cur + lprior + log((double)s_int[3] / (double)s_int[4]);
+          const bool acc = sc[2] < fmin(1.0, exp(log_ratio));
+          if (TRACE && td && tid == 0) {
+            td[6] = ml_cur; td[7] = ml_star;
+          }
+          if (TRACE && ti && tid == 0) ti[2] = acc;
+          __syncthreads();
+          if (acc) {
+            S = Ss;
+            if (tid < SMAX) s_tau[tid] = s_tas[tid];
+          }
+          __syncthreads();
+        }
+        if (GLOBM && valid) {
           const double ils = 1.0 / (lam * sig2);
           // ---- current changepoints: log-ML at mu and the density of mu under muSampler(mu | tau) (moves.py:66-73)
           const FpSummary sc_ = fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3);
@@ -519,7 +604,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
         }
       }
       // ---- counts: mu_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin == 0 (network.py:309-311)
-      {
+      if constexpr (GLOBM) {
         const int idx = it + 1;
         if (idx >= a.burn_in && ((idx - a.burn_in) % a.thin) == 0) {
           if (tid == 0) atomicAdd(&a.kept[node], 1ull);

@@ -209,7 +209,7 @@ struct dbn_handle {
   int* st_cg = nullptr;
   bool cache_valid = false;
   // full-parents globally coupled chain: global mean [n][U], per-block matrix workspace (large n only)
-  double *st_mu_fp = nullptr, *d_fp_ws = nullptr;
+  double *st_mu_fp = nullptr, *d_fp_ws = nullptr, *d_fp_bsc = nullptr;
   int fp_grid = 0;
   unsigned long long* d_counts = nullptr;
   long long counts_elems = 0;
@@ -254,6 +254,8 @@ static chain_fn pick_method(int method) {
   }
 }
 
+
+static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN; }
 
 static std::string g_create_error;
 static std::mutex g_mu;
@@ -354,6 +356,7 @@ static void free_chain(dbn_handle* h) {
   free_dev(h->st_cg);
   free_dev(h->st_mu_fp);
   free_dev(h->d_fp_ws);
+  free_dev(h->d_fp_bsc);
   h->cache_valid = false;
   free_dev(h->d_counts);
   h->have_chain = false;
@@ -594,8 +597,8 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!h || !p) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
-  if (p->method < DBN_H_DBN || p->method > DBN_VV_GLOB_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
-  if (p->method != DBN_FP_GLOB_DBN && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
+  if (p->method < DBN_H_DBN || p->method > DBN_FP_H_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (!is_fp_method(p->method) && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
   const long long U = (long long)h->n * h->cfg.n_chains;
@@ -622,7 +625,7 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
     CU(h, cudaMalloc(&h->st_cg, U * PMAX * sizeof(int)));
   }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
-  if (p->method == DBN_FP_GLOB_DBN) {
+  if (is_fp_method(p->method)) {
     h->counts_elems += (long long)h->n * h->n;  // neg[n][n]
     const int k = h->n;
     CU(h, cudaMalloc(&h->st_mu_fp, (size_t)U * k * sizeof(double)));
@@ -637,6 +640,7 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
       cudaError_t e = cudaMalloc(&h->d_fp_ws, ws);
       if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "full-parents workspace of %.2f GB does not fit: %s", ws / 1e9, cudaGetErrorString(e));
     }
+    if (p->method != DBN_FP_GLOB_DBN) CU(h, cudaMalloc(&h->d_fp_bsc, (size_t)h->fp_grid * 2 * SMAX * k * sizeof(double)));
   }
   CU(h, cudaMalloc(&h->d_counts, (size_t)h->counts_elems * sizeof(unsigned long long)));
   CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->counts_elems * sizeof(unsigned long long), h->stream));
@@ -671,7 +675,7 @@ int dbn_set_changepoints(dbn_handle* h, const int32_t* tau, int32_t len) {
 int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d, int32_t* trace_i) {
   if (!h) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: call dbn_chain_init first");
-  if (h->rp.method == DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: the full-parents method runs with dbn_run_fp");
+  if (is_fp_method(h->rp.method)) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run: the full-parents methods run with dbn_run_fp");
   if (n_iter < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: n_iter < 0");
   if ((replay_d == nullptr) != (replay_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay_d and replay_i must be given together");
   if ((replay_d != nullptr) && !(trace_d && trace_i)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run: replay mode requires trace buffers");
@@ -771,7 +775,7 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
 
 int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t* replay_i, double* trace_d, int32_t* trace_i) {
   if (!h) return DBN_ERR_INVALID;
-  if (!h->have_chain || h->rp.method != DBN_FP_GLOB_DBN) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run_fp: call dbn_chain_init with DBN_FP_GLOB_DBN first");
+  if (!h->have_chain || !is_fp_method(h->rp.method)) DBN_FAIL(h, DBN_ERR_STATE, "dbn_run_fp: call dbn_chain_init with a full-parents method first");
   if (n_iter < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: n_iter < 0");
   if ((replay_d == nullptr) != (replay_i == nullptr)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: replay_d and replay_i must be given together");
   if ((replay_d != nullptr) && !(trace_d && trace_i)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_run_fp: replay mode requires trace buffers");
@@ -801,6 +805,7 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   a.neg = a.cp_kept + h->n;
   a.counters = h->d_counters;
   a.ws = h->d_fp_ws;
+  a.bsc = h->d_fp_bsc;
   const bool trace = trace_d != nullptr, replay = replay_d != nullptr;
   double *d_rd = nullptr, *d_td = nullptr;
   int *d_ri = nullptr, *d_ti = nullptr;
@@ -832,13 +837,12 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
     a.ri = d_ri;
   }
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
-  if (trace) {
-    CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fp_glob_kernel<true><<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
-  } else {
-    CUX(cudaFuncSetAttribute((const void*)fp_glob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fp_glob_kernel<false><<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
-  }
+  typedef void (*fp_fn)(const FpArgs);
+  const bool globm = p.method == DBN_FP_GLOB_DBN;
+  const fp_fn fn = trace ? (globm ? fp_glob_kernel<true, true> : fp_glob_kernel<true, false>)
+                         : (globm ? fp_glob_kernel<false, true> : fp_glob_kernel<false, false>);
+  CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
   CUX(cudaGetLastError());
   h->it_done += n_iter;
   if (trace) {

@@ -164,7 +164,7 @@ class DbnEngine:
         return unpack_trace(td, ti)
 
     def run_fp(self, n_iter, replay=None, trace=False):
-        """dbn_run_fp: advance every unit of a full-parents globally coupled chain (method 'fp_glob_coup_nh_dbn').
+        """dbn_run_fp: advance every unit of a full-parents chain ('fp_glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_h_dbn').
         `replay`: dict with sigma2, lambda2, u_tau [U, n_iter]; mu_tau [U, n_iter, k]; beta [U, n_iter, SMAX, k];
         tau_move [U, n_iter]; tau_pick [U, n_iter, 2].  Returns the unpacked trace dict when requested."""
         U, k = self.units, self.n
@@ -178,7 +178,8 @@ class DbnEngine:
             rd = np.full((U, n_iter, L.fp_rd_stride(k)), np.nan)
             ri = np.full((U, n_iter, L.FP_RI_STRIDE), -1, dtype=np.int32)
             rd[:, :, 0], rd[:, :, 1], rd[:, :, 2] = replay['sigma2'], replay['lambda2'], replay['u_tau']
-            rd[:, :, 3:3 + k] = np.asarray(replay['mu_tau'])[:, :, :k]
+            if 'mu_tau' in replay:     # globally coupled only
+                rd[:, :, 3:3 + k] = np.asarray(replay['mu_tau'])[:, :, :k]
             rd[:, :, 3 + k:] = np.asarray(replay['beta'])[:, :, :, :k].reshape(U, n_iter, L.SMAX * k)
             ri[:, :, 0] = replay['tau_move']
             ri[:, :, 1:3] = replay['tau_pick']

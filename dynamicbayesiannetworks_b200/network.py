@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, METHOD_NAMES, FIXED_CP
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -24,6 +24,8 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Varying Parents'),
     'fp_glob_coup_nh_dbn': ('Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:246-247
     'fixed_nh_dbn': ('Bayesian Non-Homogeneous', 'Varying Parents-Fixed changepoints'),   # network.py:179-180
+    'fp_varying_nh_dbn': ('Bayesian Non-Homogeneous', 'Full Parents'),   # network.py:166-167
+    'fp_h_dbn': ('Bayesian Homogeneous', 'Full Parents'),                # network.py:201-202
     'var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Varying Parents'),   # network.py:259-260
 }
 
@@ -108,7 +110,7 @@ class Network():
             traces = []
             window = self.window or (n_iter if self.keep_chain else 100)
             done = 0
-            run = eng.run_fp if mid == FP_GLOB_DBN else eng.run
+            run = eng.run_fp if mid in FP_METHODS else eng.run
             while done < n_iter:
                 w = min(window, n_iter - done)
                 if self.keep_chain:
@@ -122,8 +124,8 @@ class Network():
         return self
 
     def _finish(self, name, mid, dims, N, counts, traces):
-        if mid == FP_GLOB_DBN:
-            return self._finish_fp(dims, N, counts, traces)
+        if mid in FP_METHODS:
+            return self._finish_fp(mid, dims, N, counts, traces)
         adj = parallel.edge_scores_from_counts(counts['edge'], counts['nonempty'])
         self.proposed_adj_matrix = [[float(v) for v in row] for row in adj]
         self.edge_scores = self.proposed_adj_matrix[-1]
@@ -140,8 +142,9 @@ class Network():
                     burned = r['tau_vector'][b:]
                     self.cps_over_response.append([burned[x] for x in range(len(burned)) if x % 10 == 0])
 
-    def _finish_fp(self, dims, N, counts, traces):
-        """network.py:303-347 for 'fp_glob_coup_nh_dbn': edge scores are credible scores of the thinned global-mean chain."""
+    def _finish_fp(self, mid, dims, N, counts, traces):
+        """network.py:303-347: edge scores are credible scores of the thinned global-mean chain ('fp_glob_coup_nh_dbn') or of
+        the thinned beta chain, every segment's vector a sample ('fp_varying_nh_dbn', 'fp_h_dbn')."""
         adj = parallel.credible_scores_from_counts(counts['edge'], counts['neg'], counts['nonempty'])
         self.network_args['scoring_method'] = 'fraq-score'
         self.proposed_adj_matrix = [[float(v) for v in row] for row in adj]
@@ -159,11 +162,13 @@ class Network():
                     'lambda_sqr_vector': [1] + [float(v) for v in cat['lambda2'][u]],
                     'sigma_sqr_vector': [1] + [float(v) for v in cat['sigma2'][u]],
                     'pi_vector': [pi],
-                    'tau_vector': [[int(c) for c in cat['tau_after'][u, it, :cat['S_after'][u, it]]] for it in range(n_iter)],
-                    'mu_vector': [np.zeros((dims, 1))] + [np.array(cat['mu_after'][u, it]).reshape(-1, 1) for it in range(n_iter)],
+                    'tau_vector': [] if mid == FP_H_DBN else
+                                  [[int(c) for c in cat['tau_after'][u, it, :cat['S_after'][u, it]]] for it in range(n_iter)],
                     'betas_vector': [[np.zeros(dims)]] + [[np.array(cat['beta'][u, it, h]) for h in range(int(cat['S'][u, it]))]
                                                           for it in range(n_iter)],
                 }
+                if mid == FP_GLOB_DBN:
+                    res['mu_vector'] = [np.zeros((dims, 1))] + [np.array(cat['mu_after'][u, it]).reshape(-1, 1) for it in range(n_iter)]
                 self.chain_results_per_node.append(res)
                 burned = res['tau_vector'][b:]
                 self.cps_over_response.append([burned[x] for x in range(len(burned)) if x % 10 == 0])

@@ -46,10 +46,14 @@ typedef enum {
   DBN_GLOB_DBN = 3, /* 'glob_coup_nh_dbn' globCoupBayesianPwLinReg.py:16-124      */
   DBN_FP_GLOB_DBN = 4, /* 'fp_glob_coup_nh_dbn' fpGlobCoupBpwLinReg.py:16-119: every other gene is a parent (design
                          width k = n), no parent-set move, globally coupled changepoint move; run with dbn_run_fp */
-  DBN_VV_GLOB_DBN = 5  /* 'var_glob_coup_nh_dbn' vvglobCoup.py:16-123: globally coupled with a segment-specific
+  DBN_VV_GLOB_DBN = 5, /* 'var_glob_coup_nh_dbn' vvglobCoup.py:16-123: globally coupled with a segment-specific
                          variance sigma^2_h (segmentSigmaSampler samplers.py:90-101), vvLogMargLikelihood
                          (marginalLikelihood.py:5-43), vvMuSampler (samplers.py:353-394), vvGlobCoupPiMove /
                          vvGlobCoupTauMove (moves.py:238-415)                                                  */
+  DBN_FP_NH_DBN = 6,   /* 'fp_varying_nh_dbn' fullParentsBpwLinReg.py:41-140: full parents, prior mean 0, the nh changepoint
+                         move (moves.py:129-236); run with dbn_run_fp                                          */
+  DBN_FP_H_DBN = 7     /* 'fp_h_dbn' fpBayesianLinearRegression.py:40-125: full parents, one segment, Gibbs draws only;
+                         run with dbn_run_fp                                                                   */
 } dbn_method;
 
 typedef struct dbn_handle dbn_handle;
@@ -220,6 +224,9 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
  *            muSampler mean (tau*) [k], beta posterior means [DBN_SMAX][k], diag of the beta covariances [DBN_SMAX][k],
  *            drawn beta_h [DBN_SMAX][k]
  *   trace_i  [units, n_iter, 16]: tau_move, tau_valid, tau_accept, S before, S after, tau[DBN_SMAX], (pad)
+ * DBN_FP_NH_DBN / DBN_FP_H_DBN use the same records (the mu fields stay NaN / zero); their sign counts are taken over the
+ * kept draws of the beta chain instead: every beta_h of iteration it with it - 1 >= burn_in and (it - 1 - burn_in) % thin
+ * == 0 is one sample (network.py:316-320, scores.py:139-153), nonempty[i] = #samples.
  * Counts for this method reuse the block below with: edge[i][j] = #kept mu samples of node i with mu_j >= 0,
  * nonempty[i] = #kept mu samples (network.py:309-311), and one more matrix appended after cp_kept:
  * neg[n][n] = #kept samples with mu_j <= 0; the edge score is max(edge, neg) / nonempty (credible_score,

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
+from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, FP_PLAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
 from oracle import dbn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -282,6 +282,8 @@ def test_network_dropin(eng_mod):
     assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)
     with pytest.raises(NotImplementedError):
         Network(data, 10, 0, 1).infer_network('fp_var_glob_coup_nh_dbn')
+    with pytest.raises(NotImplementedError):
+        Network(data, 10, 0, 1).infer_network('fp_seq_coup_nh_dbn')
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -320,6 +322,78 @@ def test_fp_glob_replay_vs_reference(eng_mod, path):
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
     assert np.array_equal(counts['cp_hist'], g['cp_hist'].astype(np.int64))
     assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
+
+
+@pytest.mark.parametrize('path', FP_PLAIN_FILES, ids=ids(FP_PLAIN_FILES))
+def test_fp_plain_replay_vs_reference(eng_mod, path):
+    """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) / fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
+    the reference's recorded draws: changepoint lists and accept flags bit-exact, log-MLs 1e-9, Gibbs parameters, and the
+    credible scores of the thinned beta chain (network.py:316-347) from the device's sign counts."""
+    from dynamicbayesiannetworks_b200 import parallel
+    g = load(path)
+    method = str(g['method'])
+    n, n_iter = g['sigma2'].shape
+    burn_in = int(g['burn_in'])
+    replay = dict(sigma2=g['sigma2'], lambda2=g['lambda2'], u_tau=g['u_tau'], beta=g['beta'], tau_move=g['tau_move'],
+                  tau_pick=g['tau_pick'])
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data_list(g))
+        e.chain_init(method, burn_in=burn_in)
+        tr = e.run_fp(n_iter, replay=replay, trace=True)
+        counts = e.counts()
+    assert np.array_equal(tr['S'], g['S']) and np.array_equal(tr['tau_after'], g['tau_after'])
+    if method != 'fp_h_dbn':
+        for key in ('tau_valid', 'tau_accept'):
+            assert np.array_equal(tr[key], g[key]), key
+    assert_close(tr['sig_shape'], g['sig_shape'], 1e-12, what='sig_shape')
+    assert_close(1.0 / tr['sig_rate'], g['sig_scale'], 1e-9, what='sig_scale')
+    assert_close(tr['lam_shape'], g['lam_shape'], 1e-12, what='lam_shape')
+    assert_close(1.0 / tr['lam_rate'], g['lam_scale'], 1e-9, what='lam_scale')
+    assert_close(tr['logml'], g['logml'][:, :, 2:4], LOGML_RTOL, what='logml')
+    assert_close(tr['beta_mean'], g['beta_mean'][..., :n], 1e-7, 1e-9, what='beta_mean')
+    assert_close(tr['beta_cov_diag'], g['beta_cov_diag'][..., :n], 1e-7, 1e-13, what='beta_cov_diag')
+    adj = parallel.credible_scores_from_counts(counts['edge'], counts['neg'], counts['nonempty'])
+    assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores of the beta chain)')
+    if 'cp_hist' in g:
+        assert np.array_equal(counts['cp_hist'], g['cp_hist'].astype(np.int64))
+        assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
+
+
+@pytest.mark.parametrize('method', ['fp_varying_nh_dbn', 'fp_h_dbn'])
+def test_fp_plain_free_running_and_dropin(eng_mod, method):
+    """Free-running Philox chains of the plain full-parents methods: the device's sign counts equal the credible scores
+    recomputed on the host from the traced beta chain (same run), the posterior-mean betas agree with the oracle's
+    free-running chain within Monte-Carlo error, and the Network drop-in returns the reference's result keys."""
+    import pickle
+    from dynamicbayesiannetworks_b200 import Network
+    g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
+    data = data_list(g)
+    X, Y = O.lagged_matrices(data)
+    n = X.shape[1]
+    net = Network(data, 400, 100, 1, keep_chain=True)
+    net.infer_network(method)
+    adj = np.array(net.proposed_adj_matrix)
+    assert adj.shape == (n, n) and (adj >= 0.5 - 1e-12)[~np.eye(n, dtype=bool)].all() and (adj <= 1).all()
+    assert np.allclose(np.diag(adj), 0)
+    for node in range(n):
+        r = net.chain_results_per_node[node]
+        assert len(r['betas_vector']) == 401 and len(r['sigma_sqr_vector']) == 401
+        assert (len(r['tau_vector']) == 400) == (method != 'fp_h_dbn')
+        burned = r['betas_vector'][2:][100:]                      # network.py:316-320
+        samples = np.array([v for x in range(len(burned)) if x % 10 == 0 for v in burned[x]])
+        row = O.credible_scores(samples, [j for j in range(n) if j != node], n)
+        assert_close(adj[node], row, 1e-14, what='credible scores node %d' % node)
+    pickle.loads(pickle.dumps(net))
+    # posterior mean of beta (segments pooled) vs the oracle's free-running chains
+    node = 0
+    mine = np.array([v for it in range(100, 400) for v in net.chain_results_per_node[node]['betas_vector'][it + 1]]).mean(axis=0)
+    rng = np.random.default_rng(3)
+    ref = []
+    for _ in range(4):
+        tr = O.run_chain(method, X, Y, node, 300, O.RngDraws(rng))
+        ref += [tr['beta'][it, h, :n] for it in range(100, 300) for h in range(tr['S'][it])]
+    ref = np.array(ref).mean(axis=0)
+    assert np.abs(mine - ref).max() < 0.25, (mine, ref)
 
 
 def test_fp_glob_large_n_workspace_path(eng_mod):
