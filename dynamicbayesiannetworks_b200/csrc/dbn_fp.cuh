@@ -21,10 +21,12 @@
 
 namespace dbn {
 
-constexpr int FP_BLOCK_MAX = 128;
+constexpr int FP_BLOCK_MAX = 256;
 // threads per block: one warp while a matrix row fits it (k <= 32: the block barriers are then warp-local and the idle
 // warps of a wider block no longer wait in them — 54 % of all stall samples at k = 11, profiles/r1_v9), else 64 / 128
-inline int fp_block_threads(int k) { return k <= 32 ? 32 : (k <= 64 ? 64 : 128); }
+// the large-k path (matrices in the global workspace, blocked routines below) always runs FP_BIG_BLOCK threads
+constexpr int FP_BIG_BLOCK = 256;
+inline int fp_block_threads(int k, bool mats_in_smem) { return !mats_in_smem ? FP_BIG_BLOCK : (k <= 32 ? 32 : (k <= 64 ? 64 : 128)); }
 #define FP_BLOCK ((int)blockDim.x)
 constexpr int FP_NMAT = 5;  // A/L, W, M (tau), M (tau*), Q
 constexpr int FP_NVEC = 12;
@@ -117,8 +119,16 @@ __device__ void fp_symv(const double* M, int ld, int k, const double* x, double*
   __syncthreads();
 }
 
+// blocked large-k routines (defined below); `stage` != nullptr selects them in the dispatching helpers
+__device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage);
+__device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage);
+__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage);
+__device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t);
+__device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red);
+
 // in-place lower Cholesky of the full symmetric matrix A (upper part left untouched); returns ln det A
-__device__ double fp_cholesky(double* A, int ld, int k, double* idiag) {  // idiag[j] = 1 / L[j][j]
+__device__ double fp_cholesky(double* A, int ld, int k, double* idiag, double* stage) {  // idiag[j] = 1 / L[j][j]
+  if (stage) return fp_potrf_big(A, ld, k, idiag, stage);
   double mant = 1.0;  // product of the pivots l_j = sqrt(d_j) as mantissa x 2^expo: one log per factorisation
   int expo = 0;
   for (int j = 0; j < k; ++j) {
@@ -148,7 +158,8 @@ __device__ double fp_cholesky(double* A, int ld, int k, double* idiag) {  // idi
 }
 
 // W = L^-1 (lower triangular, zeros above the diagonal): forward substitution on all columns at once
-__device__ void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag) {
+__device__ void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag, double* stage) {
+  if (stage) return fp_trinv_big(L, W, ld, k, idiag, stage);
   for (int c = threadIdx.x; c < k; c += FP_BLOCK) {
     for (int i = 0; i < c; ++i) W[i * ld + c] = 0.0;
     for (int i = c; i < k; ++i) {
@@ -161,7 +172,8 @@ __device__ void fp_trinv(const double* L, double* W, int ld, int k, const double
 }
 
 // t = W x (lower triangular W), thread per row
-__device__ void fp_trmv(const double* W, int ld, int k, const double* x, double* t) {
+__device__ void fp_trmv(const double* W, int ld, int k, const double* x, double* t, double* stage) {
+  if (stage) return fp_trmv_big(W, ld, k, x, t);
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
     for (int j = 0; j <= i; ++j) acc += W[i * ld + j] * x[j];
@@ -171,7 +183,8 @@ __device__ void fp_trmv(const double* W, int ld, int k, const double* x, double*
 }
 
 // y = W^T t (lower triangular W), thread per output entry: coalesced over a
-__device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y) {
+__device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y, double* stage, double* red) {
+  if (stage) return fp_trmv_t_big(W, ld, k, t, y, red);
   for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
     double acc = 0.0;
     for (int i = a; i < k; ++i) acc += W[i * ld + a] * t[i];
@@ -181,7 +194,8 @@ __device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, doubl
 }
 
 // M += I - W^T W (full symmetric)
-__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k) {
+__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage) {
+  if (stage) return fp_syrk_big(W, M, ld, k, stage);
   for (int a = 0; a < k; ++a) {
     for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
       double acc = 0.0;
@@ -189,6 +203,249 @@ __device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, i
       const double v = ((a == b) ? 1.0 : 0.0) - acc;
       M[a * ld + b] += v;
       if (a != b) M[b * ld + a] += v;
+    }
+  }
+  __syncthreads();
+}
+
+
+// =====================================================================================================================
+// Large k (the k x k matrices live in the per-block global workspace): blocked routines.  The unblocked ones above touch
+// the whole trailing matrix once per column (k^3/3 element read-modify-writes per factorisation, ~3 memory instructions
+// per FMA); these keep FP_NB accumulators per thread in registers and stream each operand once per panel.
+// Layout: the factor is stored as U = L^T in the UPPER triangle (U[j][i] at A[j * ld + i], i >= j), so that for a fixed
+// factor row j consecutive threads (consecutive i) read consecutive addresses; the inverse factor V = U^-1 = W^T likewise.
+// The strictly lower triangle of A keeps the (symmetric) input.  Every routine expects FP_BIG_BLOCK threads.
+// =====================================================================================================================
+constexpr int FP_NB = 16;   // panel width = accumulators per thread and row
+constexpr int FP_JC = 32;   // rows of the broadcast operand staged in shared memory at a time
+constexpr int FP_SY_T = 64, FP_SY_IC = 16, FP_SY_LD = 68;   // fp_syrk_big: tile, depth chunk, padded leading dimension
+constexpr int FP_STAGE_DOUBLES = 2 * FP_SY_IC * FP_SY_LD;  // largest user (potrf / trinv need FP_JC*FP_NB + FP_NB*FP_NB + FP_NB)
+
+// in-place Cholesky A = U^T U, left-looking by panels of FP_NB factor rows; returns ln det A, idiag[j] = 1 / U[j][j]
+__device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage) {
+  double* Bs = stage;                  // [FP_JC][FP_NB]  Bs[jj][c] = U[j0 + jj][p0 + c]
+  double* D = stage + FP_JC * FP_NB;   // [FP_NB][FP_NB]  diagonal block, lower factor after the in-block step
+  double* Di = D + FP_NB * FP_NB;      // [FP_NB]         reciprocal pivots of the block
+  const int tid = threadIdx.x, T = FP_BLOCK;
+  double mant = 1.0;
+  int expo = 0;
+  for (int p0 = 0; p0 < k; p0 += FP_NB) {
+    const int nb = min(FP_NB, k - p0);
+    for (int ib = p0; ib < k; ib += 2 * T) {   // two matrix columns i0, i1 of the panel's factor rows per thread
+      const int i0 = ib + tid, i1 = i0 + T;
+      const bool on0 = i0 < k, on1 = i1 < k;
+      double acc0[FP_NB], acc1[FP_NB];
+#pragma unroll
+      for (int c = 0; c < FP_NB; ++c) {   // rows p0.. of A are still the input (symmetric: entries left of the diagonal too)
+        acc0[c] = (on0 && c < nb) ? A[(long long)(p0 + c) * ld + i0] : 0.0;
+        acc1[c] = (on1 && c < nb) ? A[(long long)(p0 + c) * ld + i1] : 0.0;
+      }
+      for (int j0 = 0; j0 < p0; j0 += FP_JC) {
+        const int jn = min(FP_JC, p0 - j0);
+        __syncthreads();
+        for (int e = tid; e < jn * FP_NB; e += T) {
+          const int jj = e / FP_NB, c = e - jj * FP_NB;
+          Bs[e] = (c < nb) ? A[(long long)(j0 + jj) * ld + p0 + c] : 0.0;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < jn; ++jj) {
+          const double a0 = on0 ? A[(long long)(j0 + jj) * ld + i0] : 0.0;
+          const double a1 = on1 ? A[(long long)(j0 + jj) * ld + i1] : 0.0;
+#pragma unroll
+          for (int c = 0; c < FP_NB; ++c) {
+            const double b = Bs[jj * FP_NB + c];
+            acc0[c] = fma(-a0, b, acc0[c]);
+            acc1[c] = fma(-a1, b, acc1[c]);
+          }
+        }
+      }
+      const bool diag_pass = ib == p0;
+      if (diag_pass) {   // block-uniform: the panel's own rows are columns i0 of threads tid < nb
+        __syncthreads();
+        if (tid < nb) {
+#pragma unroll
+          for (int c = 0; c < FP_NB; ++c) D[tid * FP_NB + c] = acc0[c];
+        }
+        __syncthreads();
+        for (int c = 0; c < nb; ++c) {
+          if (tid == c) {
+            const double d = sqrt(D[c * FP_NB + c]);
+            D[c * FP_NB + c] = d;
+            Di[c] = 1.0 / d;
+          }
+          __syncthreads();
+          if (tid > c && tid < nb) D[tid * FP_NB + c] *= Di[c];
+          __syncthreads();
+          if (tid > c && tid < nb) {
+            const double l = D[tid * FP_NB + c];
+            for (int c2 = c + 1; c2 <= tid; ++c2) D[tid * FP_NB + c2] -= l * D[c2 * FP_NB + c];
+          }
+          __syncthreads();
+        }
+        for (int c = 0; c < nb; ++c) {
+          int ex;
+          mant = frexp(mant * D[c * FP_NB + c], &ex);
+          expo += ex;
+        }
+        if (tid < nb) idiag[p0 + tid] = Di[tid];
+      }
+      // rows below the block: x U_pp = acc, forward over the block's columns
+#pragma unroll
+      for (int c = 0; c < FP_NB; ++c) {
+        if (c < nb) {
+          double s0 = acc0[c], s1 = acc1[c];
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) {
+            const double d = D[c * FP_NB + c2];
+            s0 = fma(-acc0[c2], d, s0);
+            s1 = fma(-acc1[c2], d, s1);
+          }
+          acc0[c] = s0 * Di[c];
+          acc1[c] = s1 * Di[c];
+        }
+      }
+      const bool in_block = diag_pass && tid < nb;
+#pragma unroll
+      for (int c = 0; c < FP_NB; ++c) {
+        if (c < nb) {
+          if (on0 && i0 >= p0 + c) A[(long long)(p0 + c) * ld + i0] = in_block ? D[tid * FP_NB + c] : acc0[c];
+          if (on1) A[(long long)(p0 + c) * ld + i1] = acc1[c];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  return 2.0 * (log(mant) + (double)expo * 0.69314718055994530942);
+}
+
+// V = U^-1 (upper triangle of W; the lower triangle is not written and never read), thread per column, row blocks bottom-up
+__device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage) {
+  double* Us = stage;                  // [FP_JC][FP_NB]  Us[mm][r] = U[j0 + r][m0 + mm]
+  double* Ud = stage + FP_JC * FP_NB;  // [FP_NB][FP_NB]  Ud[r][r2] = U[j0 + r][j0 + r2], r2 > r
+  const int tid = threadIdx.x, T = FP_BLOCK;
+  for (int cb = 0; cb < k; cb += T) {
+    const int c = cb + tid;
+    const bool on = c < k;
+    const int cmax = min(k, cb + T) - 1;
+    for (int j0 = (cmax / FP_NB) * FP_NB; j0 >= 0; j0 -= FP_NB) {
+      const int nb = min(FP_NB, k - j0);
+      double acc[FP_NB];
+#pragma unroll
+      for (int r = 0; r < FP_NB; ++r) acc[r] = 0.0;
+      for (int m0 = j0 + nb; m0 <= cmax; m0 += FP_JC) {
+        const int mn = min(FP_JC, cmax + 1 - m0);
+        __syncthreads();
+        for (int e = tid; e < mn * FP_NB; e += T) {
+          const int r = e / mn, mm = e - r * mn;
+          Us[mm * FP_NB + r] = (r < nb) ? A[(long long)(j0 + r) * ld + m0 + mm] : 0.0;
+        }
+        __syncthreads();
+        for (int mm = 0; mm < mn; ++mm) {
+          const int m = m0 + mm;
+          const double v = (on && m <= c) ? W[(long long)m * ld + c] : 0.0;
+#pragma unroll
+          for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[mm * FP_NB + r], v, acc[r]);
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < FP_NB * FP_NB; e += T) {
+        const int r = e / FP_NB, r2 = e - r * FP_NB;
+        Ud[e] = (r < nb && r2 < nb && r2 > r) ? A[(long long)(j0 + r) * ld + j0 + r2] : 0.0;
+      }
+      __syncthreads();
+      double v[FP_NB];
+#pragma unroll
+      for (int r = FP_NB - 1; r >= 0; --r) {
+        double sacc = ((j0 + r == c) ? 1.0 : 0.0) - acc[r];
+#pragma unroll
+        for (int r2 = r + 1; r2 < FP_NB; ++r2) sacc = fma(-Ud[r * FP_NB + r2], v[r2], sacc);
+        v[r] = (r < nb && on && j0 + r <= c) ? sacc * idiag[j0 + r] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < FP_NB; ++r)
+        if (r < nb && on && j0 + r <= c) W[(long long)(j0 + r) * ld + c] = v[r];
+    }
+  }
+  __syncthreads();
+}
+
+// M += I - V V^T (= I - A^-1; full symmetric M), 64 x 64 tiles of the lower triangle, 4 x 4 outputs per thread
+__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage) {
+  double* As = stage;
+  double* Bs = stage + FP_SY_IC * FP_SY_LD;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  for (int a0 = 0; a0 < k; a0 += FP_SY_T) {
+    for (int b0 = 0; b0 <= a0; b0 += FP_SY_T) {
+      double acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+      for (int i0 = a0; i0 < k; i0 += FP_SY_IC) {   // V[a][i] = 0 for i < a, a >= a0
+        __syncthreads();
+        for (int e = tid; e < FP_SY_T * FP_SY_IC; e += FP_BIG_BLOCK) {
+          const int rr = e >> 4, ii = e & 15, i = i0 + ii;
+          const int ra = a0 + rr, rb = b0 + rr;
+          As[ii * FP_SY_LD + rr] = (ra < k && i < k && i >= ra) ? W[(long long)ra * ld + i] : 0.0;
+          Bs[ii * FP_SY_LD + rr] = (rb < k && i < k && i >= rb) ? W[(long long)rb * ld + i] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ii = 0; ii < FP_SY_IC; ++ii) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            av[p] = As[ii * FP_SY_LD + ty * 4 + p];
+            bv[p] = Bs[ii * FP_SY_LD + tx * 4 + p];
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ra = a0 + ty * 4 + p, rb = b0 + tx * 4 + q;
+          if (ra < k && rb <= ra) {
+            const double v = ((ra == rb) ? 1.0 : 0.0) - acc[p][q];
+            M[(long long)ra * ld + rb] += v;
+            if (ra != rb) M[(long long)rb * ld + ra] += v;
+          }
+        }
+    }
+  }
+  __syncthreads();
+}
+
+// t = L^-1 x = V^T x: thread per entry, coalesced over the entries
+__device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t) {
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+    double acc = 0.0;
+    for (int j = 0; j <= i; ++j) acc += W[(long long)j * ld + i] * x[j];
+    t[i] = acc;
+  }
+  __syncthreads();
+}
+
+// y = L^-T t = V t: 16 rows at a time, 16 threads per row striding its entries, partial sums through `red`
+__device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red) {
+  const int tid = threadIdx.x, rr = tid >> 4, sl = tid & 15;
+  for (int ab = 0; ab < k; ab += 16) {
+    const int ra = ab + rr;
+    double acc = 0.0;
+    if (ra < k)
+      for (int i = ra + sl; i < k; i += 16) acc += W[(long long)ra * ld + i] * t[i];
+    __syncthreads();
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < 16 && ab + tid < k) {
+      double z = 0.0;
+      for (int q = 0; q < 16; ++q) z += red[tid * 16 + q];
+      y[ab + tid] = z;
     }
   }
   __syncthreads();
@@ -211,7 +468,7 @@ struct FpSummary {
 
 template <class TauFn>
 __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, double lam, double* A, double* W, double* M, int ld, int k,
-                              double* g, double* t, double* x, double* a_sum, double* red, double* s_tmp) {
+                              double* g, double* t, double* x, double* a_sum, double* red, double* s_tmp, double* stage) {
   FpSummary r = {0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] = 0.0;
   for (int i = threadIdx.x; i < k * ld; i += FP_BLOCK) M[i] = 0.0;
@@ -221,27 +478,27 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
     const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
     fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
     r.s += *s_tmp;
-    r.ld += fp_cholesky(A, ld, k, t);
-    fp_trinv(A, W, ld, k, t);
-    fp_trmv(W, ld, k, g, t);                 // t = L^-1 g
+    r.ld += fp_cholesky(A, ld, k, t, stage);
+    fp_trinv(A, W, ld, k, t, stage);
+    fp_trmv(W, ld, k, g, t, stage);          // t = L^-1 g
     r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
-    fp_trmv_t(W, ld, k, t, x);               // x = A^-1 g
+    fp_trmv_t(W, ld, k, t, x, stage, red);   // x = A^-1 g
     for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] += x[i];
-    fp_accumulate_i_minus_ainv(W, M, ld, k);
+    fp_accumulate_i_minus_ainv(W, M, ld, k, stage);
     lo = hi;
   }
   return r;
 }
 
 // t = L^-1 g by forward substitution on the Cholesky factor (idiag[j] = 1 / L[j][j]); column-oriented, k block steps
-__device__ void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t) {
+__device__ void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t, bool upper) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) t[i] = g[i];
   __syncthreads();
   for (int j = 0; j < k; ++j) {
     if (threadIdx.x == 0) t[j] *= idiag[j];
     __syncthreads();
     const double tj = t[j];
-    for (int i = j + 1 + threadIdx.x; i < k; i += FP_BLOCK) t[i] -= L[i * ld + j] * tj;
+    for (int i = j + 1 + threadIdx.x; i < k; i += FP_BLOCK) t[i] -= (upper ? L[(long long)j * ld + i] : L[i * ld + j]) * tj;
     __syncthreads();
   }
 }
@@ -250,15 +507,15 @@ __device__ void fp_trsv(const double* L, int ld, int k, const double* idiag, con
 // s = sum y_h^T y_h, c = sum g_h^T A_h^-1 g_h and ld = sum ln det A_h are needed, so no inverse is formed
 template <class TauFn>
 __device__ FpSummary fp_sweep_plain(const Table& tb, int node, TauFn tau, int S, double lam, double* A, int ld, int k, double* g,
-                                    double* t, double* idiag, double* red, double* s_tmp) {
+                                    double* t, double* idiag, double* red, double* s_tmp, double* stage) {
   FpSummary r = {0.0, 0.0, 0.0};
   int lo = 0;
   for (int h = 0; h < S; ++h) {
     const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
     fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
     r.s += *s_tmp;
-    r.ld += fp_cholesky(A, ld, k, idiag);
-    fp_trsv(A, ld, k, idiag, g, t);
+    r.ld += fp_cholesky(A, ld, k, idiag, stage);
+    fp_trsv(A, ld, k, idiag, g, t, stage != nullptr);
     r.c += fp_dot(t, t, k, red);
     lo = hi;
   }
@@ -278,7 +535,7 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
 // fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140: nh changepoint move of moves.py:129-236) and, with with_tau == 0,
 // fp_h_dbn (fpBayesianLinearRegression.py:40-125: Gibbs draws only); their edge scores come from the thinned beta chain.
 template <bool TRACE, bool GLOBM = true>
-__global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
+__global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a) {
   extern __shared__ double sm[];
   const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
   const int tid = threadIdx.x;
@@ -292,6 +549,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
   int* s_tas = s_tau + SMAX;
   int* s_int = s_tas + SMAX;             // [8]
   double* mats = a.ws ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
+  double* stage = a.ws ? reinterpret_cast<double*>(s_int + 8) : nullptr;   // large k: staging of the blocked routines
   double* A = mats, *W = mats + (long long)ld * k, *Mc = mats + 2ll * ld * k, *Ms = mats + 3ll * ld * k, *Q = mats + 4ll * ld * k;
   double* bsc = a.bsc ? a.bsc + (long long)blockIdx.x * (2 * SMAX) * k : nullptr;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -347,16 +605,16 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
           }
           __syncthreads();
           const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
-          fp_cholesky(A, ld, k, t);
-          fp_trinv(A, W, ld, k, t);
-          fp_trmv(W, ld, k, x, t);
+          fp_cholesky(A, ld, k, t, stage);
+          fp_trinv(A, W, ld, k, t, stage);
+          fp_trmv(W, ld, k, x, t, stage);
           q_sum += rho - lam * fp_dot(t, t, k, red);
-          fp_trmv(W, ld, k, rhs, t);
-          fp_trmv_t(W, ld, k, t, mean);
+          fp_trmv(W, ld, k, rhs, t, stage);
+          fp_trmv_t(W, ld, k, t, mean, stage, red);
           ++n_segs;
           if (!replay) {
             fp_normals(z, k, gchain, unode, uit, (uint32_t)(h * 512), key);
-            fp_trmv_t(W, ld, k, z, e);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
+            fp_trmv_t(W, ld, k, z, e, stage, red);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
             for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = mean[i] - mu[i];
             __syncthreads();
             acc_dd += fp_dot(tmp, tmp, k, red);
@@ -378,7 +636,10 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
               td[10 + 3 * k + 2 * DBN_SMAX * k + h * k + i] = replay ? rd[3 + k + h * k + i] : e[i];  // completed below
               td[10 + 3 * k + h * k + i] = mean[i];
               double dg = 0.0;  // diag of A^-1 = column norms of W
-              for (int r = i; r < k; ++r) dg += W[r * ld + i] * W[r * ld + i];
+              for (int r = i; r < k; ++r) {
+                const double wv = stage ? W[(long long)i * ld + r] : W[r * ld + i];
+                dg += wv * wv;
+              }
               td[10 + 3 * k + DBN_SMAX * k + h * k + i] = lam * dg;  // x sigma^2 below
             }
           }
@@ -498,9 +759,9 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
         const int valid = s_int[1], Ss = s_int[2];
         if (!GLOBM && valid) {
           // moves.py:184-232: two plain marginal likelihoods (prior mean 0), u < min(1, exp(delta))
-          const FpSummary sc_ = fp_sweep_plain(a.tb, node, tau_cur, S, lam, A, ld, k, g, t, x, red, sc + 3);
+          const FpSummary sc_ = fp_sweep_plain(a.tb, node, tau_cur, S, lam, A, ld, k, g, t, x, red, sc + 3, stage);
           const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + sc_.s - lam * sc_.c);
-          const FpSummary ss_ = fp_sweep_plain(a.tb, node, tau_star, Ss, lam, A, ld, k, g, t, x, red, sc + 3);
+          const FpSummary ss_ = fp_sweep_plain(a.tb, node, tau_star, Ss, lam, A, ld, k, g, t, x, red, sc + 3, stage);
           const double ml_star = a.c0 - 0.5 * ss_.ld - a.T_half_plus_a * log(a.two_b + ss_.s - lam * ss_.c);
           n_segs += S + Ss;
           n_evals += 2;
@@ -521,7 +782,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
         if (GLOBM && valid) {
           const double ils = 1.0 / (lam * sig2);
           // ---- current changepoints: log-ML at mu and the density of mu under muSampler(mu | tau) (moves.py:66-73)
-          const FpSummary sc_ = fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3);
+          const FpSummary sc_ = fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3, stage);
           n_segs += S;
           const double q_cur = fp_quad_at(sc_, Mc, ld, k, a_cur, mu, lam, tmp, red);
           const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + q_cur);
@@ -534,10 +795,10 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
             rhs[i] = a_cur[i] / sig2 + mu[i];
           }
           __syncthreads();
-          const double ldq_cur = fp_cholesky(Q, ld, k, t);
-          fp_trinv(Q, W, ld, k, t);
-          fp_trmv(W, ld, k, rhs, t);
-          fp_trmv_t(W, ld, k, t, mean);
+          const double ldq_cur = fp_cholesky(Q, ld, k, t, stage);
+          fp_trinv(Q, W, ld, k, t, stage);
+          fp_trmv(W, ld, k, rhs, t, stage);
+          fp_trmv_t(W, ld, k, t, mean, stage, red);
           if (TRACE && td)
             for (int i = tid; i < k; i += FP_BLOCK) td[10 + k + i] = mean[i];
           for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu[i] - mean[i];
@@ -546,7 +807,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
           const double dQd_cur = fp_dot(x, x, k, red) + fp_dot(x, tmp, k, red) * ils;
           const double ld_cur = -0.5 * ((double)k * 1.8378770664093454836 - ldq_cur + dQd_cur);
           // ---- proposed changepoints: mu* ~ muSampler(0 | tau*), its density, log-ML at mu* (moves.py:86-93)
-          const FpSummary ss_ = fp_sweep(a.tb, node, tau_star, Ss, lam, A, W, Ms, ld, k, g, t, x, a_star, red, sc + 3);
+          const FpSummary ss_ = fp_sweep(a.tb, node, tau_star, Ss, lam, A, W, Ms, ld, k, g, t, x, a_star, red, sc + 3, stage);
           n_segs += Ss;
           for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Ms[i] * ils;
           __syncthreads();
@@ -555,16 +816,16 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
             rhs[i] = a_star[i] / sig2;
           }
           __syncthreads();
-          const double ldq_star = fp_cholesky(Q, ld, k, t);
-          fp_trinv(Q, W, ld, k, t);
-          fp_trmv(W, ld, k, rhs, t);
-          fp_trmv_t(W, ld, k, t, mean);
+          const double ldq_star = fp_cholesky(Q, ld, k, t, stage);
+          fp_trinv(Q, W, ld, k, t, stage);
+          fp_trmv(W, ld, k, rhs, t, stage);
+          fp_trmv_t(W, ld, k, t, mean, stage, red);
           if (replay) {
             for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = rd[3 + i];
             __syncthreads();
           } else {
             fp_normals(z, k, gchain, unode, uit, 8192u, key);
-            fp_trmv_t(W, ld, k, z, e);  // cov = Q^-1 = W^T W
+            fp_trmv_t(W, ld, k, z, e, stage, red);  // cov = Q^-1 = W^T W
             for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = mean[i] + e[i];
             __syncthreads();
           }
@@ -644,6 +905,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX) fp_glob_kernel(const FpArgs a) {
 inline size_t fp_smem_bytes(int k, bool mats_in_smem) {
   size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 8) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
   if (mats_in_smem) b += (size_t)FP_NMAT * fp_ld(k) * k * sizeof(double);
+  else b += (size_t)FP_STAGE_DOUBLES * sizeof(double);
   return b;
 }
 

@@ -842,7 +842,7 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   const fp_fn fn = trace ? (globm ? fp_glob_kernel<true, true> : fp_glob_kernel<true, false>)
                          : (globm ? fp_glob_kernel<false, true> : fp_glob_kernel<false, false>);
   CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<h->fp_grid, fp_block_threads(k), smem, h->stream>>>(a);
+  fn<<<h->fp_grid, fp_block_threads(k, h->d_fp_ws == nullptr), smem, h->stream>>>(a);
   CUX(cudaGetLastError());
   h->it_done += n_iter;
   if (trace) {

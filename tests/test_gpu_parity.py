@@ -396,13 +396,14 @@ def test_fp_plain_free_running_and_dropin(eng_mod, method):
     assert np.abs(mine - ref).max() < 0.25, (mine, ref)
 
 
-def test_fp_glob_large_n_workspace_path(eng_mod):
-    """n = 72 does not fit the shared-memory matrices: the global-workspace path must give the same log-MLs as the
-    oracle on the same injected stream (free draws from the oracle's own chain)."""
+@pytest.mark.parametrize('n,T,n_iter', [(72, 160, 6), (300, 420, 3)])
+def test_fp_glob_large_n_workspace_path(eng_mod, n, T, n_iter):
+    """n = 72 / 300 do not fit the shared-memory matrices: the global-workspace path (blocked Cholesky / triangular
+    inverse / rank-k update; n = 300 takes two column passes and several tiles) must give the same log-MLs as the oracle
+    on the same injected stream (free draws from the oracle's own chain)."""
     from dynamicbayesiannetworks_b200.synth import make_synthetic
-    data, _, _ = make_synthetic(72, 160, n_changepoints=2, max_fan_in=3, seed=5)
+    data, _, _ = make_synthetic(n, T, n_changepoints=2, max_fan_in=3, seed=5)
     X, Y = O.lagged_matrices([data])
-    n, n_iter = 72, 6
     # only the first 4 nodes are checked; the other units replay node 0's stream (their results are not compared).
     # the oracle's RngDraws do not record their picks: wrap them in a recording draw source
     class Rec(O.RngDraws):
