@@ -235,6 +235,7 @@ __device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* 
     for (int ib = p0; ib < k; ib += 2 * T) {   // two matrix columns i0, i1 of the panel's factor rows per thread
       const int i0 = ib + tid, i1 = i0 + T;
       const bool on0 = i0 < k, on1 = i1 < k;
+      const bool w0 = ib + (tid & ~31) < k, w1 = ib + T + (tid & ~31) < k;   // this warp has first / second columns at all
       double acc0[FP_NB], acc1[FP_NB];
 #pragma unroll
       for (int c = 0; c < FP_NB; ++c) {   // rows p0.. of A are still the input (symmetric: entries left of the diagonal too)
@@ -249,14 +250,43 @@ __device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* 
           Bs[e] = (c < nb) ? A[(long long)(j0 + jj) * ld + p0 + c] : 0.0;
         }
         __syncthreads();
-        for (int jj = 0; jj < jn; ++jj) {
-          const double a0 = on0 ? A[(long long)(j0 + jj) * ld + i0] : 0.0;
-          const double a1 = on1 ? A[(long long)(j0 + jj) * ld + i1] : 0.0;
+        // four factor rows per step: their 4 (8) loads are in flight together before the 64 (128) dependent-free FMAs
+        // (the one-row loop stalled on each load: 30 % of all samples, profiles/r1_v11); warps without a second /
+        // any column skip the arithmetic (warp-uniform branches), not the barriers
+        if (w0) {
+          int jj = 0;
+          for (; jj + 4 <= jn; jj += 4) {
+            double a0v[4], a1v[4];
 #pragma unroll
-          for (int c = 0; c < FP_NB; ++c) {
-            const double b = Bs[jj * FP_NB + c];
-            acc0[c] = fma(-a0, b, acc0[c]);
-            acc1[c] = fma(-a1, b, acc1[c]);
+            for (int q = 0; q < 4; ++q) {
+              a0v[q] = on0 ? A[(long long)(j0 + jj + q) * ld + i0] : 0.0;
+              a1v[q] = on1 ? A[(long long)(j0 + jj + q) * ld + i1] : 0.0;
+            }
+            if (w1) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int c = 0; c < FP_NB; ++c) {
+                  const double b = Bs[(jj + q) * FP_NB + c];
+                  acc0[c] = fma(-a0v[q], b, acc0[c]);
+                  acc1[c] = fma(-a1v[q], b, acc1[c]);
+                }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int c = 0; c < FP_NB; ++c) acc0[c] = fma(-a0v[q], Bs[(jj + q) * FP_NB + c], acc0[c]);
+            }
+          }
+          for (; jj < jn; ++jj) {
+            const double a0 = on0 ? A[(long long)(j0 + jj) * ld + i0] : 0.0;
+            const double a1 = on1 ? A[(long long)(j0 + jj) * ld + i1] : 0.0;
+#pragma unroll
+            for (int c = 0; c < FP_NB; ++c) {
+              const double b = Bs[jj * FP_NB + c];
+              acc0[c] = fma(-a0, b, acc0[c]);
+              acc1[c] = fma(-a1, b, acc1[c]);
+            }
           }
         }
       }
@@ -328,6 +358,7 @@ __device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const do
     const int c = cb + tid;
     const bool on = c < k;
     const int cmax = min(k, cb + T) - 1;
+    const int cw = min(k - 1, cb + (tid | 31));   // largest column of this warp
     for (int j0 = (cmax / FP_NB) * FP_NB; j0 >= 0; j0 -= FP_NB) {
       const int nb = min(FP_NB, k - j0);
       double acc[FP_NB];
@@ -341,11 +372,23 @@ __device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const do
           Us[mm * FP_NB + r] = (r < nb) ? A[(long long)(j0 + r) * ld + m0 + mm] : 0.0;
         }
         __syncthreads();
-        for (int mm = 0; mm < mn; ++mm) {
-          const int m = m0 + mm;
-          const double v = (on && m <= c) ? W[(long long)m * ld + c] : 0.0;
+        if (m0 <= cw) {   // warp-uniform: some column of this warp reaches row m0 (V[m][c] = 0 for m > c)
+          int mm = 0;
+          for (; mm + 4 <= mn; mm += 4) {   // four loads in flight before the FMAs
+            double vv[4];
 #pragma unroll
-          for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[mm * FP_NB + r], v, acc[r]);
+            for (int q = 0; q < 4; ++q) vv[q] = (on && m0 + mm + q <= c) ? W[(long long)(m0 + mm + q) * ld + c] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[(mm + q) * FP_NB + r], vv[q], acc[r]);
+          }
+          for (; mm < mn; ++mm) {
+            const int m = m0 + mm;
+            const double v = (on && m <= c) ? W[(long long)m * ld + c] : 0.0;
+#pragma unroll
+            for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[mm * FP_NB + r], v, acc[r]);
+          }
         }
       }
       __syncthreads();
