@@ -190,7 +190,8 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     is_seq = method == 'seq_coup_nh_dbn'
     is_fp = method.startswith('fp_')              # full parents: no parent-set move, design width = n
     is_fp_glob = method == 'fp_glob_coup_nh_dbn'
-    is_vv = method == 'var_glob_coup_nh_dbn'      # vvglobCoup.py: segment-specific sigma^2_h, mu* drawn in the pi move only
+    is_fp_vv = method == 'fp_var_glob_coup_nh_dbn'  # fpvvGlobCoup.py: mu redrawn every iteration (always accepted, :99-103)
+    is_vv = method == 'var_glob_coup_nh_dbn' or is_fp_vv   # segment-specific sigma^2_h, mu kept in the changepoint move
     is_glob = method == 'glob_coup_nh_dbn' or is_fp_glob or is_vv
     KM = globals()['KM'] if not is_fp else max(globals()['KM'], n)
     EVENTS.clear()
@@ -294,6 +295,13 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
             if is_seq:
                 e = ev[pos]; assert e[0] == 'gamma', (i, it, e)
                 g['del_shape'][i, it], g['del_scale'][i, it], g['delta2'][i, it] = e[1], e[2], 1.0 / e[3]
+                pos += 1
+            if is_fp_vv:   # the vvMuSampler call of fpvvGlobCoup.py:100 (bound at import, so only its MVN draw is recorded)
+                e = ev[pos]; assert e[0] == 'mvn', (i, it, e)
+                g['mus_mean'][i, it, 0] = _pad_vec(e[1], KM)
+                g['mus_cov'][i, it, 0] = _pad_mat(e[2], KM)
+                g['mus_val'][i, it, 0] = _pad_vec(e[3], KM)
+                cur_mu = e[3].copy()
                 pos += 1
             # ---- pi move
             if is_fp:
@@ -521,6 +529,11 @@ def main():
         run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
         run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
         return
+    if 'fpvv-only' in sys.argv:
+        run_chain_golden('yeast', yeast, 'fp_var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'fp_var_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+        run_chain_golden('synth200', [syn], 'fp_var_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
+        return
     if 'fp2-only' in sys.argv:      # full-parents nh / h fixtures
         run_chain_golden('yeast', yeast, 'fp_varying_nh_dbn', n_iter=240, burn_in=40, seed=1)
         run_chain_golden('mtor', mtor, 'fp_varying_nh_dbn', n_iter=60, burn_in=20, seed=2)
@@ -558,6 +571,9 @@ def main():
     run_chain_golden('synth200', [syn], 'fp_varying_nh_dbn', n_iter=100, burn_in=20, seed=3)
     run_chain_golden('yeast', yeast, 'fp_h_dbn', n_iter=240, burn_in=40, seed=1)
     run_chain_golden('mtor', mtor, 'fp_h_dbn', n_iter=60, burn_in=20, seed=2)
+    run_chain_golden('yeast', yeast, 'fp_var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'fp_var_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+    run_chain_golden('synth200', [syn], 'fp_var_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
 
 
 if __name__ == '__main__':

@@ -524,6 +524,60 @@ def test_c4_full_size_properties(eng_mod):
 # ---------------------------------------------------------------------------------------------------------
 # multi-GPU: chains sharded over two ranks + NCCL all-reduce of the counts == the unsharded run (needs 2 GPUs)
 # ---------------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[4] at full size (500 genes, T = 10000, full-parents globally coupled): the blocked k = 500 routines
+# ---------------------------------------------------------------------------------------------------------
+def test_c5_full_size_logml_and_state(eng_mod):
+    """One traced iteration of every node at n = 500, T = 10000 (30 GB prefix table, design width 500): the device's
+    log marginal likelihoods of the current and of the accepted proposed state equal the oracle's (1e-9), the Gibbs
+    rates too, and the state invariants hold for all 500 units."""
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    n, T = 500, 10000
+    data, cps, _ = make_synthetic(n, T, n_changepoints=5, max_fan_in=4, seed=20260120)
+    X, Y = O.lagged_matrices([data])
+    N = X.shape[0]
+    tau0 = [c + 1 for c in cps] + [N + 2]
+    with eng_mod(n_chains=1, seed=3) as e:
+        e.build_stats([data])
+        zz, zy, yy = e.stats_row(N)
+        e.chain_init('fp_glob_coup_nh_dbn')
+        e.set_changepoints(tau0)
+        tr = e.run_fp(1, trace=True)
+        st = e.state()
+    # the last prefix row is the full-series Gram matrix
+    Z = np.concatenate([np.ones((N, 1)), X], axis=1)
+    assert_close(zz, Z.T @ Z, 1e-11, 1e-9, what='ZZ[N]')
+    assert_close(yy, (Y * Y).sum(axis=0), 1e-11, what='YY[N]')
+    S_after = tr['S_after'][:, 0]
+    assert ((S_after >= 1) & (S_after <= 9)).all() and (tr['S'][:, 0] == len(tau0)).all()
+    for u in range(n):
+        t = tr['tau_after'][u, 0, :S_after[u]]
+        assert t[-1] == N + 2 and (np.diff(t) > 0).all() and t[0] >= 2
+    assert np.isfinite(tr['sigma2']).all() and (tr['sigma2'] > 0).all() and (tr['lambda2'] > 0).all()
+    assert np.array_equal(st['S'], S_after)
+    valid = tr['tau_valid'][:, 0] == 1
+    assert valid.sum() > n // 2 and np.isfinite(tr['logml'][valid, 0]).all()
+    c = O.method_constants('fp_glob_coup_nh_dbn', N)
+    acc_nodes = [u for u in range(n) if tr['tau_accept'][u, 0] == 1][:2]
+    for node in sorted(set([0, 250, 499] + acc_nodes)):
+        y = Y[:, node]
+        pi = [j for j in range(n) if j != node]
+        stats = O.segment_stats(X, y, pi, tau0)
+        zeros = [np.zeros(n)] * len(stats)
+        shape, rate = O.sigma2_params(stats, zeros, 1.0, c['a_sig'], c['b_sig'], c['T_sigma'])
+        assert_close(tr['sig_rate'][node, 0], rate, 1e-9, what='sigma^2 rate node %d' % node)
+        if valid[node]:
+            lam = float(tr['lambda2'][node, 0])
+            ref = O.log_ml(stats, zeros, c['a_sig'], c['b_sig'], lam, c['T_ml'])
+            assert_close(tr['logml'][node, 0, 0], ref, LOGML_RTOL, what='log-ML(tau) node %d' % node)
+            if tr['tau_accept'][node, 0] == 1:
+                tau1 = [int(v) for v in tr['tau_after'][node, 0, :S_after[node]]]
+                mu1 = tr['mu_after'][node, 0, :n]
+                stats1 = O.segment_stats(X, y, pi, tau1)
+                ref = O.log_ml(stats1, [mu1] * len(stats1), c['a_sig'], c['b_sig'], lam, c['T_ml'])
+                assert_close(tr['logml'][node, 0, 1], ref, LOGML_RTOL, what='log-ML(tau*) node %d' % node)
+
+
 def test_network_sharded_over_two_gpus_matches_unsharded():
     import subprocess
     import sys
