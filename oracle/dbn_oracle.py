@@ -32,8 +32,9 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 METHOD_IDS = {
+    'fp_var_glob_coup_nh_dbn': FP_VV_DBN,   # network.py:270-281, fpvvGlobCoup.py
     'fp_varying_nh_dbn': FP_NH_DBN,    # network.py:165-177, fullParentsBpwLinReg.py
     'fp_h_dbn': FP_H_DBN,              # network.py:200-209, fpBayesianLinearRegression.py
     'var_glob_coup_nh_dbn': VV_GLOB_DBN, 'var-glob-dbn': VV_GLOB_DBN,   # network.py:258-269, vvglobCoup.py
@@ -69,7 +70,7 @@ def method_constants(method, N):
     elif m in (SEQ_DBN, FIXED_NH_DBN):
         # seq: network.py:213-219; fixed nh: network.py:182-188 also passes num_samples - 1
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
-    elif m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN):
+    elif m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_VV_DBN):   # fp-vv: network.py:273-279, fpvvGlobCoup.py:49-50
         # network.py:237-243, :249-255, :261-267 (num_samples = N); fpGlobCoupBpwLinReg.py:49-50, vvglobCoup.py:42-43
         # (IG(0.01, 0.01)); the segment-specific-variance model uses T_h per segment instead of T (log_ml_vv)
         c.update(T_ml=N, T_sigma=N, num_samples=N, a_sig=0.01, b_sig=0.01)
@@ -529,9 +530,9 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     features = [j for j in range(n) if j != node]
     F = len(features)
     c = method_constants(m, N)
-    fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN)    # full parents: pi = every other gene, no parent-set move
-    vv = m == VV_GLOB_DBN          # vvglobCoup.py:66-123: segment-specific sigma^2_h, mu* drawn in the parent-set move only
-    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN)
+    fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN)    # full parents: pi = every other gene, no parent-set move
+    vv = m in (VV_GLOB_DBN, FP_VV_DBN)   # vvglobCoup.py:66-123: segment-specific sigma^2_h, mu kept in the changepoint move
+    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_VV_DBN)
     has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN, FP_H_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
     KM, SM = (max(5, n) if fp else 5), 10
 
@@ -611,6 +612,14 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
             tr['delta2'][it] = dlt_new
         lam, dlt = lam_new, dlt_new
 
+        mu_next = None
+        if m == FP_VV_DBN:
+            # fpvvGlobCoup.py:99-103: mu ~ vvMuSampler at (tau, sigma^2_h, lambda^2 new), always accepted, but the
+            # changepoint move below still conditions on the OLD mu (muVector[it], :106-108)
+            mean_s, Sig_s, _ = mu_posterior(stats, None, sig, lam)
+            mu_next = draws.mu_draw(it, 0, mean_s, Sig_s)
+            tr['mus_mean'][it, 0, :k] = mean_s
+            tr['mus_cov'][it, 0, :k, :k] = Sig_s
         # ---- pi move
         star = None
         if not fp:
@@ -700,6 +709,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
                     tau = star
                     if glob and not vv:
                         mu = mu_star
+        if mu_next is not None:
+            mu = mu_next
         tr['tau_after'][it, :len(tau)] = tau
         if glob:
             tr['mu_after'][it, :len(mu)] = mu

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import FP_PLAIN_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from helpers import FP_PLAIN_FILES, FP_VV_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
 from oracle import dbn_oracle as O
 
 
@@ -135,7 +135,7 @@ def test_fp_glob_chain_replay(path):
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
 
 
-@pytest.mark.parametrize('path', FP_PLAIN_FILES, ids=ids(FP_PLAIN_FILES))
+@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES))
 def test_fp_plain_chain_replay(path):
     """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) and fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
     the reference's recorded draws: changepoint lists / accept flags bit-exact, Gibbs parameters and log-MLs, and the
@@ -158,6 +158,12 @@ def test_fp_plain_chain_replay(path):
         assert_close(tr['beta_mean'], g['beta_mean'][node], 1e-7, 1e-9, what='beta_mean node %d' % node)
         assert_close(np.diagonal(tr['beta_cov'], axis1=-2, axis2=-1), g['beta_cov_diag'][node], 1e-7, 1e-13, what='beta_cov')
         assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
+        if method == 'fp_var_glob_coup_nh_dbn':      # fpvvGlobCoup.py: per-segment variances, mu redrawn every iteration
+            for key in ('sig_shape_v', 'sig_scale_v'):
+                assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+            assert_close(tr['mus_mean'][:, 0], g['mus_mean'][node][:, 0], 1e-7, 1e-9, what='mus_mean node %d' % node)
+            assert_close(np.diagonal(tr['mus_cov'][:, 0], axis1=-2, axis2=-1), g['mus_cov_diag'][node][:, 0], 1e-7, 1e-12, what='mus_cov')
+            assert_close(tr['mu_after'], g['mu_after'][node], 0, 0, what='mu_after node %d' % node)
         samples = [tr['beta'][it, h, :n] for it in range(n_iter) if O.beta_kept(it, burn_in) for h in range(tr['S'][it])]
         adj[node] = O.credible_scores(np.array(samples), [j for j in range(n) if j != node], n)
         for it in range(n_iter):
