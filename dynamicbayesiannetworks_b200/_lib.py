@@ -37,12 +37,12 @@ TI_PI_MOVE, TI_TAU_MOVE, TI_S_BEFORE, TI_STRIDE = 20, 21, 22, 24
 
 def fp_rd_stride(k):
     """doubles per replay record of dbn_run_fp (include/dbn_b200.h)"""
-    return 3 + k + SMAX * k
+    return 3 + k + SMAX * k + SMAX
 
 
 def fp_td_stride(k):
     """doubles per trace record of dbn_run_fp"""
-    return 10 + 3 * k + 3 * SMAX * k
+    return 10 + 3 * k + 3 * SMAX * k + 3 * SMAX
 
 
 FP_RI_STRIDE, FP_TI_STRIDE = 4, 16

@@ -59,8 +59,8 @@ struct FpArgs {
 
 __host__ __device__ inline int fp_ld(int k) { return k | 1; }
 // replay / trace record strides (doubles / ints per (unit, iteration)); see include/dbn_b200.h
-__host__ __device__ inline int fp_rd_stride(int k) { return 3 + k + DBN_SMAX * k; }
-__host__ __device__ inline int fp_td_stride(int k) { return 10 + 3 * k + 3 * DBN_SMAX * k; }
+__host__ __device__ inline int fp_rd_stride(int k) { return 3 + k + DBN_SMAX * k + DBN_SMAX; }   // ... , sigma^2_h[SMAX] (vv)
+__host__ __device__ inline int fp_td_stride(int k) { return 10 + 3 * k + 3 * DBN_SMAX * k + 3 * DBN_SMAX; }   // ... , sigma^2_h shape / rate / draw (vv)
 
 // ---- block-level building blocks (all threads of the block call them) -----------------------------------------------
 // sum of x over the block, the same value (same order of additions) in every thread.  Through shared memory and block
@@ -122,7 +122,7 @@ __device__ void fp_symv(const double* M, int ld, int k, const double* x, double*
 // blocked large-k routines (defined below); `stage` != nullptr selects them in the dispatching helpers
 __device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage);
 __device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage);
-__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage);
+__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale);
 __device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t);
 __device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red);
 
@@ -194,13 +194,13 @@ __device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, doubl
 }
 
 // M += I - W^T W (full symmetric)
-__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage) {
-  if (stage) return fp_syrk_big(W, M, ld, k, stage);
+__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage, double scale) {
+  if (stage) return fp_syrk_big(W, M, ld, k, stage, scale);
   for (int a = 0; a < k; ++a) {
     for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
       double acc = 0.0;
       for (int i = a; i < k; ++i) acc += W[i * ld + a] * W[i * ld + b];
-      const double v = ((a == b) ? 1.0 : 0.0) - acc;
+      const double v = scale * (((a == b) ? 1.0 : 0.0) - acc);
       M[a * ld + b] += v;
       if (a != b) M[b * ld + a] += v;
     }
@@ -414,7 +414,7 @@ __device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const do
 }
 
 // M += I - V V^T (= I - A^-1; full symmetric M), 64 x 64 tiles of the lower triangle, 4 x 4 outputs per thread
-__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage) {
+__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale) {
   double* As = stage;
   double* Bs = stage + FP_SY_IC * FP_SY_LD;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -454,7 +454,7 @@ __device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* s
         for (int q = 0; q < 4; ++q) {
           const int ra = a0 + ty * 4 + p, rb = b0 + tx * 4 + q;
           if (ra < k && rb <= ra) {
-            const double v = ((ra == rb) ? 1.0 : 0.0) - acc[p][q];
+            const double v = scale * (((ra == rb) ? 1.0 : 0.0) - acc[p][q]);
             M[(long long)ra * ld + rb] += v;
             if (ra != rb) M[(long long)rb * ld + ra] += v;
           }
@@ -511,7 +511,8 @@ struct FpSummary {
 
 template <class TauFn>
 __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, double lam, double* A, double* W, double* M, int ld, int k,
-                              double* g, double* t, double* x, double* a_sum, double* red, double* s_tmp, double* stage) {
+                              double* g, double* t, double* x, double* a_sum, double* red, double* s_tmp, double* stage,
+                              const double* wgt = nullptr) {   // wgt[h] = sigma^2_h: segment h enters M and a with 1 / sigma^2_h (vvMuSampler)
   FpSummary r = {0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] = 0.0;
   for (int i = threadIdx.x; i < k * ld; i += FP_BLOCK) M[i] = 0.0;
@@ -526,8 +527,9 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
     fp_trmv(W, ld, k, g, t, stage);          // t = L^-1 g
     r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
     fp_trmv_t(W, ld, k, t, x, stage, red);   // x = A^-1 g
-    for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] += x[i];
-    fp_accumulate_i_minus_ainv(W, M, ld, k, stage);
+    const double wh = wgt ? 1.0 / wgt[h] : 1.0;   // wgt holds the variances
+    for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] += wh * x[i];
+    fp_accumulate_i_minus_ainv(W, M, ld, k, stage, wh);
     lo = hi;
   }
   return r;
@@ -565,6 +567,36 @@ __device__ FpSummary fp_sweep_plain(const Table& tb, int node, TauFn tau, int S,
   return r;
 }
 
+// vvLogMargLikelihood (marginalLikelihood.py:5-43) at prior mean mu: per segment its own length T_h in the Gamma / pi /
+// exponent terms; needs the factor and one forward substitution per segment, no inverse.  c_seg = a ln(2b) - lgamma(a).
+template <class TauFn>
+__device__ double fp_score_vv(const Table& tb, int node, TauFn tau, int S, double lam, const double* mu, double* A, int ld, int k,
+                              double* g, double* t, double* x, double* tmp, double* idiag, double* red, double* s_tmp, double* stage,
+                              double a_sig, double c_seg, double two_b) {
+  double acc = 0.0;
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
+    fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
+    const double s = *s_tmp;
+    fp_symv(A, ld, k, mu, tmp);
+    for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+      const double gm = (tmp[i] - mu[i]) / lam;   // (G mu)_i
+      tmp[i] = gm;
+      x[i] = g[i] - gm;
+    }
+    __syncthreads();
+    const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
+    const double ldh = fp_cholesky(A, ld, k, idiag, stage);
+    fp_trsv(A, ld, k, idiag, x, t, stage != nullptr);
+    const double q = rho - lam * fp_dot(t, t, k, red);
+    const double Th = 0.5 * (double)(hi - lo);
+    acc += lgamma(Th + a_sig) + c_seg - Th * 1.1447298858494002 - 0.5 * ldh - (Th + a_sig) * log(two_b + q);
+    lo = hi;
+  }
+  return acc;
+}
+
 // sum_h r_h^T C_h^-1 r_h at mean mu from the sums
 __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k, const double* a_sum, const double* mu, double lam,
                              double* tmp, double* red) {
@@ -577,8 +609,14 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
 // GLOBM: the globally coupled model (fpGlobCoupBpwLinReg.py).  !GLOBM: the plain full-parents models, prior mean 0 —
 // fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140: nh changepoint move of moves.py:129-236) and, with with_tau == 0,
 // fp_h_dbn (fpBayesianLinearRegression.py:40-125: Gibbs draws only); their edge scores come from the thinned beta chain.
-template <bool TRACE, bool GLOBM = true>
+// FPM_VV: fp_var_glob_coup_nh_dbn (fpvvGlobCoup.py:72-121): segment-specific variances (segmentSigmaSampler), mu redrawn every
+// iteration from vvMuSampler (always accepted), the changepoint move of vvGlobCoupTauMove on the OLD mu scored by
+// vvLogMargLikelihood (per-segment T_h); edge scores from the beta chain like the plain models.
+constexpr int FPM_GLOB = 0, FPM_PLAIN = 1, FPM_VV = 2;
+template <bool TRACE, int FPM = FPM_GLOB>
 __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a) {
+  constexpr bool GLOBM = FPM == FPM_GLOB, VVM = FPM == FPM_VV;
+  constexpr bool GHR = GLOBM || VVM;   // Hastings ratios and acceptance rule of the globally coupled changepoint moves
   extern __shared__ double sm[];
   const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
   const int tid = threadIdx.x;
@@ -588,7 +626,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
   double* mean = vec + 6 * k, *a_cur = vec + 7 * k, *a_star = vec + 8 * k, *tmp = vec + 9 * k, *rhs = vec + 10 * k, *e = vec + 11 * k;
   double* red = vec + FP_NVEC * k;       // [FP_BLOCK_MAX]
   double* sc = red + FP_BLOCK_MAX;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
-  int* s_tau = reinterpret_cast<int*>(sc + 8);
+  double* sigv = sc + 8;                 // [SMAX] sigma^2_h of the iteration (vv)
+  int* s_tau = reinterpret_cast<int*>(sc + 8 + SMAX);
   int* s_tas = s_tau + SMAX;
   int* s_int = s_tas + SMAX;             // [8]
   double* mats = a.ws ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
@@ -632,6 +671,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
 
       // ======================= Gibbs pass: sigma^2, beta_h, lambda^2 (fpGlobCoupBpwLinReg.py:70-86) ================
       double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
+      double acc_ss = 0.0;   // vv: sum_h |beta_h - mu|^2 / sigma^2_h (samplers.py:275-282)
       {
         int lo = 0;
         for (int h = 0; h < S; ++h) {
@@ -651,7 +691,24 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
           fp_cholesky(A, ld, k, t, stage);
           fp_trinv(A, W, ld, k, t, stage);
           fp_trmv(W, ld, k, x, t, stage);
-          q_sum += rho - lam * fp_dot(t, t, k, red);
+          const double q_h = rho - lam * fp_dot(t, t, k, red);
+          q_sum += q_h;
+          double sig_h = 1.0;
+          if constexpr (VVM) {
+            // segmentSigmaSampler (samplers.py:90-101): sigmaSqrSampler on segment h alone, numSamples = T = T_h
+            if (tid == 0) {
+              const double shape = a.a_sig + 0.5 * (double)(hi - lo), rate = a.b_sig + 0.5 * q_h;
+              const double s2h = replay ? rd[3 + k + DBN_SMAX * k + h] : rate / gamma_draw(gchain, unode, uit, 20000u + 256u * (unsigned)h, key, shape);
+              sigv[h] = s2h;
+              if (TRACE && td) {
+                const int o = 10 + 3 * k + 3 * DBN_SMAX * k;
+                td[o + h] = shape; td[o + DBN_SMAX + h] = rate; td[o + 2 * DBN_SMAX + h] = s2h;
+                if (h == 0) { td[0] = shape; td[1] = rate; td[4] = s2h; }
+              }
+            }
+            __syncthreads();
+            sig_h = sigv[h];
+          }
           fp_trmv(W, ld, k, rhs, t, stage);
           fp_trmv_t(W, ld, k, t, mean, stage, red);
           ++n_segs;
@@ -660,9 +717,14 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
             fp_trmv_t(W, ld, k, z, e, stage, red);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
             for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = mean[i] - mu[i];
             __syncthreads();
-            acc_dd += fp_dot(tmp, tmp, k, red);
-            acc_de += fp_dot(tmp, e, k, red);
-            acc_ee += fp_dot(e, e, k, red);
+            if constexpr (VVM) {
+              const double dd = fp_dot(tmp, tmp, k, red), de = fp_dot(tmp, e, k, red), ee = fp_dot(e, e, k, red);
+              acc_ss += (dd + 2.0 * sqrt(sig_h * lam) * de) / sig_h + lam * ee;
+            } else {
+              acc_dd += fp_dot(tmp, tmp, k, red);
+              acc_de += fp_dot(tmp, e, k, red);
+              acc_ee += fp_dot(e, e, k, red);
+            }
             if constexpr (!GLOBM) {   // kept for the sign counts below (read back by the thread that writes it)
               for (int i = tid; i < k; i += FP_BLOCK) {
                 bsc[(2 * h) * k + i] = mean[i];
@@ -672,7 +734,10 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
           } else {
             for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = rd[3 + k + h * k + i] - mu[i];  // injected beta_h
             __syncthreads();
-            acc_dd += fp_dot(tmp, tmp, k, red);
+            if constexpr (VVM)
+              acc_ss += fp_dot(tmp, tmp, k, red) / sig_h;
+            else
+              acc_dd += fp_dot(tmp, tmp, k, red);
           }
           if (TRACE && td) {
             for (int i = tid; i < k; i += FP_BLOCK) {
@@ -692,25 +757,26 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
       }
       if (tid == 0) {
         const double shape = a.a_sig + a.T_sigma_half, rate = a.b_sig + 0.5 * q_sum;
-        const double s2 = replay ? rd[0] : rate / gamma_draw(gchain, unode, uit, 20000u, key, shape);
+        const double s2 = VVM ? sigv[0] : (replay ? rd[0] : rate / gamma_draw(gchain, unode, uit, 20000u, key, shape));
         const double sg = sqrt(s2 * lam);
         const double ss = replay ? acc_dd : acc_dd + 2.0 * sg * acc_de + s2 * lam * acc_ee;
-        // samplers.py:285-289: shape a + S k / 2, rate b + sum |beta_h - mu|^2 / (2 sigma^2)
-        const double lshape = a.a_lam + 0.5 * (double)(S * k), lrate = a.b_lam + 0.5 * ss / s2;
+        // samplers.py:285-289: shape a + S k / 2, rate b + sum |beta_h - mu|^2 / (2 sigma^2)  (vv: / sigma^2_h per segment)
+        const double lshape = a.a_lam + 0.5 * (double)(S * k), lrate = a.b_lam + 0.5 * (VVM ? acc_ss : ss / s2);
         const double l2 = replay ? rd[1] : lrate / gamma_draw(gchain, unode, uit, 24000u, key, lshape);
         sc[0] = s2;
         sc[1] = l2;
         if (TRACE && td) {
-          td[0] = shape; td[1] = rate; td[2] = lshape; td[3] = lrate; td[4] = s2; td[5] = l2;
+          if (!VVM) { td[0] = shape; td[1] = rate; td[4] = s2; }
+          td[2] = lshape; td[3] = lrate; td[5] = l2;
           td[6] = td[7] = td[8] = td[9] = NAN;
         }
       }
       __syncthreads();
       sig2 = sc[0];
       if (TRACE && td) {
-        const double sg = sqrt(sig2 * lam);
         for (int i = tid; i < S * k; i += FP_BLOCK) {
-          td[10 + 3 * k + DBN_SMAX * k + i] *= sig2;
+          const double s2h = VVM ? sigv[i / k] : sig2, sg = sqrt(s2h * lam);
+          td[10 + 3 * k + DBN_SMAX * k + i] *= s2h;
           if (!replay) td[10 + 3 * k + 2 * DBN_SMAX * k + i] = td[10 + 3 * k + i] + sg * td[10 + 3 * k + 2 * DBN_SMAX * k + i];
         }
       }
@@ -719,11 +785,11 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
         // it - 1 >= burn_in and (it - 1 - burn_in) % thin == 0; every segment's beta_h is one posterior sample
         // (beta_post_matrix, scores.py:139-153); pos / neg feed credible_score (scores.py:196-205)
         if (it - 1 >= a.burn_in && ((it - 1 - a.burn_in) % a.thin) == 0) {
-          const double sgb = sqrt(sig2 * lam);
           if (tid == 0) atomicAdd(&a.kept[node], (unsigned long long)S);
           for (int j = 1 + tid; j < k; j += FP_BLOCK) {
             unsigned long long npos = 0, nneg = 0;
             for (int h = 0; h < S; ++h) {
+              const double sgb = sqrt((VVM ? sigv[h] : sig2) * lam);
               const double b = replay ? rd[3 + k + h * k + j] : bsc[(2 * h) * k + j] + sgb * bsc[(2 * h + 1) * k + j];
               npos += (b >= 0.0) ? 1 : 0;
               nneg += (b <= 0.0) ? 1 : 0;
@@ -735,6 +801,36 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
         }
       }
       lam = sc[1];
+
+      if constexpr (VVM) {
+        // ---- fpvvGlobCoup.py:99-103: mu_next ~ vvMuSampler(tau, sigma^2_h, lambda^2 new), always accepted; it takes effect
+        // after the changepoint move, which still conditions on the old mu (:106-108).  Precision Q = I + sum_h A_h^-1 G_h /
+        // sigma^2_h = I + M_w / lam, mean = Q^-1 sum_h A_h^-1 g_h / sigma^2_h (samplers.py:353-379: no mu_in term)
+        fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3, stage, sigv);
+        n_segs += S;
+        const double il = 1.0 / lam;
+        for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Mc[i] * il;
+        __syncthreads();
+        for (int i = tid; i < k; i += FP_BLOCK) {
+          Q[i * ld + i] += 1.0;
+          rhs[i] = a_cur[i];
+        }
+        __syncthreads();
+        fp_cholesky(Q, ld, k, t, stage);
+        fp_trinv(Q, W, ld, k, t, stage);
+        fp_trmv(W, ld, k, rhs, t, stage);
+        fp_trmv_t(W, ld, k, t, mean, stage, red);
+        if (replay) {
+          for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = rd[3 + i];
+        } else {
+          fp_normals(z, k, gchain, unode, uit, 8192u, key);
+          fp_trmv_t(W, ld, k, z, e, stage, red);
+          for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = mean[i] + e[i];
+        }
+        if (TRACE && td)
+          for (int i = tid; i < k; i += FP_BLOCK) td[10 + k + i] = mean[i];
+        __syncthreads();
+      }
 
       // ======================= changepoint move (moves.py:25-126) =================================================
       if (a.with_tau) {
@@ -766,8 +862,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
               }
               Ss = S + 1;
               if (Ss > 9) valid = 0;  // moves.py:42 (glob) / :156 (nh: == 10)
-              hr_num = GLOBM ? ns - 1 - S : ns - S;    // moves.py:46 / :159
-              hr_den = GLOBM ? Ss : Ss - 1;
+              hr_num = GHR ? ns - 1 - S : ns - S;    // moves.py:46 / :159
+              hr_den = GHR ? Ss : Ss - 1;
             }
           } else if (S < 2) {
             valid = 0;
@@ -777,8 +873,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
             for (int j = 0; j < S; ++j)
               if (j != idx) s_tas[w_++] = s_tau[j];
             Ss = S - 1;
-            hr_num = GLOBM ? S : S - 1;  // moves.py:55 / :163
-            hr_den = GLOBM ? ns - 1 - Ss : ns - Ss;
+            hr_num = GHR ? S : S - 1;  // moves.py:55 / :163
+            hr_den = GHR ? ns - 1 - Ss : ns - Ss;
           } else {  // cpRellocationMove (:3-61)
             const int idx = replay ? ri[1] : (int)__umulhi(w.y, (uint32_t)(S - 1));
             const int last = s_tau[S - 1] - 1;
@@ -800,7 +896,30 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
         }
         __syncthreads();
         const int valid = s_int[1], Ss = s_int[2];
-        if (!GLOBM && valid) {
+        if (VVM && valid) {
+          // vvGlobCoupTauMove (moves.py:238-307): mu is kept, two vvLogMargLikelihood evaluations, u < exp(min(1, delta))
+          const double c_seg = a.a_sig * log(a.two_b) - lgamma(a.a_sig);
+          const double ml_cur = fp_score_vv(a.tb, node, tau_cur, S, lam, mu, A, ld, k, g, t, x, tmp, rhs, red, sc + 3, stage, a.a_sig,
+                                            c_seg, a.two_b);
+          const double ml_star = fp_score_vv(a.tb, node, tau_star, Ss, lam, mu, A, ld, k, g, t, x, tmp, rhs, red, sc + 3, stage,
+                                             a.a_sig, c_seg, a.two_b);
+          n_segs += S + Ss;
+          n_evals += 2;
+          const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
+          const double log_ratio = ml_star - ml_cur + lprior + log((double)s_int[3] / (double)s_int[4]);
+          const bool acc = sc[2] < exp(fmin(1.0, log_ratio));
+          if (TRACE && td && tid == 0) {
+            td[6] = ml_cur; td[7] = ml_star;
+          }
+          if (TRACE && ti && tid == 0) ti[2] = acc;
+          __syncthreads();
+          if (acc) {
+            S = Ss;
+            if (tid < SMAX) s_tau[tid] = s_tas[tid];
+          }
+          __syncthreads();
+        }
+        if (FPM == FPM_PLAIN && valid) {
           // moves.py:184-232: two plain marginal likelihoods (prior mean 0), u < min(1, exp(delta))
           const FpSummary sc_ = fp_sweep_plain(a.tb, node, tau_cur, S, lam, A, ld, k, g, t, x, red, sc + 3, stage);
           const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + sc_.s - lam * sc_.c);
@@ -907,6 +1026,10 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
           for (int j = 0; j < S - 1; ++j) atomicAdd(&a.cp_hist[(long long)node * (N + 3) + s_tau[j]], 1ull);
         }
       }
+      if constexpr (VVM) {   // the mean drawn before the changepoint move takes effect now (fpvvGlobCoup.py:103)
+        for (int i = tid; i < k; i += FP_BLOCK) mu[i] = mu_star[i];
+        __syncthreads();
+      }
       // ---- counts: mu_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin == 0 (network.py:309-311)
       if constexpr (GLOBM) {
         const int idx = it + 1;
@@ -946,7 +1069,7 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
 }
 
 inline size_t fp_smem_bytes(int k, bool mats_in_smem) {
-  size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 8) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
+  size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 8 + DBN_SMAX) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
   if (mats_in_smem) b += (size_t)FP_NMAT * fp_ld(k) * k * sizeof(double);
   else b += (size_t)FP_STAGE_DOUBLES * sizeof(double);
   return b;

@@ -255,7 +255,7 @@ static chain_fn pick_method(int method) {
 }
 
 
-static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN; }
+static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN || m == DBN_FP_VV_DBN; }
 
 static std::string g_create_error;
 static std::mutex g_mu;
@@ -597,7 +597,7 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!h || !p) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
-  if (p->method < DBN_H_DBN || p->method > DBN_FP_H_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (p->method < DBN_H_DBN || p->method > DBN_FP_VV_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
   if (!is_fp_method(p->method) && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
@@ -838,9 +838,9 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   }
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
   typedef void (*fp_fn)(const FpArgs);
-  const bool globm = p.method == DBN_FP_GLOB_DBN;
-  const fp_fn fn = trace ? (globm ? fp_glob_kernel<true, true> : fp_glob_kernel<true, false>)
-                         : (globm ? fp_glob_kernel<false, true> : fp_glob_kernel<false, false>);
+  const int fpm = p.method == DBN_FP_GLOB_DBN ? FPM_GLOB : (p.method == DBN_FP_VV_DBN ? FPM_VV : FPM_PLAIN);
+  const fp_fn fn = trace ? (fpm == FPM_GLOB ? fp_glob_kernel<true, FPM_GLOB> : fpm == FPM_VV ? fp_glob_kernel<true, FPM_VV> : fp_glob_kernel<true, FPM_PLAIN>)
+                         : (fpm == FPM_GLOB ? fp_glob_kernel<false, FPM_GLOB> : fpm == FPM_VV ? fp_glob_kernel<false, FPM_VV> : fp_glob_kernel<false, FPM_PLAIN>);
   CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fn<<<h->fp_grid, fp_block_threads(k, h->d_fp_ws == nullptr), smem, h->stream>>>(a);
   CUX(cudaGetLastError());

@@ -180,7 +180,9 @@ class DbnEngine:
             rd[:, :, 0], rd[:, :, 1], rd[:, :, 2] = replay['sigma2'], replay['lambda2'], replay['u_tau']
             if 'mu_tau' in replay:     # globally coupled only
                 rd[:, :, 3:3 + k] = np.asarray(replay['mu_tau'])[:, :, :k]
-            rd[:, :, 3 + k:] = np.asarray(replay['beta'])[:, :, :, :k].reshape(U, n_iter, L.SMAX * k)
+            rd[:, :, 3 + k:3 + k + L.SMAX * k] = np.asarray(replay['beta'])[:, :, :, :k].reshape(U, n_iter, L.SMAX * k)
+            if 'sigma2v' in replay:    # 'fp_var_glob_coup_nh_dbn': one variance per segment
+                rd[:, :, 3 + k + L.SMAX * k:] = replay['sigma2v']
             ri[:, :, 0] = replay['tau_move']
             ri[:, :, 1:3] = replay['tau_pick']
             rd, ri = np.ascontiguousarray(rd), np.ascontiguousarray(ri)
@@ -194,7 +196,10 @@ class DbnEngine:
             mu_after=td[:, :, o:o + k], mus_mean=td[:, :, o + k:o + 3 * k].reshape(U, n_iter, 2, k),
             beta_mean=td[:, :, o + 3 * k:o + 3 * k + L.SMAX * k].reshape(U, n_iter, L.SMAX, k),
             beta_cov_diag=td[:, :, o + 3 * k + L.SMAX * k:o + 3 * k + 2 * L.SMAX * k].reshape(U, n_iter, L.SMAX, k),
-            beta=td[:, :, o + 3 * k + 2 * L.SMAX * k:].reshape(U, n_iter, L.SMAX, k),
+            beta=td[:, :, o + 3 * k + 2 * L.SMAX * k:o + 3 * k + 3 * L.SMAX * k].reshape(U, n_iter, L.SMAX, k),
+            sig_shape_v=td[:, :, o + 3 * k + 3 * L.SMAX * k:o + 3 * k + 3 * L.SMAX * k + L.SMAX],
+            sig_rate_v=td[:, :, o + 3 * k + 3 * L.SMAX * k + L.SMAX:o + 3 * k + 3 * L.SMAX * k + 2 * L.SMAX],
+            sigma2v=td[:, :, o + 3 * k + 3 * L.SMAX * k + 2 * L.SMAX:],
             tau_move=ti[:, :, 0], tau_valid=ti[:, :, 1], tau_accept=ti[:, :, 2], S=ti[:, :, 3], S_after=ti[:, :, 4],
             tau_after=ti[:, :, 5:5 + L.SMAX])
 

@@ -5,8 +5,8 @@ every hyper-parameter is a literal inside that regressor's `fit()` (SURVEY.md se
 reproduces them so that the CUDA path is a drop-in; keyword arguments of `Network` / `DbnEngine.chain_init` may
 override any of them (BASELINE config 4 needs fan-in 4).
 """
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN = 0, 1, 2, 3, 4, 5, 6, 7
-FP_METHODS = (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN)   # full parents: design width k = n, run with dbn_run_fp
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8
+FP_METHODS = (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN)   # full parents: design width k = n, run with dbn_run_fp
 
 # method strings of network.py:154-281 and the CLI aliases of examples/yeast_tests.py:179-187
 METHOD_IDS = {
@@ -18,15 +18,15 @@ METHOD_IDS = {
     'var_glob_coup_nh_dbn': VV_GLOB_DBN,  # network.py:258-269 (vvglobCoup.py); CLI 'var-glob-dbn' of examples/yeast_tests.py:188-189
     'var-glob-dbn': VV_GLOB_DBN,
     'fp_varying_nh_dbn': FP_NH_DBN,       # network.py:165-177 (fullParentsBpwLinReg.py); CLI 'nh-dbn' of examples/full_parents_test.py
+    'fp_var_glob_coup_nh_dbn': FP_VV_DBN,  # network.py:270-281 (fpvvGlobCoup.py)
     'fp_h_dbn': FP_H_DBN,                 # network.py:200-209 (fpBayesianLinearRegression.py); CLI 'h-dbn' of the same script
     'fixed_nh_dbn': NH_DBN,               # network.py:178-189: the nh regressor on predefined changepoints (FIXED_CP below)
 }
 FIXED_CP = ('fixed_nh_dbn',)              # no changepoint move (bayesianPwLinearRegression.py:117), num_samples - 1
 METHOD_NAMES = {H_DBN: 'h_dbn', NH_DBN: 'varying_nh_dbn', SEQ_DBN: 'seq_coup_nh_dbn', GLOB_DBN: 'glob_coup_nh_dbn',
                 FP_GLOB_DBN: 'fp_glob_coup_nh_dbn', VV_GLOB_DBN: 'var_glob_coup_nh_dbn',
-                FP_NH_DBN: 'fp_varying_nh_dbn', FP_H_DBN: 'fp_h_dbn'}
-NOT_YET = ('fp_seq_coup_nh_dbn',
-           'fp_var_glob_coup_nh_dbn')
+                FP_NH_DBN: 'fp_varying_nh_dbn', FP_H_DBN: 'fp_h_dbn', FP_VV_DBN: 'fp_var_glob_coup_nh_dbn'}
+NOT_YET = ('fp_seq_coup_nh_dbn',)
 
 
 def method_id(method):

@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -26,6 +26,7 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'fixed_nh_dbn': ('Bayesian Non-Homogeneous', 'Varying Parents-Fixed changepoints'),   # network.py:179-180
     'fp_varying_nh_dbn': ('Bayesian Non-Homogeneous', 'Full Parents'),   # network.py:166-167
     'fp_h_dbn': ('Bayesian Homogeneous', 'Full Parents'),                # network.py:201-202
+    'fp_var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:271-272
     'var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Varying Parents'),   # network.py:259-260
 }
 
@@ -167,7 +168,9 @@ class Network():
                     'betas_vector': [[np.zeros(dims)]] + [[np.array(cat['beta'][u, it, h]) for h in range(int(cat['S'][u, it]))]
                                                           for it in range(n_iter)],
                 }
-                if mid == FP_GLOB_DBN:
+                if mid == FP_VV_DBN:   # fpvvGlobCoup.py:68,76: one variance per segment and iteration
+                    res['sigma_sqr_vector'] = [[1]] + [[float(v) for v in cat['sigma2v'][u, it, :int(cat['S'][u, it])]] for it in range(n_iter)]
+                if mid in (FP_GLOB_DBN, FP_VV_DBN):
                     res['mu_vector'] = [np.zeros((dims, 1))] + [np.array(cat['mu_after'][u, it]).reshape(-1, 1) for it in range(n_iter)]
                 self.chain_results_per_node.append(res)
                 burned = res['tau_vector'][b:]

@@ -52,8 +52,10 @@ typedef enum {
                          vvGlobCoupTauMove (moves.py:238-415)                                                  */
   DBN_FP_NH_DBN = 6,   /* 'fp_varying_nh_dbn' fullParentsBpwLinReg.py:41-140: full parents, prior mean 0, the nh changepoint
                          move (moves.py:129-236); run with dbn_run_fp                                          */
-  DBN_FP_H_DBN = 7     /* 'fp_h_dbn' fpBayesianLinearRegression.py:40-125: full parents, one segment, Gibbs draws only;
+  DBN_FP_H_DBN = 7,    /* 'fp_h_dbn' fpBayesianLinearRegression.py:40-125: full parents, one segment, Gibbs draws only;
                          run with dbn_run_fp                                                                   */
+  DBN_FP_VV_DBN = 8    /* 'fp_var_glob_coup_nh_dbn' fpvvGlobCoup.py:16-130: full parents, segment-specific variances, mu
+                         redrawn every iteration (vvMuSampler), vvGlobCoupTauMove on the previous mu; run with dbn_run_fp */
 } dbn_method;
 
 typedef struct dbn_handle dbn_handle;
@@ -217,9 +219,11 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
  * dbn_run_fp: dbn_run for DBN_FP_GLOB_DBN (fpGlobCoupBpwLinReg.py:68-110): sigma^2, beta_h, lambda^2 Gibbs draws with
  * the global mean mu as prior mean, then the globally coupled changepoint move (moves.py:25-126) with
  * mu* ~ muSampler (samplers.py:307-351).  Records are n = k wide, so their strides depend on n:
- *   replay_d [units, n_iter, 3 + k + DBN_SMAX*k]: sigma2, lambda2, u_tau, mu*[k], beta[DBN_SMAX][k]
+ *   replay_d [units, n_iter, 3 + k + DBN_SMAX*k + DBN_SMAX]: sigma2, lambda2, u_tau, mu*[k], beta[DBN_SMAX][k],
+ *            sigma2_h[DBN_SMAX] (DBN_FP_VV_DBN only; its mu*[k] is the per-iteration vvMuSampler draw)
  *   replay_i [units, n_iter, 4]: tau_move, tau_pick[2], (pad)
- *   trace_d  [units, n_iter, 10 + 3k + 3*DBN_SMAX*k]: sig_shape, sig_rate, lam_shape, lam_rate, sigma2, lambda2,
+ *   trace_d  [units, n_iter, 10 + 3k + 3*DBN_SMAX*k + 3*DBN_SMAX] (the last 3*DBN_SMAX: per-segment sigma^2_h shape, rate,
+ *            draw of DBN_FP_VV_DBN): sig_shape, sig_rate, lam_shape, lam_rate, sigma2, lambda2,
  *            logml(tau), logml(tau*), log q(mu | tau), log q(mu* | tau*), mu after [k], muSampler mean (tau) [k],
  *            muSampler mean (tau*) [k], beta posterior means [DBN_SMAX][k], diag of the beta covariances [DBN_SMAX][k],
  *            drawn beta_h [DBN_SMAX][k]

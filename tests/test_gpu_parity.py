@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, FP_PLAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
+from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, FP_PLAIN_FILES, FP_VV_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
 from oracle import dbn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -281,8 +281,6 @@ def test_network_dropin(eng_mod):
     big.infer_network('nh-dbn')
     assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)
     with pytest.raises(NotImplementedError):
-        Network(data, 10, 0, 1).infer_network('fp_var_glob_coup_nh_dbn')
-    with pytest.raises(NotImplementedError):
         Network(data, 10, 0, 1).infer_network('fp_seq_coup_nh_dbn')
 
 
@@ -324,7 +322,7 @@ def test_fp_glob_replay_vs_reference(eng_mod, path):
     assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
 
 
-@pytest.mark.parametrize('path', FP_PLAIN_FILES, ids=ids(FP_PLAIN_FILES))
+@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES))
 def test_fp_plain_replay_vs_reference(eng_mod, path):
     """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) / fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
     the reference's recorded draws: changepoint lists and accept flags bit-exact, log-MLs 1e-9, Gibbs parameters, and the
@@ -336,6 +334,9 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
     burn_in = int(g['burn_in'])
     replay = dict(sigma2=g['sigma2'], lambda2=g['lambda2'], u_tau=g['u_tau'], beta=g['beta'], tau_move=g['tau_move'],
                   tau_pick=g['tau_pick'])
+    vv = method == 'fp_var_glob_coup_nh_dbn'      # fpvvGlobCoup.py: per-segment variances, mu redrawn every iteration
+    if vv:
+        replay.update(sigma2v=g['sigma2v'], mu_tau=g['mus_val'][:, :, 0, :])
     with eng_mod(n_chains=1) as e:
         e.build_stats(data_list(g))
         e.chain_init(method, burn_in=burn_in)
@@ -352,6 +353,11 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
     assert_close(tr['logml'], g['logml'][:, :, 2:4], LOGML_RTOL, what='logml')
     assert_close(tr['beta_mean'], g['beta_mean'][..., :n], 1e-7, 1e-9, what='beta_mean')
     assert_close(tr['beta_cov_diag'], g['beta_cov_diag'][..., :n], 1e-7, 1e-13, what='beta_cov_diag')
+    if vv:
+        assert_close(tr['sig_shape_v'], g['sig_shape_v'], 1e-12, what='sig_shape_v')
+        assert_close(1.0 / tr['sig_rate_v'], g['sig_scale_v'], 1e-9, what='sig_scale_v')
+        assert_close(tr['mus_mean'][:, :, 0], g['mus_mean'][:, :, 0, :n], 1e-7, 1e-9, what='vvMuSampler mean')
+        assert_close(tr['mu_after'], g['mu_after'][..., :n], 0, 0, what='mu_after')
     adj = parallel.credible_scores_from_counts(counts['edge'], counts['neg'], counts['nonempty'])
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores of the beta chain)')
     if 'cp_hist' in g:
@@ -359,7 +365,7 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
         assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
 
 
-@pytest.mark.parametrize('method', ['fp_varying_nh_dbn', 'fp_h_dbn'])
+@pytest.mark.parametrize('method', ['fp_varying_nh_dbn', 'fp_h_dbn', 'fp_var_glob_coup_nh_dbn'])
 def test_fp_plain_free_running_and_dropin(eng_mod, method):
     """Free-running Philox chains of the plain full-parents methods: the device's sign counts equal the credible scores
     recomputed on the host from the traced beta chain (same run), the posterior-mean betas agree with the oracle's

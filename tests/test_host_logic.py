@@ -24,7 +24,7 @@ def test_method_table_matches_oracle():
                 c['a_sig'], c['b_sig'], c['a_lam'], c['b_lam'], c['a_del'], c['b_del'])
             assert p['fan_in'] == 3 and p['thin'] == 10 and p['cp_p'] == 0.125
     with pytest.raises(NotImplementedError):
-        run_params('fp_var_glob_coup_nh_dbn', 33)
+        run_params('fp_seq_coup_nh_dbn', 33)
     with pytest.raises(ValueError):
         run_params('nonsense', 33)
 
