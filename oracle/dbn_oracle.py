@@ -32,8 +32,9 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # method table: the per-method constants the reference hard-codes
 # ------------------------------------------------------------------------------------------------
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, FIXED_NH_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN = range(11)
 METHOD_IDS = {
+    'fp_seq_coup_nh_dbn': FP_SEQ_DBN,       # network.py:221-233, fpSeqCoupBpwlinReg.py (the seq loop without the parent-set move)
     'fp_var_glob_coup_nh_dbn': FP_VV_DBN,   # network.py:270-281, fpvvGlobCoup.py
     'fp_varying_nh_dbn': FP_NH_DBN,    # network.py:165-177, fullParentsBpwLinReg.py
     'fp_h_dbn': FP_H_DBN,              # network.py:200-209, fpBayesianLinearRegression.py
@@ -67,7 +68,7 @@ def method_constants(method, N):
     elif m == FP_H_DBN:
         # network.py:203-207 (num_samples + 1), fpBayesianLinearRegression.py:70,84-85,90-91: shape a + (N+1)/2, no moves
         c.update(T_ml=N, T_sigma=N + 1, num_samples=N, a_sig=0.01, b_sig=0.01)
-    elif m in (SEQ_DBN, FIXED_NH_DBN):
+    elif m in (SEQ_DBN, FIXED_NH_DBN, FP_SEQ_DBN):   # fp-seq: network.py:224-230, fpSeqCoupBpwlinReg.py:50-51
         # seq: network.py:213-219; fixed nh: network.py:182-188 also passes num_samples - 1
         c.update(T_ml=N - 1, T_sigma=N - 1, num_samples=N - 1, a_sig=0.005, b_sig=0.005)
     elif m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_VV_DBN):   # fp-vv: network.py:273-279, fpvvGlobCoup.py:49-50
@@ -530,9 +531,9 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     features = [j for j in range(n) if j != node]
     F = len(features)
     c = method_constants(m, N)
-    fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN)    # full parents: pi = every other gene, no parent-set move
+    fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN)    # full parents: pi = every other gene, no parent-set move
     vv = m in (VV_GLOB_DBN, FP_VV_DBN)   # vvglobCoup.py:66-123: segment-specific sigma^2_h, mu kept in the changepoint move
-    seq, glob = m == SEQ_DBN, m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_VV_DBN)
+    seq, glob = m in (SEQ_DBN, FP_SEQ_DBN), m in (GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_VV_DBN)
     has_tau = with_tau and m not in (H_DBN, FIXED_NH_DBN, FP_H_DBN)   # bayesianPwLinearRegression.py:117: only 'varying_nh' moves tau
     KM, SM = (max(5, n) if fp else 5), 10
 
@@ -599,7 +600,7 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
         for h, b_ in enumerate(betas):
             tr['beta'][it, h, :k] = b_
         # (fp-h: S = 1, so the nh / glob shape a + S k / 2 is samplers.py:296-305's a + k / 2)
-        shape, rate = lambda2_params(GLOB_DBN if fp else m, betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
+        shape, rate = lambda2_params(SEQ_DBN if seq else (GLOB_DBN if fp else m), betas, mu if glob else np.zeros(k), sig, c['a_lam'], c['b_lam'])
         tr['lam_shape'][it], tr['lam_scale'][it] = shape, 1.0 / rate
         lam_new = draws.inv_gamma(it, 'lambda', shape, rate)
         tr['lambda2'][it] = lam_new

@@ -187,7 +187,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     is_fixed = method == 'fixed_nh_dbn'              # segments but no changepoint move
     has_tau = method not in ('h_dbn', 'fixed_nh_dbn', 'fp_h_dbn')
     multi_seg = method != 'h_dbn'
-    is_seq = method == 'seq_coup_nh_dbn'
+    is_seq = method in ('seq_coup_nh_dbn', 'fp_seq_coup_nh_dbn')
     is_fp = method.startswith('fp_')              # full parents: no parent-set move, design width = n
     is_fp_glob = method == 'fp_glob_coup_nh_dbn'
     is_fp_vv = method == 'fp_var_glob_coup_nh_dbn'  # fpvvGlobCoup.py: mu redrawn every iteration (always accepted, :99-103)
@@ -529,6 +529,11 @@ def main():
         run_chain_golden('mtor', mtor, 'var_glob_coup_nh_dbn', n_iter=80, burn_in=20, seed=2)
         run_chain_golden('synth200', [syn], 'var_glob_coup_nh_dbn', n_iter=120, burn_in=20, seed=3)
         return
+    if 'fpseq-only' in sys.argv:
+        run_chain_golden('yeast', yeast, 'fp_seq_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+        run_chain_golden('mtor', mtor, 'fp_seq_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+        run_chain_golden('synth200', [syn], 'fp_seq_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
+        return
     if 'fpvv-only' in sys.argv:
         run_chain_golden('yeast', yeast, 'fp_var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
         run_chain_golden('mtor', mtor, 'fp_var_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
@@ -574,6 +579,9 @@ def main():
     run_chain_golden('yeast', yeast, 'fp_var_glob_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
     run_chain_golden('mtor', mtor, 'fp_var_glob_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
     run_chain_golden('synth200', [syn], 'fp_var_glob_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
+    run_chain_golden('yeast', yeast, 'fp_seq_coup_nh_dbn', n_iter=240, burn_in=40, seed=1)
+    run_chain_golden('mtor', mtor, 'fp_seq_coup_nh_dbn', n_iter=60, burn_in=20, seed=2)
+    run_chain_golden('synth200', [syn], 'fp_seq_coup_nh_dbn', n_iter=100, burn_in=20, seed=3)
 
 
 if __name__ == '__main__':

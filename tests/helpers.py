@@ -15,7 +15,8 @@ _ALL_CHAINS = sorted(glob.glob(os.path.join(GOLDEN, 'chain_*.npz')))
 _FP_ALL = [p for p in _ALL_CHAINS if '_fp_' in os.path.basename(p)]              # full-parents methods (n-wide records)
 FP_CHAIN_FILES = [p for p in _FP_ALL if 'fp_glob' in os.path.basename(p)]        # globally coupled: scored from the mu chain
 FP_VV_FILES = [p for p in _FP_ALL if 'fp_var_glob' in os.path.basename(p)]       # segment-specific variances, mu redrawn every iteration
-FP_PLAIN_FILES = [p for p in _FP_ALL if p not in FP_CHAIN_FILES + FP_VV_FILES]   # fp_varying_nh / fp_h: scored from the beta chain
+FP_SEQ_FILES = [p for p in _FP_ALL if 'fp_seq' in os.path.basename(p)]           # sequentially coupled at width n (oracle only so far)
+FP_PLAIN_FILES = [p for p in _FP_ALL if p not in FP_CHAIN_FILES + FP_VV_FILES + FP_SEQ_FILES]   # fp_varying_nh / fp_h: scored from the beta chain
 CHAIN_FILES = [p for p in _ALL_CHAINS if p not in _FP_ALL]
 
 

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import FP_PLAIN_FILES, FP_VV_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from helpers import FP_PLAIN_FILES, FP_VV_FILES, FP_SEQ_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
 from oracle import dbn_oracle as O
 
 
@@ -135,7 +135,7 @@ def test_fp_glob_chain_replay(path):
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores)')
 
 
-@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES))
+@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES + FP_SEQ_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES + FP_SEQ_FILES))
 def test_fp_plain_chain_replay(path):
     """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) and fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
     the reference's recorded draws: changepoint lists / accept flags bit-exact, Gibbs parameters and log-MLs, and the
@@ -153,8 +153,8 @@ def test_fp_plain_chain_replay(path):
         if method != 'fp_h_dbn':
             for key in ('tau_valid', 'tau_accept'):
                 assert np.array_equal(tr[key], g[key][node]), (key, node)
-        for key in ('sig_shape', 'sig_scale', 'lam_shape', 'lam_scale'):
-            assert_close(tr[key], g[key][node], 1e-9, 1e-12, what='%s node %d' % (key, node))
+        for key in ('sig_shape', 'sig_scale', 'lam_shape', 'lam_scale') + (('del_shape', 'del_scale') if 'fp_seq' in method else ()):
+            assert_close(tr[key], g[key][node], 1e-8 if 'fp_seq' in method else 1e-9, 1e-12, what='%s node %d' % (key, node))
         assert_close(tr['beta_mean'], g['beta_mean'][node], 1e-7, 1e-9, what='beta_mean node %d' % node)
         assert_close(np.diagonal(tr['beta_cov'], axis1=-2, axis2=-1), g['beta_cov_diag'][node], 1e-7, 1e-13, what='beta_cov')
         assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml node %d' % node)
