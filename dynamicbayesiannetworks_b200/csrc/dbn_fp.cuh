@@ -613,8 +613,10 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
 // iteration from vvMuSampler (always accepted), the changepoint move of vvGlobCoupTauMove on the OLD mu scored by
 // vvLogMargLikelihood (per-segment T_h); edge scores from the beta chain like the plain models.
 constexpr int FPM_GLOB = 0, FPM_PLAIN = 1, FPM_VV = 2;
-template <bool TRACE, int FPM = FPM_GLOB>
-__global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a) {
+// BIG: the matrices live in the global workspace and the blocked routines run (256 threads, 2 blocks per SM); !BIG: matrices in
+// shared memory, at most 128 threads and 96 registers so that 19+ one-warp blocks of a small network are resident per SM.
+template <bool TRACE, int FPM = FPM_GLOB, bool BIG = false>
+__global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob_kernel(const FpArgs a) {
   constexpr bool GLOBM = FPM == FPM_GLOB, VVM = FPM == FPM_VV;
   constexpr bool GHR = GLOBM || VVM;   // Hastings ratios and acceptance rule of the globally coupled changepoint moves
   extern __shared__ double sm[];
@@ -630,8 +632,8 @@ __global__ void __launch_bounds__(FP_BLOCK_MAX, 2) fp_glob_kernel(const FpArgs a
   int* s_tau = reinterpret_cast<int*>(sc + 8 + SMAX);
   int* s_tas = s_tau + SMAX;
   int* s_int = s_tas + SMAX;             // [8]
-  double* mats = a.ws ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
-  double* stage = a.ws ? reinterpret_cast<double*>(s_int + 8) : nullptr;   // large k: staging of the blocked routines
+  double* mats = BIG ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
+  double* stage = BIG ? reinterpret_cast<double*>(s_int + 8) : nullptr;   // large k: staging of the blocked routines
   double* A = mats, *W = mats + (long long)ld * k, *Mc = mats + 2ll * ld * k, *Ms = mats + 3ll * ld * k, *Q = mats + 4ll * ld * k;
   double* bsc = a.bsc ? a.bsc + (long long)blockIdx.x * (2 * SMAX) * k : nullptr;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));

@@ -839,8 +839,10 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
   typedef void (*fp_fn)(const FpArgs);
   const int fpm = p.method == DBN_FP_GLOB_DBN ? FPM_GLOB : (p.method == DBN_FP_VV_DBN ? FPM_VV : FPM_PLAIN);
-  const fp_fn fn = trace ? (fpm == FPM_GLOB ? fp_glob_kernel<true, FPM_GLOB> : fpm == FPM_VV ? fp_glob_kernel<true, FPM_VV> : fp_glob_kernel<true, FPM_PLAIN>)
-                         : (fpm == FPM_GLOB ? fp_glob_kernel<false, FPM_GLOB> : fpm == FPM_VV ? fp_glob_kernel<false, FPM_VV> : fp_glob_kernel<false, FPM_PLAIN>);
+  const bool big = h->d_fp_ws != nullptr;
+#define FP_PICK(TR, BG) (fpm == FPM_GLOB ? fp_glob_kernel<TR, FPM_GLOB, BG> : fpm == FPM_VV ? fp_glob_kernel<TR, FPM_VV, BG> : fp_glob_kernel<TR, FPM_PLAIN, BG>)
+  const fp_fn fn = trace ? (big ? FP_PICK(true, true) : FP_PICK(true, false)) : (big ? FP_PICK(false, true) : FP_PICK(false, false));
+#undef FP_PICK
   CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fn<<<h->fp_grid, fp_block_threads(k, h->d_fp_ws == nullptr), smem, h->stream>>>(a);
   CUX(cudaGetLastError());
