@@ -43,6 +43,8 @@ struct FpArgs {
   double* st_sig;
   double* st_lam;
   double* st_mu;   // [k][U]
+  double* st_del;  // delta^2 (sequentially coupled)
+  double a_del, b_del;
   unsigned long long* pos;      // [n][n]  #kept mu samples with mu_j >= 0   (credible_score, scores.py:196-205)
   unsigned long long* kept;     // [n]     #kept mu samples
   unsigned long long* cp_hist;  // [n][N+3]
@@ -567,6 +569,64 @@ __device__ FpSummary fp_sweep_plain(const Table& tb, int node, TauFn tau, int S,
   return r;
 }
 
+// x = A^-1 rhs through the inverse factor (t is scratch)
+__device__ __forceinline__ void fp_apply_ainv(const double* W, int ld, int k, const double* rhs, double* t, double* x, double* stage,
+                                              double* red) {
+  fp_trmv(W, ld, k, rhs, t, stage);
+  fp_trmv_t(W, ld, k, t, x, stage, red);
+}
+
+// sequentially coupled log marginal likelihood (marginalLikelihood.py:91-150 with method == 'seq-coup', prior means from
+// betaTildeSampler, samplers.py:4-54): bt[0] = 0, bt[1] = A_lam(G_1)^-1 lam g_1, bt[h+1] = A_dlt(G_h)^-1 (bt[h-1] + dlt g_h).
+// bt_cur / bt_prev / nxt are k-vectors of scratch.
+template <class TauFn>
+__device__ double fp_score_seq(const Table& tb, int node, TauFn tau, int S, double lam, double dlt, double* bt_cur, double* bt_prev,
+                               double* nxt, double* A, double* W, int ld, int k, double* g, double* t, double* x, double* tmp,
+                               double* rhs, double* red, double* s_tmp, double* stage, double c0, double T_half_plus_a, double two_b) {
+  for (int i = threadIdx.x; i < k; i += FP_BLOCK) bt_cur[i] = bt_prev[i] = 0.0;
+  __syncthreads();
+  double acc_ld = 0.0, acc_q = 0.0;
+  int lo = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
+    if (h == 1) {
+      fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
+      fp_cholesky(A, ld, k, t, stage);
+      fp_trinv(A, W, ld, k, t, stage);
+      for (int i = threadIdx.x; i < k; i += FP_BLOCK) rhs[i] = lam * g[i];
+      __syncthreads();
+      fp_apply_ainv(W, ld, k, rhs, t, bt_cur, stage, red);
+    }
+    const double w = (h == 0) ? lam : dlt;
+    fp_load_segment(tb, node, lo, hi, w, A, ld, k, g, s_tmp);
+    const double s = *s_tmp;
+    fp_symv(A, ld, k, bt_cur, tmp);
+    for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+      const double gm = (tmp[i] - bt_cur[i]) / w;
+      tmp[i] = gm;
+      x[i] = g[i] - gm;
+    }
+    __syncthreads();
+    const double rho = s - 2.0 * fp_dot(bt_cur, g, k, red) + fp_dot(bt_cur, tmp, k, red);
+    acc_ld += fp_cholesky(A, ld, k, t, stage);
+    fp_trinv(A, W, ld, k, t, stage);
+    fp_trmv(W, ld, k, x, t, stage);
+    acc_q += rho - w * fp_dot(t, t, k, red);
+    if (h >= 1) {
+      for (int i = threadIdx.x; i < k; i += FP_BLOCK) rhs[i] = bt_prev[i] + dlt * g[i];
+      __syncthreads();
+      fp_apply_ainv(W, ld, k, rhs, t, nxt, stage, red);
+      for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
+        bt_prev[i] = bt_cur[i];
+        bt_cur[i] = nxt[i];
+      }
+      __syncthreads();
+    }
+    lo = hi;
+  }
+  return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+}
+
 // vvLogMargLikelihood (marginalLikelihood.py:5-43) at prior mean mu: per segment its own length T_h in the Gamma / pi /
 // exponent terms; needs the factor and one forward substitution per segment, no inverse.  c_seg = a ln(2b) - lgamma(a).
 template <class TauFn>
@@ -612,12 +672,15 @@ __device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k
 // FPM_VV: fp_var_glob_coup_nh_dbn (fpvvGlobCoup.py:72-121): segment-specific variances (segmentSigmaSampler), mu redrawn every
 // iteration from vvMuSampler (always accepted), the changepoint move of vvGlobCoupTauMove on the OLD mu scored by
 // vvLogMargLikelihood (per-segment T_h); edge scores from the beta chain like the plain models.
-constexpr int FPM_GLOB = 0, FPM_PLAIN = 1, FPM_VV = 2;
+// FPM_SEQ: fp_seq_coup_nh_dbn (fpSeqCoupBpwlinReg.py:68-106): the sequentially coupled loop at width n — prior mean of segment h is
+// betaTildeSampler's beta-tilde_h (samplers.py:4-54), delta^2 replaces lambda^2 for h > 0, delta^2 Gibbs draw, nh changepoint move
+// scored by the sequentially coupled marginal likelihood.  The `mu` / `mu_star` vectors hold beta-tilde_h / beta-tilde_{h-1}.
+constexpr int FPM_GLOB = 0, FPM_PLAIN = 1, FPM_VV = 2, FPM_SEQ = 3;
 // BIG: the matrices live in the global workspace and the blocked routines run (256 threads, 2 blocks per SM); !BIG: matrices in
 // shared memory, at most 128 threads and 96 registers so that 19+ one-warp blocks of a small network are resident per SM.
 template <bool TRACE, int FPM = FPM_GLOB, bool BIG = false>
 __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob_kernel(const FpArgs a) {
-  constexpr bool GLOBM = FPM == FPM_GLOB, VVM = FPM == FPM_VV;
+  constexpr bool GLOBM = FPM == FPM_GLOB, VVM = FPM == FPM_VV, SEQM = FPM == FPM_SEQ;
   constexpr bool GHR = GLOBM || VVM;   // Hastings ratios and acceptance rule of the globally coupled changepoint moves
   extern __shared__ double sm[];
   const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
@@ -649,6 +712,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
     int S = a.st_S[u];
     if (tid < SMAX) s_tau[tid] = a.st_tau[tid * a.U + u];
     double sig2 = a.st_sig[u], lam = a.st_lam[u];
+    double dlt = SEQM ? a.st_del[u] : 1.0;
     for (int i = tid; i < k; i += FP_BLOCK) mu[i] = a.st_mu[(long long)i * a.U + u];
     __syncthreads();
     unsigned long long n_evals = 0, n_segs = 0;
@@ -674,26 +738,41 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
       // ======================= Gibbs pass: sigma^2, beta_h, lambda^2 (fpGlobCoupBpwLinReg.py:70-86) ================
       double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
       double acc_ss = 0.0;   // vv: sum_h |beta_h - mu|^2 / sigma^2_h (samplers.py:275-282)
+      auto w_of = [&](int h) -> double { return (SEQM && h > 0) ? dlt : lam; };   // weight of segment h (samplers.py:158-163)
+      if constexpr (SEQM) {
+        for (int i = tid; i < k; i += FP_BLOCK) mu[i] = mu_star[i] = 0.0;   // beta-tilde_0 = 0
+        __syncthreads();
+      }
       {
         int lo = 0;
         for (int h = 0; h < S; ++h) {
           const int hi = DBN_SEG_END(s_tau[h], h, S, N);
-          fp_load_segment(a.tb, node, lo, hi, lam, A, ld, k, g, sc + 3);
+          const double w = w_of(h);
+          if (SEQM && h == 1) {   // beta-tilde_1 from this segment's own data with lambda^2 (samplers.py:36-39)
+            fp_load_segment(a.tb, node, lo, hi, lam, A, ld, k, g, sc + 3);
+            fp_cholesky(A, ld, k, t, stage);
+            fp_trinv(A, W, ld, k, t, stage);
+            for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = lam * g[i];
+            __syncthreads();
+            fp_apply_ainv(W, ld, k, rhs, t, mu, stage, red);
+            ++n_segs;
+          }
+          fp_load_segment(a.tb, node, lo, hi, w, A, ld, k, g, sc + 3);
           const double s = sc[3];
           // G mu = (A mu - mu) / lam ; v = g - G mu ; rho = s - 2 mu.g + mu.G mu
           fp_symv(A, ld, k, mu, tmp);
           for (int i = tid; i < k; i += FP_BLOCK) {
-            const double gm = (tmp[i] - mu[i]) / lam;
+            const double gm = (tmp[i] - mu[i]) / w;
             tmp[i] = gm;
             x[i] = g[i] - gm;              // v
-            rhs[i] = mu[i] + lam * g[i];   // numerator of the posterior mean (samplers.py:210-212)
+            rhs[i] = mu[i] + w * g[i];     // numerator of the posterior mean (samplers.py:210-212)
           }
           __syncthreads();
           const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
           fp_cholesky(A, ld, k, t, stage);
           fp_trinv(A, W, ld, k, t, stage);
           fp_trmv(W, ld, k, x, t, stage);
-          const double q_h = rho - lam * fp_dot(t, t, k, red);
+          const double q_h = rho - w * fp_dot(t, t, k, red);
           q_sum += q_h;
           double sig_h = 1.0;
           if constexpr (VVM) {
@@ -722,7 +801,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
             if constexpr (VVM) {
               const double dd = fp_dot(tmp, tmp, k, red), de = fp_dot(tmp, e, k, red), ee = fp_dot(e, e, k, red);
               acc_ss += (dd + 2.0 * sqrt(sig_h * lam) * de) / sig_h + lam * ee;
-            } else {
+            } else if (!SEQM || h == 0) {   // seq: only beta_0 enters the lambda^2 rate (samplers.py:249-263)
               acc_dd += fp_dot(tmp, tmp, k, red);
               acc_de += fp_dot(tmp, e, k, red);
               acc_ee += fp_dot(e, e, k, red);
@@ -738,7 +817,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
             __syncthreads();
             if constexpr (VVM)
               acc_ss += fp_dot(tmp, tmp, k, red) / sig_h;
-            else
+            else if (!SEQM || h == 0)
               acc_dd += fp_dot(tmp, tmp, k, red);
           }
           if (TRACE && td) {
@@ -750,10 +829,20 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
                 const double wv = stage ? W[(long long)i * ld + r] : W[r * ld + i];
                 dg += wv * wv;
               }
-              td[10 + 3 * k + DBN_SMAX * k + h * k + i] = lam * dg;  // x sigma^2 below
+              td[10 + 3 * k + DBN_SMAX * k + h * k + i] = w * dg;  // x sigma^2 below
             }
           }
           __syncthreads();
+          if (SEQM && h >= 1) {   // beta-tilde_{h+1} = A_dlt(G_h)^-1 (beta-tilde_{h-1} + dlt g_h)  (samplers.py:40-46)
+            for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = mu_star[i] + dlt * g[i];
+            __syncthreads();
+            fp_apply_ainv(W, ld, k, rhs, t, z, stage, red);
+            for (int i = tid; i < k; i += FP_BLOCK) {
+              mu_star[i] = mu[i];
+              mu[i] = z[i];
+            }
+            __syncthreads();
+          }
           lo = hi;
         }
       }
@@ -763,7 +852,8 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
         const double sg = sqrt(s2 * lam);
         const double ss = replay ? acc_dd : acc_dd + 2.0 * sg * acc_de + s2 * lam * acc_ee;
         // samplers.py:285-289: shape a + S k / 2, rate b + sum |beta_h - mu|^2 / (2 sigma^2)  (vv: / sigma^2_h per segment)
-        const double lshape = a.a_lam + 0.5 * (double)(S * k), lrate = a.b_lam + 0.5 * (VVM ? acc_ss : ss / s2);
+        // (seq: shape a + (k + 1) / 2, rate b + beta_0.beta_0 / (2 sigma^2), samplers.py:249-263; acc_* hold segment 0 only)
+        const double lshape = a.a_lam + 0.5 * (double)(SEQM ? k + 1 : S * k), lrate = a.b_lam + 0.5 * (VVM ? acc_ss : ss / s2);
         const double l2 = replay ? rd[1] : lrate / gamma_draw(gchain, unode, uit, 24000u, key, lshape);
         sc[0] = s2;
         sc[1] = l2;
@@ -777,7 +867,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
       sig2 = sc[0];
       if (TRACE && td) {
         for (int i = tid; i < S * k; i += FP_BLOCK) {
-          const double s2h = VVM ? sigv[i / k] : sig2, sg = sqrt(s2h * lam);
+          const double s2h = VVM ? sigv[i / k] : sig2, sg = sqrt(s2h * w_of(i / k));
           td[10 + 3 * k + DBN_SMAX * k + i] *= s2h;
           if (!replay) td[10 + 3 * k + 2 * DBN_SMAX * k + i] = td[10 + 3 * k + i] + sg * td[10 + 3 * k + 2 * DBN_SMAX * k + i];
         }
@@ -791,7 +881,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           for (int j = 1 + tid; j < k; j += FP_BLOCK) {
             unsigned long long npos = 0, nneg = 0;
             for (int h = 0; h < S; ++h) {
-              const double sgb = sqrt((VVM ? sigv[h] : sig2) * lam);
+              const double sgb = sqrt((VVM ? sigv[h] : sig2) * w_of(h));
               const double b = replay ? rd[3 + k + h * k + j] : bsc[(2 * h) * k + j] + sgb * bsc[(2 * h + 1) * k + j];
               npos += (b >= 0.0) ? 1 : 0;
               nneg += (b <= 0.0) ? 1 : 0;
@@ -802,7 +892,63 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           }
         }
       }
+      if constexpr (SEQM) {
+        // ---- delta^2 (samplers.py:220-247): beta-tildes recomputed with (lambda^2 new, delta^2 old), beta_h centred on
+        // beta-tilde_{h-1} for h >= 1; shape a + (S - 1) k / 2, rate b + sum |beta_h - bt_{h-1}|^2 / (2 sigma^2)
+        const double lam_new = sc[1];
+        for (int i = tid; i < k; i += FP_BLOCK) mu[i] = mu_star[i] = 0.0;
+        __syncthreads();
+        double accd = 0.0;
+        const double sgd = sqrt(sig2 * dlt);
+        int lo = 0;
+        for (int h = 0; h < S; ++h) {
+          const int hi = DBN_SEG_END(s_tau[h], h, S, N);
+          if (h >= 1) {
+            if (h == 1) {
+              fp_load_segment(a.tb, node, lo, hi, lam_new, A, ld, k, g, sc + 3);
+              fp_cholesky(A, ld, k, t, stage);
+              fp_trinv(A, W, ld, k, t, stage);
+              for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = lam_new * g[i];
+              __syncthreads();
+              fp_apply_ainv(W, ld, k, rhs, t, mu, stage, red);
+              ++n_segs;
+            }
+            for (int i = tid; i < k; i += FP_BLOCK) {
+              const double b = replay ? rd[3 + k + h * k + i] : bsc[(2 * h) * k + i] + sgd * bsc[(2 * h + 1) * k + i];
+              tmp[i] = b - mu_star[i];
+            }
+            __syncthreads();
+            accd += fp_dot(tmp, tmp, k, red);
+            if (h + 1 < S) {
+              fp_load_segment(a.tb, node, lo, hi, dlt, A, ld, k, g, sc + 3);
+              fp_cholesky(A, ld, k, t, stage);
+              fp_trinv(A, W, ld, k, t, stage);
+              for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = mu_star[i] + dlt * g[i];
+              __syncthreads();
+              fp_apply_ainv(W, ld, k, rhs, t, z, stage, red);
+              for (int i = tid; i < k; i += FP_BLOCK) {
+                mu_star[i] = mu[i];
+                mu[i] = z[i];
+              }
+              __syncthreads();
+              ++n_segs;
+            }
+          }
+          lo = hi;
+        }
+        if (tid == 0) {
+          const double dshape = a.a_del + 0.5 * (double)((S - 1) * k), drate = a.b_del + 0.5 * accd / sig2;
+          const double d2 = replay ? rd[3 + k + DBN_SMAX * k] : drate / gamma_draw(gchain, unode, uit, 28000u, key, dshape);
+          sc[4] = d2;
+          if (TRACE && td) {
+            const int o = 10 + 3 * k + 3 * DBN_SMAX * k;   // entry 0 of the per-segment variance slots: delta^2's shape, rate, draw
+            td[o] = dshape; td[o + DBN_SMAX] = drate; td[o + 2 * DBN_SMAX] = d2;
+          }
+        }
+        __syncthreads();
+      }
       lam = sc[1];
+      if constexpr (SEQM) dlt = sc[4];
 
       if constexpr (VVM) {
         // ---- fpvvGlobCoup.py:99-103: mu_next ~ vvMuSampler(tau, sigma^2_h, lambda^2 new), always accepted; it takes effect
@@ -910,6 +1056,28 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
           const double log_ratio = ml_star - ml_cur + lprior + log((double)s_int[3] / (double)s_int[4]);
           const bool acc = sc[2] < exp(fmin(1.0, log_ratio));
+          if (TRACE && td && tid == 0) {
+            td[6] = ml_cur; td[7] = ml_star;
+          }
+          if (TRACE && ti && tid == 0) ti[2] = acc;
+          __syncthreads();
+          if (acc) {
+            S = Ss;
+            if (tid < SMAX) s_tau[tid] = s_tas[tid];
+          }
+          __syncthreads();
+        }
+        if (SEQM && valid) {
+          // changepointsSetMove with method 'seq-coup' (moves.py:184-232): two sequentially coupled marginal likelihoods
+          const double ml_cur = fp_score_seq(a.tb, node, tau_cur, S, lam, dlt, mu, mu_star, z, A, W, ld, k, g, t, x, tmp, rhs, red, sc + 3,
+                                             stage, a.c0, a.T_half_plus_a, a.two_b);
+          const double ml_star = fp_score_seq(a.tb, node, tau_star, Ss, lam, dlt, mu, mu_star, z, A, W, ld, k, g, t, x, tmp, rhs, red,
+                                              sc + 3, stage, a.c0, a.T_half_plus_a, a.two_b);
+          n_segs += S + Ss;
+          n_evals += 2;
+          const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
+          const double log_ratio = ml_star - ml_cur + lprior + log((double)s_int[3] / (double)s_int[4]);
+          const bool acc = sc[2] < fmin(1.0, exp(log_ratio));
           if (TRACE && td && tid == 0) {
             td[6] = ml_cur; td[7] = ml_star;
           }
@@ -1058,6 +1226,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
       a.st_S[u] = S;
       a.st_sig[u] = sig2;
       a.st_lam[u] = lam;
+      if (SEQM) a.st_del[u] = dlt;
       atomicAdd(&a.counters[0], (unsigned long long)a.n_iter);
       atomicAdd(&a.counters[1], n_evals);
       atomicAdd(&a.counters[2], n_segs);

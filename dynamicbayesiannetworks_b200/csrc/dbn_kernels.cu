@@ -255,7 +255,7 @@ static chain_fn pick_method(int method) {
 }
 
 
-static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN || m == DBN_FP_VV_DBN; }
+static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN || m == DBN_FP_VV_DBN || m == DBN_FP_SEQ_DBN; }
 
 static std::string g_create_error;
 static std::mutex g_mu;
@@ -597,7 +597,7 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!h || !p) return DBN_ERR_INVALID;
   if (!h->have_stats) DBN_FAIL(h, DBN_ERR_STATE, "dbn_chain_init: call dbn_build_stats first");
-  if (p->method < DBN_H_DBN || p->method > DBN_FP_VV_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
+  if (p->method < DBN_H_DBN || p->method > DBN_FP_SEQ_DBN) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unknown method %d", p->method);
   if (!is_fp_method(p->method) && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
@@ -798,6 +798,7 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   a.T_half_plus_a = p.T_ml / 2 + p.a_sigma;
   a.two_b = 2 * p.b_sigma;
   a.st_S = h->st_S; a.st_tau = h->st_tau; a.st_sig = h->st_sig; a.st_lam = h->st_lam; a.st_mu = h->st_mu_fp;
+  a.st_del = h->st_del; a.a_del = p.a_delta; a.b_del = p.b_delta;
   a.pos = h->d_counts;
   a.kept = a.pos + (long long)h->n * h->n;
   a.cp_hist = a.kept + h->n;
@@ -838,9 +839,9 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   }
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
   typedef void (*fp_fn)(const FpArgs);
-  const int fpm = p.method == DBN_FP_GLOB_DBN ? FPM_GLOB : (p.method == DBN_FP_VV_DBN ? FPM_VV : FPM_PLAIN);
+  const int fpm = p.method == DBN_FP_GLOB_DBN ? FPM_GLOB : (p.method == DBN_FP_VV_DBN ? FPM_VV : (p.method == DBN_FP_SEQ_DBN ? FPM_SEQ : FPM_PLAIN));
   const bool big = h->d_fp_ws != nullptr;
-#define FP_PICK(TR, BG) (fpm == FPM_GLOB ? fp_glob_kernel<TR, FPM_GLOB, BG> : fpm == FPM_VV ? fp_glob_kernel<TR, FPM_VV, BG> : fp_glob_kernel<TR, FPM_PLAIN, BG>)
+#define FP_PICK(TR, BG) (fpm == FPM_GLOB ? fp_glob_kernel<TR, FPM_GLOB, BG> : fpm == FPM_VV ? fp_glob_kernel<TR, FPM_VV, BG> : fpm == FPM_SEQ ? fp_glob_kernel<TR, FPM_SEQ, BG> : fp_glob_kernel<TR, FPM_PLAIN, BG>)
   const fp_fn fn = trace ? (big ? FP_PICK(true, true) : FP_PICK(true, false)) : (big ? FP_PICK(false, true) : FP_PICK(false, false));
 #undef FP_PICK
   CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

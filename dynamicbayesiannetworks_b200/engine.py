@@ -183,6 +183,8 @@ class DbnEngine:
             rd[:, :, 3 + k:3 + k + L.SMAX * k] = np.asarray(replay['beta'])[:, :, :, :k].reshape(U, n_iter, L.SMAX * k)
             if 'sigma2v' in replay:    # 'fp_var_glob_coup_nh_dbn': one variance per segment
                 rd[:, :, 3 + k + L.SMAX * k:] = replay['sigma2v']
+            if 'delta2' in replay:     # 'fp_seq_coup_nh_dbn': delta^2 travels in the first per-segment variance slot
+                rd[:, :, 3 + k + L.SMAX * k] = replay['delta2']
             ri[:, :, 0] = replay['tau_move']
             ri[:, :, 1:3] = replay['tau_pick']
             rd, ri = np.ascontiguousarray(rd), np.ascontiguousarray(ri)

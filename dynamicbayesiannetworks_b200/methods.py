@@ -5,8 +5,8 @@ every hyper-parameter is a literal inside that regressor's `fit()` (SURVEY.md se
 reproduces them so that the CUDA path is a drop-in; keyword arguments of `Network` / `DbnEngine.chain_init` may
 override any of them (BASELINE config 4 needs fan-in 4).
 """
-H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8
-FP_METHODS = (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN)   # full parents: design width k = n, run with dbn_run_fp
+H_DBN, NH_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+FP_METHODS = (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN)   # full parents: design width k = n, run with dbn_run_fp
 
 # method strings of network.py:154-281 and the CLI aliases of examples/yeast_tests.py:179-187
 METHOD_IDS = {
@@ -19,14 +19,16 @@ METHOD_IDS = {
     'var-glob-dbn': VV_GLOB_DBN,
     'fp_varying_nh_dbn': FP_NH_DBN,       # network.py:165-177 (fullParentsBpwLinReg.py); CLI 'nh-dbn' of examples/full_parents_test.py
     'fp_var_glob_coup_nh_dbn': FP_VV_DBN,  # network.py:270-281 (fpvvGlobCoup.py)
+    'fp_seq_coup_nh_dbn': FP_SEQ_DBN,      # network.py:221-233 (fpSeqCoupBpwlinReg.py)
     'fp_h_dbn': FP_H_DBN,                 # network.py:200-209 (fpBayesianLinearRegression.py); CLI 'h-dbn' of the same script
     'fixed_nh_dbn': NH_DBN,               # network.py:178-189: the nh regressor on predefined changepoints (FIXED_CP below)
 }
 FIXED_CP = ('fixed_nh_dbn',)              # no changepoint move (bayesianPwLinearRegression.py:117), num_samples - 1
 METHOD_NAMES = {H_DBN: 'h_dbn', NH_DBN: 'varying_nh_dbn', SEQ_DBN: 'seq_coup_nh_dbn', GLOB_DBN: 'glob_coup_nh_dbn',
                 FP_GLOB_DBN: 'fp_glob_coup_nh_dbn', VV_GLOB_DBN: 'var_glob_coup_nh_dbn',
-                FP_NH_DBN: 'fp_varying_nh_dbn', FP_H_DBN: 'fp_h_dbn', FP_VV_DBN: 'fp_var_glob_coup_nh_dbn'}
-NOT_YET = ('fp_seq_coup_nh_dbn',)
+                FP_NH_DBN: 'fp_varying_nh_dbn', FP_H_DBN: 'fp_h_dbn', FP_VV_DBN: 'fp_var_glob_coup_nh_dbn',
+                FP_SEQ_DBN: 'fp_seq_coup_nh_dbn'}
+NOT_YET = ()
 
 
 def method_id(method):
@@ -61,7 +63,7 @@ def run_params(method, N, fan_in=3, burn_in=0, thin=10, with_tau=True, **over):
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N), a_sigma=0.005, b_sigma=0.005)
     elif m == FP_H_DBN:   # network.py:203-207 passes N + 1; fpBayesianLinearRegression.py:70,84-85,90-91
         p.update(num_samples=N, T_ml=float(N), T_sigma=float(N + 1), a_sigma=0.01, b_sigma=0.01)
-    elif m == SEQ_DBN:
+    elif m in (SEQ_DBN, FP_SEQ_DBN):   # fp: network.py:224-230, fpSeqCoupBpwlinReg.py:50-51
         p.update(num_samples=N - 1, T_ml=float(N - 1), T_sigma=float(N - 1), a_sigma=0.005, b_sigma=0.005)
     else:  # glob, fp-glob, var-glob: network.py:237-243, :249-255, :261-267; IG(0.01, 0.01) in all three
         # (fpGlobCoupBpwLinReg.py:49-50, vvglobCoup.py:42-43); var-glob uses the segment lengths T_h instead of T

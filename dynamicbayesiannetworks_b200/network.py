@@ -14,7 +14,7 @@ it stays picklable (examples/utils.py:226-240).  There is no CPU fallback.
 import numpy as np
 
 from .engine import DbnEngine
-from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
+from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
 
 _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
@@ -27,6 +27,7 @@ _MODEL_ARGS = {  # network.py:155-156, :191-192, :211-212, :235-236
     'fp_varying_nh_dbn': ('Bayesian Non-Homogeneous', 'Full Parents'),   # network.py:166-167
     'fp_h_dbn': ('Bayesian Homogeneous', 'Full Parents'),                # network.py:201-202
     'fp_var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Full Parents'),   # network.py:271-272
+    'fp_seq_coup_nh_dbn': ('Sequentilly Coupled Non-Homogeneous', 'Full Parents'),             # network.py:222-223
     'var_glob_coup_nh_dbn': ('Varying Globally Coupled Non-Homogeneous', 'Varying Parents'),   # network.py:259-260
 }
 
@@ -168,6 +169,8 @@ class Network():
                     'betas_vector': [[np.zeros(dims)]] + [[np.array(cat['beta'][u, it, h]) for h in range(int(cat['S'][u, it]))]
                                                           for it in range(n_iter)],
                 }
+                if mid == FP_SEQ_DBN:  # fpSeqCoupBpwlinReg.py:67,88-90,127: delta^2 history (first per-segment variance slot)
+                    res['delta_sqr_vector'] = [1] + [float(v) for v in cat['sigma2v'][u, :, 0]]
                 if mid == FP_VV_DBN:   # fpvvGlobCoup.py:68,76: one variance per segment and iteration
                     res['sigma_sqr_vector'] = [[1]] + [[float(v) for v in cat['sigma2v'][u, it, :int(cat['S'][u, it])]] for it in range(n_iter)]
                 if mid in (FP_GLOB_DBN, FP_VV_DBN):

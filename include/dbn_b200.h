@@ -54,8 +54,11 @@ typedef enum {
                          move (moves.py:129-236); run with dbn_run_fp                                          */
   DBN_FP_H_DBN = 7,    /* 'fp_h_dbn' fpBayesianLinearRegression.py:40-125: full parents, one segment, Gibbs draws only;
                          run with dbn_run_fp                                                                   */
-  DBN_FP_VV_DBN = 8    /* 'fp_var_glob_coup_nh_dbn' fpvvGlobCoup.py:16-130: full parents, segment-specific variances, mu
+  DBN_FP_VV_DBN = 8,   /* 'fp_var_glob_coup_nh_dbn' fpvvGlobCoup.py:16-130: full parents, segment-specific variances, mu
                          redrawn every iteration (vvMuSampler), vvGlobCoupTauMove on the previous mu; run with dbn_run_fp */
+  DBN_FP_SEQ_DBN = 9   /* 'fp_seq_coup_nh_dbn' fpSeqCoupBpwlinReg.py:16-130: full parents, sequentially coupled (beta-tilde
+                         prior means, delta^2), nh changepoint move; run with dbn_run_fp.  Its delta^2 is injected /
+                         traced through the first entries of the per-segment variance slots (shape, rate, draw)  */
 } dbn_method;
 
 typedef struct dbn_handle dbn_handle;

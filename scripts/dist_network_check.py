@@ -18,7 +18,7 @@ rank = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(rank)
 dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
 for method in ('varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'var_glob_coup_nh_dbn', 'fp_glob_coup_nh_dbn',
-               'fp_varying_nh_dbn', 'fp_var_glob_coup_nh_dbn'):
+               'fp_varying_nh_dbn', 'fp_var_glob_coup_nh_dbn', 'fp_seq_coup_nh_dbn'):
     n_iter = 60 if method.startswith('fp') else 400
     sharded = Network(data, n_iter, 100 if n_iter > 100 else 10, 1, n_chains=64, device=rank, keep_chain=False)
     sharded.infer_network(method)

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, FP_PLAIN_FILES, FP_VV_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
+from helpers import KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, FP_PLAIN_FILES, FP_VV_FILES, FP_SEQ_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay
 from oracle import dbn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -280,8 +280,8 @@ def test_network_dropin(eng_mod):
     big = Network(data, 400, 100, 1, n_chains=128)
     big.infer_network('nh-dbn')
     assert big.chain_results is None and np.array(big.proposed_adj_matrix).shape == (5, 5)
-    with pytest.raises(NotImplementedError):
-        Network(data, 10, 0, 1).infer_network('fp_seq_coup_nh_dbn')
+    with pytest.raises(ValueError):
+        Network(data, 10, 0, 1).infer_network('no_such_dbn')
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -322,7 +322,7 @@ def test_fp_glob_replay_vs_reference(eng_mod, path):
     assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
 
 
-@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES))
+@pytest.mark.parametrize('path', FP_PLAIN_FILES + FP_VV_FILES + FP_SEQ_FILES, ids=ids(FP_PLAIN_FILES + FP_VV_FILES + FP_SEQ_FILES))
 def test_fp_plain_replay_vs_reference(eng_mod, path):
     """fp_varying_nh_dbn (fullParentsBpwLinReg.py:41-140) / fp_h_dbn (fpBayesianLinearRegression.py:40-125) replayed from
     the reference's recorded draws: changepoint lists and accept flags bit-exact, log-MLs 1e-9, Gibbs parameters, and the
@@ -337,6 +337,9 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
     vv = method == 'fp_var_glob_coup_nh_dbn'      # fpvvGlobCoup.py: per-segment variances, mu redrawn every iteration
     if vv:
         replay.update(sigma2v=g['sigma2v'], mu_tau=g['mus_val'][:, :, 0, :])
+    seq = method == 'fp_seq_coup_nh_dbn'          # fpSeqCoupBpwlinReg.py: beta-tilde prior means, delta^2
+    if seq:
+        replay.update(delta2=g['delta2'])
     with eng_mod(n_chains=1) as e:
         e.build_stats(data_list(g))
         e.chain_init(method, burn_in=burn_in)
@@ -351,8 +354,21 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
     assert_close(tr['lam_shape'], g['lam_shape'], 1e-12, what='lam_shape')
     assert_close(1.0 / tr['lam_rate'], g['lam_scale'], 1e-9, what='lam_scale')
     assert_close(tr['logml'], g['logml'][:, :, 2:4], LOGML_RTOL, what='logml')
-    assert_close(tr['beta_mean'], g['beta_mean'][..., :n], 1e-7, 1e-9, what='beta_mean')
+    if seq:
+        # the beta-tilde recursion chains n-wide solves on the near-collinear mTOR series: single entries that are ~1e-9 of
+        # their vector carry the reference's own inv() noise, so entries are compared at 1e-7 of the vector's scale
+        ref = g['beta_mean'][..., :n]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(tr['beta_mean']), fin)
+        scale = np.max(np.where(fin, np.abs(ref), 0.0), axis=-1, keepdims=True)
+        excess = np.where(fin, np.abs(np.where(fin, tr['beta_mean'], 0.0) - np.where(fin, ref, 0.0)) - (1e-7 * scale + 1e-9), -1.0)
+        assert excess.max() <= 0, ('beta_mean: |a - b| <= 1e-7 max|b| + 1e-9 violated by', float(excess.max()))
+    else:
+        assert_close(tr['beta_mean'], g['beta_mean'][..., :n], 1e-7, 1e-9, what='beta_mean')
     assert_close(tr['beta_cov_diag'], g['beta_cov_diag'][..., :n], 1e-7, 1e-13, what='beta_cov_diag')
+    if seq:      # delta^2's shape / rate travel in the first per-segment variance slots
+        assert_close(tr['sig_shape_v'][:, :, 0], g['del_shape'], 1e-12, what='del_shape')
+        assert_close(1.0 / tr['sig_rate_v'][:, :, 0], g['del_scale'], 1e-8, what='del_scale')
     if vv:
         assert_close(tr['sig_shape_v'], g['sig_shape_v'], 1e-12, what='sig_shape_v')
         assert_close(1.0 / tr['sig_rate_v'], g['sig_scale_v'], 1e-9, what='sig_scale_v')
@@ -365,7 +381,7 @@ def test_fp_plain_replay_vs_reference(eng_mod, path):
         assert np.array_equal(counts['cp_kept'], g['cp_kept'].astype(np.int64))
 
 
-@pytest.mark.parametrize('method', ['fp_varying_nh_dbn', 'fp_h_dbn', 'fp_var_glob_coup_nh_dbn'])
+@pytest.mark.parametrize('method', ['fp_varying_nh_dbn', 'fp_h_dbn', 'fp_var_glob_coup_nh_dbn', 'fp_seq_coup_nh_dbn'])
 def test_fp_plain_free_running_and_dropin(eng_mod, method):
     """Free-running Philox chains of the plain full-parents methods: the device's sign counts equal the credible scores
     recomputed on the host from the traced beta chain (same run), the posterior-mean betas agree with the oracle's
@@ -596,4 +612,4 @@ def test_network_sharded_over_two_gpus_matches_unsharded():
            '--master-port', '29571', os.path.join(ROOT, 'scripts', 'dist_network_check.py')]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
-    assert res.stdout.count('sharded == unsharded: True') == 14, res.stdout[-3000:]   # 7 methods x 2 ranks
+    assert res.stdout.count('sharded == unsharded: True') == 16, res.stdout[-3000:]   # 8 methods x 2 ranks

@@ -23,8 +23,8 @@ def test_method_table_matches_oracle():
             assert (p['a_sigma'], p['b_sigma'], p['a_lambda'], p['b_lambda'], p['a_delta'], p['b_delta']) == (
                 c['a_sig'], c['b_sig'], c['a_lam'], c['b_lam'], c['a_del'], c['b_del'])
             assert p['fan_in'] == 3 and p['thin'] == 10 and p['cp_p'] == 0.125
-    with pytest.raises(NotImplementedError):
-        run_params('fp_seq_coup_nh_dbn', 33)
+    p = run_params('fp_seq_coup_nh_dbn', 33)      # the last of the reference's eleven method strings (network.py:221-233)
+    assert (p['num_samples'], p['T_ml'], p['a_sigma'], p['with_tau']) == (32, 32.0, 0.005, 1)
     with pytest.raises(ValueError):
         run_params('nonsense', 33)
 
