@@ -26,6 +26,9 @@ DATA_SEED = 20260119
 METHOD = 'varying_nh_dbn'
 METRIC = 'mcmc_node_chain_iterations_per_sec'
 UNIT = 'iterations/s'
+# diagnostic only (never a bench value): DBN_BENCH_DIAG_NOREDUCE=1 drops the count all-reduce from the N > 1 step, to
+# separate the collective's cost from everything else that changes with N; the JSON line then carries "diagnostic"
+DIAG_NOREDUCE = os.environ.get('DBN_BENCH_DIAG_NOREDUCE') == '1'
 
 
 def workload():
@@ -222,7 +225,7 @@ def main():
         snapshotted on the kernel's stream and reduced on NCCL's stream (async_op), so the next window's kernel does
         not wait for the collective; a snapshot buffer is reused only after its reduction has finished."""
         eng.run(WINDOW)
-        if world > 1:
+        if world > 1 and not DIAG_NOREDUCE:
             j = step_no[0] & 1
             step_no[0] += 1
             if pending[j] is not None:
@@ -332,6 +335,8 @@ def main():
         'gpu_launches': K * (1 if world == 1 else 1),
         'clocks': clocks,
     }
+    if DIAG_NOREDUCE:
+        line['diagnostic'] = 'count all-reduce skipped: NOT a bench value'
     if not args.no_cpu_baseline and world == 1:
         it_s, ev_s, cores, sample = cpu_port_rate()
         line['cpu_baseline'] = {'value': it_s, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,

@@ -35,7 +35,7 @@ def run(label, data, method, chains, window, reps, **kw):
     if method == 'fixed_nh_dbn':
         N = eng.N
         eng.set_changepoints([N // 3, 2 * N // 3, N + 2])
-    step = eng.run_fp if method == 'fp_glob_coup_nh_dbn' else eng.run
+    step = eng.run_fp if method.startswith('fp_') else eng.run
     for _ in range(3):
         step(window)
     torch.cuda.synchronize()
@@ -73,6 +73,10 @@ def main():
     run('yeast fp-glob-dbn, 64 chains', yeast, 'fp_glob_coup_nh_dbn', 64, 20, 5)
     run('mTOR fp-glob-dbn, 256 chains', mtor, 'fp_glob_coup_nh_dbn', 256, 10, 3)
     run('synthetic 40 genes T=400 fp-glob-dbn, 64 chains', [syn40], 'fp_glob_coup_nh_dbn', 64, 5, 2)
+    run('mTOR fp-nh-dbn, 256 chains', mtor, 'fp_varying_nh_dbn', 256, 10, 3)
+    run('mTOR fp-h-dbn, 256 chains', mtor, 'fp_h_dbn', 256, 10, 3)
+    run('mTOR fp-var-glob-dbn, 256 chains', mtor, 'fp_var_glob_coup_nh_dbn', 256, 10, 3)
+    run('mTOR fp-seq-dbn, 256 chains', mtor, 'fp_seq_coup_nh_dbn', 256, 10, 3)
 
 
 if __name__ == '__main__':
