@@ -203,6 +203,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        parallel.nccl_small_footprint()
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     K, W = args.steps, max(3, args.warmup)
 

@@ -33,6 +33,15 @@ def counts_tensor(engine):
     return torch.as_tensor(_DevicePtr(ptr, n), device='cuda:%d' % engine.device)
 
 
+def nccl_small_footprint():
+    """Call before init_process_group('nccl').  The only collective on the path is a 1.7 MB all-reduce per thinning
+    window that overlaps the next window's chain kernel; with NCCL's default channel count its kernel takes enough SMs
+    from the (issue-bound, all-SM) chain kernel to cost 8 % of the step at N = 2 (1.79 vs 1.66 ms); one channel hides
+    it (1.68 ms; `profiles/r1_v13/n2_diag.txt`).  setdefault: an explicit NCCL_MAX_NCHANNELS of the caller wins."""
+    import os
+    os.environ.setdefault('NCCL_MAX_NCHANNELS', '1')
+
+
 def allreduce_counts(local, out=None, async_op=False):
     """Sum the count block over all ranks.  `local` is a torch tensor (CUDA for NCCL, CPU for gloo); the sum is
     written to `out` (a copy) so that the local accumulators keep counting only their own shard."""
