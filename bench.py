@@ -28,6 +28,7 @@ METRIC = 'mcmc_node_chain_iterations_per_sec'
 UNIT = 'iterations/s'
 # diagnostic only (never a bench value): DBN_BENCH_DIAG_NOREDUCE=1 drops the count all-reduce from the N > 1 step, to
 # separate the collective's cost from everything else that changes with N; the JSON line then carries "diagnostic"
+NCCL_OVERLAP_CTAS = int(os.environ.get('DBN_BENCH_NCCL_CTAS', '2'))
 DIAG_NOREDUCE = os.environ.get('DBN_BENCH_DIAG_NOREDUCE') == '1'
 
 
@@ -203,8 +204,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        parallel.nccl_small_footprint()
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # default group: 2 CTAs, for the all-reduce that overlaps the chain kernel; `wide`: NCCL defaults, for the
+        # end-to-end read that waits for the reduced counts
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                pg_options=parallel.nccl_small_footprint_options(NCCL_OVERLAP_CTAS))
+        wide = dist.new_group(backend='nccl')
     K, W = args.steps, max(3, args.warmup)
 
     data, _, _ = make_synthetic(N_GENES, T_SERIES, 3, 4, DATA_SEED)
@@ -279,13 +283,15 @@ def main():
     # D2H of the count matrices (the chains carry on across steps, so the work per step equals the device-timed one)
     Ke = max(5, min(K, 40))
     h2d = data.nbytes
+    if world > 1:           # untimed: the first collective of a group sets up its communicator
+        parallel.allreduce_counts(local_counts, out=global_counts[0], group=wide)
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
         eng.build_stats([data])
         eng.run(WINDOW)
         if world > 1:       # the caller reads the counts of ALL chains: reduce over the ranks, then device -> host
-            g = parallel.allreduce_counts(local_counts, out=global_counts[0])
+            g = parallel.allreduce_counts(local_counts, out=global_counts[0], group=wide)
             host_counts = g.cpu().numpy()
             d2h = host_counts.nbytes
         else:

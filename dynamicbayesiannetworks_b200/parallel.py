@@ -33,16 +33,21 @@ def counts_tensor(engine):
     return torch.as_tensor(_DevicePtr(ptr, n), device='cuda:%d' % engine.device)
 
 
-def nccl_small_footprint():
-    """Call before init_process_group('nccl').  The only collective on the path is a 1.7 MB all-reduce per thinning
-    window that overlaps the next window's chain kernel; with NCCL's default channel count its kernel takes enough SMs
-    from the (issue-bound, all-SM) chain kernel to cost 8 % of the step at N = 2 (1.79 vs 1.66 ms); one channel hides
-    it (1.68 ms; `profiles/r1_v13/n2_diag.txt`).  setdefault: an explicit NCCL_MAX_NCHANNELS of the caller wins."""
-    import os
-    os.environ.setdefault('NCCL_MAX_NCHANNELS', '1')
+def nccl_small_footprint_options(max_ctas=2):
+    """ProcessGroupNCCL options for the group whose all-reduce OVERLAPS the chain kernel.  The only collective on the
+    path is a 1.7 MB all-reduce per thinning window, running beside the next window's (issue-bound, all-SM) chain
+    kernel; with NCCL's default CTA count it costs 8 % of the step (1.79 vs 1.66 ms at N = 2 and N = 8), with two
+    CTAs 1.3 % (`profiles/r1_v13/nccl_diag.txt`).  A caller that WAITS for the reduced counts (the
+    end-to-end read) should use a second group with default options (`dist.new_group()`): alone on the GPU the wide
+    all-reduce is the faster one."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return opts
 
 
-def allreduce_counts(local, out=None, async_op=False):
+def allreduce_counts(local, out=None, async_op=False, group=None):
     """Sum the count block over all ranks.  `local` is a torch tensor (CUDA for NCCL, CPU for gloo); the sum is
     written to `out` (a copy) so that the local accumulators keep counting only their own shard."""
     import torch
@@ -51,7 +56,7 @@ def allreduce_counts(local, out=None, async_op=False):
         out = torch.empty_like(local)
     out.copy_(local)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        work = dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=async_op)
+        work = dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=async_op, group=group)
         if async_op:
             return out, work
     return (out, None) if async_op else out
