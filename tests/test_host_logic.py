@@ -115,3 +115,14 @@ def test_count_allreduce_two_ranks_gloo(tmp_path):
     assert np.array_equal(got['cp_kept'], cpk.astype(np.int64))
     adj = parallel.edge_scores_from_counts(got['edge'], got['nonempty'])
     assert np.allclose(adj, np.nan_to_num(O.edge_scores(edge, ne)))
+
+
+def test_overlapped_allreduce_group_is_limited_to_a_few_ctas():
+    """The all-reduce that runs beside the chain kernel must not take its SMs (profiles/r1_v13/nccl_diag.txt)."""
+    dist = pytest.importorskip('torch.distributed')
+    if not hasattr(dist, 'ProcessGroupNCCL'):
+        pytest.skip('torch built without NCCL')
+    from dynamicbayesiannetworks_b200 import parallel
+    opts = parallel.nccl_small_footprint_options()
+    assert opts.config.max_ctas == 2 and opts.config.min_ctas == 1
+    assert parallel.nccl_small_footprint_options(1).config.max_ctas == 1
