@@ -87,7 +87,7 @@ __device__ __forceinline__ double fp_dot(const double* a, const double* b, int k
 __device__ __forceinline__ int fp_col(int a, int node) { return a == 0 ? 0 : (a - 1 < node ? a : a + 1); }
 
 // A = I + lam (P[hi] - P[lo]) restricted to the node's design columns (full symmetric), g, s
-__device__ void fp_load_segment(const Table& tb, int node, int lo, int hi, double lam, double* A, int ld, int k, double* g,
+__device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi, double lam, double* A, int ld, int k, double* g,
                                 double* s_out) {
   const double* __restrict__ ph = tb.base + (long long)hi * tb.row_stride;
   const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
@@ -112,7 +112,7 @@ __device__ void fp_load_segment(const Table& tb, int node, int lo, int hi, doubl
 }
 
 // y = M x for a full symmetric (or any square) k x k matrix; thread per output row, x broadcast from shared memory
-__device__ void fp_symv(const double* M, int ld, int k, const double* x, double* y) {
+__device__ inline void fp_symv(const double* M, int ld, int k, const double* x, double* y) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
     for (int j = 0; j < k; ++j) acc += M[j * ld + i] * x[j];  // column i of a symmetric matrix: coalesced over i
@@ -122,14 +122,14 @@ __device__ void fp_symv(const double* M, int ld, int k, const double* x, double*
 }
 
 // blocked large-k routines (defined below); `stage` != nullptr selects them in the dispatching helpers
-__device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage);
-__device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage);
-__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale);
-__device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t);
-__device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red);
+__device__ inline double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage);
+__device__ inline void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage);
+__device__ inline void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale);
+__device__ inline void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t);
+__device__ inline void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red);
 
 // in-place lower Cholesky of the full symmetric matrix A (upper part left untouched); returns ln det A
-__device__ double fp_cholesky(double* A, int ld, int k, double* idiag, double* stage) {  // idiag[j] = 1 / L[j][j]
+__device__ inline double fp_cholesky(double* A, int ld, int k, double* idiag, double* stage) {  // idiag[j] = 1 / L[j][j]
   if (stage) return fp_potrf_big(A, ld, k, idiag, stage);
   double mant = 1.0;  // product of the pivots l_j = sqrt(d_j) as mantissa x 2^expo: one log per factorisation
   int expo = 0;
@@ -160,7 +160,7 @@ __device__ double fp_cholesky(double* A, int ld, int k, double* idiag, double* s
 }
 
 // W = L^-1 (lower triangular, zeros above the diagonal): forward substitution on all columns at once
-__device__ void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag, double* stage) {
+__device__ inline void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag, double* stage) {
   if (stage) return fp_trinv_big(L, W, ld, k, idiag, stage);
   for (int c = threadIdx.x; c < k; c += FP_BLOCK) {
     for (int i = 0; i < c; ++i) W[i * ld + c] = 0.0;
@@ -174,7 +174,7 @@ __device__ void fp_trinv(const double* L, double* W, int ld, int k, const double
 }
 
 // t = W x (lower triangular W), thread per row
-__device__ void fp_trmv(const double* W, int ld, int k, const double* x, double* t, double* stage) {
+__device__ inline void fp_trmv(const double* W, int ld, int k, const double* x, double* t, double* stage) {
   if (stage) return fp_trmv_big(W, ld, k, x, t);
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
@@ -185,7 +185,7 @@ __device__ void fp_trmv(const double* W, int ld, int k, const double* x, double*
 }
 
 // y = W^T t (lower triangular W), thread per output entry: coalesced over a
-__device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y, double* stage, double* red) {
+__device__ inline void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y, double* stage, double* red) {
   if (stage) return fp_trmv_t_big(W, ld, k, t, y, red);
   for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
     double acc = 0.0;
@@ -196,7 +196,7 @@ __device__ void fp_trmv_t(const double* W, int ld, int k, const double* t, doubl
 }
 
 // M += I - W^T W (full symmetric)
-__device__ void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage, double scale) {
+__device__ inline void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage, double scale) {
   if (stage) return fp_syrk_big(W, M, ld, k, stage, scale);
   for (int a = 0; a < k; ++a) {
     for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
@@ -225,7 +225,7 @@ constexpr int FP_SY_T = 64, FP_SY_IC = 16, FP_SY_LD = 68;   // fp_syrk_big: tile
 constexpr int FP_STAGE_DOUBLES = 2 * FP_SY_IC * FP_SY_LD;  // largest user (potrf / trinv need FP_JC*FP_NB + FP_NB*FP_NB + FP_NB)
 
 // in-place Cholesky A = U^T U, left-looking by panels of FP_NB factor rows; returns ln det A, idiag[j] = 1 / U[j][j]
-__device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage) {
+__device__ inline double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage) {
   double* Bs = stage;                  // [FP_JC][FP_NB]  Bs[jj][c] = U[j0 + jj][p0 + c]
   double* D = stage + FP_JC * FP_NB;   // [FP_NB][FP_NB]  diagonal block, lower factor after the in-block step
   double* Di = D + FP_NB * FP_NB;      // [FP_NB]         reciprocal pivots of the block
@@ -352,7 +352,7 @@ __device__ double fp_potrf_big(double* A, int ld, int k, double* idiag, double* 
 }
 
 // V = U^-1 (upper triangle of W; the lower triangle is not written and never read), thread per column, row blocks bottom-up
-__device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage) {
+__device__ inline void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage) {
   double* Us = stage;                  // [FP_JC][FP_NB]  Us[mm][r] = U[j0 + r][m0 + mm]
   double* Ud = stage + FP_JC * FP_NB;  // [FP_NB][FP_NB]  Ud[r][r2] = U[j0 + r][j0 + r2], r2 > r
   const int tid = threadIdx.x, T = FP_BLOCK;
@@ -416,7 +416,7 @@ __device__ void fp_trinv_big(const double* A, double* W, int ld, int k, const do
 }
 
 // M += I - V V^T (= I - A^-1; full symmetric M), 64 x 64 tiles of the lower triangle, 4 x 4 outputs per thread
-__device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale) {
+__device__ inline void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale) {
   double* As = stage;
   double* Bs = stage + FP_SY_IC * FP_SY_LD;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -467,7 +467,7 @@ __device__ void fp_syrk_big(const double* W, double* M, int ld, int k, double* s
 }
 
 // t = L^-1 x = V^T x: thread per entry, coalesced over the entries
-__device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t) {
+__device__ inline void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
     for (int j = 0; j <= i; ++j) acc += W[(long long)j * ld + i] * x[j];
@@ -477,7 +477,7 @@ __device__ void fp_trmv_big(const double* W, int ld, int k, const double* x, dou
 }
 
 // y = L^-T t = V t: 16 rows at a time, 16 threads per row striding its entries, partial sums through `red`
-__device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red) {
+__device__ inline void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red) {
   const int tid = threadIdx.x, rr = tid >> 4, sl = tid & 15;
   for (int ab = 0; ab < k; ab += 16) {
     const int ra = ab + rr;
@@ -497,7 +497,7 @@ __device__ void fp_trmv_t_big(const double* W, int ld, int k, const double* t, d
 }
 
 // z[0..k) ~ N(0,1), Philox slots base + i/2
-__device__ void fp_normals(double* z, int k, uint32_t chain, uint32_t node, uint32_t it, uint32_t base, uint2 key) {
+__device__ inline void fp_normals(double* z, int k, uint32_t chain, uint32_t node, uint32_t it, uint32_t base, uint2 key) {
   for (int p = threadIdx.x; 2 * p < k; p += FP_BLOCK) {
     const double2 zz = normal_pair(chain, node, it, base + (uint32_t)p, key);
     z[2 * p] = zz.x;
@@ -538,7 +538,7 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
 }
 
 // t = L^-1 g by forward substitution on the Cholesky factor (idiag[j] = 1 / L[j][j]); column-oriented, k block steps
-__device__ void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t, bool upper) {
+__device__ inline void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t, bool upper) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) t[i] = g[i];
   __syncthreads();
   for (int j = 0; j < k; ++j) {
@@ -580,7 +580,7 @@ __device__ __forceinline__ void fp_apply_ainv(const double* W, int ld, int k, co
 // betaTildeSampler, samplers.py:4-54): bt[0] = 0, bt[1] = A_lam(G_1)^-1 lam g_1, bt[h+1] = A_dlt(G_h)^-1 (bt[h-1] + dlt g_h).
 // bt_cur / bt_prev / nxt are k-vectors of scratch.
 template <class TauFn>
-__device__ double fp_score_seq(const Table& tb, int node, TauFn tau, int S, double lam, double dlt, double* bt_cur, double* bt_prev,
+__device__ inline double fp_score_seq(const Table& tb, int node, TauFn tau, int S, double lam, double dlt, double* bt_cur, double* bt_prev,
                                double* nxt, double* A, double* W, int ld, int k, double* g, double* t, double* x, double* tmp,
                                double* rhs, double* red, double* s_tmp, double* stage, double c0, double T_half_plus_a, double two_b) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) bt_cur[i] = bt_prev[i] = 0.0;
@@ -630,7 +630,7 @@ __device__ double fp_score_seq(const Table& tb, int node, TauFn tau, int S, doub
 // vvLogMargLikelihood (marginalLikelihood.py:5-43) at prior mean mu: per segment its own length T_h in the Gamma / pi /
 // exponent terms; needs the factor and one forward substitution per segment, no inverse.  c_seg = a ln(2b) - lgamma(a).
 template <class TauFn>
-__device__ double fp_score_vv(const Table& tb, int node, TauFn tau, int S, double lam, const double* mu, double* A, int ld, int k,
+__device__ inline double fp_score_vv(const Table& tb, int node, TauFn tau, int S, double lam, const double* mu, double* A, int ld, int k,
                               double* g, double* t, double* x, double* tmp, double* idiag, double* red, double* s_tmp, double* stage,
                               double a_sig, double c_seg, double two_b) {
   double acc = 0.0;
@@ -658,7 +658,7 @@ __device__ double fp_score_vv(const Table& tb, int node, TauFn tau, int S, doubl
 }
 
 // sum_h r_h^T C_h^-1 r_h at mean mu from the sums
-__device__ double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k, const double* a_sum, const double* mu, double lam,
+__device__ inline double fp_quad_at(const FpSummary& sm, const double* M, int ld, int k, const double* a_sum, const double* mu, double lam,
                              double* tmp, double* red) {
   fp_symv(M, ld, k, mu, tmp);
   const double mMm = fp_dot(mu, tmp, k, red);

@@ -12,6 +12,7 @@
 
 #include "dbn_chain_fast.cuh"
 #include "dbn_fp.cuh"
+#include "dbn_launch.h"
 
 namespace dbn {
 
@@ -240,20 +241,6 @@ __global__ void set_tau_kernel(int U, TauList t, int* S, int* tau) {
   S[u] = t.len;
   for (int j = 0; j < DBN_SMAX; ++j) tau[j * U + u] = (j < t.len) ? t.c[j] : 0;
 }
-
-typedef void (*chain_fn)(const ChainArgs);
-
-template <int KM, bool TRACE>
-static chain_fn pick_method(int method) {
-  switch (method) {
-    case DBN_H_DBN: return chain_fast_kernel<DBN_H_DBN, KM, TRACE>;
-    case DBN_NH_DBN: return chain_fast_kernel<DBN_NH_DBN, KM, TRACE>;
-    case DBN_SEQ_DBN: return chain_kernel<DBN_SEQ_DBN, KM, TRACE>;
-    case DBN_VV_GLOB_DBN: return chain_kernel<DBN_VV_GLOB_DBN, KM, TRACE>;
-    default: return chain_kernel<DBN_GLOB_DBN, KM, TRACE>;
-  }
-}
-
 
 static inline bool is_fp_method(int m) { return m == DBN_FP_GLOB_DBN || m == DBN_FP_NH_DBN || m == DBN_FP_H_DBN || m == DBN_FP_VV_DBN || m == DBN_FP_SEQ_DBN; }
 
@@ -748,19 +735,13 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
     a.rd = d_rd;
     a.ri = d_ri;
   }
-  const bool km4 = p.fan_in <= 3;
-  chain_fn fn = trace ? (km4 ? pick_method<4, true>(p.method) : pick_method<5, true>(p.method))
-                      : (km4 ? pick_method<4, false>(p.method) : pick_method<5, false>(p.method));
-  size_t smem = 0;
-  int block = CHAIN_BLOCK;
-  if (p.method == DBN_H_DBN || p.method == DBN_NH_DBN) {
-    block = FAST_BLOCK;
-    smem = fast_smem_bytes(km4 ? 4 : 5);
-    CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  const int km = p.fan_in <= 3 ? 4 : 5;
+  const bool fast = p.method == DBN_H_DBN || p.method == DBN_NH_DBN;
+  const int block = fast ? FAST_BLOCK : CHAIN_BLOCK;
+  const size_t smem = fast ? fast_smem_bytes(km) : 0;
   const unsigned grid = (unsigned)((h->U + block - 1) / block);
-  fn<<<grid, block, smem, h->stream>>>(a);
-  CUX(cudaGetLastError());
+  if (fast) CUX((trace ? launch_fast_trace : launch_fast_plain)(p.method, km, grid, block, smem, h->stream, a));
+  else CUX((trace ? launch_chain_trace : launch_chain_plain)(p.method, km, grid, block, smem, h->stream, a));
   h->cache_valid = true;
   h->it_done += n_iter;
   if (trace) {
@@ -838,15 +819,11 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
     a.ri = d_ri;
   }
   const size_t smem = fp_smem_bytes(k, h->d_fp_ws == nullptr);
-  typedef void (*fp_fn)(const FpArgs);
   const int fpm = p.method == DBN_FP_GLOB_DBN ? FPM_GLOB : (p.method == DBN_FP_VV_DBN ? FPM_VV : (p.method == DBN_FP_SEQ_DBN ? FPM_SEQ : FPM_PLAIN));
   const bool big = h->d_fp_ws != nullptr;
-#define FP_PICK(TR, BG) (fpm == FPM_GLOB ? fp_glob_kernel<TR, FPM_GLOB, BG> : fpm == FPM_VV ? fp_glob_kernel<TR, FPM_VV, BG> : fpm == FPM_SEQ ? fp_glob_kernel<TR, FPM_SEQ, BG> : fp_glob_kernel<TR, FPM_PLAIN, BG>)
-  const fp_fn fn = trace ? (big ? FP_PICK(true, true) : FP_PICK(true, false)) : (big ? FP_PICK(false, true) : FP_PICK(false, false));
-#undef FP_PICK
-  CUX(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<h->fp_grid, fp_block_threads(k, h->d_fp_ws == nullptr), smem, h->stream>>>(a);
-  CUX(cudaGetLastError());
+  const int fp_block = fp_block_threads(k, !big);
+  CUX((trace ? (big ? launch_fp_trace_big : launch_fp_trace_small) : (big ? launch_fp_plain_big : launch_fp_plain_small))(
+      fpm, (unsigned)h->fp_grid, fp_block, smem, h->stream, a));
   h->it_done += n_iter;
   if (trace) {
     CUX(cudaMemcpyAsync(trace_d, d_td, rec * tds * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
