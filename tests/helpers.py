@@ -82,3 +82,70 @@ def assert_close_mat(a, b, rtol, what=''):
     bad = err > rtol * scale
     assert not bad.any(), '%s: max matrix-relative err %.3e (rtol %.1e) at %d entries' % (
         what, float((err / np.maximum(scale, 1e-300)).max()), rtol, int(bad.sum()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle chains with every draw recorded -> replay records for the device (the fixtures the reference cannot give:
+# fan-in 4, T beyond its overflow limit)
+# ---------------------------------------------------------------------------------------------------------
+def recording_draws(rng):
+    """oracle.RngDraws that logs every draw so that the same stream can be injected into the device chain."""
+    from oracle import dbn_oracle as O
+
+    class Rec(O.RngDraws):
+        def __init__(self, rng_):
+            super().__init__(rng_)
+            self.log = {}
+
+        def inv_gamma(self, it, which, shape, rate):
+            v = super().inv_gamma(it, which, shape, rate); self.log[(it, which)] = v; return v
+
+        def inv_gamma_seg(self, it, h, shape, rate):
+            v = super().inv_gamma_seg(it, h, shape, rate); self.log[(it, 'sigv', h)] = v; return v
+
+        def move(self, it, which):
+            v = super().move(it, which); self.log[(it, which, 'move')] = v; return v
+
+        def picker(self, it, which):
+            inner = super().picker(it, which); lst = self.log.setdefault((it, which, 'pick'), [])
+
+            def f(m):
+                v = inner(m); lst.append(v); return v
+            return f
+
+        def uniform(self, it, which):
+            v = super().uniform(it, which); self.log[(it, which, 'u')] = v; return v
+
+        def mu_draw(self, it, slot, mean, Sigma):
+            v = super().mu_draw(it, slot, mean, Sigma); self.log[(it, 'mu', slot)] = v; return v
+    return Rec(rng)
+
+
+def oracle_replay(n_units, n_iter, chains):
+    """Replay dict (engine.pack_replay layout) for `n_units` units from recorded oracle chains `chains` = {unit: (trace,
+    Rec)}.  Units without a recorded chain get a stream of moves that are always valid to execute: delete / death with
+    pick 0 (invalid once the parent set is empty / only the pseudo changepoint is left), unit Gibbs draws."""
+    K, S = 5, 10
+    r = dict(sigma2=np.ones((n_units, n_iter)), lambda2=np.ones((n_units, n_iter)), delta2=np.ones((n_units, n_iter)),
+             u_pi=np.full((n_units, n_iter), 0.5), u_tau=np.full((n_units, n_iter), 0.5),
+             beta=np.zeros((n_units, n_iter, S, K)), pi_move=np.ones((n_units, n_iter), dtype=np.int32),
+             pi_pick=np.zeros((n_units, n_iter, 2), dtype=np.int32), tau_move=np.ones((n_units, n_iter), dtype=np.int32),
+             tau_pick=np.zeros((n_units, n_iter, 2), dtype=np.int32), mu_pi=np.zeros((n_units, n_iter, K)),
+             mu_tau=np.zeros((n_units, n_iter, K)), sigma2v=np.ones((n_units, n_iter, S)))
+    for u, (t, rec) in chains.items():
+        r['sigma2'][u], r['lambda2'][u] = t['sigma2'], t['lambda2']
+        r['delta2'][u] = np.nan_to_num(t['delta2'], nan=1.0)
+        r['beta'][u] = np.nan_to_num(t['beta'][:, :, :K])
+        r['sigma2v'][u] = np.nan_to_num(t['sigma2v'], nan=1.0)
+        for it in range(n_iter):
+            for which, mv, pk, uu in (('pi', 'pi_move', 'pi_pick', 'u_pi'), ('tau', 'tau_move', 'tau_pick', 'u_tau')):
+                if (it, which, 'move') in rec.log:
+                    r[mv][u, it] = rec.log[(it, which, 'move')]
+                    picks = rec.log.get((it, which, 'pick'), [])
+                    r[pk][u, it, :len(picks)] = picks
+                    r[uu][u, it] = rec.log.get((it, which, 'u'), 0.5)
+            for slot, key in ((0, 'mu_pi'), (3, 'mu_tau')):
+                if (it, 'mu', slot) in rec.log:
+                    v = rec.log[(it, 'mu', slot)]
+                    r[key][u, it, :len(v)] = v
+    return r

@@ -177,7 +177,7 @@ def test_chain_replay_split_launches(eng_mod):
 # free-running Philox chains: statistical agreement with the oracle's free-running chains
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'seq_coup_nh_dbn', 'glob_coup_nh_dbn', 'var_glob_coup_nh_dbn'])
-def test_free_running_edge_posteriors(eng_mod, method):
+def test_free_running_state_sanity(eng_mod, method):
     g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
     data = data_list(g)
     X, Y = O.lagged_matrices(data)
@@ -197,20 +197,9 @@ def test_free_running_edge_posteriors(eng_mod, method):
     assert np.isfinite(st['sigma2']).all() and (st['sigma2'] > 0).all()
     assert np.isfinite(st['lambda2']).all() and (st['lambda2'] > 0).all()
     gpu = c['edge'] / np.maximum(c['nonempty'], 1)[:, None]
-    # oracle free-running chains (fewer, they are slow): compare edge frequencies within Monte-Carlo error
-    edge = np.zeros((n, n)); nonempty = np.zeros(n); cph = np.zeros((n, N + 3)); cpk = np.zeros(n)
-    rng = np.random.default_rng(99)
-    n_or = 6
-    for node in range(n):
-        for _ in range(n_or):
-            tr = O.run_chain(method, X, Y, node, 600, O.RngDraws(rng))
-            O.accumulate_counts(tr, node, n, N, 200, edge, nonempty, cph, cpk)
-    ref = O.edge_scores(edge, nonempty)
-    off = ~np.eye(n, dtype=bool)
-    # autocorrelated chains: effective sample size of the oracle side is small, so the bound is loose but it
-    # catches a wrong acceptance rule / prior / Hastings ratio (those shift frequencies by >0.2)
-    assert np.abs(gpu[off] - ref[off]).max() < 0.2, (gpu, ref)
-    assert np.abs(gpu[off] - ref[off]).mean() < 0.07, (gpu, ref)
+    assert np.isfinite(gpu).all() and (gpu >= 0).all() and (gpu <= 1).all() and (np.diag(gpu) == 0).all()
+    # the comparison with the oracle's free-running chains (Monte-Carlo error bound) is
+    # tests/test_gpu_pinning.py::test_free_running_edge_posteriors_within_mc_error
 
 
 @pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn'])
