@@ -1,6 +1,6 @@
 """Build the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m dynamicbayesiannetworks_b200.build [--force] [--verbose] [-DNAME[=VALUE] ...] [--out path.so]
+    python -m dynamicbayesiannetworks_b200.build [--force] [--verbose] [--slim] [-DNAME[=VALUE] ...] [--out path.so]
 
 Produces dynamicbayesiannetworks_b200/libdbn_b200.so, which ctypes loads (see _lib.py) and which travels to the
 GPU box with the repo snapshot.  The kernel families are separate objects (csrc/dbn_inst.cu compiled once per
@@ -30,7 +30,9 @@ OBJECTS = {
     'fp_plain_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=0', 'DBN_INST_BIG=1'], ['dbn_fp.cuh']),
     'fp_trace_small': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=0'], ['dbn_fp.cuh']),
     'fp_trace_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=1'], ['dbn_fp.cuh']),
+    'stubs': ('dbn_stub_launchers.cu', [], []),   # --slim only
 }
+SLIM = ('abi', 'fast_plain', 'fast_trace', 'stubs')   # kernel A/B builds of the h / nh family (build_variants/*.so)
 
 
 def nvcc_path():
@@ -61,7 +63,7 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for name in OBJECTS for d in _deps(name))
+    return any(os.path.getmtime(d) > t for name in OBJECTS if name != 'stubs' for d in _deps(name))
 
 
 def _compile(name, defines, force, verbose):
@@ -81,17 +83,18 @@ def _compile(name, defines, force, verbose):
     return obj, res.stdout
 
 
-def build(force=False, verbose=False, out=None, defines=(), jobs=None):
+def build(force=False, verbose=False, out=None, defines=(), jobs=None, slim=False):
     """`out` / `defines`: build a variant (e.g. a different launch bound) beside the default library."""
     if out is None and not force and not defines and not is_stale():
         return LIB
     out = out or LIB
     os.makedirs(OBJDIR, exist_ok=True)
     jobs = jobs or min(len(OBJECTS), os.cpu_count() or 1)
+    names = [n for n in OBJECTS if (n in SLIM if slim else n != 'stubs')]
     with ThreadPoolExecutor(jobs) as ex:
-        results = list(ex.map(lambda n: _compile(n, defines, force, verbose), OBJECTS))
+        results = list(ex.map(lambda n: _compile(n, defines, force, verbose), names))
     if verbose:
-        for name, (_, log) in zip(OBJECTS, results):
+        for name, (_, log) in zip(names, results):
             if log:
                 print('---- %s\n%s' % (name, log))
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + [o for o, _ in results]
@@ -105,4 +108,4 @@ if __name__ == '__main__':
     argv = sys.argv[1:]
     out = argv[argv.index('--out') + 1] if '--out' in argv else None
     defines = [a[2:] for a in argv if a.startswith('-D')]
-    print(build(force='--force' in argv, verbose='--verbose' in argv, out=out, defines=defines))
+    print(build(force='--force' in argv, verbose='--verbose' in argv, out=out, defines=defines, slim='--slim' in argv))

@@ -43,7 +43,7 @@ struct ChainArgs {
   unsigned long long* nonempty;
   unsigned long long* cp_hist;
   unsigned long long* cp_kept;
-  unsigned long long* counters;  // [8]
+  unsigned long long* counters;  // [8] (+ 16 probe counters of the diagnostic builds)
   // replay / trace (device copies, may be null)
   const double* rd;
   const int* ri;

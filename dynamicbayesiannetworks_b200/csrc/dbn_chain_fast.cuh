@@ -6,19 +6,25 @@
 // by the L1 miss-request path (one 32-byte sector request per gathered double, ~1 request/cycle/SM) at 12 warps/SM.
 // Here
 //   * cache[j][pair][unit], j < 9, holds prefix-table row b_j (the end boundary of the unit's j-th segment, in time
-//     order) restricted to the unit's design columns (15 + 5 + 1 doubles at KM = 5, as 16-byte pairs).  Threads of a
-//     warp read the same (j, pair) of consecutive units: fully coalesced, 11 x 16 bytes per thread, segment and sweep.
-//     A segment's statistics (G_h, g_h, s_h) are the difference of two consecutive rows, taken between two
-//     shared-memory staging buffers (three buffers: current row, previous row, the one being prefetched).  Rows are
-//     kept physically ordered, because a per-unit row indirection scatters the warp's addresses again (measured:
-//     profiles/r1_v1).  Caching boundary rows rather than their differences (v6/v7) makes every update a copy: no
-//     table row has to be gathered again when a move is accepted.
+//     order) restricted to the unit's design columns, as 16-byte pairs: 14 + 5 + 1 doubles at KM = 5 (the (0, 0) entry
+//     of ZZ is not stored: sum 1 * 1 over the rows before b is b itself, so a segment's G[0][0] is its length).  Threads
+//     of a warp read the same (j, pair) of consecutive units: fully coalesced, 10 x 16 bytes per thread, segment and
+//     sweep.  A segment's statistics (G_h, g_h, s_h) are the difference of two consecutive rows, taken between two
+//     shared-memory staging buffers.  Rows are kept physically ordered, because a per-unit row indirection scatters
+//     the warp's addresses again (measured: profiles/r1_v1).  Caching boundary rows rather than their differences
+//     (v6/v7) makes every update a copy: no table row has to be gathered again when a move is accepted.
+//   * round 2: everything a sweep step needs is requested one step ahead by cp.async and nothing is gathered with a
+//     dependent load inside a sweep any more (profiles/r1_v10: 37 % of all long-scoreboard stalls were the candidate
+//     column's six scattered loads per segment, 12 % the gather of the changepoint move's new boundary row).  A step
+//     first moves its operands from the staging buffers into registers and only then issues the next step's copies,
+//     so two row buffers suffice; the third holds the changepoint proposal's new boundary row, requested before the
+//     parent-set sweep starts, and a six-double slot holds the candidate column at the next boundary.
 //   * the parent-set move scores pi and pi* in ONE sweep: both column sets share a base of <= KM-1 columns, which is
 //     factorised once per segment (A_B = L D L^T); the column only pi has and the column only pi* has are two
 //     alternative last rows of that factorisation.  Only the new column (<= KM+1 values per boundary) is gathered.
 //   * the changepoint move re-evaluates only the segments a birth / death / reallocation changes (<= 2 old, <= 2 new)
 //     from the <= 3 cached boundary rows around the change and ONE gathered table row, the new boundary (none for a
-//     death) (profiles/r1_v7: waiting for gathered table rows was 30 % of all stall samples).
+//     death).
 //   * accepted moves rewrite the owner's rows: the new column in every row (parent-set move), or one row inserted /
 //     removed / replaced (changepoint move), as 16-byte pairs.  Only the thread that owns a unit ever writes that
 //     unit's rows: handing this work to the other lanes of the warp (v4/v5) needs votes and shuffles, and those
@@ -47,16 +53,20 @@ template <int KM>
 struct FastDims {
   static constexpr int KB = KM - 1;
   static constexpr int KT = KM * (KM + 1) / 2;
-  static constexpr int NE = KT + KM + 1;  // entries per cached row: ZZ packed by slot | ZY by slot | YY
-  static constexpr int NP = (NE + 1) / 2; // 16-byte pairs per cached row
+  static constexpr int NE = KT + KM;      // entries per cached row: ZZ packed by slot without (0, 0) | ZY by slot | YY
+  static constexpr int NP = NE / 2;       // 16-byte pairs per cached row
+  static constexpr int NC = KB + 2;       // candidate column at one boundary: cross terms with the base | diagonal | ZY
+  static_assert(NE % 2 == 0, "a cached row is a whole number of 16-byte pairs (KM = 4: 14 entries, KM = 5: 20)");
 };
 
 // Cache layout: row r of unit u is NP pairs of doubles, pair p at doubles ((r * NP + p) * U + u) * 2: the two
 // entries of a pair are adjacent, so a row moves as NP 16-byte copies per thread, consecutive threads 16 bytes apart.
-__host__ __device__ inline int fast_cache_row_doubles(int km) { return 2 * ((km * (km + 1) / 2 + km + 1 + 1) / 2); }
+// Entry ids: ZZ(i, j) (i >= j, not both 0) -> DBN_TRI(i, j) - 1; ZY(i) -> KT - 1 + i; YY -> KT - 1 + KM.
+__host__ __device__ inline int fast_cache_row_doubles(int km) { return km * (km + 1) / 2 + km; }
 inline size_t fast_smem_bytes(int km) {
-  return (size_t)3 * fast_cache_row_doubles(km) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(unsigned short);
+  return (size_t)(3 * fast_cache_row_doubles(km) + km + 1) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(unsigned short);
 }
+#define DBN_EZZ(i, j) (DBN_TRI(i, j) - 1)
 // entry e of a row whose pair 0 is at `p` (global: pair stride = 2 * U doubles; shared staging: 2 * FAST_BLOCK doubles)
 #define DBN_CE(p, e) (p)[(long long)((e) >> 1) * (2 * U) + ((e) & 1)]
 #define DBN_SE(p, e) (p)[((e) >> 1) * (2 * FAST_BLOCK) + ((e) & 1)]
@@ -78,21 +88,63 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// Block barrier that does NOT assume the warp arrives converged.  `__syncthreads()` is the .aligned form: ptxas emits
+// the WARPSYNC.ALL in front of it only where its own analysis sees possible divergence, and in the h-dbn instantiations
+// it saw none, although warps do reach the barrier in two parts (lanes that needed a second try in a rejection loop of
+// a called function; measured with __activemask probes, profiles/r2_notes.md).  Each part then counted as a whole warp,
+// the barrier opened before every warp had arrived, and the late warps ran one phase behind for the rest of the
+// launch: their work counters were added after the block's totals had been published.  The non-aligned form counts
+// threads and rejoins the warp.
+__device__ __forceinline__ void block_barrier() {
+#if defined(DBN_BARRIER_NONALIGNED)
+  asm volatile("barrier.sync 0;" ::: "memory");
+#elif defined(DBN_BARRIER_NONE)
+#else
+  __syncthreads();
+#endif
+}
+// Rejoin the lanes of the warp.  Reconvergence after divergent code is opportunistic on this hardware (the
+// BSYNC.RECONVERGENT ptxas places after a loop or a branch lets the lanes that arrive first run on), and ptxas drops a
+// plain __syncwarp() wherever ITS analysis says the warp is converged.  Lanes whose segment count is smaller left the
+// sweeps early and ran the rest of the iteration as a warp of their own: a third of all lanes were in split warps at
+// every probe of the nh kernel (profiles/r2_notes.md), i.e. the same instructions were issued two or three times.  The
+// sync is therefore placed under a condition that always holds but that the compiler cannot see through (`opaque` is a
+// per-thread run-time value >= 0), which makes it keep the WARPSYNC.
+#ifndef DBN_REJOIN
+#define DBN_REJOIN 1   // 0: never, 1: in front of the block barriers, 2: also after the sweeps and the accepted-move updates
+#endif
+template <int LEVEL>
+__device__ __forceinline__ void warp_rejoin(int opaque) {
+  if (LEVEL <= DBN_REJOIN && opaque >= 0) __syncwarp();
+}
+
+#ifdef DBN_DIAG_SPLIT2   // diagnostic build: range checks, the largest violated code lands in counters[23]
+#define DBN_CHECK(cond, code) do { if (!(cond)) atomicMax(&a.counters[23], (unsigned long long)(code)); } while (0)
+#else
+#define DBN_CHECK(cond, code) do { } while (0)
+#endif
 
 template <int METHOD, int KM, bool TRACE>
 __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(const ChainArgs a) {
   constexpr bool HOMOG = METHOD == DBN_H_DBN;
-  constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NE = FastDims<KM>::NE, NP = FastDims<KM>::NP;
+  constexpr int KB = FastDims<KM>::KB, KT = FastDims<KM>::KT, NP = FastDims<KM>::NP, NC = FastDims<KM>::NC;
   constexpr int KBT = KB * (KB + 1) / 2;
+  constexpr int E_ZY = KT - 1, E_YY = KT - 1 + KM;  // entry ids of ZY(0) and YY
 
-  // dynamic shared memory: [3][NP][BLOCK][2] doubles (boundary rows staged by cp.async) | tau | tau* (16-bit: the host
-  // refuses series with N + 2 > 65535 for this kernel)
+  // dynamic shared memory: [3][NP][BLOCK][2] doubles (boundary rows staged by cp.async) | [NC][BLOCK] candidate column
+  // | tau | tau* (16-bit: the host refuses series with N + 2 > 65535 for this kernel)
   extern __shared__ __align__(16) double s_dyn[];
   double* const s_row = s_dyn;
   constexpr int BUF = (2 * NP) * FAST_BLOCK;  // doubles per staging buffer
-  unsigned short* const s_tau = reinterpret_cast<unsigned short*>(s_dyn + 3 * BUF);
+  double* const s_cand = s_dyn + 3 * BUF;
+  unsigned short* const s_tau = reinterpret_cast<unsigned short*>(s_cand + NC * FAST_BLOCK);
   unsigned short* const s_tas = s_tau + SMAX * FAST_BLOCK;
   const int tid = threadIdx.x;
+  __shared__ unsigned long long s_tot[8];  // work counters of the block
+  __shared__ unsigned int s_done;          // threads of the block that have added theirs
+  if (tid < 8) s_tot[tid] = 0ull;
+  if (tid == 8) s_done = 0u;
+  __syncthreads();  // kernel entry: every warp is converged here
   const int u_raw = blockIdx.x * FAST_BLOCK + tid;
   const bool active = u_raw < a.U;
   const int u = active ? u_raw : 0;
@@ -105,6 +157,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   auto tau_cur = [&](int j) { return (int)s_tau[j * FAST_BLOCK + tid]; };
   auto tau_star = [&](int j) { return (int)s_tas[j * FAST_BLOCK + tid]; };
   double* const sbuf = s_row + 2 * tid;  // this thread's slice of staging buffer 0; buffer b at sbuf + b * BUF
+  double* const cand = s_cand + tid;     // this thread's candidate-column slot: value i at cand[i * FAST_BLOCK]
   double* const cbase = a.cache + 2ll * u;
   auto crow = [&](int row) -> double* { return cbase + (long long)row * NP * (2 * U); };  // pair 0 of cached row `row`
   const int nb = a.tb.zz_size + node * (n + 2);  // table offset of this node's ZY / YY block
@@ -114,14 +167,17 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   int pi[PMAX];
 #pragma unroll
   for (int j = 0; j < PMAX; ++j) pi[j] = a.st_pi[j * a.U + u];
-  int S = active ? a.st_S[u] : 0;  // lanes past the end keep step with the warp (ballots below) on an empty state
+  int S = active ? a.st_S[u] : 0;  // lanes past the end run the barriers of the loop on an empty state
   for (int j = 0; j < SMAX; ++j) TAU(j) = (unsigned short)a.st_tau[j * a.U + u];
   double sig2 = a.st_sig[u], lam = a.st_lam[u];
   int cg[KM];  // gene id held by column slot s (>= 1), -1 = empty; slot 0 is the intercept
   cg[0] = -1;
+  auto bnd = [&](int j) { return DBN_SEG_END(tau_cur(j), j, S, N); };  // table row of the end boundary of segment j
 
-  // prefix-table row `t` restricted to the slots' columns (zeros for empty slots); put(entry, value) stores it
-  auto gather = [&](int t, auto&& put) {
+  // request prefix-table row `t`, restricted to the slots' columns, into the staging buffer `dst` (8-byte cp.async per
+  // entry; zeros are stored directly for empty slots).  The caller commits and waits.
+  auto request_row = [&](int t, double* dst) {
+    DBN_CHECK(t >= 0 && t <= N, 1);
     const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
 #pragma unroll
     for (int i = 0; i < KM; ++i) {
@@ -129,47 +185,28 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       const int fi = (i == 0) ? 0 : cg[i] + 1;
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
+        if (i == 0) continue;  // ZZ(0, 0) = t is not stored
         const bool oj = (j == 0) || cg[j] >= 0;
         const int fj = (j == 0) ? 0 : cg[j] + 1;
-        const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
-        put(DBN_TRI(i, j), (oi && oj) ? __ldg(row + off) : 0.0);
+        const int hi = max(fi, fj), lo = min(fi, fj);
+        if (oi && oj) cp_async8(&DBN_SE(dst, DBN_EZZ(i, j)), row + hi * (hi + 1) / 2 + lo);
+        else DBN_SE(dst, DBN_EZZ(i, j)) = 0.0;
       }
-      put(KT + i, oi ? __ldg(row + nb + fi) : 0.0);
+      if (oi) cp_async8(&DBN_SE(dst, E_ZY + i), row + nb + fi);
+      else DBN_SE(dst, E_ZY + i) = 0.0;
     }
-    put(KT + KM, __ldg(row + nb + n + 1));
+    cp_async8(&DBN_SE(dst, E_YY), row + nb + n + 1);
   };
 
   if (a.refresh) {
-    // (re)build the cache from the table: canonical slots = parent positions, end boundary of segment j -> row j
+    // (re)build the cache from the table: canonical slots = parent positions, end boundary of segment j -> row j;
+    // three rows per round trip through the three staging buffers, written out as the rows' 16-byte pairs
 #pragma unroll
     for (int s = 1; s < KM; ++s) cg[s] = (s - 1 < npi) ? pi[s - 1] : -1;
-    // three rows per round trip: their table entries are requested with 8-byte cp.async into the three staging
-    // buffers, then each buffer is written out as the row's 16-byte pairs
     for (int j0 = 0; j0 < S; j0 += 3) {
 #pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const int j = j0 + b;
-        if (j < S) {
-          const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
-          double* dst = sbuf + b * BUF;
-#pragma unroll
-          for (int i = 0; i < KM; ++i) {
-            const bool oi = (i == 0) || cg[i] >= 0;
-            const int fi = (i == 0) ? 0 : cg[i] + 1;
-#pragma unroll
-            for (int jj = 0; jj <= i; ++jj) {
-              const bool oj = (jj == 0) || cg[jj] >= 0;
-              const int fj = (jj == 0) ? 0 : cg[jj] + 1;
-              const int hi = max(fi, fj), lo = min(fi, fj);
-              if (oi && oj) cp_async8(&DBN_SE(dst, DBN_TRI(i, jj)), row + hi * (hi + 1) / 2 + lo);
-              else DBN_SE(dst, DBN_TRI(i, jj)) = 0.0;
-            }
-            if (oi) cp_async8(&DBN_SE(dst, KT + i), row + nb + fi);
-            else DBN_SE(dst, KT + i) = 0.0;
-          }
-          cp_async8(&DBN_SE(dst, KT + KM), row + nb + n + 1);
-        }
-      }
+      for (int b = 0; b < 3; ++b)
+        if (j0 + b < S) request_row(bnd(j0 + b), sbuf + b * BUF);
       cp_async_commit();
       cp_async_wait<0>();
 #pragma unroll
@@ -189,8 +226,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     for (int s = 1; s < KM; ++s) cg[s] = a.st_cg[(s - 1) * a.U + u];
   }
 
-  // Philox counter = (global chain, node, iteration, slot); slots: Gibbs normals 4h + {0,1,2}, discrete picks and
-  // accept uniforms 48..50, sigma^2 gamma 64.., lambda^2 gamma 256..
+  // Philox counter = (global chain, node, iteration, slot); slots: Gibbs normals h (four per block) and 32 + h / 4 (the
+  // fifth of four consecutive segments), discrete picks and accept uniforms 48..50, sigma^2 gamma 64.., lambda^2
+  // gamma 256..
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   const uint32_t gchain = a.chain_offset + (unsigned)chain, unode = (unsigned)node;
   Work wk = {0, 0, 0, 0};
@@ -198,33 +236,35 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   unsigned n_pacc = 0, n_tacc = 0;  // accepted parent-set / changepoint moves
   const bool replay = TRACE && a.rd != nullptr;
 
-  // start the asynchronous copy of cached row j into staging buffer `buf` (one commit group per call, possibly
-  // empty, so that wait_group<1> always means "the previous call's row has landed")
-  auto stage_row = [&](int j, int buf) {
-    if (j < S) {
-      const double* src = crow(j);
-      double* dst = sbuf + buf * BUF;
+  // start the asynchronous copy of cached row j into staging buffer `buf` (the caller commits)
+  auto issue_row = [&](int j, int buf) {
+    DBN_CHECK(j >= 0 && j < BSLOTS && buf >= 0 && buf < 2, 2);
+    const double* src = crow(j);
+    double* dst = sbuf + buf * BUF;
 #pragma unroll
-      for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
-    }
-    cp_async_commit();
+    for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
   };
-  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment between the boundary rows in
-  // the staging buffers `lo` (null: table row 0 = zeros) and `hi`
-  auto seg_eval = [&](const double* lo, const double* hi, double& prod, double& q) {
+  // pivot product and quadratic form r^T C^-1 r (mu = 0, all KM slots) of the segment of `len` rows between the
+  // boundary rows in the staging buffers `lo` (null: table row 0 = zeros) and `hi`
+  auto seg_eval = [&](const double* lo, const double* hi, int len, double& prod, double& q) {
     double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
     const bool hl = lo != nullptr;
     const double* l_ = hl ? lo : hi;
+    G[0] = (double)len;
 #pragma unroll
-    for (int e = 0; e < KT; ++e) G[e] = DBN_SE(hi, e) - (hl ? DBN_SE(l_, e) : 0.0);
+    for (int e = 1; e < KT; ++e) G[e] = DBN_SE(hi, e - 1) - (hl ? DBN_SE(l_, e - 1) : 0.0);
 #pragma unroll
-    for (int i = 0; i < KM; ++i) g[i] = DBN_SE(hi, KT + i) - (hl ? DBN_SE(l_, KT + i) : 0.0);
-    s = DBN_SE(hi, KT + KM) - (hl ? DBN_SE(l_, KT + KM) : 0.0);
+    for (int i = 0; i < KM; ++i) g[i] = DBN_SE(hi, E_ZY + i) - (hl ? DBN_SE(l_, E_ZY + i) : 0.0);
+    s = DBN_SE(hi, E_YY) - (hl ? DBN_SE(l_, E_YY) : 0.0);
     form_a<KM>(G, lam, A);
     prod = ldl_factor<KM>(A, dinv);
     q = segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
     ++n_fact;
   };
+
+  // row 0 of the first Gibbs sweep (every later iteration requests it at its end)
+  if (S > 0) issue_row(0, 0);
+  cp_async_commit();
 
   for (int li = 0; li < a.n_iter; ++li) {
     const int it = a.it0 + li;
@@ -232,13 +272,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // The step is ~8k instructions of mostly straight-line code per thread, far more than the instruction cache
     // holds; warps that drift apart each stream it from L2 on their own (stall_no_instruction, profiles/r1_v4).
     // Block-wide barriers keep the block's warps on the same stretch of code so one fetch serves all of them.
-    __syncthreads();
+    warp_rejoin<1>(S);
+#ifdef DBN_DIAG_SPLIT2   // diagnostic build: lanes that reach probe k in a split warp -> counters[8 + k]
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[8], 1ull);
+#endif
+    block_barrier();
     const double* rd = replay ? a.rd + ((long long)u * a.n_iter + li) * DBN_RD_STRIDE : nullptr;
     const int* ri = replay ? a.ri + ((long long)u * a.n_iter + li) * DBN_RI_STRIDE : nullptr;
     double* td = (TRACE && a.td && active) ? a.td + ((long long)u * a.n_iter + li) * DBN_TD_STRIDE : nullptr;
     int* ti = (TRACE && a.ti && active) ? a.ti + ((long long)u * a.n_iter + li) * DBN_TI_STRIDE : nullptr;
     if (TRACE && ti) ti[DBN_TI_S_BEFORE] = S;
     int k = npi + 1;
+    DBN_CHECK(npi >= 0 && npi <= PMAX && S >= 0 && S <= SEG_ROWS, 8);
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) DBN_CHECK(j >= npi || (pi[j] >= 0 && pi[j] < n && pi[j] != node), 9);
 
     // rank of each slot's column in the reference's sorted design matrix (trace only; utils.py:202-204)
     int rank[KM];
@@ -256,27 +303,30 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // =========================== Gibbs pass: sigma^2, beta, lambda^2 ===========================================
     // One sweep with the OLD lambda^2 (samplers.py:103-127, :189-218, :265-305).  beta_h = mean_h + sigma e_h with
     // e_h independent of sigma^2, so sum_h |beta_h|^2 is assembled from (|m|^2, m.e, |e|^2) after sigma^2 is drawn.
+    // Row h arrives in staging buffer h & 1; once a step has its operands in registers it requests row h + 1 into the
+    // buffer of row h - 1.
     double q_sum = 0.0, acc_dd = 0.0, acc_de = 0.0, acc_ee = 0.0;
     {
-      double z_spare = 0.0;
-      stage_row(0, 0);
-      int bc = 0;  // staging buffer of the current boundary row; the previous row is in (bc + 2) % 3
+      float4 z5 = make_float4(0.f, 0.f, 0.f, 0.f);  // KM = 5: the fifth normal of four consecutive segments
+      int bprev = 0;
       for (int h = 0; h < S; ++h) {
-        const int bn = (bc == 2) ? 0 : bc + 1, bp = (bc == 0) ? 2 : bc - 1;
-        stage_row(h + 1, bn);
-        cp_async_wait<1>();
-        const double* sr = sbuf + bc * BUF;
-        const double* sp = sbuf + bp * BUF;
+        cp_async_wait<0>();
+        const double* sr = sbuf + (h & 1) * BUF;
+        const double* sp = sbuf + ((h & 1) ^ 1) * BUF;
         const bool hp = h > 0;
-        bc = bn;
-        double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
+        const int bcur = bnd(h);
+        double G[KT], g[KM], s, A[KT], dinv[KM], rs[KM], wv[KM];
+        G[0] = (double)(bcur - bprev);
+        bprev = bcur;
 #pragma unroll
-        for (int e = 0; e < KT; ++e) G[e] = DBN_SE(sr, e) - (hp ? DBN_SE(sp, e) : 0.0);
+        for (int e = 1; e < KT; ++e) G[e] = DBN_SE(sr, e - 1) - (hp ? DBN_SE(sp, e - 1) : 0.0);
 #pragma unroll
-        for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, KT + i) - (hp ? DBN_SE(sp, KT + i) : 0.0);
-        s = DBN_SE(sr, KT + KM) - (hp ? DBN_SE(sp, KT + KM) : 0.0);
+        for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, E_ZY + i) - (hp ? DBN_SE(sp, E_ZY + i) : 0.0);
+        s = DBN_SE(sr, E_YY) - (hp ? DBN_SE(sp, E_YY) : 0.0);
+        if (h + 1 < S) issue_row(h + 1, (h + 1) & 1);
+        cp_async_commit();
         form_a<KM>(G, lam, A);
-        ldl_factor<KM>(A, dinv);
+        ldl_factor_rs<KM>(A, dinv, rs);
         ++n_fact;
         q_sum += segment_q<KM, false>(G, g, s, g, lam, A, dinv, wv);
         wk.segment(k, false);
@@ -288,19 +338,16 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (!replay) {
           double e[KM];
           const double sw = sqrt(lam);
-#pragma unroll
-          for (int i = 0; i < KM; i += 2) {
-            // KM odd: the last slot needs one normal of a pair; odd segments use the one an even segment left over
-            double2 z;
-            if ((KM & 1) && i == KM - 1 && (h & 1)) {
-              z = make_double2(z_spare, 0.0);
-            } else {
-              z = normal_pair(gchain, unode, uit, (uint32_t)(4 * h + i / 2), key);
-              if ((KM & 1) && i == KM - 1) z_spare = z.y;
-            }
-            e[i] = ((i == 0) || cg[i] >= 0) ? sw * z.x * sqrt(dinv[i]) : 0.0;
-            if (i + 1 < KM) e[i + 1] = (cg[i + 1] >= 0) ? sw * z.y * sqrt(dinv[i + 1]) : 0.0;
+          const float4 z4 = normal4_fast(gchain, unode, uit, (uint32_t)h, key);
+          float zl = 0.f;
+          if (KM == 5) {
+            if ((h & 3) == 0) z5 = normal4_fast(gchain, unode, uit, 32u + (uint32_t)(h >> 2), key);
+            const int w_ = h & 3;
+            zl = (w_ == 0) ? z5.x : ((w_ == 1) ? z5.y : ((w_ == 2) ? z5.z : z5.w));
           }
+          const float zf[5] = {z4.x, z4.y, z4.z, z4.w, zl};
+#pragma unroll
+          for (int i = 0; i < KM; ++i) e[i] = ((i == 0) || cg[i] >= 0) ? sw * (double)zf[i] * rs[i] : 0.0;
           solve_upper<KM>(A, e);  // e = sqrt(lam) L^-T D^-1/2 z: cov = sigma^2 lam A^-1 (samplers.py:214-216)
           acc_dd += dot<KM>(mean, mean);
           acc_de += dot<KM>(mean, e);
@@ -339,10 +386,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     }
+    warp_rejoin<2>(S);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[9], 1ull);
+#endif
+    // row 0 of the parent-set sweep: on its way while sigma^2, lambda^2 and the proposals are drawn
+    if (S > 0) issue_row(0, 0);
+    cp_async_commit();
     {
       const double shape = a.a_sig + a.T_sigma_half;
       const double rate = a.b_sig + 0.5 * q_sum;
-      sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / gamma_draw(gchain, unode, uit, 64u, key, shape);
+      sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / gamma_draw_fast(gchain, unode, uit, 64u, key, shape);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[10], 1ull);
+#endif
       if (TRACE && td) {
         td[DBN_TD_SIG_SHAPE] = shape;
         td[DBN_TD_SIG_RATE] = rate;
@@ -364,7 +421,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       // nh: samplers.py:285-289 shape a + S k/2 ; h: :301 shape a + k/2 ; rate b + ss / (2 sigma^2)
       const double shape = a.a_lam + 0.5 * (double)(HOMOG ? k : S * k);
       const double rate = a.b_lam + 0.5 * ss / sig2;
-      lam = replay ? rd[DBN_RD_LAMBDA2] : rate / gamma_draw(gchain, unode, uit, 256u, key, shape);
+      lam = replay ? rd[DBN_RD_LAMBDA2] : rate / gamma_draw_fast(gchain, unode, uit, 256u, key, shape);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[11], 1ull);
+#endif
       if (TRACE && td) {
         td[DBN_TD_LAM_SHAPE] = shape;
         td[DBN_TD_LAM_RATE] = rate;
@@ -376,7 +436,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       }
     }
 
-    __syncthreads();  // the Gibbs sweep's trip count differs per lane: regroup the block's warps (measured +1.3 %)
+#ifndef DBN_NO_MID_BAR
+    warp_rejoin<1>(S);
+    block_barrier();  // the Gibbs sweep's trip count differs per lane: regroup the block's warps (measured +1.3 %)
+#endif
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[12], 1ull);
+#endif
     // ============================ proposals (no scoring yet) ==================================================
     // all discrete picks and both accept uniforms of the iteration come from three Philox blocks
     uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
@@ -384,6 +450,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       wa = philox_block(gchain, unode, uit, 48u, key);
       wb = philox_block(gchain, unode, uit, 49u, key);
       wc = philox_block(gchain, unode, uit, 50u, key);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[13], 1ull);
+#endif
     }
     auto pick = [](uint32_t word, int m) { return (int)__umulhi(word, (uint32_t)m); };
     auto unif = [](uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; };
@@ -511,6 +580,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     }
+    warp_rejoin<2>(S);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[14], 1ull);
+#endif
     if (TRACE && ti) {
       ti[DBN_TI_PI_MOVE] = pmove;
       ti[DBN_TI_PI_VALID] = pvalid;
@@ -521,7 +594,16 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         ti[DBN_TI_TAU_ACCEPT] = 0;
       }
     }
+    const bool birth = tmove == 0, death = tmove == 1;
+    const bool t_new = tvalid && !death;  // the changepoint proposal has a new boundary row (table row `trow`)
+    double* const b0 = sbuf;
+    double* const b1 = sbuf + BUF;
+    double* const b2 = sbuf + 2 * BUF;
 
+#ifdef DBN_BAR_PI
+    warp_rejoin<1>(S);
+    block_barrier();
+#endif
     // ============================ parent-set move: pi and pi* in one sweep (a4) ===============================
     // position p of the sweep holds slot perm[p]; the last position is the slot that leaves (delete / exchange) or
     // the free slot that would be filled (add).  current = base + last position, star = base + new column.
@@ -554,9 +636,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
       for (int p = 0; p < KB; ++p) {
 #pragma unroll
-        for (int q = 0; q <= p; ++q) eb[DBN_TRI(p, q)] = DBN_TRI(perm[p], perm[q]);  // perm is increasing on the base
-        et[p] = (tslot > perm[p]) ? DBN_TRI(tslot, perm[p]) : DBN_TRI(perm[p], tslot);
-        ezy[p] = KT + perm[p];
+        for (int q = 0; q <= p; ++q) eb[DBN_TRI(p, q)] = DBN_EZZ(perm[p], perm[q]);  // perm is increasing on the base; (0, 0) unused
+        et[p] = (tslot > perm[p]) ? DBN_EZZ(tslot, perm[p]) : DBN_EZZ(perm[p], tslot);
+        ezy[p] = E_ZY + perm[p];
         // perm[p] is p or p + 1: selects keep cg in registers (a run-time index sends the array to local memory)
         const int cgp = (p == 0) ? -1 : ((p < tslot) ? cg[p] : cg[p + 1 < KM ? p + 1 : p]);
         const int fp = (p == 0) ? 0 : cgp + 1;  // 0 when the slot is empty; masked by o2 < 0
@@ -564,10 +646,28 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         const int hi = max(cf, fp), lo = min(cf, fp);
         o2[p] = (has_new && occ) ? hi * (hi + 1) / 2 + lo : -1;
       }
-      ezyt = KT + tslot;
-      ett = DBN_TRI(tslot, tslot);
+      ezyt = E_ZY + tslot;
+      ett = DBN_EZZ(tslot, tslot);
       o2d = has_new ? cf * (cf + 1) / 2 + cf : -1;
       o2y = has_new ? nb + cf : -1;
+      // request the candidate column (<= KM + 1 table entries) at table row t into the slot `cand`
+      auto request_cand = [&](int t) {
+        DBN_CHECK(t >= 0 && t <= N, 3);
+        DBN_CHECK(o2d >= 0 && o2d < a.tb.zz_size && o2y >= a.tb.zz_size && o2y < a.tb.row_stride, 4);
+#pragma unroll
+        for (int p = 0; p < KB; ++p) DBN_CHECK(o2[p] < a.tb.zz_size, 5);
+        const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
+#pragma unroll
+        for (int p = 0; p < KB; ++p)
+          if (o2[p] >= 0) cp_async8(cand + p * FAST_BLOCK, row + o2[p]);
+        cp_async8(cand + KB * FAST_BLOCK, row + o2d);
+        cp_async8(cand + (KB + 1) * FAST_BLOCK, row + o2y);
+      };
+      // with row 0 (requested after the Gibbs sweep): the candidate column at the first boundary and the new boundary
+      // row of the changepoint proposal (into the third staging buffer, where it stays until the changepoint move)
+      if (has_new && S > 0) request_cand(bnd(0));
+      if (t_new) request_row(trow, b2);
+      cp_async_commit();
 
       // ln det of the base blocks: the pivot products are accumulated as mantissa x 2^exponent (one log per sweep)
       double mB = 1.0, R1 = 1.0, R2 = 1.0, q1 = 0.0, q2 = 0.0;
@@ -575,35 +675,33 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       double n_prev[KB + 2];  // new column at the previous boundary: cross terms, diagonal, ZY
 #pragma unroll
       for (int i = 0; i < KB + 2; ++i) n_prev[i] = 0.0;
-      stage_row(0, 0);
-      int bc = 0;
+      int bprev = 0;
       for (int h = 0; h < S; ++h) {
-        const int bn = (bc == 2) ? 0 : bc + 1, bp = (bc == 0) ? 2 : bc - 1;
-        stage_row(h + 1, bn);
-        cp_async_wait<1>();
-        const double* sr = sbuf + bc * BUF;
-        const double* sp = sbuf + bp * BUF;
+        cp_async_wait<0>();
+        const double* sr = sbuf + (h & 1) * BUF;
+        const double* sp = sbuf + ((h & 1) ^ 1) * BUF;
         const bool hp = h > 0;
-        bc = bn;
+        const int bcur = bnd(h);
         auto seg = [&](int e) { return DBN_SE(sr, e) - (hp ? DBN_SE(sp, e) : 0.0); };  // entry e of this segment's statistics
         double A[KBT], gB[KB], t1[KB], t2[KB], dinv[KB];
+        A[0] = (double)(bcur - bprev);
+        bprev = bcur;
 #pragma unroll
-        for (int e = 0; e < KBT; ++e) A[e] = seg(eb[e]);
+        for (int e = 1; e < KBT; ++e) A[e] = seg(eb[e]);
 #pragma unroll
         for (int p = 0; p < KB; ++p) {
           gB[p] = seg(ezy[p]);
           t1[p] = seg(et[p]);
         }
         const double t1d = seg(ett), t1y = seg(ezyt);
-        const double s = seg(KT + KM);
+        const double s = seg(E_YY);
         double t2d = 0.0, t2y = 0.0;
         if (has_new) {
-          const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(h), h, S, N) * a.tb.row_stride;
           double cur[KB + 2];
 #pragma unroll
-          for (int p = 0; p < KB; ++p) cur[p] = (o2[p] >= 0) ? __ldg(row + o2[p]) : 0.0;
-          cur[KB] = __ldg(row + o2d);
-          cur[KB + 1] = __ldg(row + o2y);
+          for (int p = 0; p < KB; ++p) cur[p] = (o2[p] >= 0) ? cand[p * FAST_BLOCK] : 0.0;
+          cur[KB] = cand[KB * FAST_BLOCK];
+          cur[KB + 1] = cand[(KB + 1) * FAST_BLOCK];
 #pragma unroll
           for (int p = 0; p < KB; ++p) t2[p] = cur[p] - n_prev[p];
           t2d = cur[KB] - n_prev[KB];
@@ -614,6 +712,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
           for (int p = 0; p < KB; ++p) t2[p] = 0.0;
         }
+        // this step's operands are in registers: request the next step's (row h + 1 into the buffer of row h - 1, the
+        // candidate column at boundary h + 1 into its slot)
+        if (h + 1 < S) {
+          issue_row(h + 1, (h + 1) & 1);
+          if (has_new) request_cand(bnd(h + 1));
+        }
+        cp_async_commit();
         // base factorisation of A_B = I + lam G_B
 #pragma unroll
         for (int p = 0; p < KB; ++p)
@@ -688,40 +793,63 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           ++n_pacc;
         }
       }
+    } else {
+      cp_async_wait<0>();  // row 0 was requested for a sweep that does not run
     }
-    // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row.
-    // Its table entries at all S boundaries (<= 9 x (KM + 1) values) are fetched in ONE round trip, by cp.async into
-    // the staging buffers (free between the sweeps), instead of one dependent round trip per boundary.
+    warp_rejoin<2>(S);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[16], 1ull);
+#endif
+    // ---- accepted parent-set move: the new column (zeros for a delete) takes slot `tslot` in every cached row and in
+    // the changepoint proposal's new boundary row (staging buffer 2).  Its table entries at those <= S + 1 boundaries
+    // are fetched by cp.async into the two row buffers (free between the sweeps), RB boundaries per round trip.
     if (p_acc) {
-      // value v = j * (KB + 2) + p lives in this thread's own slices of the three buffers (2 NP doubles each)
-      static_assert(SEG_ROWS * (KB + 2) <= 3 * 2 * NP, "the staging buffers hold the new column at every boundary");
+      DBN_CHECK(tslot >= 1 && tslot < KM && ett >= 0 && ett < FastDims<KM>::NE && ezyt >= 0 && ezyt < FastDims<KM>::NE, 6);
+#pragma unroll
+      for (int p = 0; p < KB; ++p) DBN_CHECK(et[p] >= 0 && et[p] < FastDims<KM>::NE, 7);
+      constexpr int RB = (2 * 2 * NP) / NC;  // boundaries per round: value v = j * NC + p lives in buffers 0 / 1
       auto stash = [&](int v) -> double* {
         const int b_ = v / (2 * NP), w_ = v - b_ * (2 * NP);
         return sbuf + b_ * BUF + (w_ >> 1) * (2 * FAST_BLOCK) + (w_ & 1);
       };
       const bool fetch = o2d >= 0;
-      if (fetch) {
-        for (int j = 0; j < S; ++j) {
-          const double* __restrict__ row = a.tb.base + (long long)DBN_SEG_END(tau_cur(j), j, S, N) * a.tb.row_stride;
-          const int v0 = j * (KB + 2);
+      const int nbnd = S + (t_new ? 1 : 0);
+      for (int j0 = 0; j0 < nbnd; j0 += RB) {
+        const int j1 = min(j0 + RB, nbnd);
+        if (fetch) {
+          for (int j = j0; j < j1; ++j) {
+            const double* __restrict__ row = a.tb.base + (long long)((j < S) ? bnd(j) : trow) * a.tb.row_stride;
+            const int v0 = (j - j0) * NC;
 #pragma unroll
-          for (int p = 0; p < KB; ++p)
-            if (o2[p] >= 0) cp_async8(stash(v0 + p), row + o2[p]);
-          cp_async8(stash(v0 + KB), row + o2d);
-          cp_async8(stash(v0 + KB + 1), row + o2y);
+            for (int p = 0; p < KB; ++p)
+              if (o2[p] >= 0) cp_async8(stash(v0 + p), row + o2[p]);
+            cp_async8(stash(v0 + KB), row + o2d);
+            cp_async8(stash(v0 + KB + 1), row + o2y);
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        for (int j = j0; j < j1; ++j) {
+          const int v0 = (j - j0) * NC;
+          if (j < S) {
+            double* c = crow(j);
+#pragma unroll
+            for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (fetch && o2[p] >= 0) ? *stash(v0 + p) : 0.0;
+            DBN_CE(c, ett) = fetch ? *stash(v0 + KB) : 0.0;
+            DBN_CE(c, ezyt) = fetch ? *stash(v0 + KB + 1) : 0.0;
+          } else {
+#pragma unroll
+            for (int p = 0; p < KB; ++p) DBN_SE(b2, et[p]) = (fetch && o2[p] >= 0) ? *stash(v0 + p) : 0.0;
+            DBN_SE(b2, ett) = fetch ? *stash(v0 + KB) : 0.0;
+            DBN_SE(b2, ezyt) = fetch ? *stash(v0 + KB + 1) : 0.0;
+          }
         }
       }
-      cp_async_commit();
-      cp_async_wait<0>();
-      for (int j = 0; j < S; ++j) {
-        const int v0 = j * (KB + 2);
-        double* c = crow(j);
-#pragma unroll
-        for (int p = 0; p < KB; ++p) DBN_CE(c, et[p]) = (fetch && o2[p] >= 0) ? *stash(v0 + p) : 0.0;
-        DBN_CE(c, ett) = fetch ? *stash(v0 + KB) : 0.0;
-        DBN_CE(c, ezyt) = fetch ? *stash(v0 + KB + 1) : 0.0;
-      }
     }
+    warp_rejoin<2>(S);
+#ifdef DBN_DIAG_SPLIT2
+    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[17], 1ull);
+#endif
     // ---- counts: pi_vector[it+1] is kept iff idx >= burn_in and (idx - burn_in) % thin != 0 (network.py:358-359)
     {
       const int idx = it + 1;
@@ -737,50 +865,70 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       }
     }
 
+#ifdef DBN_BAR_TAU
+    warp_rejoin<1>(S);
+    block_barrier();
+#endif
     // ============================ changepoint move: only the changed segments (a5) ============================
     if (do_tau) {
       bool t_acc = false;
-      const bool birth = tmove == 0, death = tmove == 1;
-      double* const b0 = sbuf;                             // staging buffers: free between the sweeps
-      double* const b1 = sbuf + BUF;
-      double* const b2 = sbuf + 2 * BUF;
       const int ja = tj - 1;  // cached row the move inserts before (birth), removes (death) or replaces (reallocation)
       if (tvalid) {
         // The boundaries around the change: left = row ja-1 (table row 0 when ja == 0), mid = row ja (death,
-        // reallocation), right = row ja (birth) or ja+1; they are cached rows.  The new boundary (birth,
-        // reallocation) is the only table row that has to be gathered; it replaces mid in b1.
+        // reallocation), right = row ja (birth) or ja+1; they are cached rows.  The new boundary (birth, reallocation)
+        // is the only table row that had to be gathered: it has been in staging buffer 2 since the parent-set sweep.
         //   old segments: (left, mid), (mid, right)   or, for a birth, (left, right)
         //   new segments: (left, new), (new, right)   or, for a death, (left, right)
+        // Buffers: left -> 0, mid -> 1, new -> 2; right -> 1 (birth), 2 (death), or, for a reallocation, 0 once the
+        // two segments that start at the left boundary are done.
         const bool has_l = ja >= 1;
-        {
-          auto stage = [&](int row, double* dst) {
-            const double* src = crow(row);
+        const bool realloc = !birth && !death;
+        auto stage = [&](int row, double* dst) {
+          const double* src = crow(row);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
-          };
-          if (has_l) stage(ja - 1, b0);
-          if (!birth) stage(ja, b1);
-          stage(birth ? ja : ja + 1, b2);
-          cp_async_commit();
-          cp_async_wait<0>();
-        }
+          for (int p = 0; p < NP; ++p) cp_async16(dst + p * (2 * FAST_BLOCK), src + (long long)p * (2 * U));
+        };
+        if (has_l) stage(ja - 1, b0);
+        stage(ja, b1);
+        if (death) stage(ja + 1, b2);
+        cp_async_commit();
+        const int t_l = has_l ? bnd(ja - 1) : 0;
+        const int t_m = bnd(ja);                              // birth: this is the right boundary
+        const int t_r = birth ? t_m : bnd(ja + 1);
+        cp_async_wait<0>();
         const double* lo0 = has_l ? b0 : nullptr;
+        const double* right = birth ? b1 : (death ? b2 : b0);
         double prod_old = 1.0, q_old = 0.0, prod_new = 1.0, q_new = 0.0;
-        // steps 0, 1: the old segments; 2, 3: the new ones (b1 holds the new boundary from step 2 on)
+        // steps 0, 1: the segments that start at the left boundary (old, new); 2, 3: those that end at the right one
         for (int step = 0; step < 4; ++step) {
-          const bool two = (step < 2) ? !birth : !death;  // does this side have two segments?
-          if (step == 2 && two) gather(trow, [&](int e, double v) { DBN_SE(b1, e) = v; });
-          if ((step & 1) && !two) continue;
-          const double* lo = (step & 1) ? b1 : lo0;
-          const double* hi = ((step & 1) || !two) ? b2 : b1;
-          double pr, qq;
-          seg_eval(lo, hi, pr, qq);
+          const bool is_new = step & 1;
+          if (step >= 2 && (is_new ? death : birth)) continue;  // that side has one segment only
+          if (step == 2 && realloc) {
+            stage(ja + 1, b0);
+            cp_async_commit();
+            cp_async_wait<0>();
+          }
+          const double* lo;
+          const double* hi;
+          int len;
           if (step < 2) {
-            prod_old *= pr;
-            q_old += qq;
+            lo = lo0;
+            const bool to_right = is_new ? death : birth;     // the only segment of its side spans left .. right
+            hi = to_right ? right : (is_new ? b2 : b1);
+            len = (to_right ? t_r : (is_new ? trow : t_m)) - t_l;
           } else {
+            lo = is_new ? b2 : b1;
+            hi = right;
+            len = t_r - (is_new ? trow : t_m);
+          }
+          double pr, qq;
+          seg_eval(lo, hi, len, pr, qq);
+          if (is_new) {
             prod_new *= pr;
             q_new += qq;
+          } else {
+            prod_old *= pr;
+            q_old += qq;
           }
         }
         const double ld_star = ld_now + dlog(prod_new / prod_old);
@@ -800,7 +948,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       }
       // ---- accepted changepoint move: a birth inserts the new boundary's row before row ja (rows ja .. S-1 move up by
       // one), a death removes row ja (rows ja+1 .. S-1 move down by one), a reallocation replaces row ja.  The new
-      // boundary's row is still in b1.  A row moves as NP 16-byte pairs.
+      // boundary's row is in staging buffer 2.  A row moves as NP 16-byte pairs.
       if (t_acc) {
         double2* cu = reinterpret_cast<double2*>(a.cache) + u;  // pair p of row r at cu[(r * NP + p) * U]
         auto move_row = [&](int dst, int src) {
@@ -834,7 +982,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         if (!death) {
 #pragma unroll
           for (int p = 0; p < NP; ++p)
-            cu[((long long)ja * NP + p) * U] = *reinterpret_cast<const double2*>(b1 + p * (2 * FAST_BLOCK));
+            cu[((long long)ja * NP + p) * U] = *reinterpret_cast<const double2*>(b2 + p * (2 * FAST_BLOCK));
         }
       }
       if (t_acc) {
@@ -852,7 +1000,11 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       ti[DBN_TI_S] = S;
       for (int j = 0; j < SMAX; ++j) ti[DBN_TI_TAU + j] = (j < S) ? TAU(j) : -1;
     }
+    // row 0 of the next iteration's Gibbs sweep (after this iteration's own updates of the cached rows)
+    if (S > 0 && li + 1 < a.n_iter) issue_row(0, 0);
+    cp_async_commit();
   }
+  cp_async_wait<0>();
 
   // ---- store state
   if (active) {
@@ -866,19 +1018,22 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
     for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
   }
-  // ---- work counters: summed per block through shared memory (the staging buffers are free now), one global
-  // atomic per counter and block
-  unsigned long long* const s_cnt = reinterpret_cast<unsigned long long*>(s_dyn);
+  // ---- work counters: summed per block with shared-memory atomics; the thread that finishes LAST publishes the block's
+  // totals (one global atomic per counter and block).  No barrier here: the loop's barriers are a scheduling aid only,
+  // and a warp that ran them in two parts may be a phase behind the rest of its block (see block_barrier).
   const unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
                                    (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
-  __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 8; ++c) s_cnt[c * FAST_BLOCK + tid] = v[c];
-  __syncthreads();
-  if (tid < 8) {
-    unsigned long long t = 0;
-    for (int i = 0; i < FAST_BLOCK; ++i) t += s_cnt[tid * FAST_BLOCK + i];
-    if (t) atomicAdd(&a.counters[tid], t);
+  for (int c = 0; c < 8; ++c)
+    if (v[c]) atomicAdd(&s_tot[c], v[c]);
+  __threadfence_block();
+  if (atomicAdd(&s_done, 1u) + 1u == (unsigned)FAST_BLOCK) {
+    __threadfence_block();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const unsigned long long t = *(volatile unsigned long long*)&s_tot[c];
+      if (t) atomicAdd(&a.counters[c], t);
+    }
   }
 }
 
@@ -902,20 +1057,22 @@ __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* count
     const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N);
     const double* row = a.tb.base + (long long)t * a.tb.row_stride;
     const double* c = a.cache + 2ll * u + (long long)j * NP * (2 * U);
+    bad += (row[0] != (double)t) ? 1 : 0;  // the entry the cache does not store: ZZ(0, 0) at boundary t is t
     for (int i = 0; i < KM; ++i) {
       const bool oi = (i == 0) || cg[i] >= 0;
       const int fi = (i == 0) ? 0 : cg[i] + 1;
       for (int jj = 0; jj <= i; ++jj) {
+        if (i == 0) continue;
         const bool oj = (jj == 0) || cg[jj] >= 0;
         const int fj = (jj == 0) ? 0 : cg[jj] + 1;
         const int hi = max(fi, fj), lo = min(fi, fj), off = hi * (hi + 1) / 2 + lo;
         const double ex = (oi && oj) ? row[off] : 0.0;
-        bad += (ex != DBN_CE(c, DBN_TRI(i, jj))) ? 1 : 0;
+        bad += (ex != DBN_CE(c, DBN_EZZ(i, jj))) ? 1 : 0;
       }
       const double ex = oi ? row[nb + fi] : 0.0;
-      bad += (ex != DBN_CE(c, KT + i)) ? 1 : 0;
+      bad += (ex != DBN_CE(c, KT - 1 + i)) ? 1 : 0;
     }
-    bad += (row[nb + n + 1] != DBN_CE(c, KT + KM)) ? 1 : 0;
+    bad += (row[nb + n + 1] != DBN_CE(c, KT - 1 + KM)) ? 1 : 0;
   }
   if (bad) {
     atomicAdd(&counts[0], 1ull);

@@ -307,8 +307,8 @@ int dbn_create(const dbn_config* cfg, dbn_handle** out) {
     return DBN_ERR_CUDA;
   }
   h->stream = h->own_stream;
-  e = cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+  e = cudaMalloc(&h->d_counters, 32 * sizeof(unsigned long long));   // [8] work counters (+ 16 probe counters of diagnostic builds)
+  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 32 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
     cudaStreamDestroy(h->own_stream);
@@ -914,6 +914,17 @@ int dbn_read_counters(dbn_handle* h, uint64_t out[8]) {
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaMemcpyAsync(out, h->d_counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+#ifdef DBN_DIAG_SPLIT2
+  {
+    unsigned long long d[16];
+    CU(h, cudaMemcpy(d, h->d_counters + 8, sizeof(d), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "split-warp probes:");
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %llu", d[i]);
+    fprintf(stderr, "  check code %llu", d[15]);
+    fprintf(stderr, "\n");
+    CU(h, cudaMemset(h->d_counters + 8, 0, sizeof(d)));
+  }
+#endif
   return DBN_OK;
 }
 

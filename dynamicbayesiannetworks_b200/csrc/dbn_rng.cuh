@@ -65,7 +65,10 @@ struct Rng {
     z1 = r * s;
   }
 
-  // Gamma(shape, scale=1) by Marsaglia-Tsang; shape < 1 handled by the u^(1/shape) boost
+  // Gamma(shape, scale=1) by Marsaglia-Tsang; shape < 1 handled by the u^(1/shape) boost.
+  // ONE exit: lanes of a warp leave the rejection loop after different numbers of tries; with a `return` inside the loop
+  // each of them would return to the caller on its own and the warp would stay split there (ptxas treats a call as
+  // convergent and emits no reconvergence point after it) -- see the note at gamma_draw_fast.
   __device__ double gamma(double shape) {
     double boost = 1.0;
     if (shape < 1.0) {
@@ -74,16 +77,22 @@ struct Rng {
     }
     const double d = shape - 1.0 / 3.0;
     const double c = rsqrt(9.0 * d);
-    for (int tries = 0; tries < 64; ++tries) {
+    double out = d;  // unreachable in practice (acceptance > 0.95 per try)
+    bool done = false;
+    for (int tries = 0; tries < 64 && !done; ++tries) {
       double x, unused;
       normal2(x, unused);
       double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      double u = 1.0 - uniform();
-      if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+      const double u = 1.0 - uniform();
+      if (v > 0.0) {
+        v = v * v * v;
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+          out = d * v;
+          done = true;
+        }
+      }
     }
-    return boost * d;  // unreachable in practice (acceptance > 0.95 per try)
+    return boost * out;
   }
 };
 
@@ -108,7 +117,7 @@ __device__ __noinline__ inline double2 normal_pair(uint32_t chain, uint32_t node
   return make_double2(rad * c, rad * s);
 }
 
-// Gamma(shape, 1) by Marsaglia-Tsang on the counter range [ctr0, ctr0 + 192)
+// Gamma(shape, 1) by Marsaglia-Tsang on the counter range [ctr0, ctr0 + 192); one exit (see gamma_draw_fast)
 __device__ __noinline__ inline double gamma_draw(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr0, uint2 key, double shape) {
   double boost = 1.0;
   uint32_t ctr = ctr0;
@@ -120,18 +129,101 @@ __device__ __noinline__ inline double gamma_draw(uint32_t chain, uint32_t node, 
   }
   const double d = shape - 1.0 / 3.0;
   const double c = rsqrt(9.0 * d);
-  for (int tries = 0; tries < 64; ++tries) {
+  double out = d;  // unreachable in practice (acceptance > 0.95 per try)
+  bool done = false;
+  for (int tries = 0; tries < 64 && !done; ++tries) {
     const double2 z = normal_pair(chain, node, it, ctr++, key);
     const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
     double v = 1.0 + c * z.x;
+    if (v > 0.0) {
+      v = v * v * v;
+      const double u = 1.0 - (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+      const double x2 = z.x * z.x;
+      // Marsaglia-Tsang squeeze (inside the exact test's region), then the exact test
+      if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d - d * v + d * log(v)) {
+        out = d * v;
+        done = true;
+      }
+    }
+  }
+  return boost * out;
+}
+
+// ---- fast free-running normals (h / nh kernel) -------------------------------------------------------------------
+// Box-Muller with the transcendental part in single precision on the SFU (MUFU.LG2 / MUFU.SIN / MUFU.COS / MUFU.SQRT):
+// FOUR N(0,1) variates per Philox block (two radius / angle pairs from four 32-bit words) instead of two from the FP64
+// log / sincospi expansions, which were 17.6 % of the kernel's executed instructions (profiles/r1_v10).  The variates
+// carry the resolution of their 32-bit uniforms: |z| <= 6.76 (radius word 0 -> u = 2^-33), absolute error of a variate
+// below 1e-6 (MUFU accuracy ~2^-21.4 on sin / cos over [-pi, pi], 2^-22 on log2), far below the Monte-Carlo error of
+// any chain length this library runs; the model arithmetic itself stays FP64.  Only the free-running mode draws them:
+// replay mode injects the reference's draws, so every replay parity test is unaffected; the distribution is pinned by
+// tests/test_gpu_pinning.py::test_free_running_gibbs_draw_moments and the free-running edge-posterior tests.
+__device__ __forceinline__ float2 box_muller_f32(uint32_t a, uint32_t b) {
+  const float u = fmaf(__uint2float_rn(a), 0x1.0p-32f, 0x1.0p-33f);       // (0, 1]
+  const float ang = __int2float_rn((int)b) * (6.283185307179586f * 0x1.0p-32f);  // [-pi, pi]
+  const float rad = sqrtf(fmaxf(0.0f, -1.3862943611198906f * __log2f(u)));  // sqrt(-2 ln u)
+  float s, c;
+  __sincosf(ang, &s, &c);
+  return make_float2(rad * c, rad * s);
+}
+__device__ __noinline__ inline float4 normal4_fast(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr, uint2 key) {
+  const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr), key);
+  const float2 p = box_muller_f32(r.x, r.y), q = box_muller_f32(r.z, r.w);
+  return make_float4(p.x, p.y, q.x, q.y);
+}
+
+// Gamma(shape, 1) by Marsaglia-Tsang, ONE Philox block per try: words 0, 1 -> the normal, words 2, 3 -> the 53-bit uniform.
+// ONE exit.  Lanes leave the rejection loop after different numbers of tries.  With `return` statements inside the loop
+// (round 1) every lane returned to the call site on its own, and because ptxas treats a call as convergent there is no
+// reconvergence point after it: the warp stayed split until the next WARPSYNC, ran `__syncthreads()` in two parts, each
+// counted as a whole warp, and the block's barrier phases slipped (the h-dbn instantiations have no WARPSYNC.ALL before
+// their barriers at all).  Symptoms: garbage work counters of the h-dbn kernel (profiles/r1_v13/methods.jsonl), and the
+// lost cooperative updates of profiles/r1_notes.md.  With a single exit the loop's own reconvergence point rejoins the
+// lanes inside the function.
+__device__ __noinline__ inline double gamma_draw_fast(uint32_t chain, uint32_t node, uint32_t it, uint32_t ctr0, uint2 key, double shape) {
+  double boost = 1.0;
+  uint32_t ctr = ctr0;
+  if (shape < 1.0) {
+    const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
+    const double u = (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+    boost = pow(1.0 - u, 1.0 / shape);
+    shape += 1.0;
+  }
+  const double d = shape - 1.0 / 3.0;
+  const double c = rsqrt(9.0 * d);
+#ifdef DBN_GAMMA_EARLY   // experiment: the round-1 shape (lanes return from inside the loop)
+  for (int tries = 0; tries < 64; ++tries) {
+    const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
+    const double x = (double)box_muller_f32(r.x, r.y).x;
+    double v = 1.0 + c * x;
     if (v <= 0.0) continue;
     v = v * v * v;
-    const double u = 1.0 - (double)((((uint64_t)r.x << 32) | r.y) >> 11) * 0x1.0p-53;
-    const double x2 = z.x * z.x;
-    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;  // Marsaglia-Tsang squeeze: inside the exact test's region
+    const double u = 1.0 - (double)((((uint64_t)r.z << 32) | r.w) >> 11) * 0x1.0p-53;
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
     if (log(u) < 0.5 * x2 + d - d * v + d * log(v)) return boost * d * v;
   }
-  return boost * d;  // unreachable in practice (acceptance > 0.95 per try)
+  return boost * d;
+#else
+  double out = d;  // unreachable in practice (acceptance > 0.95 per try)
+  bool done = false;
+  for (int tries = 0; tries < 64 && !done; ++tries) {
+    const uint4 r = philox4x32_10(make_uint4(chain, node, it, ctr++), key);
+    const double x = (double)box_muller_f32(r.x, r.y).x;
+    double v = 1.0 + c * x;
+    if (v > 0.0) {
+      v = v * v * v;
+      const double u = 1.0 - (double)((((uint64_t)r.z << 32) | r.w) >> 11) * 0x1.0p-53;
+      const double x2 = x * x;
+      // Marsaglia-Tsang squeeze (inside the exact test's region), then the exact test
+      if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d - d * v + d * log(v)) {
+        out = d * v;
+        done = true;
+      }
+    }
+  }
+  return boost * out;
+#endif
 }
 
 }  // namespace dbn

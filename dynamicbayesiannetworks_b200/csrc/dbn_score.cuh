@@ -83,6 +83,15 @@ __device__ __forceinline__ double pivot_rcp(double d) {
 #endif
 }
 
+// 1 / sqrt(d) of a pivot (same domain as pivot_rcp): hardware seed (rsqrt.approx.ftz.f64, ~2^-20 relative) and one
+// third-order step r += r e (1/2 + 3/8 e), e = 1 - d r^2: relative error ~e^3, i.e. below 1 ulp.
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d * r, r, 1.0);
+  return fma(r * e, fma(0.375, e, 0.5), r);
+}
+
 // ----- KM x KM symmetric positive definite algebra on packed lower triangles ------------------------------
 // In place A -> unit-lower L (strict part) ; returns prod_j d_j and fills dinv[j] = 1/d_j.
 template <int KM>
@@ -104,6 +113,27 @@ __device__ __forceinline__ double ldl_factor(double (&A)[KM * (KM + 1) / 2], dou
     for (int i = j + 1; i < KM; ++i) A[DBN_TRI(i, j)] *= di;
   }
   return prod;
+}
+
+// Same factorisation with the pivots returned as rs[j] = 1 / sqrt(d_j) and dinv[j] = rs[j]^2 (one SFU seed per pivot
+// serves both): the Gibbs sweep needs sqrt(1 / d_j) to scale its normals (samplers.py:214-216).
+template <int KM>
+__device__ __forceinline__ void ldl_factor_rs(double (&A)[KM * (KM + 1) / 2], double (&dinv)[KM], double (&rs)[KM]) {
+#pragma unroll
+  for (int j = 0; j < KM; ++j) {
+    const double r = pivot_rsqrt(A[DBN_TRI(j, j)]);
+    const double di = r * r;
+    rs[j] = r;
+    dinv[j] = di;
+#pragma unroll
+    for (int i = j + 1; i < KM; ++i) {
+      const double l = A[DBN_TRI(i, j)] * di;
+#pragma unroll
+      for (int m = j + 1; m <= i; ++m) A[DBN_TRI(i, m)] -= l * A[DBN_TRI(m, j)];
+    }
+#pragma unroll
+    for (int i = j + 1; i < KM; ++i) A[DBN_TRI(i, j)] *= di;
+  }
 }
 
 // w <- L^-1 w (unit lower)
