@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   unsigned short* const s_tas = s_tau + SMAX * FAST_BLOCK;
   const int tid = threadIdx.x;
   __shared__ unsigned long long s_tot[8];  // work counters of the block
-  __shared__ unsigned int s_done;          // threads of the block that have added theirs
+  __shared__ unsigned int s_done;          // warps of the block that have added theirs
   if (tid < 8) s_tot[tid] = 0ull;
   if (tid == 8) s_done = 0u;
   __syncthreads();  // kernel entry: every warp is converged here
@@ -393,13 +393,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // row 0 of the parent-set sweep: on its way while sigma^2, lambda^2 and the proposals are drawn
     if (S > 0) issue_row(0, 0);
     cp_async_commit();
+    // sigma^2 and lambda^2 draws (after the Gibbs sweep's sums; before anything that uses the new lambda^2)
+    auto draw_sigma_lambda = [&]() {
     {
       const double shape = a.a_sig + a.T_sigma_half;
       const double rate = a.b_sig + 0.5 * q_sum;
       sig2 = replay ? rd[DBN_RD_SIGMA2] : rate / gamma_draw_fast(gchain, unode, uit, 64u, key, shape);
-#ifdef DBN_DIAG_SPLIT2
-    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[10], 1ull);
-#endif
       if (TRACE && td) {
         td[DBN_TD_SIG_SHAPE] = shape;
         td[DBN_TD_SIG_RATE] = rate;
@@ -422,9 +421,6 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       const double shape = a.a_lam + 0.5 * (double)(HOMOG ? k : S * k);
       const double rate = a.b_lam + 0.5 * ss / sig2;
       lam = replay ? rd[DBN_RD_LAMBDA2] : rate / gamma_draw_fast(gchain, unode, uit, 256u, key, shape);
-#ifdef DBN_DIAG_SPLIT2
-    if (__activemask() != 0xffffffffu) atomicAdd(&a.counters[11], 1ull);
-#endif
       if (TRACE && td) {
         td[DBN_TD_LAM_SHAPE] = shape;
         td[DBN_TD_LAM_RATE] = rate;
@@ -435,6 +431,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         for (int i = 0; i < KMAX; ++i) td[DBN_TD_MU + i] = NAN;
       }
     }
+    };
+#ifndef DBN_LATE_DRAWS
+    draw_sigma_lambda();
+#endif
 
 #ifndef DBN_NO_MID_BAR
     warp_rejoin<1>(S);
@@ -668,6 +668,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       if (has_new && S > 0) request_cand(bnd(0));
       if (t_new) request_row(trow, b2);
       cp_async_commit();
+#ifdef DBN_LATE_DRAWS   // the scattered requests above are in flight while the two gamma variates are drawn
+      draw_sigma_lambda();
+#endif
 
       // ln det of the base blocks: the pivot products are accumulated as mantissa x 2^exponent (one log per sweep)
       double mB = 1.0, R1 = 1.0, R2 = 1.0, q1 = 0.0, q2 = 0.0;
@@ -794,6 +797,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
       }
     } else {
+#ifdef DBN_LATE_DRAWS
+      draw_sigma_lambda();
+#endif
       cp_async_wait<0>();  // row 0 was requested for a sweep that does not run
     }
     warp_rejoin<2>(S);
@@ -1018,21 +1024,31 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
     for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
   }
-  // ---- work counters: summed per block with shared-memory atomics; the thread that finishes LAST publishes the block's
-  // totals (one global atomic per counter and block).  No barrier here: the loop's barriers are a scheduling aid only,
-  // and a warp that ran them in two parts may be a phase behind the rest of its block (see block_barrier).
-  const unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
-                                   (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
+  // ---- work counters: summed per warp with shuffles (behind a WARPSYNC that the compiler cannot drop, see warp_rejoin),
+  // then per block with one shared-memory atomic per counter and warp; the warp that finishes LAST publishes the
+  // block's totals (one global atomic per counter and block).  No block barrier here: the loop's barriers are a
+  // scheduling aid only, and a warp that ran them in two parts may be a phase behind the rest of its block.
+  // (192 threads x 8 64-bit shared-memory atomics on 8 addresses were 5.8 % of the launch, profiles/r2_a.)
+  unsigned long long v[8] = {active ? (unsigned long long)a.n_iter : 0ull, wk.evals, wk.segs, wk.bytes, wk.flops,
+                             (unsigned long long)n_pacc, n_fact, (unsigned long long)n_tacc};
+  warp_rejoin<0>(S);
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (v[c]) atomicAdd(&s_tot[c], v[c]);
-  __threadfence_block();
-  if (atomicAdd(&s_done, 1u) + 1u == (unsigned)FAST_BLOCK) {
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], off);
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (v[c]) atomicAdd(&s_tot[c], v[c]);
     __threadfence_block();
+    if (atomicAdd(&s_done, 1u) + 1u == (unsigned)(FAST_BLOCK / 32)) {
+      __threadfence_block();
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const unsigned long long t = *(volatile unsigned long long*)&s_tot[c];
-      if (t) atomicAdd(&a.counters[c], t);
+      for (int c = 0; c < 8; ++c) {
+        const unsigned long long t = *(volatile unsigned long long*)&s_tot[c];
+        if (t) atomicAdd(&a.counters[c], t);
+      }
     }
   }
 }
