@@ -77,6 +77,7 @@ SYMBOLS = {
     'dbn_score_batch': (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
                                   _ip, _ip, _ip, _ip, _ip, _dp, _dp, _dp, _dp]),
     'dbn_chain_init': (C.c_int, [_P, C.POINTER(DbnRunParams)]),
+    'dbn_set_unit_range': (C.c_int, [_P, C.c_int64, C.c_int64]),
     'dbn_set_changepoints': (C.c_int, [_P, _ip, C.c_int32]),
     'dbn_run': (C.c_int, [_P, C.c_int32, _dp, _ip, _dp, _ip]),
     'dbn_run_fp': (C.c_int, [_P, C.c_int32, _dp, _ip, _dp, _ip]),

@@ -18,7 +18,8 @@ struct ChainArgs {
   Table tb;
   int method, fan_in, with_tau, num_samples, burn_in, thin;
   int C;        // local chains per node
-  int U;        // units = n * C
+  int U;        // units of this handle (a contiguous range of the n * C grid)
+  int unit0;    // grid index node * C + chain of local unit 0
   int it0;      // global index of the first iteration of this launch
   int n_iter;
   unsigned int chain_offset;
@@ -183,8 +184,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
   const bool active = u_raw < a.U;   // lanes past the end run zero iterations so warp-wide reductions stay full
   const int u = active ? u_raw : 0;
   const int n_it = active ? a.n_iter : 0;
-  const int node = u / a.C;
-  const int chain = u - node * a.C;
+  const int node = (a.unit0 + u) / a.C;
+  const int chain = (a.unit0 + u) - node * a.C;
   const int n = a.tb.n, N = a.tb.N, F = n - 1;
   auto TAU = [&](int j) -> int& { return s_tau[j * CHAIN_BLOCK + tid]; };
   auto TAS = [&](int j) -> int& { return s_tas[j * CHAIN_BLOCK + tid]; };

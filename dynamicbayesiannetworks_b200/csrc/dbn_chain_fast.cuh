@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   const int u_raw = blockIdx.x * FAST_BLOCK + tid;
   const bool active = u_raw < a.U;
   const int u = active ? u_raw : 0;
-  const int node = u / a.C;
-  const int chain = u - node * a.C;
+  const int node = (a.unit0 + u) / a.C;
+  const int chain = (a.unit0 + u) - node * a.C;
   const int n = a.tb.n, N = a.tb.N, F = n - 1;
   const long long U = a.U;
   auto TAU = [&](int j) -> unsigned short& { return s_tau[j * FAST_BLOCK + tid]; };
@@ -1062,7 +1062,7 @@ __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* count
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= a.U) return;
   const long long U = a.U;
-  const int node = u / a.C, n = a.tb.n, N = a.tb.N;
+  const int node = (a.unit0 + u) / a.C, n = a.tb.n, N = a.tb.N;
   const int nb = a.tb.zz_size + node * (n + 2);
   const int S = a.st_S[u];
   int cg[KM];

@@ -35,6 +35,7 @@ struct FpArgs {
   Table tb;
   int num_samples, burn_in, thin, with_tau;
   int C, U, it0, n_iter;
+  int unit0;       // grid index node * C + chain of local unit 0
   unsigned int chain_offset;
   unsigned long long seed;
   double T_sigma_half, a_sig, b_sig, a_lam, b_lam, log_p, log_1mp, c0, T_half_plus_a, two_b;
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
   auto tau_star = [&](int j) { return s_tas[j]; };
 
   for (int u = blockIdx.x; u < a.U; u += gridDim.x) {
-    const int node = u / a.C, chain = u - node * a.C;
+    const int node = (a.unit0 + u) / a.C, chain = (a.unit0 + u) - node * a.C;
     const uint32_t gchain = a.chain_offset + (unsigned)chain, unode = (unsigned)node;
     __syncthreads();
     int S = a.st_S[u];

@@ -201,7 +201,8 @@ struct dbn_handle {
   // chain
   bool have_chain = false;
   dbn_run_params rp;
-  int U = 0;
+  int U = 0;          // units of this handle
+  long long unit0 = 0, unit_count = -1;   // dbn_set_unit_range (count < 0: the whole n * n_chains grid)
   int it_done = 0;
   int *st_npi = nullptr, *st_pi = nullptr, *st_S = nullptr, *st_tau = nullptr;
   double *st_sig = nullptr, *st_lam = nullptr, *st_del = nullptr, *st_mu = nullptr;
@@ -588,8 +589,12 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (!is_fp_method(p->method) && (p->fan_in < 1 || p->fan_in > PMAX)) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: fan_in must be in 1..%d", PMAX);
   if (p->thin < 1 || p->burn_in < 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: bad burn_in/thin");
   if (p->num_samples < 2 || p->num_samples > h->N) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: num_samples must be in 2..N");
-  const long long U = (long long)h->n * h->cfg.n_chains;
-  if (U > 0x7fffffffll) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: too many units");
+  const long long grid_units = (long long)h->n * h->cfg.n_chains;
+  if (grid_units > 0x7fffffffll) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: too many units");
+  if (h->unit_count >= 0 && (h->unit0 < 0 || h->unit0 + h->unit_count > grid_units || h->unit_count < 1))
+    DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: unit range [%lld, %lld) outside the %lld units of the grid", h->unit0, h->unit0 + h->unit_count, grid_units);
+  const long long U = h->unit_count >= 0 ? h->unit_count : grid_units;
+  if (h->unit_count < 0) h->unit0 = 0;
   CU(h, cudaSetDevice(h->cfg.device));
   free_chain(h);
   h->rp = *p;
@@ -639,6 +644,19 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   return DBN_OK;
 }
 
+int dbn_set_unit_range(dbn_handle* h, int64_t first_unit, int64_t n_units) {
+  if (!h) return DBN_ERR_INVALID;
+  if (first_unit < 0 || n_units == 0) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_set_unit_range: first_unit >= 0 and n_units != 0 (negative: the whole grid)");
+  h->unit0 = n_units < 0 ? 0 : first_unit;
+  h->unit_count = n_units < 0 ? -1 : n_units;
+  if (h->have_chain) {   // the range takes effect with the next dbn_chain_init
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    free_chain(h);
+  }
+  return DBN_OK;
+}
+
 int dbn_set_changepoints(dbn_handle* h, const int32_t* tau, int32_t len) {
   if (!h || !tau) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_set_changepoints: call dbn_chain_init first");
@@ -681,6 +699,7 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   a.thin = p.thin;
   a.C = h->cfg.n_chains;
   a.U = h->U;
+  a.unit0 = (int)h->unit0;
   a.it0 = h->it_done;
   a.n_iter = n_iter;
   a.chain_offset = (unsigned)h->cfg.chain_offset;
@@ -769,7 +788,7 @@ int dbn_run_fp(dbn_handle* h, int32_t n_iter, const double* replay_d, const int3
   memset(&a, 0, sizeof(a));
   a.tb = make_table(h);
   a.num_samples = p.num_samples; a.burn_in = p.burn_in; a.thin = p.thin; a.with_tau = p.with_tau;
-  a.C = h->cfg.n_chains; a.U = h->U; a.it0 = h->it_done; a.n_iter = n_iter;
+  a.C = h->cfg.n_chains; a.U = h->U; a.unit0 = (int)h->unit0; a.it0 = h->it_done; a.n_iter = n_iter;
   a.chain_offset = (unsigned)h->cfg.chain_offset;
   a.seed = h->cfg.seed;
   a.T_sigma_half = p.T_sigma / 2;
@@ -939,6 +958,7 @@ int dbn_verify_cache(dbn_handle* h, uint64_t out[2]) {
   a.tb = make_table(h);
   a.C = h->cfg.n_chains;
   a.U = h->U;
+  a.unit0 = (int)h->unit0;
   a.st_S = h->st_S; a.st_tau = h->st_tau; a.st_cg = h->st_cg; a.cache = h->d_cache;
   unsigned long long* d = nullptr;
   CU(h, cudaMalloc(&d, 2 * sizeof(unsigned long long)));

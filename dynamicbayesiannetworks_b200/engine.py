@@ -27,7 +27,10 @@ class DbnEngine:
     time-series segments `Network` receives, `chain_init(method)` + `run(n_iter)` advance every node and chain.
     """
 
-    def __init__(self, n_chains=1, device=0, seed=0xDB20B200, chain_offset=0):
+    def __init__(self, n_chains=1, device=0, seed=0xDB20B200, chain_offset=0, unit_range=None):
+        """`unit_range` = (first, count): this engine runs only that contiguous slice of the (node, chain) grid
+        u = node * n_chains + chain (dbn_set_unit_range); state / trace / replay arrays are then indexed by the local
+        unit.  None: the whole grid."""
         self._lib = L.load()
         self._h = C.c_void_p()
         cfg = L.DbnConfig(int(device), int(n_chains), int(chain_offset), int(seed))
@@ -38,6 +41,7 @@ class DbnEngine:
             raise DbnError('dbn_create failed (%d): %s' % (rc, (msg or b'').decode()))
         self.n_chains = int(n_chains)
         self.device = int(device)
+        self.unit_range = None if unit_range is None else (int(unit_range[0]), int(unit_range[1]))
         self.n = self.N = None
         self.params = None
 
@@ -137,8 +141,10 @@ class DbnEngine:
         p = run_params(method, self.N, **kw)
         self.params = p
         rp = L.DbnRunParams(**p)
+        if self.unit_range is not None:
+            self._check(self._lib.dbn_set_unit_range(self._h, self.unit_range[0], self.unit_range[1]), 'dbn_set_unit_range')
         self._check(self._lib.dbn_chain_init(self._h, C.byref(rp)), 'dbn_chain_init')
-        self.units = self.n * self.n_chains
+        self.units = self.n * self.n_chains if self.unit_range is None else self.unit_range[1]
         return self
 
     def set_changepoints(self, tau):

@@ -1,4 +1,5 @@
-"""Multi-GPU plumbing: one process per GPU, (node, chain) units sharded by chain, one all-reduce of the count
+"""Multi-GPU plumbing: one process per GPU, the flat (node, chain) unit list split over the ranks (`shard_units`; the
+weak-scaling bench keeps every node on every rank and splits the chains, `shard_chains`), one all-reduce of the count
 matrices per thinning window.
 
 Nodes are independent regressions (network.py:413-416) and chains are independent by construction, so the sampling
@@ -16,6 +17,35 @@ def shard_chains(total_chains, rank, world_size):
     n_local = base + (1 if rank < rem else 0)
     offset = rank * base + min(rank, rem)
     return offset, n_local
+
+
+def shard_units(total_units, rank, world_size):
+    """Contiguous split of the flat unit list u = node * n_chains + chain: returns (first_unit, n_local).
+    Works for any number of chains, one included (the reference's own use: network.py:413-416 loops over the nodes of a
+    single chain), and splits e.g. 500 nodes x 9 chains into 563 / 562 units per rank on 8 ranks.  Philox counters are
+    keyed by the grid's (chain, node), so the union of the shards is identical to an unsharded run."""
+    base, rem = divmod(int(total_units), int(world_size))
+    n_local = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n_local
+
+
+def default_device():
+    """CUDA device of this process when the caller names none: under torch.distributed (one process per GPU) the
+    process's LOCAL_RANK / current torch device, so that the ranks of a sharded run do not all land on cuda:0; else 0."""
+    import os
+    rank, world = dist_rank_world()
+    if world > 1:
+        if 'LOCAL_RANK' in os.environ:
+            return int(os.environ['LOCAL_RANK'])
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return int(torch.cuda.current_device())
+        except ImportError:
+            pass
+        return rank
+    return 0
 
 
 class _DevicePtr:

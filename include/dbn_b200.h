@@ -142,6 +142,17 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
  * and zeroed count matrices.  Unit index u = node * n_chains + chain.
  */
 int dbn_chain_init(dbn_handle* h, const dbn_run_params* p);
+/*
+ * Restrict the handle to the contiguous range [first_unit, first_unit + n_units) of the (node, chain) grid
+ * u = node * n_chains + chain (n_units < 0: the whole grid again).  This is SURVEY.md 8e's partitioning: the reference
+ * loops over the nodes (network.py:413-416) and every (node, chain) unit is independent, so a rank takes a slice of the
+ * flat unit list, whatever the number of chains; `Network.fit(i)` of one node is the slice [i * n_chains, (i + 1) *
+ * n_chains).  Philox counters use the grid's (chain, node), so the union of the slices is bit-identical to one handle
+ * running the whole grid.  State, trace and replay arrays are indexed by the LOCAL unit (0 .. n_units - 1); the count
+ * matrices keep their full [n, ...] shape (rows of nodes outside the slice stay zero) so that they can be summed over
+ * ranks.  Takes effect with the next dbn_chain_init (an existing chain is dropped).
+ */
+int dbn_set_unit_range(dbn_handle* h, int64_t first_unit, int64_t n_units);
 
 /* replay record per (unit, iteration): the reference's recorded draws */
 #define DBN_RD_SIGMA2 0

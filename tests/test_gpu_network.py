@@ -1,0 +1,122 @@
+"""GPU tests of the drop-in surface added in round 2: `Network.fit` / `Network.score_edges` (network.py:143,283), the
+flat (node, chain) unit range behind them (`dbn_set_unit_range`), `padded_betas` / `betas_over_time` /
+`scores_over_time` of a device-run chain, bounded trace windows."""
+import numpy as np
+import pytest
+
+from helpers import CHAIN_FILES, load, data_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _series(name):
+    return data_list(load([p for p in CHAIN_FILES if ('%s_varying' % name) in p][0]))
+
+
+@pytest.mark.parametrize('method', ['varying_nh_dbn', 'seq_coup_nh_dbn', 'fp_glob_coup_nh_dbn', 'fp_varying_nh_dbn'])
+def test_unit_ranges_reproduce_the_full_grid(method):
+    """Three engines on the slices [0, 7), [7, 8), [8, U) of the unit grid: their states are the matching slices of the
+    full grid's state and their counts add up to the full grid's counts, bit for bit."""
+    from dynamicbayesiannetworks_b200.engine import DbnEngine
+    data = _series('yeast')
+    C, n_iter = 3, 60
+    fp = method.startswith('fp_')
+
+    def run(rng):
+        with DbnEngine(n_chains=C, seed=9, unit_range=rng) as e:
+            e.build_stats(data)
+            e.chain_init(method, burn_in=10)
+            (e.run_fp if fp else e.run)(n_iter)
+            return e.state(), e.counts()
+    full_st, full_c = run(None)
+    U = 5 * C
+    acc = None
+    for first, count in ((0, 7), (7, 1), (8, U - 8)):
+        st, c = run((first, count))
+        for key in ('S', 'sigma2', 'lambda2') + (() if fp else ('npi',)):
+            assert np.array_equal(st[key], full_st[key][first:first + count]), (method, key, first)
+        for u in range(count):      # entries past the list lengths are not part of the state
+            assert np.array_equal(st['tau'][u, :st['S'][u]], full_st['tau'][first + u, :st['S'][u]]), (method, 'tau', first + u)
+            if not fp:
+                assert np.array_equal(st['pi'][u, :st['npi'][u]], full_st['pi'][first + u, :st['npi'][u]]), (method, 'pi', first + u)
+        acc = c if acc is None else {k: acc[k] + c[k] for k in c}
+    for k in full_c:
+        assert np.array_equal(acc[k], full_c[k]), (method, k)
+
+
+@pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_glob_coup_nh_dbn'])
+def test_fit_score_edges_sequence_equals_infer_network(method):
+    """The reference's own calling sequence (network.py:413-416) node by node gives what infer_network gives for all
+    nodes at once: adjacency rows, changepoint chains, histories (same Philox streams, keyed by (chain, node))."""
+    from dynamicbayesiannetworks_b200 import Network
+    data = _series('yeast')
+    n = data[0].shape[1]
+    a = Network(data, 220, 60, 1)
+    a.infer_network(method)
+    b = Network(data, 220, 60, 1)
+    for i in range(n):
+        b.set_network_configuration(i)
+        b.fit(method)
+        b.score_edges(i, method)
+        for key in a.chain_results_per_node[i]:
+            x, y = a.chain_results_per_node[i][key], b.chain_results[key]
+            assert len(x) == len(y), (method, i, key)
+    assert np.array_equal(np.array(a.proposed_adj_matrix), np.array(b.proposed_adj_matrix))
+    assert a.cps_over_response == b.cps_over_response
+    assert a.network_args['scoring_method'] == b.network_args['scoring_method']
+    if method != 'fp_h_dbn':
+        assert len(a.betas_over_time) == n and len(b.betas_over_time) == n
+        for i in range(n):
+            assert np.array_equal(np.stack(a.betas_over_time[i]), np.stack(b.betas_over_time[i]))
+    with pytest.raises(RuntimeError):
+        Network(data, 10, 0, 1).fit(method)                       # no configuration set
+
+
+def test_chain_results_keys_and_diagnostics_shapes():
+    from dynamicbayesiannetworks_b200 import Network
+    data = _series('yeast')
+    n, N = 5, 33
+    net = Network(data, 300, 100, 1)
+    net.infer_network('varying_nh_dbn')
+    r = net.chain_results
+    assert len(r['padded_betas']) == 301 and r['padded_betas'][0][0].shape == (n,)
+    for it in range(1, 301):       # one padded vector per segment of the draw; zeros exactly where the gene is no parent
+        pi = set(int(p) for p in r['pi_vector'][it - 1])
+        assert len(r['padded_betas'][it]) == len(r['betas_vector'][it])
+        for v in r['padded_betas'][it]:
+            assert v.shape == (n,) and all(v[d] == 0 for d in range(1, n) if d not in pi)
+    assert len(net.betas_over_time) == n and len(net.betas_over_time[0]) == N and net.betas_over_time[0][0].shape == (20, n)
+    assert net.scores_over_time == []                   # varying-parents methods have none (network.py:370-396)
+    fp = Network(data, 300, 100, 1)
+    fp.infer_network('fp_varying_nh_dbn')
+    assert len(fp.scores_over_time) == n and fp.scores_over_time[0].shape == (N, n - 1)
+    assert (np.abs(fp.scores_over_time[0]) <= 0.5).all()
+    h = Network(data, 300, 100, 1)
+    h.infer_network('h_dbn')
+    assert all(c == [N + 2] for c in h.cps_over_response[0]) and len(h.cps_over_response) == n     # network.py:376-383
+
+
+def test_kept_history_is_traced_in_bounded_windows():
+    """keep_chain runs are traced window by window (one launch for the whole chain allocated
+    units x iterations x 3 KB on the device): a small window gives the same histories as one launch."""
+    from dynamicbayesiannetworks_b200 import Network, network as NW
+    data = _series('yeast')
+    a = Network(data, 130, 20, 1, window=130)
+    a.infer_network('seq_coup_nh_dbn')
+    b = Network(data, 130, 20, 1, window=17)
+    b.infer_network('seq_coup_nh_dbn')
+    assert np.array_equal(np.array(a.proposed_adj_matrix), np.array(b.proposed_adj_matrix))
+    assert a.chain_results['tau_vector'] == b.chain_results['tau_vector']
+    assert a.chain_results['sigma_sqr_vector'] == b.chain_results['sigma_sqr_vector']
+    saved = NW.TRACE_WINDOW_BYTES
+    try:
+        NW.TRACE_WINDOW_BYTES = 64 << 10           # forces several windows through the default planner
+        c = Network(data, 130, 20, 1)
+        keep, window = c._plan(2, 5, 5, 130, 1)
+        assert keep and 1 <= window < 130
+        c.infer_network('seq_coup_nh_dbn')
+        assert c.chain_results['tau_vector'] == a.chain_results['tau_vector']
+    finally:
+        NW.TRACE_WINDOW_BYTES = saved
+    with pytest.raises(MemoryError):                # a history that cannot fit is refused before anything is allocated
+        Network(data, 10 ** 9, 0, 1, keep_chain=True)._plan(1, 5, 5, 10 ** 9, 1)

@@ -261,7 +261,8 @@ def test_network_dropin(eng_mod):
         pickle.loads(pickle.dumps(net))
     fixed = Network(data, 300, 100, 1, [12, 23, 35])          # network.py:178-189: predefined change points
     fixed.infer_network('fixed_nh_dbn')
-    assert all(t == [12, 23, 35] for t in fixed.chain_results['tau_vector'])
+    assert fixed.chain_results['tau_vector'] == []      # only the 'varying_nh' regressor records tau (bayesianPwLinearRegression.py:117-121)
+    assert all(c == [35] for c in fixed.cps_over_response[0])   # network.py:376-383: the artificial [N + 2] list
     assert np.isfinite(np.array(fixed.proposed_adj_matrix)).all()
     assert fixed.network_args['type'] == 'Varying Parents-Fixed changepoints'
     with pytest.raises(RuntimeError):                          # the list must end with the pseudo changepoint N + 2
@@ -601,4 +602,4 @@ def test_network_sharded_over_two_gpus_matches_unsharded():
            '--master-port', '29571', os.path.join(ROOT, 'scripts', 'dist_network_check.py')]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
-    assert res.stdout.count('sharded == unsharded: True') == 16, res.stdout[-3000:]   # 8 methods x 2 ranks
+    assert res.stdout.count('sharded == unsharded: True') == 22, res.stdout[-3000:]   # 11 cases x 2 ranks

@@ -1,11 +1,12 @@
 """CPU tests of the host-side logic: method table vs the oracle's, chain sharding, count reduction (gloo, 2 ranks)."""
+import glob
 import os
 import sys
 
 import numpy as np
 import pytest
 
-from helpers import ROOT, CHAIN_FILES, load, data_list
+from helpers import ROOT, GOLDEN, CHAIN_FILES, load, data_list
 from oracle import dbn_oracle as O
 
 
@@ -62,7 +63,7 @@ def test_network_api_surface():
     pickle.loads(pickle.dumps(net))
 
 
-def _gloo_worker(rank, world, port, tmp):
+def _gloo_worker(rank, world, port, tmp, mode='chains', total_chains=4):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -75,13 +76,17 @@ def _gloo_worker(rank, world, port, tmp):
     g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
     X, Y = O.lagged_matrices(data_list(g))
     N, n = X.shape
-    total_chains, n_iter, burn = 4, 60, 10
-    off, cnt = parallel.shard_chains(total_chains, rank, world)
+    n_iter, burn = 60, 10
+    if mode == 'chains':     # every node on every rank, the chains split (the weak-scaling bench)
+        off, cnt = parallel.shard_chains(total_chains, rank, world)
+        mine = [(node, c) for node in range(n) for c in range(off, off + cnt)]
+    else:                    # the flat unit list u = node * C + chain split over the ranks
+        first, cnt = parallel.shard_units(n * total_chains, rank, world)
+        mine = [(u // total_chains, u % total_chains) for u in range(first, first + cnt)]
     edge = np.zeros((n, n)); ne = np.zeros(n); cph = np.zeros((n, N + 3)); cpk = np.zeros(n)
-    for node in range(n):
-        for c in range(off, off + cnt):      # chain streams are keyed by the GLOBAL chain id
-            tr = O.run_chain('varying_nh_dbn', X, Y, node, n_iter, O.RngDraws(np.random.default_rng(1000 * node + c)))
-            O.accumulate_counts(tr, node, n, N, burn, edge, ne, cph, cpk)
+    for node, c in mine:     # streams are keyed by the grid's (node, chain)
+        tr = O.run_chain('varying_nh_dbn', X, Y, node, n_iter, O.RngDraws(np.random.default_rng(1000 * node + c)))
+        O.accumulate_counts(tr, node, n, N, burn, edge, ne, cph, cpk)
     flat = np.concatenate([edge.ravel(), ne, cph.ravel(), cpk]).astype(np.int64)
     local = torch.from_numpy(flat.copy())
     out = parallel.allreduce_counts(local)
@@ -90,14 +95,15 @@ def _gloo_worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-def test_count_allreduce_two_ranks_gloo(tmp_path):
-    """world_size-2 gloo run of the N>1 host path: shard chains, accumulate per-rank counts, all-reduce; the result
-    must equal the single-process accumulation over all chains."""
+@pytest.mark.parametrize('mode,total_chains', [('chains', 4), ('units', 1), ('units', 3)])
+def test_count_allreduce_two_ranks_gloo(tmp_path, mode, total_chains):
+    """world_size-2 gloo run of the N>1 host path: shard chains (or the flat unit list, one chain included), accumulate
+    per-rank counts, all-reduce; the result must equal the single-process accumulation over all units."""
     import torch.multiprocessing as mp
     from dynamicbayesiannetworks_b200.engine import split_counts
     from dynamicbayesiannetworks_b200 import parallel
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 2000) + (0 if mode == 'chains' else 7 * total_chains)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path), mode, total_chains), nprocs=2, join=True)
     s0 = np.load(tmp_path / 'sum_0.npy'); s1 = np.load(tmp_path / 'sum_1.npy')
     assert np.array_equal(s0, s1)
     g = load([p for p in CHAIN_FILES if 'yeast_varying' in p][0])
@@ -105,7 +111,7 @@ def test_count_allreduce_two_ranks_gloo(tmp_path):
     N, n = X.shape
     edge = np.zeros((n, n)); ne = np.zeros(n); cph = np.zeros((n, N + 3)); cpk = np.zeros(n)
     for node in range(n):
-        for c in range(4):
+        for c in range(total_chains):
             tr = O.run_chain('varying_nh_dbn', X, Y, node, 60, O.RngDraws(np.random.default_rng(1000 * node + c)))
             O.accumulate_counts(tr, node, n, N, 10, edge, ne, cph, cpk)
     got = split_counts(s0, n, N)
@@ -126,3 +132,86 @@ def test_overlapped_allreduce_group_is_limited_to_a_few_ctas():
     opts = parallel.nccl_small_footprint_options()
     assert opts.config.max_ctas == 2 and opts.config.min_ctas == 1
     assert parallel.nccl_small_footprint_options(1).config.max_ctas == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Network.score_edges' host-side derivations against the reference's own outputs (tests/golden/network_*.npz,
+# generated by tests/golden/make_network_golden.py from the unmodified reference): padded_betas, cps_over_response,
+# betas_over_time, scores_over_time (network.py:316-338, :370-396; scores.py:106-137;
+# bayesianLinearRegression.py:40-67)
+# ---------------------------------------------------------------------------------------------------------
+NETWORK_FILES = sorted(p for p in glob.glob(os.path.join(GOLDEN, 'network_*.npz')) if 'lag2' not in p)
+
+
+@pytest.mark.parametrize('path', NETWORK_FILES, ids=[os.path.basename(p)[8:-4] for p in NETWORK_FILES])
+def test_network_diagnostics_vs_reference(path):
+    from dynamicbayesiannetworks_b200 import Network, scores as S
+    from dynamicbayesiannetworks_b200.methods import method_id, FP_METHODS
+    g = dict(np.load(path, allow_pickle=False))
+    method = str(g['method'])
+    mid = method_id(method)
+    data = [g['data_seg%d' % s] for s in range(int(g['n_data_segments']))]
+    n, n_iter, burn = data[0].shape[1], int(g['n_iter']), int(g['burn_in'])
+    N = sum(d.shape[0] - 1 for d in data)
+    fp = mid in FP_METHODS
+    net = Network(data, n_iter, burn, 1, diagnostics=True)
+    for node in range(n):
+        pi_vec = [g['pi'][node, it, :g['npi'][node, it]] for it in range(n_iter + 1)]
+        has_tau = (g['tau'][node, 0] >= 0).any()
+        tau_vec = [[int(c) for c in g['tau'][node, it] if c >= 0] for it in range(n_iter)] if has_tau else []
+        width = n if fp else None
+        betas = []
+        for it in range(n_iter + 1):
+            S_ = int(g['nseg'][node, it])
+            betas.append([g['betas'][node, it, h][np.isfinite(g['betas'][node, it, h])] for h in range(S_)])
+        res = {'pi_vector': pi_vec, 'tau_vector': tau_vec, 'betas_vector': betas}
+        if not fp:
+            if not g['nseg'][node].any():
+                # the h-dbn and glob regressors return no 'betas_vector': their padded_betas ARE the only record of the
+                # draws, so only the downstream functions are checked for them
+                padded = [[v for v in g['padded_betas'][node, it] if np.isfinite(v).all()] for it in range(n_iter + 1)]
+            else:
+                # transform_beta_coef on the draw of iteration it - 1, conditioned on the parent set before it
+                padded = [[np.zeros(n)]] + [S.transform_beta_coef(betas[it], pi_vec[it - 1], n - 1) for it in range(1, n_iter + 1)]
+                for it in range(n_iter + 1):
+                    for h, v in enumerate(padded[it]):
+                        assert np.array_equal(v, g['padded_betas'][node, it, h]), (node, it, h)
+            res['padded_betas'] = padded
+        net._diagnostics(mid, method, node, N, res)
+        ref_cps = [[int(c) for c in row if c >= 0] for row in g['cps_over_response'][node]]
+        assert net.cps_over_response[node] == ref_cps, node
+        if 'betas_over_time' in g:
+            got = np.stack(net.betas_over_time[node])
+            assert got.shape == g['betas_over_time'][node].shape
+            assert np.array_equal(got, g['betas_over_time'][node]), node
+        if 'scores_over_time' in g:
+            assert np.array_equal(net.scores_over_time[node], g['scores_over_time'][node]), node
+
+
+def test_lag2_network_configuration_vs_reference():
+    """set_network_configuration with lag = 2 (network.py:92-122): labels, zero-padded lagged columns, response."""
+    from dynamicbayesiannetworks_b200 import Network
+    g = dict(np.load(os.path.join(GOLDEN, 'network_yeast_lag2_config.npz'), allow_pickle=False))
+    data = [g['data_seg%d' % s] for s in range(int(g['n_data_segments']))]
+    n = data[0].shape[1]
+    net = Network(data, 10, 0, 2)
+    for i in range(n):
+        net.set_network_configuration(i)
+        cfg = net.network_configuration
+        labels = [int(l[1:]) for l in cfg['features']]
+        assert labels == g['labels_%d' % i].tolist(), i
+        assert np.array_equal(np.stack([cfg['features']['X%d' % l] for l in labels], axis=1), g['features_%d' % i]), i
+        assert np.array_equal(cfg['response']['y'], g['response_%d' % i]), i
+        assert net.network_args['network_configs'][i]['response'] == 'X%d' % i
+
+
+def test_shard_units_covers_the_grid():
+    from dynamicbayesiannetworks_b200 import parallel
+    for total, world in ((4500, 8), (11 * 256, 4), (5, 8), (100, 1), (7, 7)):
+        got = [parallel.shard_units(total, r, world) for r in range(world)]
+        assert sum(c for _, c in got) == total
+        pos = 0
+        for first, count in got:
+            assert first == pos
+            pos += count
+        assert max(c for _, c in got) - min(c for _, c in got) <= 1
