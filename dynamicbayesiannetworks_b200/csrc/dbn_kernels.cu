@@ -55,10 +55,16 @@ __global__ void __launch_bounds__(256) chunk_scan_kernel(double* __restrict__ ch
   const long long p = blockIdx.x * 256ll + threadIdx.x;
   if (p >= R) return;
   double acc = 0.0;
-  for (int c = 0; c < n_chunks; ++c) {
-    const double v = chunk[(long long)c * R + p];
-    chunk[(long long)c * R + p] = acc;
-    acc += v;
+  // 16 loads in flight per thread: a load-add-store chain per chunk is one L2 round trip per chunk (19 us for 63 chunks)
+  for (int c0 = 0; c0 < n_chunks; c0 += 16) {
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < n_chunks) ? __ldcg(chunk + (long long)(c0 + j) * R + p) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (c0 + j < n_chunks) chunk[(long long)(c0 + j) * R + p] = acc;
+      acc += v[j];
+    }
   }
 }
 
@@ -195,6 +201,7 @@ struct dbn_handle {
   unsigned short *d_colA = nullptr, *d_colB = nullptr;
   double* d_chunk = nullptr;
   double* d_table = nullptr;
+
   bool have_stats = false;
   void* pinned = nullptr;  // host bounce buffer of dbn_read_counts
   size_t pinned_bytes = 0;
@@ -364,7 +371,18 @@ void dbn_destroy(dbn_handle* h) {
 
 int dbn_set_stream(dbn_handle* h, void* cuda_stream) {
   if (!h) return DBN_ERR_INVALID;
-  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  if (next == h->stream) return DBN_OK;
+  // work already queued on the previous stream (prefix kernels, the memsets and init kernel of dbn_chain_init, earlier
+  // dbn_run windows) must be ordered before whatever the next calls launch on the new one
+  CU(h, cudaSetDevice(h->cfg.device));
+  cudaEvent_t ev;
+  CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, h->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(next, ev, 0);
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_CUDA, "dbn_set_stream: %s", cudaGetErrorString(e));
+  h->stream = next;
   return DBN_OK;
 }
 
@@ -383,7 +401,9 @@ static int launch_prefix(dbn_handle* h) {
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
   prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   CU(h, cudaGetLastError());
-  if (h->n_chunks > PREFIX_SCAN_CHUNKS) {
+  int scan_from = PREFIX_SCAN_CHUNKS;
+  if (const char* e = getenv("DBN_PREFIX_SCAN_FROM")) scan_from = atoi(e);  // tuning knob
+  if (h->n_chunks > scan_from) {
     chunk_scan_kernel<<<(unsigned)((h->R + 255) / 256), 256, 0, h->stream>>>(h->d_chunk, h->R, h->n_chunks);
     CU(h, cudaGetLastError());
     prefix_kernel<true, true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
@@ -470,11 +490,23 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
   }
   // same geometry: the table is rebuilt in place and the chain state (if any) carries on over the new data
   CU(h, cudaMemcpyAsync(h->d_raw, data, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  bool must_sync = false;
   if (!same_geometry || h->seg_len != std::vector<int>(seg_len, seg_len + n_seg)) {
     CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     h->seg_len.assign(seg_len, seg_len + n_seg);
+    must_sync = true;                        // the staging vector goes out of scope
   }
-  CU(h, cudaStreamSynchronize(h->stream));  // the caller's buffer and the staging vector are free again
+  {
+    // a pageable caller buffer has been staged by the time cudaMemcpyAsync returns; a PINNED one is read by the copy
+    // engine later, and the caller keeps it unchanged until the next synchronising call (dbn_sync, dbn_read_*): no host
+    // synchronisation on this path then (include/dbn_b200.h)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, data) != cudaSuccess) {
+      cudaGetLastError();
+      must_sync = true;
+    }
+  }
+  if (must_sync) CU(h, cudaStreamSynchronize(h->stream));
   int rc = launch_prefix(h);                 // asynchronous: overlaps whatever the host does next
   if (rc != DBN_OK) return rc;
   h->have_stats = true;

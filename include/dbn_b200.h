@@ -97,7 +97,9 @@ int dbn_create(const dbn_config* cfg, dbn_handle** out);
 void dbn_destroy(dbn_handle* h);
 /* message of the last failure on this handle (or of the last failed dbn_create when h == NULL) */
 const char* dbn_last_error(const dbn_handle* h);
-/* launch on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own */
+/* launch on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own.
+ * Ordering contract: everything the handle queued on its previous stream is ordered before the work later calls
+ * queue on the new one (an event recorded on the old stream is waited for on the new stream). */
 int dbn_set_stream(dbn_handle* h, void* cuda_stream);
 int dbn_sync(dbn_handle* h);
 
@@ -110,6 +112,9 @@ int dbn_sync(dbn_handle* h);
  * (N = sum(seg_len - 1) regression rows, z_r = [1, x_r], y_r = x_{r+1}):
  *    ZZ[t] = sum_{r<t} z_r z_r^T (packed lower triangle), ZY[t][i] = sum_{r<t} z_r y_{r,i}, YY[t][i] = sum y_{r,i}^2
  * so any segment's Gram statistics are one difference of two rows.
+ * The call returns once `data` has been handed to the copy engine: a pageable buffer is free again on return; a
+ * PINNED (page-locked) buffer is read asynchronously and must stay unchanged until the next synchronising call on the
+ * handle (dbn_sync, dbn_read_*), in exchange for no host synchronisation on this path.
  */
 int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, int32_t n_seg, int32_t n, int32_t lag);
 /* re-run the prefix kernels on the data already resident on the device (timing / roofline of kernel 1) */
