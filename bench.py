@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_GENES, T_SERIES, CHAINS_PER_GPU, FAN_IN, WINDOW = 100, 2000, 1024, 4, 10
+BURN_IN_ITERATIONS = 200      # the timed region starts after 200 iterations, whatever --warmup says
 DATA_SEED = 20260119
 METHOD = 'varying_nh_dbn'
 METRIC = 'mcmc_node_chain_iterations_per_sec'
@@ -158,6 +159,114 @@ def cpu_literal_rate(budget_s=6.0):
     return n_ev / (time.perf_counter() - t0)
 
 
+def _import_dyban_ref():
+    """The UNMODIFIED reference installed by `pip install --target baseline/_ref` (git-ignored, travels to the GPU box),
+    with the two import shims of SURVEY Appendix E (matplotlib stub, np.asscalar).  None when it is not there."""
+    import tempfile
+    import types
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'dyban')):
+        return None
+    for m in ('matplotlib', 'matplotlib.pyplot'):
+        if m not in sys.modules:
+            sys.modules[m] = types.ModuleType(m)
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    if not hasattr(np, 'asscalar'):
+        np.asscalar = lambda a: np.asarray(a).item()
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    os.environ.setdefault('TQDM_DISABLE', '1')
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix='dyban_ref_'))     # dyban/scores.py opens ./output.log at import time
+    try:
+        import dyban
+        import dyban.network  # noqa: F401
+    except Exception:
+        return None
+    finally:
+        os.chdir(cwd)
+    return dyban
+
+
+def _literal_worker(task):
+    """One node of a literal-reference run: (kind, node, n_iter) -> (unit-iterations, log-ML evaluations, seconds)."""
+    import contextlib
+    import io
+    import random
+    kind, node, n_iter = task
+    dyban = _import_dyban_ref()
+    import dyban.moves as mv
+    import dyban.marginalLikelihood as ml
+    calls = [0]
+    for name in ('calculateMarginalLikelihoodWithChangepoints', 'calculateMarginalLikelihood'):
+        orig = getattr(mv, name)
+        def counted(*a, _o=orig, **k):
+            calls[0] += 1
+            return _o(*a, **k)
+        setattr(mv, name, counted)
+    if kind == 'c4':
+        # BASELINE.md line B: the literal T_h x T_h code cannot evaluate T >= 344 (gamma overflows, pi ** (-T / 2)
+        # underflows, marginalLikelihood.py:116-118); guard exactly those scalars, keep all of its O(T_h^3) NumPy work
+        import math as _m
+
+        class _Math:
+            pi = _m.pi
+
+            @staticmethod
+            def log(x):
+                x = float(x)
+                return _m.log(x) if 0.0 < x < float('inf') else 0.0
+
+            @staticmethod
+            def exp(x):
+                x = float(x)
+                return _m.exp(min(x, 700.0)) if x == x else 1.0
+
+            def __getattr__(self, name):
+                return getattr(_m, name)
+        ml.math = _Math()
+        ml.gamma = lambda x: 1.0
+        mv.math = _Math()
+        from dynamicbayesiannetworks_b200.synth import make_synthetic
+        data = [make_synthetic(N_GENES, T_SERIES, 3, 4, DATA_SEED)[0]]
+        method = 'varying_nh_dbn'
+    else:
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'chain_%s_varying_nh_dbn.npz' % ('yeast' if kind == 'c2' else 'mtor')))
+        data = [g['data_seg%d' % s_] for s_ in range(int(g['n_data_segments']))]
+        method = 'varying_nh_dbn' if kind == 'c2' else 'seq_coup_nh_dbn'
+    np.random.seed(100 + node); random.seed(100 + node)
+    net = dyban.Network(data, n_iter, 0, 1)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+        net.set_network_configuration(node)
+        net.fit(method)
+    return n_iter, calls[0], time.perf_counter() - t0
+
+
+def literal_reference_rates():
+    """BASELINE.md lines A and B: dyban's OWN code (baseline/_ref) timed on the host cores.  A: unmodified, on the shipped
+    yeast (c2, nh-dbn) and mTOR (c3, seq-dbn) series, one node per process.  B: the c4 series with the overflow guards.
+    Returns a dict for the JSON line, or {'unavailable': why}."""
+    import multiprocessing as mp
+    if _import_dyban_ref() is None:
+        return {'unavailable': 'baseline/_ref/dyban is not installed (pip install --target baseline/_ref /root/reference)'}
+    cores = os.cpu_count() or 1
+    for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[v] = '1'
+    out = {'cores': cores, 'what': "dyban's own regressors (unmodified install under baseline/_ref), one node per process"}
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        for kind, n_nodes, n_iter in (('c2', 5, 400), ('c3', 11, 60), ('c4', min(cores, 8), 3)):
+            t0 = time.perf_counter()
+            res = pool.map(_literal_worker, [(kind, node, n_iter) for node in range(n_nodes)])
+            wall = time.perf_counter() - t0
+            out[kind] = {'unit_iterations_per_sec': sum(r[0] for r in res) / wall, 'ml_evals_per_sec': sum(r[1] for r in res) / wall,
+                         'units': n_nodes, 'iterations': n_iter, 'wall_s': wall,
+                         'series': {'c2': 'yeast nh-dbn (N = 33)', 'c3': 'mTOR seq-dbn (N = 119)',
+                                    'c4': 'synthetic nh-dbn (N = 1999), gamma / pi ** (-T / 2) guarded'}[kind]}
+    return out
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -171,8 +280,50 @@ def run_reference_arm(args, rank, world):
             'dtype': 'f64', 'data': 'synthetic', 'config': workload(), 'ml_evals_per_sec': ev_s,
             'cpu_baseline': {'value': it_s, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': it_s, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'gpu_launches': 0,
+            'note': ("value = the Gram-form NumPy port of the path (oracle/dbn_oracle.py), which is ~1000x faster than dyban's own "
+                     "T_h x T_h code on this workload; dyban's own code is timed in 'literal_reference' (BASELINE.md lines A, B)"),
+            'literal_reference': literal_reference_rates()}
     print(json.dumps(line))
+
+
+def c5_sample(device, fp64_peak):
+    """BASELINE configs[4] (500 genes, T = 10000, full-parents globally coupled, design width k = 500) on one GPU: a bounded
+    sample -- 500 units (one chain per node) started at the true changepoints, 1 untimed + 2 timed iterations -- of the one
+    contraction-shaped kernel of the path.  Roofline: FP64 (k^3/3 + 4k^2 flops per segment evaluation, counted on
+    the device), against the DFMA peak measured in this run."""
+    import torch
+    from dynamicbayesiannetworks_b200.engine import DbnEngine
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    n, T = 500, 10000
+    data, cps, _ = make_synthetic(n, T, n_changepoints=5, max_fan_in=4, seed=20260120)
+    eng = DbnEngine(n_chains=1, device=device, seed=11)
+    try:
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        eng.build_stats([data])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.rebuild_stats(); e1.record(); torch.cuda.synchronize()
+        prefix_ms = e0.elapsed_time(e1)
+        info = eng.stats_info()
+        eng.chain_init('fp_glob_coup_nh_dbn')
+        eng.set_changepoints([c + 1 for c in cps] + [eng.N + 2])
+        eng.run_fp(1)
+        torch.cuda.synchronize()
+        eng.reset_counters()
+        iters = 2
+        e0.record(); eng.run_fp(iters); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        c = eng.counters()
+    finally:
+        eng.close()
+    gf = c['algorithmic_flops'] / ms / 1e6
+    return {'workload': 'synthetic fp-glob-dbn: 500 genes, T=10000, 1 chain per node (BASELINE configs[4]), %d timed iterations' % iters,
+            'metric': METRIC, 'value': n * iters / ms * 1e3, 'unit': UNIT, 'ms_per_iteration': ms / iters,
+            'ml_evals_per_sec': c['ml_evals'] / ms * 1e3,
+            'roofline': {'kernel': 'fp_glob_kernel<glob, BIG>', 'bound': 'fp64', 'achieved': gf / 1e3, 'peak': fp64_peak / 1e3,
+                         'unit': 'TFLOP/s', 'frac': gf / fp64_peak, 'peak_source': 'DFMA microbenchmark in this run',
+                         'algorithmic_gbs': c['algorithmic_bytes'] / ms / 1e6},
+            'prefix_build': {'table_gb': info['algorithmic_bytes'] / 1e9, 'ms': prefix_ms, 'gbs': info['algorithmic_bytes'] / prefix_ms / 1e6}}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -183,6 +334,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (the contract): 1024 chains per GPU; strong: 1024 chains in total, the flat (node, chain) unit list split over the ranks')
+    ap.add_argument('--no-c5', action='store_true', help='skip the BASELINE configs[4] sample (extra.c5)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -209,11 +363,17 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                                 pg_options=parallel.nccl_small_footprint_options(NCCL_OVERLAP_CTAS))
         wide = dist.new_group(backend='nccl')
-    K, W = args.steps, max(3, args.warmup)
+    K = args.steps
+    W = max(3, args.warmup, (BURN_IN_ITERATIONS + WINDOW - 1) // WINDOW)   # >= 200 untimed iterations: a stationary timed region
 
     data, _, _ = make_synthetic(N_GENES, T_SERIES, 3, 4, DATA_SEED)
     data = torch.from_numpy(data).pin_memory().numpy()      # the host series lives in pinned memory (e2e copies from it)
-    eng = DbnEngine(n_chains=CHAINS_PER_GPU, device=local_rank, seed=0xDB20B200, chain_offset=rank * CHAINS_PER_GPU)
+    strong = args.scaling == 'strong' and world > 1
+    if strong:      # 1024 chains in total, rank r takes a contiguous slice of the 102 400 units
+        first, count = parallel.shard_units(N_GENES * CHAINS_PER_GPU, rank, world)
+        eng = DbnEngine(n_chains=CHAINS_PER_GPU, device=local_rank, seed=0xDB20B200, unit_range=(first, count))
+    else:
+        eng = DbnEngine(n_chains=CHAINS_PER_GPU, device=local_rank, seed=0xDB20B200, chain_offset=rank * CHAINS_PER_GPU)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -223,6 +383,7 @@ def main():
     global_counts = [torch.empty_like(local_counts), torch.empty_like(local_counts)]
     pending = [None, None]
     units = N_GENES * CHAINS_PER_GPU
+    total_units = units if strong else units * world
     step_no = [0]
 
     def step():
@@ -277,12 +438,13 @@ def main():
         tot_evals = float(c[0].item())
     else:
         tot_evals = float(ctr['ml_evals'])
-    value = units * world * WINDOW * K / (ms * 1e-3)
+    value = total_units * WINDOW * K / (ms * 1e-3)
 
     # ---- end-to-end through the C ABI with HOST buffers: per step, H2D of the series + prefix build + one window +
     # D2H of the count matrices (the chains carry on across steps, so the work per step equals the device-timed one)
     Ke = max(5, min(K, 40))
     h2d = data.nbytes
+    host_counts = torch.empty(local_counts.shape, dtype=local_counts.dtype, pin_memory=True)
     if world > 1:           # untimed: the first collective of a group sets up its communicator
         parallel.allreduce_counts(local_counts, out=global_counts[0], group=wide)
     barrier()
@@ -290,10 +452,13 @@ def main():
     for _ in range(Ke):
         eng.build_stats([data])
         eng.run(WINDOW)
-        if world > 1:       # the caller reads the counts of ALL chains: reduce over the ranks, then device -> host
-            g = parallel.allreduce_counts(local_counts, out=global_counts[0], group=wide)
-            host_counts = g.cpu().numpy()
-            d2h = host_counts.nbytes
+        if world > 1:       # the caller reads the counts of ALL chains on rank 0: reduce over the ranks, then device -> pinned host
+            global_counts[0].copy_(local_counts)
+            dist.reduce(global_counts[0], dst=0, op=dist.ReduceOp.SUM, group=wide)
+            if rank == 0:
+                host_counts.copy_(global_counts[0], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            d2h = host_counts.numel() * host_counts.element_size()
         else:
             cnt = eng.counts()
             d2h = sum(v.nbytes for v in cnt.values())
@@ -303,7 +468,7 @@ def main():
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = units * world * WINDOW * Ke / e2e_s
+    e2e_value = total_units * WINDOW * Ke / e2e_s
 
     if rank != 0:
         if world > 1:
@@ -314,41 +479,67 @@ def main():
     per_launch_bytes = ctr['algorithmic_bytes'] / K
     avg_launch_s = ms * 1e-3 / K
     achieved = per_launch_bytes / avg_launch_s / 1e9
-    traffic = None
+    traffic = issue_active = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get('chain_kernel_dram_bytes_per_launch')
+                tj = json.load(f)
+            traffic = tj.get('chain_kernel_dram_bytes_per_launch')
+            issue_active = tj.get('chain_kernel_issue_active_pct')
         except Exception:
             traffic = None
     fp64_peak = eng.fp64_peak_gflops()
+    cfg = workload()
+    if strong:
+        cfg['parallelism'] = 'flat (node, chain) unit list split over ranks (1024 chains in total), no data-path collective'
+        cfg['chains_total'] = CHAINS_PER_GPU
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': workload(),
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': cfg,
         'ml_evals_per_sec': tot_evals / (ms * 1e-3),
         'ml_evals_per_iteration': ctr['ml_evals'] / max(1, ctr['unit_iterations']),
         'accept_rate': {'pi': ctr['pi_accepts'] / max(1, ctr['unit_iterations']),
                         'tau': ctr['tau_accepts'] / max(1, ctr['unit_iterations'])},
         'segment_factorisations_per_iteration': ctr['segment_factorisations'] / max(1, ctr['unit_iterations']),
+        'burn_in_iterations': W * WINDOW,
+        # bound: the nearest roofline of the two the contract names.  frac = ALGORITHMIC bytes (16 (k(k+1)/2 + k + 1)
+        # per executed segment evaluation, counted on the device) / time / measured HBM peak.  The kernel does not move
+        # those bytes: unchanged segments come from the per-unit boundary-row cache, so the DRAM traffic ncu measures
+        # (traffic, dram_frac) is lower, and what limits the kernel is dependent-issue latency at 12 warps per SM plus
+        # instruction delivery (limiter, issue_active_pct; profiles/r2_notes.md).
         'roofline': {'kernel': 'chain_fast_kernel<nh-dbn, KM=5>', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,
+                     'dram_frac': (traffic / avg_launch_s / 1e9 / peaks['hbm_gbs']) if traffic else None,
+                     'limiter': 'latency / issue (FP64 dependency chains at 12 warps per SM, ~100 KB loop body), not HBM',
+                     'issue_active_pct': issue_active,
                      'algorithmic_bytes_per_launch': per_launch_bytes,
                      'fp64': {'achieved_gflops': ctr['algorithmic_flops'] / K / avg_launch_s / 1e9,
                               'peak_gflops_measured_dfma': fp64_peak}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'steps': Ke, 'what': 'dbn_build_stats(host series) + dbn_run(10 iterations) + (N > 1: all-reduce of the counts) + counts to host, per step'},
-        'gpu_launches': K * (1 if world == 1 else 1),
+                'steps': Ke, 'what': 'dbn_build_stats(pinned host series) + dbn_run(10 iterations) + (N > 1: reduce of the counts to rank 0) + counts to host, per step'},
+        'gpu_launches': K,
         'clocks': clocks,
     }
     if DIAG_NOREDUCE:
         line['diagnostic'] = 'count all-reduce skipped: NOT a bench value'
+    if world == 1 and not args.no_c5:
+        eng.close()
+        del local_counts, global_counts
+        torch.cuda.empty_cache()
+        try:
+            line['extra'] = {'c5': c5_sample(local_rank, fp64_peak)}
+        except Exception as exc:      # the sample must never cost the contract line
+            line['extra'] = {'c5': {'unavailable': '%s: %s' % (type(exc).__name__, exc)}}
     if not args.no_cpu_baseline and world == 1:
         it_s, ev_s, cores, sample = cpu_port_rate()
         line['cpu_baseline'] = {'value': it_s, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                                 'ml_evals_per_sec': ev_s,
-                                'literal_T_h_x_T_h_form_ml_evals_per_sec_1core': cpu_literal_rate()}
+                                'literal_T_h_x_T_h_form_ml_evals_per_sec_1core': cpu_literal_rate(),
+                                'note': ("kind 'port' = the Gram-form NumPy restatement, ~1000x faster than dyban's own T_h x T_h "
+                                         "code on this workload; dyban's own code is in 'literal_reference'"),
+                                'literal_reference': literal_reference_rates()}
     else:
         line['cpu_baseline'] = None
     print(json.dumps(line))
