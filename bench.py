@@ -70,9 +70,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (the timed region); nvidia-smi needs ~100 ms to deliver its first
+        sample, so the sampler is started before the warm-up and, if the timed region was shorter than one sampling
+        period, the samples taken under the identical warm-up load are used and the line says so."""
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -82,7 +85,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.02)]
+        window = 'timed region'
+        if not rows:
+            rows, window = [r for _, r in self.rows], 'warm-up + timed region (same load)'
+        for r in rows:
             try:
                 sm.append(float(r[1])); smax.append(float(r[2]))
             except Exception:
@@ -91,7 +98,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -409,24 +416,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step()
     drain()
     barrier()
     eng.reset_counters()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     ev0.record()
     for _ in range(K):
         step()
     drain()          # the last reductions are inside the timed region
     ev1.record()
     barrier()
+    t_end = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ctr = eng.counters()
     if world > 1:
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)

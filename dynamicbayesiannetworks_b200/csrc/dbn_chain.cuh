@@ -20,6 +20,8 @@ struct ChainArgs {
   int C;        // local chains per node
   int U;        // units of this handle (a contiguous range of the n * C grid)
   int unit0;    // grid index node * C + chain of local unit 0
+  int n_genes;  // nodes = genes; tb.n = n_genes * lag candidate feature columns (column l * n_genes + g = lag-(l+1) copy of gene g)
+  int lag;
   int it0;      // global index of the first iteration of this launch
   int n_iter;
   unsigned int chain_offset;
@@ -68,23 +70,39 @@ __device__ __forceinline__ void sort4(int (&a)[PMAX], int n) {
   }
 }
 
-// p-th (0-based) gene id in {0..n-1} \ ({node} u pi), ascending  (np.setdiff1d(possibleFeaturesSet, pi)[p])
-__device__ __forceinline__ int nth_candidate(int p, int node, const int (&sorted_pi)[PMAX], int npi) {
+// p-th (0-based) column in {0..n_cols-1} \ ({node, node + n_genes, ..} u pi), ascending
+// (np.setdiff1d(possibleFeaturesSet, pi)[p]; with lag > 1 the node's own copy in every lag block is no feature,
+// network.py:85,92-104).  `sorted_pi` ascending; the own copies are ascending too, merged on the fly.
+__device__ __forceinline__ int nth_candidate(int p, int node, const int (&sorted_pi)[PMAX], int npi, int n_genes = 0, int lag = 1) {
   int c = p;
-  bool node_done = false;
+  int own = node;        // next own copy not yet passed
+  int own_left = lag;
 #pragma unroll
   for (int j = 0; j < PMAX; ++j) {
     if (j < npi) {
       const int e = sorted_pi[j];
-      if (!node_done && node < e) {
-        if (node <= c) ++c;
-        node_done = true;
-      }
+      for (; own_left > 0 && own < e; --own_left, own += n_genes)
+        if (own <= c) ++c;
       if (e <= c) ++c;
     }
   }
-  if (!node_done && node <= c) ++c;
+  for (; own_left > 0; --own_left, own += n_genes)
+    if (own <= c) ++c;
   return c;
+}
+
+// kept parent set -> edge counts: a gene counts once when any of its lag copies is a parent (scores.py:172-178)
+__device__ __forceinline__ void count_edges(unsigned long long* edge_row, const int (&pi)[PMAX], int npi, int n_genes) {
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) {
+    if (j < npi) {
+      const int gene = pi[j] % n_genes;
+      bool dup = false;
+#pragma unroll
+      for (int q = 0; q < PMAX; ++q) dup = dup || (q < j && pi[q] % n_genes == gene);
+      if (!dup) atomicAdd(&edge_row[gene], 1ull);
+    }
+  }
 }
 
 // design columns of a parent set: f[0] = 0, f[1..] = sorted ids + 1
@@ -186,7 +204,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
   const int n_it = active ? a.n_iter : 0;
   const int node = (a.unit0 + u) / a.C;
   const int chain = (a.unit0 + u) - node * a.C;
-  const int n = a.tb.n, N = a.tb.N, F = n - 1;
+  const int n = a.tb.n, N = a.tb.N, F = n - a.lag;   // n feature columns (genes x lag), the node's own copies are no candidates
   auto TAU = [&](int j) -> int& { return s_tau[j * CHAIN_BLOCK + tid]; };
   auto TAS = [&](int j) -> int& { return s_tas[j * CHAIN_BLOCK + tid]; };
   auto tau_cur = [&](int j) { return s_tau[j * CHAIN_BLOCK + tid]; };
@@ -510,7 +528,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           valid = false;
         } else {
           const int p = replay ? ri[DBN_RI_PI_PICK] : rng.below(ncand);
-          const int c = nth_candidate(p, node, spi, npi);
+          const int c = nth_candidate(p, node, spi, npi, a.n_genes, a.lag);
 #pragma unroll
           for (int j = 0; j < PMAX; ++j)
             if (j == npi) star[j] = c;
@@ -546,7 +564,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
               valid = false;
             } else {
               const int p = replay ? ri[DBN_RI_PI_PICK + 1] : rng.below(ncand);
-              const int c = nth_candidate(p, node, spi, npi);
+              const int c = nth_candidate(p, node, spi, npi, a.n_genes, a.lag);
 #pragma unroll
               for (int j = 0; j < PMAX; ++j)
                 if (j == npi - 1) star[j] = c;
@@ -669,9 +687,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       const int idx = it + 1;
       if (idx >= a.burn_in && ((idx - a.burn_in) % a.thin) != 0 && npi > 0) {
         atomicAdd(&a.nonempty[node], 1ull);
-#pragma unroll
-        for (int j = 0; j < PMAX; ++j)
-          if (j < npi) atomicAdd(&a.edge[(long long)node * n + pi[j]], 1ull);
+        count_edges(a.edge + (long long)node * a.n_genes, pi, npi, a.n_genes);
       }
       if (TRACE && ti) {
         ti[DBN_TI_NPI] = npi;

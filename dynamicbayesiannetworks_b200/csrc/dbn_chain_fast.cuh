@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   const int u = active ? u_raw : 0;
   const int node = (a.unit0 + u) / a.C;
   const int chain = (a.unit0 + u) - node * a.C;
-  const int n = a.tb.n, N = a.tb.N, F = n - 1;
+  const int n = a.tb.n, N = a.tb.N, F = n - a.lag;   // n feature columns (genes x lag), the node's own copies are no candidates
   const long long U = a.U;
   auto TAU = [&](int j) -> unsigned short& { return s_tau[j * FAST_BLOCK + tid]; };
   auto TAS = [&](int j) -> unsigned short& { return s_tas[j * FAST_BLOCK + tid]; };
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
           pvalid = false;
         } else {
           const int p = replay ? ri[DBN_RI_PI_PICK] : pick(wa.y, ncand);
-          cnew = nth_candidate(p, node, spi, npi);
+          cnew = nth_candidate(p, node, spi, npi, a.n_genes, a.lag);
 #pragma unroll
           for (int j = 0; j < PMAX; ++j)
             if (j == npi) star[j] = cnew;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
             pvalid = false;
           } else {
             const int p = replay ? ri[DBN_RI_PI_PICK + 1] : pick(wa.z, ncand);
-            cnew = nth_candidate(p, node, spi, npi);
+            cnew = nth_candidate(p, node, spi, npi, a.n_genes, a.lag);
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
               if (j == npi - 1) star[j] = cnew;
@@ -861,9 +861,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       const int idx = it + 1;
       if (active && idx >= a.burn_in && ((idx - a.burn_in) % a.thin) != 0 && npi > 0) {
         atomicAdd(&a.nonempty[node], 1ull);
-#pragma unroll
-        for (int j = 0; j < PMAX; ++j)
-          if (j < npi) atomicAdd(&a.edge[(long long)node * n + pi[j]], 1ull);
+        count_edges(a.edge + (long long)node * a.n_genes, pi, npi, a.n_genes);
       }
       if (TRACE && ti) {
         ti[DBN_TI_NPI] = npi;

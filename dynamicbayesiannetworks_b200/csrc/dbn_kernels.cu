@@ -26,16 +26,21 @@ namespace dbn {
 
 constexpr int PREFIX_BLOCK = 256;
 
-// gather the lag-1 matrices: V[t] = [1, raw[xrow[t]], raw[xrow[t] + 1]]
-__global__ void build_v_kernel(const double* __restrict__ raw, const int* __restrict__ xrow, int N, int n,
-                               double* __restrict__ V) {
-  const int W = 2 * n + 1;
+// gather the lagged rows: V[t] = [1, x_t, x_{t-1}, .., x_{t-lag+1}, y_t] with x_{t-l} = raw[xrow[t] - l] (zeros for the first l
+// rows of a series segment: the reference pads every lagged copy with zeros, network.py:106-113) and y_t = raw[xrow[t] + 1]
+__global__ void build_v_kernel(const double* __restrict__ raw, const int* __restrict__ xrow, const int* __restrict__ xpos, int N, int n,
+                               int lag, double* __restrict__ V) {
+  const int nv = n * lag;          // feature columns: block l = lag-(l+1) copies of the n genes
+  const int W = 1 + nv + n;
   const long long total = (long long)N * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / W), c = (int)(i - (long long)t * W);
     double v = 1.0;
-    if (c >= 1 && c <= n) v = raw[(long long)xrow[t] * n + (c - 1)];
-    if (c > n) v = raw[(long long)(xrow[t] + 1) * n + (c - n - 1)];
+    if (c >= 1 && c <= nv) {
+      const int l = (c - 1) / n, g = (c - 1) - l * n;
+      v = (xpos[t] >= l) ? raw[(long long)(xrow[t] - l) * n + g] : 0.0;
+    }
+    if (c > nv) v = raw[(long long)(xrow[t] + 1) * n + (c - nv - 1)];
     V[i] = v;
   }
 }
@@ -191,6 +196,8 @@ struct dbn_handle {
   std::string err;
   // data / table
   int n = 0, N = 0, W = 0, n_chunks = 0, Lc = 0;
+  int lag = 1, nv = 0;        // nv = n * lag feature columns (lag > 1: zero-padded lagged copies, network.py:92-122)
+  int* d_xpos = nullptr;      // position of regression row t inside its series segment
   long long raw_rows = 0;
   long long R = 0;
   int zz_size = 0;
@@ -330,6 +337,7 @@ int dbn_create(const dbn_config* cfg, dbn_handle** out) {
 static void free_stats(dbn_handle* h) {
   free_dev(h->d_raw);
   free_dev(h->d_xrow);
+  free_dev(h->d_xpos);
   free_dev(h->d_V);
   free_dev(h->d_colA);
   free_dev(h->d_colB);
@@ -395,7 +403,7 @@ int dbn_sync(dbn_handle* h) {
 
 static int launch_prefix(dbn_handle* h) {
   const int n = h->n, N = h->N, W = h->W;
-  build_v_kernel<<<296, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, N, n, h->d_V);
+  build_v_kernel<<<296, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, h->d_xpos, N, n, h->lag, h->d_V);
   CU(h, cudaGetLastError());
   const size_t smem = (size_t)h->Lc * W * sizeof(double);
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
@@ -417,8 +425,9 @@ static int launch_prefix(dbn_handle* h) {
 int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, int32_t n_seg, int32_t n, int32_t lag) {
   if (!h) return DBN_ERR_INVALID;
   if (!data || !seg_len || n_seg < 1 || n < 2) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: bad arguments (need n >= 2, n_seg >= 1)");
-  if (lag != 1) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: only lag == 1 is implemented (network.py:92-122 lag > 1 is a 'next' row)");
-  if (2 * n + 1 > 65535) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: n too large for the 16-bit column map");
+  if (lag < 1 || lag > 2)
+    DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: lag must be 1 or 2 (the reference scores lag-1 and highest-lag copies only, scores.py:172-178)");
+  if ((lag + 1) * n + 1 > 65535) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_build_stats: n too large for the 16-bit column map");
   CU(h, cudaSetDevice(h->cfg.device));
   long long rows = 0, N = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -427,41 +436,47 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     N += seg_len[s] - 1;
   }
   // regression row t -> raw row of x_t (network.py:105-118: rows [:len-1] of each segment, concatenated)
-  std::vector<int> xrow((size_t)N);
+  std::vector<int> xrow((size_t)N), xpos((size_t)N);
   {
     long long base = 0, t = 0;
     for (int s = 0; s < n_seg; ++s) {
-      for (int j = 0; j + 1 < seg_len[s]; ++j) xrow[(size_t)t++] = (int)(base + j);
+      for (int j = 0; j + 1 < seg_len[s]; ++j) {
+        xpos[(size_t)t] = j;
+        xrow[(size_t)t++] = (int)(base + j);
+      }
       base += seg_len[s];
     }
   }
-  const bool same_geometry = h->have_stats && h->n == n && h->N == (int)N && h->raw_rows == rows;
+  const bool same_geometry = h->have_stats && h->n == n && h->lag == lag && h->N == (int)N && h->raw_rows == rows;
   if (!same_geometry) {
     free_stats(h);
     free_chain(h);
     h->n = n;
+    h->lag = lag;
+    const int nv = n * lag;      // feature columns z = (1, x_t, x_{t-1}, ..): every kernel sees `nv` candidate columns
+    h->nv = nv;
     h->N = (int)N;
     h->raw_rows = rows;
-    h->W = 2 * n + 1;
-    h->zz_size = (n + 1) * (n + 2) / 2;
-    h->R = (long long)h->zz_size + (long long)n * (n + 2);
-    // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[n+1+i]; YY(i) = v[n+1+i]^2
+    h->W = 1 + nv + n;
+    h->zz_size = (nv + 1) * (nv + 2) / 2;
+    h->R = (long long)h->zz_size + (long long)n * (nv + 2);
+    // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[nv+1+i]; YY(i) = v[nv+1+i]^2
     std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
     {
       size_t p = 0;
-      for (int a = 0; a <= n; ++a)
+      for (int a = 0; a <= nv; ++a)
         for (int b = 0; b <= a; ++b) {
           ca[p] = (unsigned short)a;
           cb[p] = (unsigned short)b;
           ++p;
         }
       for (int i = 0; i < n; ++i) {
-        for (int a = 0; a <= n; ++a) {
+        for (int a = 0; a <= nv; ++a) {
           ca[p] = (unsigned short)a;
-          cb[p] = (unsigned short)(n + 1 + i);
+          cb[p] = (unsigned short)(nv + 1 + i);
           ++p;
         }
-        ca[p] = cb[p] = (unsigned short)(n + 1 + i);
+        ca[p] = cb[p] = (unsigned short)(nv + 1 + i);
         ++p;
       }
     }
@@ -478,6 +493,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     CU(h, cudaFuncSetAttribute(prefix_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
     CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
+    CU(h, cudaMalloc(&h->d_xpos, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));
     CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
     CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
@@ -493,6 +509,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
   bool must_sync = false;
   if (!same_geometry || h->seg_len != std::vector<int>(seg_len, seg_len + n_seg)) {
     CU(h, cudaMemcpyAsync(h->d_xrow, xrow.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_xpos, xpos.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     h->seg_len.assign(seg_len, seg_len + n_seg);
     must_sync = true;                        // the staging vector goes out of scope
   }
@@ -545,7 +562,7 @@ static Table make_table(const dbn_handle* h) {
   Table t;
   t.base = h->d_table;
   t.row_stride = h->R;
-  t.n = h->n;
+  t.n = h->nv;      // candidate feature columns (n genes x lag)
   t.N = h->N;
   t.zz_size = h->zz_size;
   return t;
@@ -568,7 +585,7 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
     if (node[b] < 0 || node[b] >= h->n || pi_len[b] < 0 || pi_len[b] > PMAX || tau_len[b] < 1 || tau_len[b] > SMAX)
       DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d out of range", b);
     for (int j = 0; j < pi_len[b]; ++j)
-      if (pi[b * PMAX + j] < 0 || pi[b * PMAX + j] >= h->n || pi[b * PMAX + j] == node[b])
+      if (pi[b * PMAX + j] < 0 || pi[b * PMAX + j] >= h->nv || pi[b * PMAX + j] % h->n == node[b])
         DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d has an invalid parent", b);
     int prev = 1;
     for (int j = 0; j + 1 < tau_len[b]; ++j) {
@@ -650,6 +667,7 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
   if (is_fp_method(p->method)) {
+    if (h->lag != 1) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: the full-parents kernels take lag == 1 only");
     h->counts_elems += (long long)h->n * h->n;  // neg[n][n]
     const int k = h->n;
     CU(h, cudaMalloc(&h->st_mu_fp, (size_t)U * k * sizeof(double)));
@@ -732,6 +750,8 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   a.C = h->cfg.n_chains;
   a.U = h->U;
   a.unit0 = (int)h->unit0;
+  a.n_genes = h->n;
+  a.lag = h->lag;
   a.it0 = h->it_done;
   a.n_iter = n_iter;
   a.chain_offset = (unsigned)h->cfg.chain_offset;
@@ -991,6 +1011,8 @@ int dbn_verify_cache(dbn_handle* h, uint64_t out[2]) {
   a.C = h->cfg.n_chains;
   a.U = h->U;
   a.unit0 = (int)h->unit0;
+  a.n_genes = h->n;
+  a.lag = h->lag;
   a.st_S = h->st_S; a.st_tau = h->st_tau; a.st_cg = h->st_cg; a.cache = h->d_cache;
   unsigned long long* d = nullptr;
   CU(h, cudaMalloc(&d, 2 * sizeof(unsigned long long)));

@@ -81,6 +81,8 @@ class DbnEngine:
         seg_len = np.array([s.shape[0] for s in segs], dtype=np.int32)
         self._check(self._lib.dbn_build_stats(self._h, _dptr(flat), _iptr(seg_len), len(segs), n, int(lag)), 'dbn_build_stats')
         self.n = n
+        self.lag = int(lag)
+        self.nv = n * int(lag)      # candidate feature columns: column l * n + g is the lag-(l + 1) copy of gene g
         self.N = int(sum(s.shape[0] - 1 for s in segs))
         self.h2d_bytes = flat.nbytes
         return self
@@ -94,16 +96,16 @@ class DbnEngine:
         return dict(N=N.value, row_doubles=R.value, algorithmic_bytes=B.value)
 
     def stats_row(self, t):
-        """Table row t split into ZZ[n+1, n+1] (symmetric), ZY[n, n+1] (node, column), YY[n]."""
+        """Table row t split into ZZ[nv+1, nv+1] (symmetric), ZY[n, nv+1] (node, column), YY[n]; nv = n * lag."""
         info = self.stats_info()
         row = np.empty(info['row_doubles'])
         self._check(self._lib.dbn_read_stats_row(self._h, int(t), _dptr(row)), 'dbn_read_stats_row')
-        n = self.n
-        zz = np.zeros((n + 1, n + 1))
-        zz[np.tril_indices(n + 1)] = row[:(n + 1) * (n + 2) // 2]
+        n, nv = self.n, self.nv
+        zz = np.zeros((nv + 1, nv + 1))
+        zz[np.tril_indices(nv + 1)] = row[:(nv + 1) * (nv + 2) // 2]
         zz = zz + np.tril(zz, -1).T
-        blocks = row[(n + 1) * (n + 2) // 2:].reshape(n, n + 2)
-        return zz, blocks[:, :n + 1].copy(), blocks[:, n + 1].copy()
+        blocks = row[(nv + 1) * (nv + 2) // 2:].reshape(n, nv + 2)
+        return zz, blocks[:, :nv + 1].copy(), blocks[:, nv + 1].copy()
 
     # ---- kernel 2
     def score_batch(self, node, pi, tau, lambda2, delta2=None, mu=None, alpha=0.005, beta=0.005, T=None, seq=False):

@@ -110,9 +110,9 @@ class Network():
     def _resolve(self, method):
         mid = method_id(method)
         name = method if method in FIXED_CP else METHOD_NAMES[mid]
-        if int(self.lag) != 1:
-            raise NotImplementedError('lag > 1 (network.py:92-122): set_network_configuration builds the lagged design, '
-                                      'the device path takes lag == 1 only')
+        if int(self.lag) not in (1, 2) or (int(self.lag) != 1 and mid in FP_METHODS):
+            raise NotImplementedError('the device path takes lag 1 or 2 (varying-parents methods) and lag 1 (full-parents methods); '
+                                      'set_network_configuration builds the lagged design dict for any lag')
         self.network_args['model'], self.network_args['type'] = _MODEL_ARGS[name]
         return mid, name
 
@@ -191,7 +191,7 @@ class Network():
         if cat is not None:
             u = 0      # chain 0 of the node's slice
             self.chain_results = (self._chain_results_fp(cat, u, mid, n, node) if mid in FP_METHODS
-                                  else self._chain_results(cat, u, mid, n, name))
+                                  else self._chain_results(cat, u, mid, n, name, node, int(self.lag)))
         else:
             self.chain_results = None
         return self
@@ -214,6 +214,8 @@ class Network():
             adj = parallel.edge_scores_from_counts(counts['edge'], counts['nonempty'])
             self.network_args['scoring_method'] = 'edge-scores'
         row = [float(v) for v in adj[node]]
+        if int(self.lag) > 1:      # calculateFeatureScores returns len(features) + 1 entries, the genes first (scores.py:156,192)
+            row = row + [0.0] * (int(self.lag) * (n - 1) + 1 - n)
         self.proposed_adj_matrix.append(row)
         self.edge_scores = row
         if res is not None:
@@ -241,7 +243,8 @@ class Network():
             want = N * max(len(betas), 1) * n * 8 * n <= DIAGNOSTIC_BYTES
         if not want or mid == FP_H_DBN:      # network.py:329-333: no betas over time for 'fp_h_dbn'
             return
-        bot = S.get_betas_over_time(N, cps, betas, n)
+        # network.py:386-394: beta_dim = len(currFeatures) + 1 (lag copies included) for the varying-parents methods
+        bot = S.get_betas_over_time(N, cps, betas, n if mid in FP_METHODS else int(self.lag) * (n - 1) + 1)
         self.betas_over_time.append(bot)
         if mid in FP_METHODS:
             self.scores_over_time.append(S.get_scores_over_time(bot, feats, n))
@@ -263,7 +266,7 @@ class Network():
             if cat is not None:
                 u = node * C - first
                 res = (self._chain_results_fp(cat, u, mid, dims, node) if mid in FP_METHODS
-                       else self._chain_results(cat, u, mid, dims, name))
+                       else self._chain_results(cat, u, mid, dims, name, node, int(self.lag)))
                 self.chain_results_per_node.append(res)
             self._score_node(mid, name, node, N, counts, res)
         if cat is not None:
@@ -296,12 +299,21 @@ class Network():
         return res
 
     @staticmethod
-    def _chain_results(t, u, mid, dims, name):
+    def _chain_results(t, u, mid, dims, name, node=0, lag=1):
         """Per-iteration histories of one unit as the reference's result dict (bayesianPwLinearRegression.py:134-141):
-        lists of length num_iter + 1 starting from the initial state."""
+        lists of length num_iter + 1 starting from the initial state.  The device works on feature COLUMNS (column
+        l * n + g = lag-(l + 1) copy of gene g); the reference labels the lag-1 block by gene id and every further block
+        by a running counter over the node's features (network.py:92-104), which is what `pi_vector` carries."""
         n_iter = t['sigma2'].shape[1]
-        F = dims - 1
-        pi_vec = [[]] + [np.array(t['pi_after'][u, it, :t['npi'][u, it]]) for it in range(n_iter)]
+        F = lag * (dims - 1)
+
+        def label(col):
+            col = int(col)
+            if col < dims:
+                return col
+            blk, g = divmod(col, dims)
+            return dims + (blk - 1) * (dims - 1) + (g if g < node else g - 1)
+        pi_vec = [[]] + [np.array([label(c) for c in t['pi_after'][u, it, :t['npi'][u, it]]], dtype=np.int64) for it in range(n_iter)]
         fixed = name in FIXED_CP
         res = {
             'lambda_sqr_vector': [1] + [float(v) for v in t['lambda2'][u]],

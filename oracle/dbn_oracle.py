@@ -83,15 +83,44 @@ def method_constants(method, N):
 # ------------------------------------------------------------------------------------------------
 # a1 — data slicing (network.py:54-141, utils.py:128-269)
 # ------------------------------------------------------------------------------------------------
-def lagged_matrices(data_list):
-    """Lag-1 feature/response matrices shared by all nodes.
+def lagged_matrices(data_list, lag=1):
+    """Feature / response matrices shared by all nodes.
 
     network.py:105-118: features of a segment are rows [:len-1]; :126-130: responses are rows [1:len];
-    segments are concatenated.  Returns (X[N, n], Y[N, n]); node i regresses Y[:, i] on X[:, j != i].
+    segments are concatenated.  Returns (X[N, n * lag], Y[N, n]); node i regresses Y[:, i] on the columns of X that
+    are not copies of gene i.  lag > 1 (network.py:92-122): block l of X holds the series shifted by l more rows,
+    zero-padded at the start of every segment; column l * n + g is the lag-(l + 1) copy of gene g.
     """
-    X = np.concatenate([np.asarray(s, dtype=np.float64)[:-1, :] for s in data_list], axis=0)
+    n = np.asarray(data_list[0]).shape[1]
+    blocks = []
+    for l in range(int(lag)):
+        rows = []
+        for s in data_list:
+            s = np.asarray(s, dtype=np.float64)
+            rows.append(np.concatenate([np.zeros((l, n)), s[:s.shape[0] - (l + 1), :]], axis=0))
+        blocks.append(np.concatenate(rows, axis=0))
+    X = np.concatenate(blocks, axis=1)
     Y = np.concatenate([np.asarray(s, dtype=np.float64)[1:, :] for s in data_list], axis=0)
     return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def label_to_column(label, node, n):
+    """Reference parent label -> column of X for node `node` (network.py:92-104): the lag-1 block is labelled by gene id,
+    every further block by a running counter over the node's features, so label n + j (j-th feature of the node) is the
+    lag-2 copy of gene j (+ 1 if j >= node)."""
+    label = int(label)
+    if label < n:
+        return label
+    blk, j = divmod(label - n, n - 1)
+    return (blk + 1) * n + (j if j < node else j + 1)
+
+
+def column_to_label(col, node, n):
+    col = int(col)
+    if col < n:
+        return col
+    blk, g = divmod(col, n)
+    return n + (blk - 1) * (n - 1) + (g if g < node else g - 1)
 
 
 def segment_bounds(tau, N):
@@ -517,6 +546,7 @@ def _accept_glob(log_ratio, u):
 
 
 def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_tau=None):
+    # X may hold several lag blocks (lagged_matrices(..., lag)): the node's own copies in every block are excluded
     """One (node, chain) unit for `n_iter` iterations; returns a trace dict shaped like the golden files.
 
     Order of updates per iteration follows bayesianLinearRegression.py:114-147 (h),
@@ -528,7 +558,8 @@ def run_chain(method, X, Y, node, n_iter, draws, fan_in=3, with_tau=True, init_t
     m = METHOD_IDS[method] if isinstance(method, str) else method
     N, n = X.shape
     y = Y[:, node]
-    features = [j for j in range(n) if j != node]
+    n_genes = Y.shape[1]
+    features = [j for j in range(n) if j % n_genes != node]
     F = len(features)
     c = method_constants(m, N)
     fp = m in (FP_GLOB_DBN, FP_NH_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN)    # full parents: pi = every other gene, no parent-set move
@@ -744,8 +775,9 @@ def accumulate_counts(trace, node, n, N, burn_in, edge, nonempty, cp_hist, cp_ke
             k = int(trace['npi'][it])
             if k > 0:
                 nonempty[node] += 1
-                for p in trace['pi_after'][it, :k]:
-                    edge[node, int(p)] += 1
+                # lag > 1: a gene counts once when any of its copies is a parent (scores.py:172-178 for lag 2)
+                for gene in sorted({int(p) % n for p in trace['pi_after'][it, :k]}):
+                    edge[node, gene] += 1
         if tau_kept(it, burn_in) and trace['tau_valid'][it] >= 0:
             cp_kept[node] += 1
             for c_ in trace['tau_after'][it]:

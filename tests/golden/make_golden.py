@@ -180,7 +180,7 @@ def _parse_move(ev, pos, end):
     return rec, pos
 
 
-def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_points=None):
+def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_points=None, lag=1):
     """Run Network.infer_network(method) with recording and write chain_<name>_<method>.npz.
     `change_points`: the predefined list of 'fixed_nh_dbn' (network.py:178-189), ending with the pseudo changepoint."""
     n = data_list[0].shape[1]
@@ -199,7 +199,7 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
     random.seed(seed)
     _install_hooks()
     try:
-        net = Network([d.copy() for d in data_list], n_iter, burn_in, 1, list(change_points) if is_fixed else [])
+        net = Network([d.copy() for d in data_list], n_iter, burn_in, lag, list(change_points) if is_fixed else [])
         per_node = []
         with contextlib.redirect_stdout(io.StringIO()):
             for i in range(n):
@@ -403,7 +403,9 @@ def run_chain_golden(name, data_list, method, n_iter, burn_in, seed, change_poin
                     hist[i, c] += 1
         out['cp_hist'] = hist
         out['cp_kept'] = kept
-    path = os.path.join(HERE, 'chain_%s_%s.npz' % (name, method))
+    out['lag'] = np.array(lag)
+    # lag > 1 (network.py:92-122): parents are LABELS -- gene ids for the lag-1 block, n + position for the lag-2 block
+    path = os.path.join(HERE, ('chain_%s_%s.npz' if lag == 1 else 'lag%dchain_%%s_%%s.npz' % lag) % (name, method))
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
@@ -520,6 +522,13 @@ def main():
     syn, _, _ = make_synthetic(8, 200, n_changepoints=3, max_fan_in=3, seed=7)
     syn_long, _, _ = make_synthetic(6, 341, n_changepoints=2, max_fan_in=3, seed=11)
 
+    if 'lag2-only' in sys.argv:     # lag-2 designs (zero-padded lagged copies, network.py:92-122)
+        run_chain_golden('yeast', yeast, 'varying_nh_dbn', n_iter=240, burn_in=40, seed=5, lag=2)
+        run_chain_golden('yeast', yeast, 'h_dbn', n_iter=240, burn_in=40, seed=5, lag=2)
+        run_chain_golden('yeast', yeast, 'seq_coup_nh_dbn', n_iter=160, burn_in=40, seed=5, lag=2)
+        run_chain_golden('yeast', yeast, 'glob_coup_nh_dbn', n_iter=160, burn_in=40, seed=5, lag=2)
+        run_chain_golden('synth200', [syn], 'varying_nh_dbn', n_iter=120, burn_in=20, seed=6, lag=2)
+        return
     if 'fixed-only' in sys.argv:    # add the fixed-changepoint fixtures without re-minting the others
         run_chain_golden('yeast', yeast, 'fixed_nh_dbn', n_iter=240, burn_in=40, seed=1, change_points=[12, 23, 35])
         run_chain_golden('synth200', [syn], 'fixed_nh_dbn', n_iter=120, burn_in=20, seed=3, change_points=[51, 101, 151, 201])

@@ -18,6 +18,8 @@ FP_VV_FILES = [p for p in _FP_ALL if 'fp_var_glob' in os.path.basename(p)]      
 FP_SEQ_FILES = [p for p in _FP_ALL if 'fp_seq' in os.path.basename(p)]           # sequentially coupled at width n (oracle only so far)
 FP_PLAIN_FILES = [p for p in _FP_ALL if p not in FP_CHAIN_FILES + FP_VV_FILES + FP_SEQ_FILES]   # fp_varying_nh / fp_h: scored from the beta chain
 CHAIN_FILES = [p for p in _ALL_CHAINS if p not in _FP_ALL]
+# lag-2 designs (network.py:92-122): parents are LABELS (gene id for the lag-1 block, n + position for the lag-2 block)
+LAG_CHAIN_FILES = sorted(glob.glob(os.path.join(GOLDEN, 'lag*chain_*.npz')))
 
 
 def load(path):
@@ -45,6 +47,17 @@ def assert_close(a, b, rtol, atol=0.0, what=''):
     bad = err > tol
     assert not bad.any(), '%s: max rel err %.3e (rtol %.1e) at %d/%d entries' % (
         what, float((err / np.maximum(np.abs(b[fb]), 1e-300)).max()), rtol, int(bad.sum()), bad.size)
+
+
+def labels_to_columns(pi_after, n):
+    """[n, n_iter, k] parent LABELS of a lag > 1 golden -> feature columns (column l * n + g = lag-(l + 1) copy of gene g)."""
+    out = np.array(pi_after, dtype=np.int32)
+    for node in range(out.shape[0]):
+        lab = out[node]
+        m = lab >= n
+        blk, j = np.divmod(lab[m] - n, n - 1)
+        lab[m] = (blk + 1) * n + np.where(j < node, j, j + 1)
+    return out
 
 
 def golden_replay(g):

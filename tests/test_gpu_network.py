@@ -4,7 +4,8 @@ flat (node, chain) unit range behind them (`dbn_set_unit_range`), `pa
 import numpy as np
 import pytest
 
-from helpers import CHAIN_FILES, load, data_list
+from helpers import CHAIN_FILES, LAG_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close, assert_close_mat, golden_replay, labels_to_columns
+from oracle import dbn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -120,3 +121,77 @@ def test_kept_history_is_traced_in_bounded_windows():
         NW.TRACE_WINDOW_BYTES = saved
     with pytest.raises(MemoryError):                # a history that cannot fit is refused before anything is allocated
         Network(data, 10 ** 9, 0, 1, keep_chain=True)._plan(1, 5, 5, 10 ** 9, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lag = 2 (network.py:92-122): zero-padded lagged copies as extra feature columns
+# ---------------------------------------------------------------------------------------------------------
+def test_lag2_prefix_rows():
+    from dynamicbayesiannetworks_b200.engine import DbnEngine
+    data = _series('yeast')                   # two series segments: the lag-2 block restarts with a zero row in each
+    X, Y = O.lagged_matrices(data, 2)
+    N, nv = X.shape
+    Z = np.concatenate([np.ones((N, 1)), X], axis=1)
+    with DbnEngine(n_chains=1) as e:
+        e.build_stats(data, lag=2)
+        assert e.stats_info()['N'] == N
+        for t in (0, 1, 2, 17, 18, 19, N):
+            zz, zy, yy = e.stats_row(t)
+            assert_close(zz, Z[:t].T @ Z[:t], 1e-12, 1e-12, what='ZZ[%d]' % t)
+            assert_close(zy, (Z[:t].T @ Y[:t]).T, 1e-12, 1e-12, what='ZY[%d]' % t)
+            assert_close(yy, (Y[:t] ** 2).sum(axis=0), 1e-12, 1e-12, what='YY[%d]' % t)
+
+
+@pytest.mark.parametrize('path', LAG_CHAIN_FILES, ids=ids(LAG_CHAIN_FILES))
+def test_lag2_chain_replay_vs_reference(path):
+    """The reference's recorded lag-2 chains replayed on the device: parents (as feature columns), changepoints and accept
+    flags bit-exact, log-MLs and Gibbs parameters 1e-9, adjacency rows 1e-14."""
+    from dynamicbayesiannetworks_b200.engine import DbnEngine
+    g = load(path)
+    method, lag = str(g['method']), int(g['lag'])
+    data = data_list(g)
+    n, n_iter = g['sigma2'].shape
+    cols = labels_to_columns(g['pi_after'], n)
+    with DbnEngine(n_chains=1) as e:
+        e.build_stats(data, lag=lag)
+        e.chain_init(method, burn_in=int(g['burn_in']))
+        tr = e.run(n_iter, replay=golden_replay(g), trace=True)
+        counts = e.counts()
+        assert e.verify_cache() == (0, 0)
+    for key in ('pi_valid', 'pi_accept', 'npi', 'S'):
+        assert np.array_equal(tr[key], g[key]), key
+    assert np.array_equal(tr['pi_after'], cols), 'pi_after'
+    assert np.array_equal(tr['tau_after'], g['tau_after']), 'tau_after'
+    if method != 'h_dbn':
+        for key in ('tau_valid', 'tau_accept'):
+            assert np.array_equal(tr[key], g[key]), key
+    assert_close(tr['logml'], g['logml'], LOGML_RTOL, what='logml')
+    assert_close(1.0 / tr['sig_rate'], g['sig_scale'], 1e-9, what='sig_scale')
+    assert_close(1.0 / tr['lam_rate'], g['lam_scale'], 1e-9, what='lam_scale')
+    assert_close(tr['beta_mean'], g['beta_mean'], 1e-8, 1e-11, what='beta_mean')
+    assert_close_mat(tr['beta_cov'], g['beta_cov'], 1e-9, what='beta_cov')
+    adj = counts['edge'] / np.maximum(counts['nonempty'], 1)[:, None]
+    ref = g['proposed_adj_matrix']
+    ok = np.isfinite(ref).all(axis=1)
+    assert_close(adj[ok], ref[ok][:, :n], 1e-14, what='proposed_adj_matrix')
+    if 'cp_hist' in g:
+        assert np.array_equal(counts['cp_hist'], g['cp_hist'].astype(np.int64))
+
+
+def test_lag2_network_dropin():
+    from dynamicbayesiannetworks_b200 import Network
+    data = _series('yeast')
+    n = 5
+    net = Network(data, 300, 100, 2)
+    net.infer_network('varying_nh_dbn')
+    adj = np.array(net.proposed_adj_matrix)
+    assert adj.shape == (n, 2 * (n - 1) + 1) and (adj[:, n:] == 0).all() and (adj >= 0).all() and (adj <= 1).all()
+    r = net.chain_results
+    labels = np.concatenate([np.asarray(p).ravel() for p in r['pi_vector'][1:]])
+    assert labels.max() >= n and labels.max() <= n + (n - 1) - 1            # lag-2 labels n .. 2n - 2 (network.py:92-104)
+    assert r['padded_betas'][5][0].shape == (2 * (n - 1) + 1,)
+    assert len(net.betas_over_time) == n and net.betas_over_time[0][0].shape[1] == 2 * (n - 1) + 1
+    with pytest.raises(NotImplementedError):
+        Network(data, 10, 0, 2).infer_network('fp_glob_coup_nh_dbn')
+    with pytest.raises(NotImplementedError):
+        Network(data, 10, 0, 3).infer_network('varying_nh_dbn')

@@ -4,7 +4,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import FP_PLAIN_FILES, FP_VV_FILES, FP_SEQ_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
+from helpers import LAG_CHAIN_FILES, labels_to_columns, FP_PLAIN_FILES, FP_VV_FILES, FP_SEQ_FILES, KAT_FILES, CHAIN_FILES, FP_CHAIN_FILES, LOGML_RTOL, load, data_list, ids, assert_close
 from oracle import dbn_oracle as O
 
 
@@ -174,3 +174,36 @@ def test_fp_plain_chain_replay(path):
     assert_close(adj, g['proposed_adj_matrix'], 1e-14, what='proposed_adj_matrix (credible scores of the beta chain)')
     if 'cp_hist' in g:
         assert np.array_equal(cp_hist, g['cp_hist']) and np.array_equal(cp_kept, g['cp_kept'])
+
+
+@pytest.mark.parametrize('path', LAG_CHAIN_FILES, ids=ids(LAG_CHAIN_FILES))
+def test_lagged_design_chain_replay(path):
+    """lag = 2 (network.py:92-122: zero-padded lagged copies, relabelled): the oracle on the lagged design reproduces the
+    reference's recorded chains -- parents, changepoints, accept flags, log-MLs, Gibbs parameters, adjacency rows."""
+    g = load(path)
+    method, lag = str(g['method']), int(g['lag'])
+    data = data_list(g)
+    n = data[0].shape[1]
+    X, Y = O.lagged_matrices(data, lag)
+    assert X.shape[1] == n * lag
+    N = X.shape[0]
+    n_iter = g['sigma2'].shape[1]
+    cols = labels_to_columns(g['pi_after'], n)
+    assert (cols >= n).any()                     # the fixture does use lag-2 parents
+    edge = np.zeros((n, n)); ne = np.zeros(n); cph = np.zeros((n, N + 3)); cpk = np.zeros(n)
+    for node in range(n):
+        tr = O.run_chain(method, X, Y, node, n_iter, O.ReplayDraws(g, node))
+        assert np.array_equal(tr['pi_after'], cols[node]), node
+        lab = np.vectorize(lambda c: -1 if c < 0 else O.column_to_label(c, node, n))(tr['pi_after'])
+        assert np.array_equal(lab, g['pi_after'][node])
+        assert np.array_equal(tr['tau_after'], g['tau_after'][node])
+        for key in ('pi_valid', 'pi_accept', 'npi', 'S'):
+            assert np.array_equal(tr[key], g[key][node]), key
+        assert_close(tr['logml'], g['logml'][node], LOGML_RTOL, what='logml')
+        assert_close(tr['sig_scale'], g['sig_scale'][node], 1e-9, what='sig_scale')
+        assert_close(tr['lam_scale'], g['lam_scale'][node], 1e-9, what='lam_scale')
+        O.accumulate_counts(tr, node, n, N, int(g['burn_in']), edge, ne, cph, cpk)
+    ref = g['proposed_adj_matrix']
+    ok = np.isfinite(ref).all(axis=1)
+    assert ref.shape[1] == lag * (n - 1) + 1 and (ref[ok][:, n:] == 0).all()      # scores.py:156: len(features) + 1 entries
+    assert_close(O.edge_scores(edge, ne)[ok], ref[ok][:, :n], 1e-14, what='proposed_adj_matrix')
