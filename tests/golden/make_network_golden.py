@@ -143,5 +143,43 @@ def main():
     lag2('yeast', yeast)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and 'evaluation-only' not in sys.argv:
     main()
+
+
+def evaluation(name):
+    """examples/utils.py:24-131 on the reference's own adjacency matrices (lag 1 and lag 2 fixtures) against the yeast truth
+    of examples/yeast_tests.py:58-64: transformResults' outputs and the two AUCs the example drivers print."""
+    import importlib.util
+    import types
+    for m in ('pandas',):
+        pass
+    spec = importlib.util.spec_from_file_location('ref_examples_utils', '/root/reference/examples/utils.py')
+    mod = importlib.util.module_from_spec(spec)
+    cwd = os.getcwd()
+    import tempfile
+    os.chdir(tempfile.mkdtemp(prefix='dyban_ref_'))     # the module opens ./output.log at import time
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        os.chdir(cwd)
+    from sklearn.metrics import roc_curve, auc, precision_recall_curve
+    true_inc = [[0, 0, 1, 0, 1], [1, 0, 0, 1, 0], [0, 1, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 1, 0, 0]]
+    g = dict(true_inc=np.array(true_inc))
+    for tag, path in (('lag1', os.path.join(HERE, 'chain_yeast_varying_nh_dbn.npz')), ('lag2', os.path.join(HERE, 'lag2chain_yeast_varying_nh_dbn.npz'))):
+        adj = np.load(path)['proposed_adj_matrix']
+        flat_true, flat_scores = mod.transformResults([list(r) for r in true_inc], [list(map(float, r)) for r in adj])
+        fpr, tpr, _ = roc_curve(flat_true, flat_scores)
+        pr, rc, _ = precision_recall_curve(flat_true, flat_scores)
+        g['adj_' + tag] = adj
+        g['flat_true_' + tag] = np.array(flat_true)
+        g['flat_scores_' + tag] = np.array(flat_scores, dtype=float)
+        g['roc_auc_' + tag] = auc(fpr, tpr)
+        g['pr_auc_' + tag] = auc(rc, pr)
+    path = os.path.join(HERE, 'evaluation_%s.npz' % name)
+    np.savez_compressed(path, **g)
+    print(path, float(g['roc_auc_lag1']), float(g['pr_auc_lag1']), float(g['roc_auc_lag2']), float(g['pr_auc_lag2']))
+
+
+if __name__ == '__main__' and 'evaluation-only' in sys.argv:
+    evaluation('yeast')

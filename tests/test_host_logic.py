@@ -215,3 +215,38 @@ def test_shard_units_covers_the_grid():
             assert first == pos
             pos += count
         assert max(c for _, c in got) - min(c for _, c in got) <= 1
+
+
+def test_evaluation_helpers_vs_reference(tmp_path):
+    """examples/utils.py:24-131, :226-261: transformResults (diagonal removal, lag-2 fold), the ROC / PR AUCs the example
+    drivers print, save_chain / load_chain -- against outputs of the reference's own helpers (tests/golden/evaluation_yeast.npz,
+    generated by tests/golden/make_network_golden.py evaluation-only)."""
+    from dynamicbayesiannetworks_b200 import evaluation as E, Network
+    g = dict(np.load(os.path.join(GOLDEN, 'evaluation_yeast.npz'), allow_pickle=False))
+    true_inc = [list(map(int, r)) for r in g['true_inc']]
+    for tag in ('lag1', 'lag2'):
+        adj = [list(map(float, r)) for r in g['adj_' + tag]]
+        ft, fs = E.transformResults(true_inc, adj)
+        assert ft == g['flat_true_' + tag].tolist()
+        assert np.array_equal(np.array(fs), g['flat_scores_' + tag])
+        res = E.adjMatrixRoc(fs, ft, False)
+        assert abs(res['roc_auc'] - float(g['roc_auc_' + tag])) < 1e-12
+        assert abs(res['pr_auc'] - float(g['pr_auc_' + tag])) < 1e-12
+    # the AUCs agree with scikit-learn on random scores with ties as well
+    sk = pytest.importorskip('sklearn.metrics')
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        y = rng.integers(0, 2, 40)
+        if y.min() == y.max():
+            continue
+        s = np.round(rng.random(40), 1)
+        fpr, tpr, _ = sk.roc_curve(y, s)
+        pr, rc, _ = sk.precision_recall_curve(y, s)
+        assert abs(E.roc_auc(y, s) - sk.auc(fpr, tpr)) < 1e-12
+        assert abs(E.pr_auc(y, s) - sk.auc(rc, pr)) < 1e-12
+    net = Network([g['adj_lag1']], 10, 0, 1)
+    net.proposed_adj_matrix = [list(map(float, r)) for r in g['adj_lag1']]
+    E.save_chain('net.pckl', net, folder=str(tmp_path))
+    back = E.load_chain('net.pckl', folder=str(tmp_path))
+    assert back.proposed_adj_matrix == net.proposed_adj_matrix
+    assert E.load_chain('missing.pckl', folder=str(tmp_path)) is None
