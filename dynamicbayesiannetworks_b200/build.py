@@ -21,15 +21,15 @@ _H = lambda *names: [os.path.join(CSRC, f) for f in names] + [os.path.join(ROOT,
 COMMON = _H('dbn_score.cuh', 'dbn_rng.cuh', 'dbn_chain.cuh', 'dbn_launch.h')
 # object name -> (source, defines, headers it depends on beside COMMON)
 OBJECTS = {
-    'abi': ('dbn_kernels.cu', [], ['dbn_chain_fast.cuh', 'dbn_fp.cuh', 'dbn_coupled.cuh', 'dbn_warp.cuh']),
+    'abi': ('dbn_kernels.cu', [], ['dbn_chain_fast.cuh', 'dbn_fp.cuh', 'dbn_fp_big.cuh', 'dbn_coupled.cuh', 'dbn_warp.cuh']),
     'fast_plain': ('dbn_inst.cu', ['DBN_INST_FAMILY=1', 'DBN_INST_TRACE=0'], ['dbn_chain_fast.cuh']),
     'fast_trace': ('dbn_inst.cu', ['DBN_INST_FAMILY=1', 'DBN_INST_TRACE=1'], ['dbn_chain_fast.cuh']),
     'chain_plain': ('dbn_inst.cu', ['DBN_INST_FAMILY=2', 'DBN_INST_TRACE=0'], ['dbn_coupled.cuh']),
     'chain_trace': ('dbn_inst.cu', ['DBN_INST_FAMILY=2', 'DBN_INST_TRACE=1'], ['dbn_coupled.cuh']),
-    'fp_plain_small': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=0', 'DBN_INST_BIG=0'], ['dbn_fp.cuh']),
-    'fp_plain_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=0', 'DBN_INST_BIG=1'], ['dbn_fp.cuh']),
-    'fp_trace_small': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=0'], ['dbn_fp.cuh']),
-    'fp_trace_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=1'], ['dbn_fp.cuh']),
+    'fp_plain_small': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=0', 'DBN_INST_BIG=0'], ['dbn_fp.cuh', 'dbn_fp_big.cuh']),
+    'fp_plain_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=0', 'DBN_INST_BIG=1'], ['dbn_fp.cuh', 'dbn_fp_big.cuh']),
+    'fp_trace_small': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=0'], ['dbn_fp.cuh', 'dbn_fp_big.cuh']),
+    'fp_trace_big': ('dbn_inst.cu', ['DBN_INST_FAMILY=3', 'DBN_INST_TRACE=1', 'DBN_INST_BIG=1'], ['dbn_fp.cuh', 'dbn_fp_big.cuh']),
     'stubs': ('dbn_stub_launchers.cu', [], []),   # --slim only
 }
 SLIM = ('abi', 'fast_plain', 'fast_trace', 'stubs')   # kernel A/B builds of the h / nh family (build_variants/*.so)

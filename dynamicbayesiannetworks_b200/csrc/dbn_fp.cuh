@@ -18,14 +18,15 @@
 // so one sweep per changepoint list scores ANY mu (the proposed mu* is only known after the sweep).
 #pragma once
 #include "dbn_chain.cuh"
+#include "dbn_fp_big.cuh"
 
 namespace dbn {
 
-constexpr int FP_BLOCK_MAX = 256;
+constexpr int FP_BLOCK_MAX = 512;
 // threads per block: one warp while a matrix row fits it (k <= 32: the block barriers are then warp-local and the idle
 // warps of a wider block no longer wait in them — 54 % of all stall samples at k = 11, profiles/r1_v9), else 64 / 128
-// the large-k path (matrices in the global workspace, blocked routines below) always runs FP_BIG_BLOCK threads
-constexpr int FP_BIG_BLOCK = 256;
+// the large-k path (matrices in the global workspace, tiled routines of dbn_fp_big.cuh) always runs FP_BIG_BLOCK threads, one block per SM
+constexpr int FP_BIG_BLOCK = FPB_THREADS;
 inline int fp_block_threads(int k, bool mats_in_smem) { return !mats_in_smem ? FP_BIG_BLOCK : (k <= 32 ? 32 : (k <= 64 ? 64 : 128)); }
 #define FP_BLOCK ((int)blockDim.x)
 constexpr int FP_NMAT = 5;  // A/L, W, M (tau), M (tau*), Q
@@ -74,7 +75,21 @@ __device__ __forceinline__ double fp_block_sum(double x, double* red) {
   red[threadIdx.x] = x;
   __syncthreads();
   double t = 0.0;
-  for (int w = 0; w < FP_BLOCK; ++w) t += red[w];
+  if (FP_BLOCK <= 128) {
+    for (int w = 0; w < FP_BLOCK; ++w) t += red[w];
+    return t;
+  }
+  // wide blocks (large k): 32 partial sums of FP_BLOCK / 32 consecutive entries, then every thread adds the 32
+  double* red2 = red + FP_BLOCK_MAX;
+  if (threadIdx.x < 32) {
+    const int g = FP_BLOCK >> 5;
+    double p = 0.0;
+    for (int w = 0; w < g; ++w) p += red[threadIdx.x * g + w];
+    red2[threadIdx.x] = p;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 32; ++w) t += red2[w];
   return t;
 }
 
@@ -93,6 +108,19 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
   const double* __restrict__ ph = tb.base + (long long)hi * tb.row_stride;
   const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
   const int nb = tb.zz_size + node * (tb.n + 2);
+  if (FP_BLOCK > 128) {
+    // large k: a warp per matrix row, lanes along the row (table entries of a row are contiguous but for the node's own column)
+    for (int a = threadIdx.x >> 5; a < k; a += FP_BLOCK >> 5) {
+      const int fa = fp_col(a, node);
+      const long long ro = (long long)fa * (fa + 1) / 2;
+      for (int b = threadIdx.x & 31; b <= a; b += 32) {
+        const long long off = ro + fp_col(b, node);
+        const double v = lam * (__ldg(ph + off) - __ldg(pl + off)) + (a == b ? 1.0 : 0.0);
+        A[(long long)a * ld + b] = v;
+        A[(long long)b * ld + a] = v;
+      }
+    }
+  } else {
   for (int e = threadIdx.x; e < k * (k + 1) / 2; e += FP_BLOCK) {
     int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);  // row of packed entry e; corrected for rounding below
     while (a * (a + 1) / 2 > e) --a;
@@ -103,6 +131,7 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
     const double v = lam * (__ldg(ph + off) - __ldg(pl + off)) + (a == b ? 1.0 : 0.0);
     A[a * ld + b] = v;
     A[b * ld + a] = v;
+  }
   }
   for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
     const int fa = fp_col(a, node);
@@ -122,16 +151,9 @@ __device__ inline void fp_symv(const double* M, int ld, int k, const double* x, 
   __syncthreads();
 }
 
-// blocked large-k routines (defined below); `stage` != nullptr selects them in the dispatching helpers
-__device__ inline double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage);
-__device__ inline void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage);
-__device__ inline void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale);
-__device__ inline void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t);
-__device__ inline void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red);
-
 // in-place lower Cholesky of the full symmetric matrix A (upper part left untouched); returns ln det A
 __device__ inline double fp_cholesky(double* A, int ld, int k, double* idiag, double* stage) {  // idiag[j] = 1 / L[j][j]
-  if (stage) return fp_potrf_big(A, ld, k, idiag, stage);
+  if (stage) return fpb_factor(A, nullptr, ld, k, idiag, stage);
   double mant = 1.0;  // product of the pivots l_j = sqrt(d_j) as mantissa x 2^expo: one log per factorisation
   int expo = 0;
   for (int j = 0; j < k; ++j) {
@@ -162,7 +184,6 @@ __device__ inline double fp_cholesky(double* A, int ld, int k, double* idiag, do
 
 // W = L^-1 (lower triangular, zeros above the diagonal): forward substitution on all columns at once
 __device__ inline void fp_trinv(const double* L, double* W, int ld, int k, const double* idiag, double* stage) {
-  if (stage) return fp_trinv_big(L, W, ld, k, idiag, stage);
   for (int c = threadIdx.x; c < k; c += FP_BLOCK) {
     for (int i = 0; i < c; ++i) W[i * ld + c] = 0.0;
     for (int i = c; i < k; ++i) {
@@ -174,9 +195,17 @@ __device__ inline void fp_trinv(const double* L, double* W, int ld, int k, const
   __syncthreads();
 }
 
+// Cholesky factor and inverse factor W = L^-1 in one call (large k: fused per panel, dbn_fp_big.cuh); returns ln det A
+__device__ inline double fp_factor_inv(double* A, double* W, int ld, int k, double* idiag, double* stage) {
+  if (stage) return fpb_factor(A, W, ld, k, idiag, stage);
+  const double ldet = fp_cholesky(A, ld, k, idiag, nullptr);
+  fp_trinv(A, W, ld, k, idiag, nullptr);
+  return ldet;
+}
+
 // t = W x (lower triangular W), thread per row
 __device__ inline void fp_trmv(const double* W, int ld, int k, const double* x, double* t, double* stage) {
-  if (stage) return fp_trmv_big(W, ld, k, x, t);
+  if (stage) return fpb_trmv(W, ld, k, x, t, stage);
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
     for (int j = 0; j <= i; ++j) acc += W[i * ld + j] * x[j];
@@ -187,7 +216,7 @@ __device__ inline void fp_trmv(const double* W, int ld, int k, const double* x, 
 
 // y = W^T t (lower triangular W), thread per output entry: coalesced over a
 __device__ inline void fp_trmv_t(const double* W, int ld, int k, const double* t, double* y, double* stage, double* red) {
-  if (stage) return fp_trmv_t_big(W, ld, k, t, y, red);
+  if (stage) return fpb_trmv_t(W, ld, k, t, y);
   for (int a = threadIdx.x; a < k; a += FP_BLOCK) {
     double acc = 0.0;
     for (int i = a; i < k; ++i) acc += W[i * ld + a] * t[i];
@@ -198,7 +227,7 @@ __device__ inline void fp_trmv_t(const double* W, int ld, int k, const double* t
 
 // M += I - W^T W (full symmetric)
 __device__ inline void fp_accumulate_i_minus_ainv(const double* W, double* M, int ld, int k, double* stage, double scale) {
-  if (stage) return fp_syrk_big(W, M, ld, k, stage, scale);
+  if (stage) return fpb_syrk(W, M, ld, k, stage, scale);
   for (int a = 0; a < k; ++a) {
     for (int b = threadIdx.x; b <= a; b += FP_BLOCK) {
       double acc = 0.0;
@@ -211,291 +240,6 @@ __device__ inline void fp_accumulate_i_minus_ainv(const double* W, double* M, in
   __syncthreads();
 }
 
-
-// =====================================================================================================================
-// Large k (the k x k matrices live in the per-block global workspace): blocked routines.  The unblocked ones above touch
-// the whole trailing matrix once per column (k^3/3 element read-modify-writes per factorisation, ~3 memory instructions
-// per FMA); these keep FP_NB accumulators per thread in registers and stream each operand once per panel.
-// Layout: the factor is stored as U = L^T in the UPPER triangle (U[j][i] at A[j * ld + i], i >= j), so that for a fixed
-// factor row j consecutive threads (consecutive i) read consecutive addresses; the inverse factor V = U^-1 = W^T likewise.
-// The strictly lower triangle of A keeps the (symmetric) input.  Every routine expects FP_BIG_BLOCK threads.
-// =====================================================================================================================
-constexpr int FP_NB = 16;   // panel width = accumulators per thread and row
-constexpr int FP_JC = 32;   // rows of the broadcast operand staged in shared memory at a time
-constexpr int FP_SY_T = 64, FP_SY_IC = 16, FP_SY_LD = 68;   // fp_syrk_big: tile, depth chunk, padded leading dimension
-constexpr int FP_STAGE_DOUBLES = 2 * FP_SY_IC * FP_SY_LD;  // largest user (potrf / trinv need FP_JC*FP_NB + FP_NB*FP_NB + FP_NB)
-
-// in-place Cholesky A = U^T U, left-looking by panels of FP_NB factor rows; returns ln det A, idiag[j] = 1 / U[j][j]
-__device__ inline double fp_potrf_big(double* A, int ld, int k, double* idiag, double* stage) {
-  double* Bs = stage;                  // [FP_JC][FP_NB]  Bs[jj][c] = U[j0 + jj][p0 + c]
-  double* D = stage + FP_JC * FP_NB;   // [FP_NB][FP_NB]  diagonal block, lower factor after the in-block step
-  double* Di = D + FP_NB * FP_NB;      // [FP_NB]         reciprocal pivots of the block
-  const int tid = threadIdx.x, T = FP_BLOCK;
-  double mant = 1.0;
-  int expo = 0;
-  for (int p0 = 0; p0 < k; p0 += FP_NB) {
-    const int nb = min(FP_NB, k - p0);
-    for (int ib = p0; ib < k; ib += 2 * T) {   // two matrix columns i0, i1 of the panel's factor rows per thread
-      const int i0 = ib + tid, i1 = i0 + T;
-      const bool on0 = i0 < k, on1 = i1 < k;
-      const bool w0 = ib + (tid & ~31) < k, w1 = ib + T + (tid & ~31) < k;   // this warp has first / second columns at all
-      double acc0[FP_NB], acc1[FP_NB];
-#pragma unroll
-      for (int c = 0; c < FP_NB; ++c) {   // rows p0.. of A are still the input (symmetric: entries left of the diagonal too)
-        acc0[c] = (on0 && c < nb) ? A[(long long)(p0 + c) * ld + i0] : 0.0;
-        acc1[c] = (on1 && c < nb) ? A[(long long)(p0 + c) * ld + i1] : 0.0;
-      }
-      for (int j0 = 0; j0 < p0; j0 += FP_JC) {
-        const int jn = min(FP_JC, p0 - j0);
-        __syncthreads();
-        for (int e = tid; e < jn * FP_NB; e += T) {
-          const int jj = e / FP_NB, c = e - jj * FP_NB;
-          Bs[e] = (c < nb) ? A[(long long)(j0 + jj) * ld + p0 + c] : 0.0;
-        }
-        __syncthreads();
-        // four factor rows per step: their 4 (8) loads are in flight together before the 64 (128) dependent-free FMAs
-        // (the one-row loop stalled on each load: 30 % of all samples, profiles/r1_v11); warps without a second /
-        // any column skip the arithmetic (warp-uniform branches), not the barriers
-        if (w0) {
-          int jj = 0;
-          for (; jj + 4 <= jn; jj += 4) {
-            double a0v[4], a1v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              a0v[q] = on0 ? A[(long long)(j0 + jj + q) * ld + i0] : 0.0;
-              a1v[q] = on1 ? A[(long long)(j0 + jj + q) * ld + i1] : 0.0;
-            }
-            if (w1) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int c = 0; c < FP_NB; ++c) {
-                  const double b = Bs[(jj + q) * FP_NB + c];
-                  acc0[c] = fma(-a0v[q], b, acc0[c]);
-                  acc1[c] = fma(-a1v[q], b, acc1[c]);
-                }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int c = 0; c < FP_NB; ++c) acc0[c] = fma(-a0v[q], Bs[(jj + q) * FP_NB + c], acc0[c]);
-            }
-          }
-          for (; jj < jn; ++jj) {
-            const double a0 = on0 ? A[(long long)(j0 + jj) * ld + i0] : 0.0;
-            const double a1 = on1 ? A[(long long)(j0 + jj) * ld + i1] : 0.0;
-#pragma unroll
-            for (int c = 0; c < FP_NB; ++c) {
-              const double b = Bs[jj * FP_NB + c];
-              acc0[c] = fma(-a0, b, acc0[c]);
-              acc1[c] = fma(-a1, b, acc1[c]);
-            }
-          }
-        }
-      }
-      const bool diag_pass = ib == p0;
-      if (diag_pass) {   // block-uniform: the panel's own rows are columns i0 of threads tid < nb
-        __syncthreads();
-        if (tid < nb) {
-#pragma unroll
-          for (int c = 0; c < FP_NB; ++c) D[tid * FP_NB + c] = acc0[c];
-        }
-        __syncthreads();
-        for (int c = 0; c < nb; ++c) {
-          if (tid == c) {
-            const double d = sqrt(D[c * FP_NB + c]);
-            D[c * FP_NB + c] = d;
-            Di[c] = 1.0 / d;
-          }
-          __syncthreads();
-          if (tid > c && tid < nb) D[tid * FP_NB + c] *= Di[c];
-          __syncthreads();
-          if (tid > c && tid < nb) {
-            const double l = D[tid * FP_NB + c];
-            for (int c2 = c + 1; c2 <= tid; ++c2) D[tid * FP_NB + c2] -= l * D[c2 * FP_NB + c];
-          }
-          __syncthreads();
-        }
-        for (int c = 0; c < nb; ++c) {
-          int ex;
-          mant = frexp(mant * D[c * FP_NB + c], &ex);
-          expo += ex;
-        }
-        if (tid < nb) idiag[p0 + tid] = Di[tid];
-      }
-      // rows below the block: x U_pp = acc, forward over the block's columns
-#pragma unroll
-      for (int c = 0; c < FP_NB; ++c) {
-        if (c < nb) {
-          double s0 = acc0[c], s1 = acc1[c];
-#pragma unroll
-          for (int c2 = 0; c2 < c; ++c2) {
-            const double d = D[c * FP_NB + c2];
-            s0 = fma(-acc0[c2], d, s0);
-            s1 = fma(-acc1[c2], d, s1);
-          }
-          acc0[c] = s0 * Di[c];
-          acc1[c] = s1 * Di[c];
-        }
-      }
-      const bool in_block = diag_pass && tid < nb;
-#pragma unroll
-      for (int c = 0; c < FP_NB; ++c) {
-        if (c < nb) {
-          if (on0 && i0 >= p0 + c) A[(long long)(p0 + c) * ld + i0] = in_block ? D[tid * FP_NB + c] : acc0[c];
-          if (on1) A[(long long)(p0 + c) * ld + i1] = acc1[c];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  return 2.0 * (log(mant) + (double)expo * 0.69314718055994530942);
-}
-
-// V = U^-1 (upper triangle of W; the lower triangle is not written and never read), thread per column, row blocks bottom-up
-__device__ inline void fp_trinv_big(const double* A, double* W, int ld, int k, const double* idiag, double* stage) {
-  double* Us = stage;                  // [FP_JC][FP_NB]  Us[mm][r] = U[j0 + r][m0 + mm]
-  double* Ud = stage + FP_JC * FP_NB;  // [FP_NB][FP_NB]  Ud[r][r2] = U[j0 + r][j0 + r2], r2 > r
-  const int tid = threadIdx.x, T = FP_BLOCK;
-  for (int cb = 0; cb < k; cb += T) {
-    const int c = cb + tid;
-    const bool on = c < k;
-    const int cmax = min(k, cb + T) - 1;
-    const int cw = min(k - 1, cb + (tid | 31));   // largest column of this warp
-    for (int j0 = (cmax / FP_NB) * FP_NB; j0 >= 0; j0 -= FP_NB) {
-      const int nb = min(FP_NB, k - j0);
-      double acc[FP_NB];
-#pragma unroll
-      for (int r = 0; r < FP_NB; ++r) acc[r] = 0.0;
-      for (int m0 = j0 + nb; m0 <= cmax; m0 += FP_JC) {
-        const int mn = min(FP_JC, cmax + 1 - m0);
-        __syncthreads();
-        for (int e = tid; e < mn * FP_NB; e += T) {
-          const int r = e / mn, mm = e - r * mn;
-          Us[mm * FP_NB + r] = (r < nb) ? A[(long long)(j0 + r) * ld + m0 + mm] : 0.0;
-        }
-        __syncthreads();
-        if (m0 <= cw) {   // warp-uniform: some column of this warp reaches row m0 (V[m][c] = 0 for m > c)
-          int mm = 0;
-          for (; mm + 4 <= mn; mm += 4) {   // four loads in flight before the FMAs
-            double vv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) vv[q] = (on && m0 + mm + q <= c) ? W[(long long)(m0 + mm + q) * ld + c] : 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[(mm + q) * FP_NB + r], vv[q], acc[r]);
-          }
-          for (; mm < mn; ++mm) {
-            const int m = m0 + mm;
-            const double v = (on && m <= c) ? W[(long long)m * ld + c] : 0.0;
-#pragma unroll
-            for (int r = 0; r < FP_NB; ++r) acc[r] = fma(Us[mm * FP_NB + r], v, acc[r]);
-          }
-        }
-      }
-      __syncthreads();
-      for (int e = tid; e < FP_NB * FP_NB; e += T) {
-        const int r = e / FP_NB, r2 = e - r * FP_NB;
-        Ud[e] = (r < nb && r2 < nb && r2 > r) ? A[(long long)(j0 + r) * ld + j0 + r2] : 0.0;
-      }
-      __syncthreads();
-      double v[FP_NB];
-#pragma unroll
-      for (int r = FP_NB - 1; r >= 0; --r) {
-        double sacc = ((j0 + r == c) ? 1.0 : 0.0) - acc[r];
-#pragma unroll
-        for (int r2 = r + 1; r2 < FP_NB; ++r2) sacc = fma(-Ud[r * FP_NB + r2], v[r2], sacc);
-        v[r] = (r < nb && on && j0 + r <= c) ? sacc * idiag[j0 + r] : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < FP_NB; ++r)
-        if (r < nb && on && j0 + r <= c) W[(long long)(j0 + r) * ld + c] = v[r];
-    }
-  }
-  __syncthreads();
-}
-
-// M += I - V V^T (= I - A^-1; full symmetric M), 64 x 64 tiles of the lower triangle, 4 x 4 outputs per thread
-__device__ inline void fp_syrk_big(const double* W, double* M, int ld, int k, double* stage, double scale) {
-  double* As = stage;
-  double* Bs = stage + FP_SY_IC * FP_SY_LD;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  for (int a0 = 0; a0 < k; a0 += FP_SY_T) {
-    for (int b0 = 0; b0 <= a0; b0 += FP_SY_T) {
-      double acc[4][4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
-      for (int i0 = a0; i0 < k; i0 += FP_SY_IC) {   // V[a][i] = 0 for i < a, a >= a0
-        __syncthreads();
-        for (int e = tid; e < FP_SY_T * FP_SY_IC; e += FP_BIG_BLOCK) {
-          const int rr = e >> 4, ii = e & 15, i = i0 + ii;
-          const int ra = a0 + rr, rb = b0 + rr;
-          As[ii * FP_SY_LD + rr] = (ra < k && i < k && i >= ra) ? W[(long long)ra * ld + i] : 0.0;
-          Bs[ii * FP_SY_LD + rr] = (rb < k && i < k && i >= rb) ? W[(long long)rb * ld + i] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int ii = 0; ii < FP_SY_IC; ++ii) {
-          double av[4], bv[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            av[p] = As[ii * FP_SY_LD + ty * 4 + p];
-            bv[p] = Bs[ii * FP_SY_LD + tx * 4 + p];
-          }
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ra = a0 + ty * 4 + p, rb = b0 + tx * 4 + q;
-          if (ra < k && rb <= ra) {
-            const double v = scale * (((ra == rb) ? 1.0 : 0.0) - acc[p][q]);
-            M[(long long)ra * ld + rb] += v;
-            if (ra != rb) M[(long long)rb * ld + ra] += v;
-          }
-        }
-    }
-  }
-  __syncthreads();
-}
-
-// t = L^-1 x = V^T x: thread per entry, coalesced over the entries
-__device__ inline void fp_trmv_big(const double* W, int ld, int k, const double* x, double* t) {
-  for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
-    double acc = 0.0;
-    for (int j = 0; j <= i; ++j) acc += W[(long long)j * ld + i] * x[j];
-    t[i] = acc;
-  }
-  __syncthreads();
-}
-
-// y = L^-T t = V t: 16 rows at a time, 16 threads per row striding its entries, partial sums through `red`
-__device__ inline void fp_trmv_t_big(const double* W, int ld, int k, const double* t, double* y, double* red) {
-  const int tid = threadIdx.x, rr = tid >> 4, sl = tid & 15;
-  for (int ab = 0; ab < k; ab += 16) {
-    const int ra = ab + rr;
-    double acc = 0.0;
-    if (ra < k)
-      for (int i = ra + sl; i < k; i += 16) acc += W[(long long)ra * ld + i] * t[i];
-    __syncthreads();
-    red[tid] = acc;
-    __syncthreads();
-    if (tid < 16 && ab + tid < k) {
-      double z = 0.0;
-      for (int q = 0; q < 16; ++q) z += red[tid * 16 + q];
-      y[ab + tid] = z;
-    }
-  }
-  __syncthreads();
-}
 
 // z[0..k) ~ N(0,1), Philox slots base + i/2
 __device__ inline void fp_normals(double* z, int k, uint32_t chain, uint32_t node, uint32_t it, uint32_t base, uint2 key) {
@@ -525,8 +269,7 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
     const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
     fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
     r.s += *s_tmp;
-    r.ld += fp_cholesky(A, ld, k, t, stage);
-    fp_trinv(A, W, ld, k, t, stage);
+    r.ld += fp_factor_inv(A, W, ld, k, t, stage);
     fp_trmv(W, ld, k, g, t, stage);          // t = L^-1 g
     r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
     fp_trmv_t(W, ld, k, t, x, stage, red);   // x = A^-1 g
@@ -592,8 +335,7 @@ __device__ inline double fp_score_seq(const Table& tb, int node, TauFn tau, int 
     const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
     if (h == 1) {
       fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
-      fp_cholesky(A, ld, k, t, stage);
-      fp_trinv(A, W, ld, k, t, stage);
+      fp_factor_inv(A, W, ld, k, t, stage);
       for (int i = threadIdx.x; i < k; i += FP_BLOCK) rhs[i] = lam * g[i];
       __syncthreads();
       fp_apply_ainv(W, ld, k, rhs, t, bt_cur, stage, red);
@@ -609,8 +351,7 @@ __device__ inline double fp_score_seq(const Table& tb, int node, TauFn tau, int 
     }
     __syncthreads();
     const double rho = s - 2.0 * fp_dot(bt_cur, g, k, red) + fp_dot(bt_cur, tmp, k, red);
-    acc_ld += fp_cholesky(A, ld, k, t, stage);
-    fp_trinv(A, W, ld, k, t, stage);
+    acc_ld += fp_factor_inv(A, W, ld, k, t, stage);
     fp_trmv(W, ld, k, x, t, stage);
     acc_q += rho - w * fp_dot(t, t, k, red);
     if (h >= 1) {
@@ -680,24 +421,25 @@ constexpr int FPM_GLOB = 0, FPM_PLAIN = 1, FPM_VV = 2, FPM_SEQ = 3;
 // BIG: the matrices live in the global workspace and the blocked routines run (256 threads, 2 blocks per SM); !BIG: matrices in
 // shared memory, at most 128 threads and 96 registers so that 19+ one-warp blocks of a small network are resident per SM.
 template <bool TRACE, int FPM = FPM_GLOB, bool BIG = false>
-__global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob_kernel(const FpArgs a) {
+__global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob_kernel(const FpArgs a) {
   constexpr bool GLOBM = FPM == FPM_GLOB, VVM = FPM == FPM_VV, SEQM = FPM == FPM_SEQ;
   constexpr bool GHR = GLOBM || VVM;   // Hastings ratios and acceptance rule of the globally coupled changepoint moves
   extern __shared__ double sm[];
-  const int n = a.tb.n, N = a.tb.N, k = n, ld = fp_ld(k);
+  const int n = a.tb.n, N = a.tb.N, k = n, ld = BIG ? fp_ld_big(k) : fp_ld(k);
   const int tid = threadIdx.x;
   // shared layout: vectors | reduction scratch | ints | (matrices, when they fit)
   double* vec = sm;
   double* g = vec + 0 * k, *mu = vec + 1 * k, *mu_star = vec + 2 * k, *t = vec + 3 * k, *x = vec + 4 * k, *z = vec + 5 * k;
   double* mean = vec + 6 * k, *a_cur = vec + 7 * k, *a_star = vec + 8 * k, *tmp = vec + 9 * k, *rhs = vec + 10 * k, *e = vec + 11 * k;
-  double* red = vec + FP_NVEC * k;       // [FP_BLOCK_MAX]
-  double* sc = red + FP_BLOCK_MAX;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
+  double* red = vec + FP_NVEC * k;       // [FP_BLOCK_MAX + 32]
+  double* sc = red + FP_BLOCK_MAX + 32;                  // scalars published by thread 0: [0] sig2 [1] lam [2] u [3] s_tmp ...
   double* sigv = sc + 8;                 // [SMAX] sigma^2_h of the iteration (vv)
   int* s_tau = reinterpret_cast<int*>(sc + 8 + SMAX);
   int* s_tas = s_tau + SMAX;
   int* s_int = s_tas + SMAX;             // [8]
   double* mats = BIG ? a.ws + (long long)blockIdx.x * FP_NMAT * ld * k : reinterpret_cast<double*>(s_int + 8);
-  double* stage = BIG ? reinterpret_cast<double*>(s_int + 8) : nullptr;   // large k: staging of the blocked routines
+  // large k: staging area of the tiled routines (16-byte aligned: cp.async / 128-bit shared loads)
+  double* stage = BIG ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_int + 8) + 15) & ~(uintptr_t)15) : nullptr;
   double* A = mats, *W = mats + (long long)ld * k, *Mc = mats + 2ll * ld * k, *Ms = mats + 3ll * ld * k, *Q = mats + 4ll * ld * k;
   double* bsc = a.bsc ? a.bsc + (long long)blockIdx.x * (2 * SMAX) * k : nullptr;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -751,8 +493,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           const double w = w_of(h);
           if (SEQM && h == 1) {   // beta-tilde_1 from this segment's own data with lambda^2 (samplers.py:36-39)
             fp_load_segment(a.tb, node, lo, hi, lam, A, ld, k, g, sc + 3);
-            fp_cholesky(A, ld, k, t, stage);
-            fp_trinv(A, W, ld, k, t, stage);
+            fp_factor_inv(A, W, ld, k, t, stage);
             for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = lam * g[i];
             __syncthreads();
             fp_apply_ainv(W, ld, k, rhs, t, mu, stage, red);
@@ -770,8 +511,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           }
           __syncthreads();
           const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
-          fp_cholesky(A, ld, k, t, stage);
-          fp_trinv(A, W, ld, k, t, stage);
+          fp_factor_inv(A, W, ld, k, t, stage);
           fp_trmv(W, ld, k, x, t, stage);
           const double q_h = rho - w * fp_dot(t, t, k, red);
           q_sum += q_h;
@@ -827,7 +567,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
               td[10 + 3 * k + h * k + i] = mean[i];
               double dg = 0.0;  // diag of A^-1 = column norms of W
               for (int r = i; r < k; ++r) {
-                const double wv = stage ? W[(long long)i * ld + r] : W[r * ld + i];
+                const double wv = W[(long long)r * ld + i];
                 dg += wv * wv;
               }
               td[10 + 3 * k + DBN_SMAX * k + h * k + i] = w * dg;  // x sigma^2 below
@@ -907,8 +647,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           if (h >= 1) {
             if (h == 1) {
               fp_load_segment(a.tb, node, lo, hi, lam_new, A, ld, k, g, sc + 3);
-              fp_cholesky(A, ld, k, t, stage);
-              fp_trinv(A, W, ld, k, t, stage);
+              fp_factor_inv(A, W, ld, k, t, stage);
               for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = lam_new * g[i];
               __syncthreads();
               fp_apply_ainv(W, ld, k, rhs, t, mu, stage, red);
@@ -922,8 +661,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
             accd += fp_dot(tmp, tmp, k, red);
             if (h + 1 < S) {
               fp_load_segment(a.tb, node, lo, hi, dlt, A, ld, k, g, sc + 3);
-              fp_cholesky(A, ld, k, t, stage);
-              fp_trinv(A, W, ld, k, t, stage);
+              fp_factor_inv(A, W, ld, k, t, stage);
               for (int i = tid; i < k; i += FP_BLOCK) rhs[i] = mu_star[i] + dlt * g[i];
               __syncthreads();
               fp_apply_ainv(W, ld, k, rhs, t, z, stage, red);
@@ -965,8 +703,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
           rhs[i] = a_cur[i];
         }
         __syncthreads();
-        fp_cholesky(Q, ld, k, t, stage);
-        fp_trinv(Q, W, ld, k, t, stage);
+        fp_factor_inv(Q, W, ld, k, t, stage);
         fp_trmv(W, ld, k, rhs, t, stage);
         fp_trmv_t(W, ld, k, t, mean, stage, red);
         if (replay) {
@@ -1128,8 +865,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
             rhs[i] = a_cur[i] / sig2 + mu[i];
           }
           __syncthreads();
-          const double ldq_cur = fp_cholesky(Q, ld, k, t, stage);
-          fp_trinv(Q, W, ld, k, t, stage);
+          const double ldq_cur = fp_factor_inv(Q, W, ld, k, t, stage);
           fp_trmv(W, ld, k, rhs, t, stage);
           fp_trmv_t(W, ld, k, t, mean, stage, red);
           if (TRACE && td)
@@ -1149,8 +885,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
             rhs[i] = a_star[i] / sig2;
           }
           __syncthreads();
-          const double ldq_star = fp_cholesky(Q, ld, k, t, stage);
-          fp_trinv(Q, W, ld, k, t, stage);
+          const double ldq_star = fp_factor_inv(Q, W, ld, k, t, stage);
           fp_trmv(W, ld, k, rhs, t, stage);
           fp_trmv_t(W, ld, k, t, mean, stage, red);
           if (replay) {
@@ -1241,10 +976,11 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 2 : 5) fp_glob
 }
 
 inline size_t fp_smem_bytes(int k, bool mats_in_smem) {
-  size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 8 + DBN_SMAX) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
+  size_t b = (size_t)(FP_NVEC * k + FP_BLOCK_MAX + 32 + 8 + DBN_SMAX) * sizeof(double) + (2 * DBN_SMAX + 8) * sizeof(int);
   if (mats_in_smem) b += (size_t)FP_NMAT * fp_ld(k) * k * sizeof(double);
-  else b += (size_t)FP_STAGE_DOUBLES * sizeof(double);
+  else b += (size_t)FPB_SMEM_DOUBLES * sizeof(double) + 16;
   return b;
 }
+inline size_t fp_ws_doubles_per_block(int k) { return (size_t)FP_NMAT * fp_ld_big(k) * k; }
 
 }  // namespace dbn

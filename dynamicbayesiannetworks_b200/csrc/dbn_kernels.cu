@@ -675,10 +675,13 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
     cudaDeviceProp prop;
     CU(h, cudaGetDeviceProperties(&prop, h->cfg.device));
     const bool in_smem = fp_smem_bytes(k, true) <= 160 * 1024;
-    if (12 * (size_t)k * sizeof(double) > 200 * 1024) DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: n too large for the full-parents kernel");
-    h->fp_grid = (int)(in_smem ? U : (U < 2ll * prop.multiProcessorCount ? U : 2ll * prop.multiProcessorCount));
+    if (!in_smem && fp_smem_bytes(k, false) > (size_t)prop.sharedMemPerBlockOptin)
+      DBN_FAIL(h, DBN_ERR_INVALID, "dbn_chain_init: n = %d is too large for the full-parents kernel (%zu bytes of shared memory per block, %zu available)",
+               k, fp_smem_bytes(k, false), (size_t)prop.sharedMemPerBlockOptin);
+    // large k: one block of FP_BIG_BLOCK threads per SM (fewer workspaces in flight, dbn_fp_big.cuh)
+    h->fp_grid = (int)(in_smem ? U : (U < (long long)prop.multiProcessorCount ? U : (long long)prop.multiProcessorCount));
     if (!in_smem) {
-      const size_t ws = (size_t)h->fp_grid * FP_NMAT * fp_ld(k) * k * sizeof(double);
+      const size_t ws = (size_t)h->fp_grid * fp_ws_doubles_per_block(k) * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_fp_ws, ws);
       if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "full-parents workspace of %.2f GB does not fit: %s", ws / 1e9, cudaGetErrorString(e));
     }
