@@ -281,6 +281,49 @@ __device__ FpSummary fp_sweep(const Table& tb, int node, TauFn tau, int S, doubl
   return r;
 }
 
+// does the changepoint list `tau` (S segments) contain the segment (lo, hi]?
+template <class TauFn>
+__device__ __forceinline__ bool fp_has_segment(TauFn tau, int S, int N, int lo, int hi) {
+  int l = 0;
+  for (int h = 0; h < S; ++h) {
+    const int e = DBN_SEG_END(tau(h), h, S, N);
+    if (l == lo && e == hi) return true;
+    l = e;
+  }
+  return false;
+}
+
+// Delta form of fp_sweep for the changepoint move: a birth / death / reallocation changes at most two segments, and the
+// five sums are sums over segments, so the segments `tau` shares with `other` are evaluated once for both lists.
+// Segments of `tau` that also occur in `other` add to set 0 (M0, a0, r0), the others to set 1; with skip_common the shared
+// segments are not evaluated at all (second pass: only the proposal's new segments).  Returns the number of segments
+// evaluated.  The caller zeroes what it wants zeroed.
+template <class TauFn, class OtherFn>
+__device__ int fp_sweep_split(const Table& tb, int node, TauFn tau, int S, OtherFn other, int So, bool skip_common, double lam, double* A,
+                              double* W, int ld, int k, double* M0, double* a0, FpSummary& r0, double* M1, double* a1, FpSummary& r1,
+                              double* g, double* t, double* x, double* red, double* s_tmp, double* stage) {
+  int lo = 0, n_eval = 0;
+  for (int h = 0; h < S; ++h) {
+    const int hi = DBN_SEG_END(tau(h), h, S, tb.N);
+    const bool common = fp_has_segment(other, So, tb.N, lo, hi);
+    if (!(common && skip_common)) {
+      FpSummary& r = common ? r0 : r1;
+      double* a_sum = common ? a0 : a1;
+      fp_load_segment(tb, node, lo, hi, lam, A, ld, k, g, s_tmp);
+      r.s += *s_tmp;
+      r.ld += fp_factor_inv(A, W, ld, k, t, stage);
+      fp_trmv(W, ld, k, g, t, stage);          // t = L^-1 g
+      r.c += fp_dot(t, t, k, red);             // g^T A^-1 g
+      fp_trmv_t(W, ld, k, t, x, stage, red);   // x = A^-1 g
+      for (int i = threadIdx.x; i < k; i += FP_BLOCK) a_sum[i] += x[i];
+      fp_accumulate_i_minus_ainv(W, common ? M0 : M1, ld, k, stage, 1.0);
+      ++n_eval;
+    }
+    lo = hi;
+  }
+  return n_eval;
+}
+
 // t = L^-1 g by forward substitution on the Cholesky factor (idiag[j] = 1 / L[j][j]); column-oriented, k block steps
 __device__ inline void fp_trsv(const double* L, int ld, int k, const double* idiag, const double* g, double* t, bool upper) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) t[i] = g[i];
@@ -851,18 +894,29 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
         }
         if (GLOBM && valid) {
           const double ils = 1.0 / (lam * sig2);
-          // ---- current changepoints: log-ML at mu and the density of mu under muSampler(mu | tau) (moves.py:66-73)
-          const FpSummary sc_ = fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3, stage);
-          n_segs += S;
-          const double q_cur = fp_quad_at(sc_, Mc, ld, k, a_cur, mu, lam, tmp, red);
+          // ---- current changepoints: log-ML at mu and the density of mu under muSampler(mu | tau) (moves.py:66-73).  The
+          // segments tau shares with tau* go to (Mc, a_cur), the one or two the proposal changes to (Ms, a_star) ...
+          for (int i = tid; i < k; i += FP_BLOCK) a_cur[i] = a_star[i] = 0.0;
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Mc[i] = Ms[i] = 0.0;
+          __syncthreads();
+          FpSummary s_com = {0.0, 0.0, 0.0}, s_old = {0.0, 0.0, 0.0};
+          n_segs += fp_sweep_split(a.tb, node, tau_cur, S, tau_star, Ss, false, lam, A, W, ld, k, Mc, a_cur, s_com, Ms, a_star, s_old, g, t, x,
+                                   red, sc + 3, stage);
+          // ... then (Ms, a_star) become the sums of tau, (Mc, a_cur) stay the shared part, to which the second pass adds tau*'s new segments
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Ms[i] += Mc[i];
+          for (int i = tid; i < k; i += FP_BLOCK) a_star[i] += a_cur[i];
+          __syncthreads();
+          const FpSummary sc_ = {s_com.c + s_old.c, s_com.s + s_old.s, s_com.ld + s_old.ld};
+          double* const M_cur = Ms, *const M_star = Mc, *const av_cur = a_star, *const av_star = a_cur;
+          const double q_cur = fp_quad_at(sc_, M_cur, ld, k, av_cur, mu, lam, tmp, red);
           const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + q_cur);
           ++n_evals;
           // Q = I + M / (lam s2); mean = Q^-1 (a / s2 + mu)   (samplers.py:324, :336: the input mu is added)
-          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Mc[i] * ils;
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = M_cur[i] * ils;
           __syncthreads();
           for (int i = tid; i < k; i += FP_BLOCK) {
             Q[i * ld + i] += 1.0;
-            rhs[i] = a_cur[i] / sig2 + mu[i];
+            rhs[i] = av_cur[i] / sig2 + mu[i];
           }
           __syncthreads();
           const double ldq_cur = fp_factor_inv(Q, W, ld, k, t, stage);
@@ -872,17 +926,18 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             for (int i = tid; i < k; i += FP_BLOCK) td[10 + k + i] = mean[i];
           for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu[i] - mean[i];
           __syncthreads();
-          fp_symv(Mc, ld, k, x, tmp);
+          fp_symv(M_cur, ld, k, x, tmp);
           const double dQd_cur = fp_dot(x, x, k, red) + fp_dot(x, tmp, k, red) * ils;
           const double ld_cur = -0.5 * ((double)k * 1.8378770664093454836 - ldq_cur + dQd_cur);
           // ---- proposed changepoints: mu* ~ muSampler(0 | tau*), its density, log-ML at mu* (moves.py:86-93)
-          const FpSummary ss_ = fp_sweep(a.tb, node, tau_star, Ss, lam, A, W, Ms, ld, k, g, t, x, a_star, red, sc + 3, stage);
-          n_segs += Ss;
-          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Ms[i] * ils;
+          FpSummary ss_ = s_com;
+          n_segs += fp_sweep_split(a.tb, node, tau_star, Ss, tau_cur, S, true, lam, A, W, ld, k, M_star, av_star, ss_, M_star, av_star, ss_, g, t,
+                                   x, red, sc + 3, stage);
+          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = M_star[i] * ils;
           __syncthreads();
           for (int i = tid; i < k; i += FP_BLOCK) {
             Q[i * ld + i] += 1.0;
-            rhs[i] = a_star[i] / sig2;
+            rhs[i] = av_star[i] / sig2;
           }
           __syncthreads();
           const double ldq_star = fp_factor_inv(Q, W, ld, k, t, stage);
@@ -901,10 +956,10 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             for (int i = tid; i < k; i += FP_BLOCK) td[10 + 2 * k + i] = mean[i];
           for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu_star[i] - mean[i];
           __syncthreads();
-          fp_symv(Ms, ld, k, x, tmp);
+          fp_symv(M_star, ld, k, x, tmp);
           const double dQd_star = fp_dot(x, x, k, red) + fp_dot(x, tmp, k, red) * ils;
           const double ld_star = -0.5 * ((double)k * 1.8378770664093454836 - ldq_star + dQd_star);
-          const double q_star = fp_quad_at(ss_, Ms, ld, k, a_star, mu_star, lam, tmp, red);
+          const double q_star = fp_quad_at(ss_, M_star, ld, k, av_star, mu_star, lam, tmp, red);
           const double ml_star = a.c0 - 0.5 * ss_.ld - a.T_half_plus_a * log(a.two_b + q_star);
           ++n_evals;
           const double lp_star = -0.5 * ((double)k * 1.8378770664093454836 + fp_dot(mu_star, mu_star, k, red));

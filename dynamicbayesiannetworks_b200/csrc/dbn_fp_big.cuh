@@ -68,16 +68,19 @@ struct FpbCoord {
   int a, b;     // first row / column of this LANE's elements: warp origin + lane / 4, warp origin + 2 (lane % 4)
   int fa, fb;   // operand fragment offsets: (lane % 4) rows down, warp origin + lane / 4 along
   int kr;       // lane % 4
-  int wa;       // first row of the warp
+  int wa, wb;   // first row / column of the warp
 };
 __device__ __forceinline__ FpbCoord fpb_coord() {
+  // warp w: rows 16 (w % 4), columns 32 (w / 4): the four warps of a scheduler (w % 4 fixed) cover all four column groups, so
+  // tiles whose right half is masked (fpb_gemm's `ncols`) halve the work of every scheduler
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FpbCoord c;
-  c.wa = (w >> 2) * 16;
+  c.wa = (w & 3) * 16;
+  c.wb = (w >> 2) * 32;
   c.a = c.wa + (lane >> 2);
-  c.b = (w & 3) * 32 + 2 * (lane & 3);
+  c.b = c.wb + 2 * (lane & 3);
   c.fa = c.wa + (lane >> 2);
-  c.fb = (w & 3) * 32 + (lane >> 2);
+  c.fb = c.wb + (lane >> 2);
   c.kr = lane & 3;
   return c;
 }
@@ -110,7 +113,7 @@ __device__ __forceinline__ void fpb_mma_rows(FpbAcc& acc, const FpbCoord& co, co
 
 // acc[a][b] += sum_{j_lo <= j < j_hi} X[j][xc0 + a] * Y[j][yc0 + b]; columns >= ncol (even) read as zero
 __device__ inline void fpb_gemm(FpbAcc& acc, const FpbCoord& co, const double* __restrict__ X, int xc0, const double* __restrict__ Y, int yc0,
-                                int j_lo, int j_hi, int ld, int ncol, double* pipe) {
+                                int j_lo, int j_hi, int ld, int ncol, double* pipe, int ncols = FPB_TN) {   // ncols: tile columns that are needed (64 or 128)
   const int tid = threadIdx.x;
   const int nst = (j_hi - j_lo + FPB_KD - 1) / FPB_KD;
   const int xr = tid >> 5, xc = (tid & 31) * 2;   // X stage: 16 rows x 32 chunks of 16 bytes
@@ -144,7 +147,7 @@ __device__ inline void fpb_gemm(FpbAcc& acc, const FpbCoord& co, const double* _
     if (s + FPB_NSTAGE - 1 < nst) load(s + FPB_NSTAGE - 1);
     fpb_commit();
     const double* buf = pipe + (s % FPB_NSTAGE) * FPB_STAGE;
-    fpb_mma_rows(acc, co, buf, FPB_LDX, buf + FPB_KD * FPB_LDX, FPB_LDY, FPB_KD / 4);
+    if (co.wb < ncols) fpb_mma_rows(acc, co, buf, FPB_LDX, buf + FPB_KD * FPB_LDX, FPB_LDY, FPB_KD / 4);   // warp-uniform
   }
 }
 
@@ -194,7 +197,7 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
         }
       }
       fpb_zero(acc);
-      fpb_gemm(acc, co, A, p0, A, c0, 0, p0, ld, ncol, pipe);
+      fpb_gemm(acc, co, A, p0, A, c0, 0, p0, ld, ncol, pipe, c0 + 64 >= k ? 64 : FPB_TN);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -308,10 +311,10 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
         }
         if (tid < 64 && p0 + tid < k) idiag[p0 + tid] = dinv[tid];
       }
-      // the warps whose columns are the diagonal block run the product on stale data and drop the result
-      fpb_apply_li(acc, co, li, pipe);
-      const bool keep = c0 != p0 || co.b >= 64;   // warp-uniform
+      // the solve, skipped (warp-uniform, no barrier inside) by the warps whose columns are the diagonal block or lie past k
+      const bool keep = (c0 != p0 || co.wb >= 64) && c0 + co.wb < k;
       if (keep) {
+        fpb_apply_li(acc, co, li, pipe);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int row = p0 + co.a + 8 * i;
@@ -329,7 +332,7 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
       for (int b0 = 0; b0 < p0; b0 += FPB_TN) {
         FpbAcc acc;
         fpb_zero(acc);
-        fpb_gemm(acc, co, A, p0, W, b0, b0, p0, ld, ncol, pipe);
+        fpb_gemm(acc, co, A, p0, W, b0, b0, p0, ld, ncol, pipe, b0 + 64 >= p0 ? 64 : FPB_TN);   // columns >= p0 are the diagonal block
 #pragma unroll
         for (int i = 0; i < 2; ++i)
           if (p0 + co.a + 8 * i >= k) {
@@ -338,14 +341,16 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
           }
         fpb_stage_tile(acc, co, pipe);
         __syncthreads();
-        fpb_apply_li(acc, co, li, pipe);
+        if (b0 + co.wb < p0) {   // warp-uniform
+          fpb_apply_li(acc, co, li, pipe);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int row = p0 + co.a + 8 * i;
+          for (int i = 0; i < 2; ++i) {
+            const int row = p0 + co.a + 8 * i;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = b0 + co.b + 8 * j;   // p0 is even: a pair is never cut by the diagonal block
-            if (row < k && col < p0) *reinterpret_cast<double2*>(W + (long long)row * ld + col) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+            for (int j = 0; j < 4; ++j) {
+              const int col = b0 + co.b + 8 * j;   // p0 is even: a pair is never cut by the diagonal block
+              if (row < k && col < p0) *reinterpret_cast<double2*>(W + (long long)row * ld + col) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+            }
           }
         }
       }
@@ -376,7 +381,7 @@ static __device__ __noinline__ void fpb_syrk(const double* W, double* M, int ld,
         }
       }
       fpb_zero(acc);
-      fpb_gemm(acc, co, W, a0, W, b0, max(a0, b0), k, ld, ncol, sm);
+      fpb_gemm(acc, co, W, a0, W, b0, max(a0, b0), k, ld, ncol, sm, (b0 == a0 || b0 + 64 >= k) ? 64 : FPB_TN);   // b <= a only
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int ra = a0 + co.a + 8 * i;
