@@ -109,15 +109,30 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
   const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
   const int nb = tb.zz_size + node * (tb.n + 2);
   if (FP_BLOCK > 128) {
-    // large k: a warp per matrix row, lanes along the row (table entries of a row are contiguous but for the node's own column)
+    // large k: a warp per matrix row, lanes along the row (table entries of a row are contiguous but for the node's own column);
+    // eight table loads in flight per lane before the first store (one pair per step left the loop waiting for DRAM:
+    // 15 % of all stall samples of the c5 launch, profiles/r2_c5/c5_fp_glob_stall_lines.txt)
     for (int a = threadIdx.x >> 5; a < k; a += FP_BLOCK >> 5) {
       const int fa = fp_col(a, node);
       const long long ro = (long long)fa * (fa + 1) / 2;
-      for (int b = threadIdx.x & 31; b <= a; b += 32) {
-        const long long off = ro + fp_col(b, node);
-        const double v = lam * (__ldg(ph + off) - __ldg(pl + off)) + (a == b ? 1.0 : 0.0);
-        A[(long long)a * ld + b] = v;
-        A[(long long)b * ld + a] = v;
+      for (int b0 = threadIdx.x & 31; b0 <= a; b0 += 128) {
+        double vh[4], vl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + 32 * u;
+          const long long off = ro + fp_col(b <= a ? b : a, node);
+          vh[u] = __ldg(ph + off);
+          vl[u] = __ldg(pl + off);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + 32 * u;
+          if (b <= a) {
+            const double v = lam * (vh[u] - vl[u]) + (a == b ? 1.0 : 0.0);
+            A[(long long)a * ld + b] = v;
+            A[(long long)b * ld + a] = v;
+          }
+        }
       }
     }
   } else {
@@ -145,7 +160,19 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
 __device__ inline void fp_symv(const double* M, int ld, int k, const double* x, double* y) {
   for (int i = threadIdx.x; i < k; i += FP_BLOCK) {
     double acc = 0.0;
-    for (int j = 0; j < k; ++j) acc += M[j * ld + i] * x[j];  // column i of a symmetric matrix: coalesced over i
+    int j = 0;
+    if (FP_BLOCK > 128) {   // large k (matrix in global memory): eight loads in flight
+      double s4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (; j + 8 <= k; j += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = M[(long long)(j + q) * ld + i];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s4[q & 3] = fma(v[q], x[j + q], s4[q & 3]);
+      }
+      acc = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    }
+    for (; j < k; ++j) acc += M[j * ld + i] * x[j];  // column i of a symmetric matrix: coalesced over i
     y[i] = acc;
   }
   __syncthreads();
@@ -903,7 +930,11 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
           n_segs += fp_sweep_split(a.tb, node, tau_cur, S, tau_star, Ss, false, lam, A, W, ld, k, Mc, a_cur, s_com, Ms, a_star, s_old, g, t, x,
                                    red, sc + 3, stage);
           // ... then (Ms, a_star) become the sums of tau, (Mc, a_cur) stay the shared part, to which the second pass adds tau*'s new segments
-          for (int i = tid; i < k * ld; i += FP_BLOCK) Ms[i] += Mc[i];
+          for (int i = tid; i < k * ld; i += FP_BLOCK) {   // ... and Q = I + M / (lam s2) of tau in the same pass (diagonal added below)
+            const double m = Ms[i] + Mc[i];
+            Ms[i] = m;
+            Q[i] = m * ils;
+          }
           for (int i = tid; i < k; i += FP_BLOCK) a_star[i] += a_cur[i];
           __syncthreads();
           const FpSummary sc_ = {s_com.c + s_old.c, s_com.s + s_old.s, s_com.ld + s_old.ld};
@@ -912,8 +943,6 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
           const double ml_cur = a.c0 - 0.5 * sc_.ld - a.T_half_plus_a * log(a.two_b + q_cur);
           ++n_evals;
           // Q = I + M / (lam s2); mean = Q^-1 (a / s2 + mu)   (samplers.py:324, :336: the input mu is added)
-          for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = M_cur[i] * ils;
-          __syncthreads();
           for (int i = tid; i < k; i += FP_BLOCK) {
             Q[i * ld + i] += 1.0;
             rhs[i] = av_cur[i] / sig2 + mu[i];
