@@ -182,6 +182,91 @@ __device__ __forceinline__ double sqnorm_k(const double (&x)[KM]) {
   return dot<KM>(x, x);
 }
 
+// ---- boundary-row cache of the coupled chain kernel ----------------------------------------------------------------------
+// Row j of a unit holds the prefix-table row at the end boundary of the current state's segment j, restricted to the
+// state's design columns in design order ([ZZ packed | ZY | YY | pad], zeros in the padding), as 16-byte pairs: pair p of row
+// j of unit u at doubles ((j * NP + p) * U + u) * 2, so a warp moves a pair of consecutive units as one coalesced 512-byte
+// request instead of 64 scattered sectors.  Rows are exact copies of table entries and a segment is the same difference of
+// two rows, so the statistics are bit-identical to the gathered ones.  A pass streams the rows through two shared-memory
+// staging buffers with cp.async, one row ahead: the L2 latency of row h + 1 is hidden behind the factorisation of segment h
+// (reading the rows with plain loads was measured SLOWER than the round-1 gathers on the small mTOR table, whose gathers hit
+// L1: profiles/r2_coupled).  Row SEG_ROW_NEW holds the one boundary a changepoint proposal adds; the row of boundary j of
+// the scored changepoint list is  j == r_new ? SEG_ROW_NEW : j + (j > r_from ? r_shift : 0).
+constexpr int SEG_ROW_NEW = 9, SEG_ROWS_CACHED = 10;
+template <int KM>
+struct SegDims {
+  static constexpr int KT = KM * (KM + 1) / 2, NE = KT + KM + 1, NP = (NE + 1) / 2;
+};
+inline size_t chain_smem_bytes(int km) { return (size_t)2 * ((km * (km + 1) / 2 + km + 2) / 2) * 2 * CHAIN_BLOCK * sizeof(double); }
+inline size_t chain_cache_doubles_per_unit(int km) { return (size_t)SEG_ROWS_CACHED * ((km * (km + 1) / 2 + km + 2) / 2) * 2; }
+
+__device__ __forceinline__ void seg_cp_async16(double* smem, const double* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void seg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void seg_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int KM, class TauFn>
+struct SegFromCache {
+  static constexpr int KT = SegDims<KM>::KT, NP = SegDims<KM>::NP;
+  const double* cu;   // cache + 2 u
+  long long U;
+  TauFn tau;
+  int S, N;
+  int r_new, r_from, r_shift;
+  double* st;         // this thread's slice of the staging area: pair p of buffer b at st + (b * NP + p) * 2 * CHAIN_BLOCK
+  __device__ __forceinline__ int row(int j) const { return j == r_new ? SEG_ROW_NEW : j + (j > r_from ? r_shift : 0); }
+  __device__ __forceinline__ void issue(int j, int b) const {
+    const double* p = cu + (long long)row(j) * NP * (2 * U);
+    double* d = st + b * NP * (2 * CHAIN_BLOCK);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) seg_cp_async16(d + q * (2 * CHAIN_BLOCK), p + (long long)q * (2 * U));
+  }
+  __device__ __forceinline__ void begin() const {
+    if (S > 0) issue(0, 0);
+    seg_cp_commit();
+  }
+  __device__ __forceinline__ int operator()(int h, double (&G)[KT], double (&g)[KM], double& s) const {
+    const int lo = h ? DBN_SEG_END(tau(h - 1), h - 1, S, N) : 0;
+    const int hi = DBN_SEG_END(tau(h), h, S, N);
+    seg_cp_wait_all();
+    const double* bh = st + (h & 1) * NP * (2 * CHAIN_BLOCK);
+    const double* bl = st + ((h & 1) ^ 1) * NP * (2 * CHAIN_BLOCK);
+    const bool hl = h > 0;   // segment 0 starts at table row 0, which is all zeros
+#define DBN_SEGE(b, e) (b)[((e) >> 1) * (2 * CHAIN_BLOCK) + ((e) & 1)]
+#pragma unroll
+    for (int e = 0; e < KT; ++e) G[e] = DBN_SEGE(bh, e) - (hl ? DBN_SEGE(bl, e) : 0.0);
+#pragma unroll
+    for (int i = 0; i < KM; ++i) g[i] = DBN_SEGE(bh, KT + i) - (hl ? DBN_SEGE(bl, KT + i) : 0.0);
+    s = DBN_SEGE(bh, KT + KM) - (hl ? DBN_SEGE(bl, KT + KM) : 0.0);
+#undef DBN_SEGE
+    // the operands are in registers: the next row may overwrite the buffer of row h - 1
+    if (h + 1 < S) issue(h + 1, (h + 1) & 1);
+    seg_cp_commit();
+    return hi - lo;
+  }
+};
+// one table row -> cache row j of this unit (cu = cache + 2 u)
+template <int KM>
+__device__ __forceinline__ void seg_cache_fill_row(double* cu, long long U, int j, const Table& t, const Cols<KM>& c, int table_row) {
+  constexpr int KT = SegDims<KM>::KT, NE = SegDims<KM>::NE, NP = SegDims<KM>::NP;
+  const double* __restrict__ p = t.base + (long long)table_row * t.row_stride;
+  double v[2 * NP];
+#pragma unroll
+  for (int i = 0; i < KM; ++i) {
+    const bool on = i < c.k;
+    v[KT + i] = on ? __ldg(p + c.zy[i]) : 0.0;
+#pragma unroll
+    for (int q = 0; q <= i; ++q) v[DBN_TRI(i, q)] = on ? __ldg(p + c.zz[DBN_TRI(i, q)]) : 0.0;
+  }
+  v[KT + KM] = __ldg(p + c.yy);
+  if (NE < 2 * NP) v[2 * NP - 1] = 0.0;
+  double2* dst = reinterpret_cast<double2*>(cu) + (long long)j * NP * U;
+#pragma unroll
+  for (int q = 0; q < NP; ++q) dst[(long long)q * U] = make_double2(v[2 * q], v[2 * q + 1]);
+}
+
 #ifndef DBN_CHAIN_MINB
 #define DBN_CHAIN_MINB 1
 #endif
@@ -228,6 +313,13 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
   rng.init(a.seed, a.chain_offset + (unsigned)chain, (unsigned)node);
   Work wk = {0, 0, 0, 0};
   const bool replay = TRACE && a.rd != nullptr;
+  // per-unit boundary-row cache of the current state (SegFromCache, dbn_score.cuh): every pass over the current parent set
+  // reads coalesced cached rows; only the proposed parent set is gathered from the table.  Round 1 gathered 2 x 21 scattered
+  // doubles per segment in every pass and was bound by the L1 request path (profiles/r1_v0).
+  extern __shared__ __align__(16) double s_stage[];   // [2][NP][CHAIN_BLOCK][2] staging of cached rows
+  double* const cu = a.cache + 2ll * u;
+  const long long U = a.U;
+  double* const st = s_stage + 2 * tid;
 
   for (int li = 0; li < n_it; ++li) {
     const int it = a.it0 + li;
@@ -248,6 +340,13 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       for (int i = 0; i < KM; ++i) fk[i] = f[i];
       make_cols<KM>(cols, a.tb, node, fk, k);
     }
+    // rows 0..S-1 of the cache <- table rows at the current segment ends, current design columns (launch start, accepted moves)
+    auto fill_rows = [&]() {
+      for (int j = 0; j < S; ++j) seg_cache_fill_row<KM>(cu, U, j, a.tb, cols, DBN_SEG_END(tau_cur(j), j, S, N));
+      __threadfence_block();   // the stores are ordered before the asynchronous copies that read the rows back
+    };
+    if (li == 0) fill_rows();
+    auto seg_cur = [&]() { return SegFromCache<KM, decltype(tau_cur)>{cu, U, tau_cur, S, N, -1, 99, 0, st}; };
 
     // =========================== Gibbs pass: sigma^2, beta, lambda^2 (, delta^2) ===========================
     // One sweep over the segments with the OLD lambda^2/delta^2.  beta_h = mean_h + sqrt(sigma^2) e_h with
@@ -261,10 +360,11 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
 #pragma unroll
       for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
       int lo = 0;
+      seg_cur().begin();
       for (int h = 0; h < S; ++h) {
         const int hi = DBN_SEG_END(tau_cur(h), h, S, N);
         double G[KT], g[KM], s, A[KT], dinv[KM], wv[KM];
-        load_segment<KM>(a.tb, cols, lo, hi, G, g, s);
+        seg_cur()(h, G, g, s);
         if (SEQ && h == 1) {
           form_a<KM>(G, lam, A);
           ldl_factor<KM>(A, dinv);
@@ -443,11 +543,12 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
 #pragma unroll
         for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
         int lo = 0;
+        seg_cur().begin();
         for (int h = 0; h < S; ++h) {
           const int hi = DBN_SEG_END(tau_cur(h), h, S, N);
+          double G[KT], g[KM], s, A[KT], dinv[KM];
+          seg_cur()(h, G, g, s);   // the rows are streamed in order: segment 0 is staged although only its end row is used
           if (h >= 1) {
-            double G[KT], g[KM], s, A[KT], dinv[KM];
-            load_segment<KM>(a.tb, cols, lo, hi, G, g, s);
             if (h == 1) {
               form_a<KM>(G, lam_new, A);
               ldl_factor<KM>(A, dinv);
@@ -493,16 +594,16 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       lam = lam_new;
     }
 
-    // unified scorer for the current method
-    auto score = [&](const Cols<KM>& c, auto tau_fn, int S_, const double(&mu_)[KM]) -> double {
+    // unified scorer for the current method; `seg` = segment source (table gather or cached rows)
+    auto score = [&](auto seg, int S_, int k_, const double(&mu_)[KM]) -> double {
       if constexpr (SEQ)
-        return score_seq<KM>(a.tb, c, tau_fn, S_, lam, dlt, a.c0, a.T_half_plus_a, a.two_b, wk);
+        return score_seq_seg<KM>(seg, S_, k_, lam, dlt, a.c0, a.T_half_plus_a, a.two_b, wk);
       else if constexpr (VV)
-        return score_vv<KM>(a.tb, c, tau_fn, S_, lam, mu_, a.a_sig, vv_c, a.two_b, wk);
+        return score_vv_seg<KM>(seg, S_, k_, lam, mu_, a.a_sig, vv_c, a.two_b, wk);
       else if constexpr (GLOB)
-        return score_plain<KM, true>(a.tb, c, tau_fn, S_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
+        return score_plain_seg<KM, true>(seg, S_, k_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
       else
-        return score_plain<KM, false>(a.tb, c, tau_fn, S_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
+        return score_plain_seg<KM, false>(seg, S_, k_, lam, mu_, a.c0, a.T_half_plus_a, a.two_b, wk);
     };
 
     // ======================================= parent-set move (a4 / a6) =======================================
@@ -604,7 +705,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         if constexpr (GLOB) {
           // moves.py:476-491: mu* ~ muSampler(0 | pi*), reverse density muSampler(mu | pi) at the current mu
           // (VV: moves.py:361-375; vvMuSampler has segment-specific variances and no mu_in term, samplers.py:353-394)
-          mu_posterior<KM>(a.tb, cstar, tau_cur, S, lam, sig_of, Qs, m0s, wk);
+          mu_posterior_seg<KM>(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {
@@ -622,9 +723,9 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             gs.sample(z, mu_star);
           }
           const double ld_star = gs.logpdf(mu_star, Qs, ks);
-          ml_star = score(cstar, tau_cur, S, mu_star);
-          ml_cur = score(cols, tau_cur, S, mu);
-          mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig_of, Qc, m0c, wk);
+          ml_star = score(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, mu_star);
+          ml_cur = score(seg_cur(), S, k, mu);
+          mu_posterior_seg<KM>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
           have_qc = true;
           double mc[KM];
 #pragma unroll
@@ -652,8 +753,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
               for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 1 * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? cv[DBN_TRI(i, j)] : NAN;
           }
         } else {
-          ml_star = score(cstar, tau_cur, S, mu_star);   // moves.py:574-576 / :569-571 / :672
-          ml_cur = score(cols, tau_cur, S, mu);          // moves.py:599-600 / :594-595 / :681
+          ml_star = score(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, mu_star);   // moves.py:574-576 / :569-571 / :672
+          ml_cur = score(seg_cur(), S, k, mu);          // moves.py:599-600 / :594-595 / :681
           log_ratio = ml_star - ml_cur + log_hr;         // uniform parent-set prior cancels (priors.py:48-68)
         }
         const double uacc = replay ? rd[DBN_RD_U_PI] : rng.uniform();
@@ -672,6 +773,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
 #pragma unroll
           for (int j = 0; j < PMAX; ++j) pi[j] = star[j];
           cols = cstar;
+          fill_rows();   // the cached rows follow the accepted parent set
           if (GLOB) {
 #pragma unroll
             for (int i = 0; i < KM; ++i) {
@@ -702,6 +804,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
       bool valid = true;
       int Ss = S;
       double log_hr = 0.0;
+      int r_new = -1, r_from = 99, r_shift = 0, new_cp = 0;   // cached row of boundary j of tau* (SegFromCache) and the added changepoint
       if (move == 0) {  // cpBirthMove (changepointMoves.py:93-124)
         int inside = 0;
         for (int j = 0; j < S - 1; ++j) inside += (TAU(j) >= 2 && TAU(j) <= ns) ? 1 : 0;
@@ -717,6 +820,9 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           bool placed = false;
           for (int j = 0; j < S; ++j) {
             if (!placed && c < TAU(j)) {
+              r_new = r_from = w_;
+              r_shift = -1;
+              new_cp = c;
               TAS(w_++) = c;
               placed = true;
             }
@@ -735,6 +841,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         for (int j = 0; j < S; ++j)
           if (j != idx) TAS(w_++) = TAU(j);
         Ss = S - 1;
+        r_from = idx - 1;
+        r_shift = 1;
         // moves.py:163 (nh/seq) / :55 (glob)
         log_hr = GLOB ? log((double)S / (double)(ns - 1 - Ss)) : log((double)(S - 1) / (double)(ns - Ss));
       } else {  // cpRellocationMove (:3-61)
@@ -749,6 +857,8 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           const int p = replay ? ri[DBN_RI_TAU_PICK + 1] : rng.below(ncand);
           int c = left + 1 + p;
           if (c >= TAU(idx)) ++c;
+          r_new = idx;
+          new_cp = c;
           for (int j = 0; j < S; ++j) TAS(j) = (j == idx) ? c : TAU(j);
         }
       }
@@ -758,7 +868,12 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         ti[DBN_TI_TAU_ACCEPT] = 0;
       }
       if (valid) {
-        double ml_cur = have_ml_now ? ml_now : score(cols, tau_cur, S, mu);  // moves.py:184-191 / :67-69
+        if (r_new >= 0) {   // the one boundary tau* adds
+          seg_cache_fill_row<KM>(cu, U, SEG_ROW_NEW, a.tb, cols, new_cp - 1);
+          __threadfence_block();
+        }
+        const SegFromCache<KM, decltype(tau_star)> seg_star{cu, U, tau_star, Ss, N, r_new, r_from, r_shift, st};
+        double ml_cur = have_ml_now ? ml_now : score(seg_cur(), S, k, mu);  // moves.py:184-191 / :67-69
         double ml_star, log_ratio;
         const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
         double mu_star[KM];
@@ -768,11 +883,11 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           // vvGlobCoupTauMove (moves.py:238-307): mu is kept, so only the two marginal likelihoods enter
 #pragma unroll
           for (int i = 0; i < KM; ++i) mu_star[i] = mu[i];
-          ml_star = score(cols, tau_star, Ss, mu);        // :283-284
+          ml_star = score(seg_star, Ss, k, mu);        // :283-284
           log_ratio = ml_star - ml_cur + lprior + log_hr;  // :291-295
         } else if constexpr (GLOB) {
           // moves.py:72-93: density of the current mu under muSampler(mu | tau), then mu* ~ muSampler(0 | tau*)
-          if (!have_qc) mu_posterior<KM>(a.tb, cols, tau_cur, S, lam, sig_of, Qc, m0c, wk);
+          if (!have_qc) mu_posterior_seg<KM>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
           double mc[KM];
 #pragma unroll
           for (int i = 0; i < KM; ++i) mc[i] = m0c[i] + mu[i];
@@ -780,7 +895,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           gc.setup(Qc, mc);
           const double ld_cur = gc.logpdf(mu, Qc, k);
           double Qs[KT], m0s[KM];
-          mu_posterior<KM>(a.tb, cols, tau_star, Ss, lam, sig_of, Qs, m0s, wk);
+          mu_posterior_seg<KM>(seg_star, Ss, k, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {
@@ -798,7 +913,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             gs.sample(z, mu_star);
           }
           const double ld_star = gs.logpdf(mu_star, Qs, k);
-          ml_star = score(cols, tau_star, Ss, mu_star);
+          ml_star = score(seg_star, Ss, k, mu_star);
           const double lp_star = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu_star));
           const double lp_cur = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu));
           log_ratio = ml_star - ml_cur + lprior + lp_star - lp_cur + ld_cur - ld_star + log_hr;  // moves.py:112-117
@@ -818,7 +933,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
               for (int j = 0; j <= i; ++j) td[DBN_TD_MUS_COV + 3 * DBN_KTRI + DBN_TRI(i, j)] = (i < k) ? cv[DBN_TRI(i, j)] : NAN;
           }
         } else {
-          ml_star = score(cols, tau_star, Ss, mu_star);  // moves.py:209-216
+          ml_star = score(seg_star, Ss, k, mu_star);  // moves.py:209-216
           log_ratio = ml_star - ml_cur + lprior + log_hr;  // moves.py:225
         }
         const double uacc = replay ? rd[DBN_RD_U_TAU] : rng.uniform();
@@ -831,6 +946,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         if (acc) {
           S = Ss;
           for (int j = 0; j < Ss; ++j) TAU(j) = TAS(j);
+          fill_rows();   // the cached rows follow the accepted changepoints
           if (GLOB) {
 #pragma unroll
             for (int i = 0; i < KM; ++i) mu[i] = mu_star[i];

@@ -26,7 +26,7 @@ namespace dbn {
 
 template <class Fn, class Args>
 static cudaError_t launch_(Fn fn, unsigned grid, int block, size_t smem, cudaStream_t s, const Args& a) {
-  if (smem > 48 * 1024) {
+  if (smem > 16 * 1024) {   // static + dynamic shared memory above 48 KB needs the opt-in as well (the var-glob kernel has 20 KB static)
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

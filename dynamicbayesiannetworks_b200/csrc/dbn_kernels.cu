@@ -664,6 +664,12 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
     cudaError_t e = cudaMalloc(&h->d_cache, cache_bytes);
     if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "boundary-row cache of %.2f GB does not fit: %s", cache_bytes / 1e9, cudaGetErrorString(e));
     CU(h, cudaMalloc(&h->st_cg, U * PMAX * sizeof(int)));
+  } else if (!is_fp_method(p->method)) {
+    // coupled methods (seq / glob / var-glob): boundary rows of the current state + the proposal's new row + a zero row (dbn_score.cuh)
+    const int km = p->fan_in <= 3 ? 4 : 5;
+    const size_t cache_bytes = chain_cache_doubles_per_unit(km) * U * sizeof(double);
+    cudaError_t e = cudaMalloc(&h->d_cache, cache_bytes);
+    if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "boundary-row cache of %.2f GB does not fit: %s", cache_bytes / 1e9, cudaGetErrorString(e));
   }
   h->counts_elems = (long long)h->n * h->n + h->n + (long long)h->n * (h->N + 3) + h->n;
   if (is_fp_method(p->method)) {
@@ -812,7 +818,7 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   const int km = p.fan_in <= 3 ? 4 : 5;
   const bool fast = p.method == DBN_H_DBN || p.method == DBN_NH_DBN;
   const int block = fast ? FAST_BLOCK : CHAIN_BLOCK;
-  const size_t smem = fast ? fast_smem_bytes(km) : 0;
+  const size_t smem = fast ? fast_smem_bytes(km) : chain_smem_bytes(km);
   const unsigned grid = (unsigned)((h->U + block - 1) / block);
   if (fast) CUX((trace ? launch_fast_trace : launch_fast_plain)(p.method, km, grid, block, smem, h->stream, a));
   else CUX((trace ? launch_chain_trace : launch_chain_plain)(p.method, km, grid, block, smem, h->stream, a));
@@ -1006,7 +1012,9 @@ int dbn_verify_cache(dbn_handle* h, uint64_t out[2]) {
   if (!h || !out) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_verify_cache: call dbn_chain_init first");
   out[0] = out[1] = 0;
-  if (!h->d_cache || !h->cache_valid) return DBN_OK;  // seq / glob methods keep no cache; nothing cached before the first dbn_run
+  // only the h / nh kernel keeps a cache across launches (the coupled kernel refills its rows at every launch start);
+  // nothing is cached before the first dbn_run
+  if (!h->d_cache || !h->cache_valid || !(h->rp.method == DBN_H_DBN || h->rp.method == DBN_NH_DBN)) return DBN_OK;
   CU(h, cudaSetDevice(h->cfg.device));
   ChainArgs a;
   memset(&a, 0, sizeof(a));

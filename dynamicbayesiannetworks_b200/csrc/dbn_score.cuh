@@ -232,81 +232,108 @@ struct Work {
 // end row (exclusive) of segment h: tau[h] - 1, N for the last one (utils.py:179,262)
 #define DBN_SEG_END(tau_h, h, S, N) (((h) == (S)-1) ? (N) : ((tau_h)-1))
 
+// ----- segment sources: seg.begin() starts a pass, seg(h, G, g, s) loads the statistics of segment h (h = 0, 1, .. in order)
+// and returns its length.  The coupled chain kernel has a second source that reads cached boundary rows (dbn_chain.cuh).
+// From the prefix table (two gathered rows per segment):
+template <int KM, class TauFn>
+struct SegFromTable {
+  const Table& t;
+  const Cols<KM>& c;
+  TauFn tau;
+  int S;
+  __device__ __forceinline__ void begin() const {}
+  __device__ __forceinline__ int operator()(int h, double (&G)[KM * (KM + 1) / 2], double (&g)[KM], double& s) const {
+    const int lo = h ? DBN_SEG_END(tau(h - 1), h - 1, S, t.N) : 0;
+    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
+    load_segment<KM>(t, c, lo, hi, G, g, s);
+    return hi - lo;
+  }
+};
+template <int KM, class TauFn>
+__device__ __forceinline__ SegFromTable<KM, TauFn> seg_from_table(const Table& t, const Cols<KM>& c, TauFn tau, int S) {
+  return SegFromTable<KM, TauFn>{t, c, tau, S};
+}
+
 // ----- a2/a3: log marginal likelihood, one prior mean for all segments (nh/h: zeros; glob: mu) ------------
 // tau(h) is a callable returning the h-th changepoint.  c0 = lgamma(T/2+a) - lgamma(a) - (T/2) ln(pi) + a ln(2b).
+template <int KM, bool HAS_MU, class SegFn>
+__device__ __forceinline__ double score_plain_seg(SegFn seg, int S, int k, double lam, const double (&mu)[KM], double c0, double T_half_plus_a,
+                                                  double two_b, Work& wk) {
+  double acc_ld = 0.0, acc_q = 0.0;
+  seg.begin();
+  for (int h = 0; h < S; ++h) {
+    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
+    seg(h, G, g, s);
+    form_a<KM>(G, lam, A);
+    acc_ld += log(ldl_factor<KM>(A, dinv));
+    acc_q += segment_q<KM, HAS_MU>(G, g, s, mu, lam, A, dinv, wv);
+    wk.segment(k, HAS_MU);
+  }
+  wk.eval();
+  return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+}
 template <int KM, bool HAS_MU, class TauFn>
 __device__ __forceinline__ double score_plain(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam,
                                               const double (&mu)[KM], double c0, double T_half_plus_a, double two_b,
                                               Work& wk) {
-  double acc_ld = 0.0, acc_q = 0.0;
-  int lo = 0;
-  for (int h = 0; h < S; ++h) {
-    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
-    double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
-    load_segment<KM>(t, c, lo, hi, G, g, s);
-    form_a<KM>(G, lam, A);
-    acc_ld += log(ldl_factor<KM>(A, dinv));
-    acc_q += segment_q<KM, HAS_MU>(G, g, s, mu, lam, A, dinv, wv);
-    wk.segment(c.k, HAS_MU);
-    lo = hi;
-  }
-  wk.eval();
-  return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+  return score_plain_seg<KM, HAS_MU>(seg_from_table<KM>(t, c, tau, S), S, c.k, lam, mu, c0, T_half_plus_a, two_b, wk);
 }
 
 // ----- vvLogMargLikelihood (marginalLikelihood.py:5-43): segment-specific variances ---------------------------
 // The sum over the segments of single-segment log marginal likelihoods, each with its own length T_h in the Gamma, pi
 // and exponent terms (:29-30, :39), lambda^2 and the prior mean mu shared (:13, :32).
 // c_seg = a ln(2b) - lgamma(a); ln(pi) = 1.1447298858494002.
-template <int KM, class TauFn>
-__device__ __forceinline__ double score_vv(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam,
-                                           const double (&mu)[KM], double a_sig, double c_seg, double two_b, Work& wk) {
+template <int KM, class SegFn>
+__device__ __forceinline__ double score_vv_seg(SegFn seg, int S, int k, double lam, const double (&mu)[KM], double a_sig, double c_seg,
+                                               double two_b, Work& wk) {
   double acc = 0.0;
-  int lo = 0;
+  seg.begin();
   for (int h = 0; h < S; ++h) {
-    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
     double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
-    load_segment<KM>(t, c, lo, hi, G, g, s);
+    const int len = seg(h, G, g, s);
     form_a<KM>(G, lam, A);
     const double ld = log(ldl_factor<KM>(A, dinv));
     const double q = segment_q<KM, true>(G, g, s, mu, lam, A, dinv, wv);
-    const double Th_half = 0.5 * (double)(hi - lo);
+    const double Th_half = 0.5 * (double)len;
     acc += lgamma(Th_half + a_sig) + c_seg - Th_half * 1.1447298858494002 - 0.5 * ld - (Th_half + a_sig) * log(two_b + q);
-    wk.segment(c.k, true);
+    wk.segment(k, true);
     wk.flops += 12;
-    lo = hi;
   }
   wk.eval();
   return acc;
 }
+template <int KM, class TauFn>
+__device__ __forceinline__ double score_vv(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam,
+                                           const double (&mu)[KM], double a_sig, double c_seg, double two_b, Work& wk) {
+  return score_vv_seg<KM>(seg_from_table<KM>(t, c, tau, S), S, c.k, lam, mu, a_sig, c_seg, two_b, wk);
+}
 // ----- a2 + a8: sequentially coupled log marginal likelihood ------------------------------------------------
 // Prior means are betaTildeSampler's (samplers.py:4-54): bt[0] = 0, bt[1] = (I/lam + G_1)^-1 g_1,
 // bt[h] = (I/dlt + G_{h-1})^-1 (bt[h-2]/dlt + g_{h-1}); C_h uses dlt for h > 0 (marginalLikelihood.py:104-107).
-template <int KM, class TauFn>
-__device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, double dlt,
-                                            double c0, double T_half_plus_a, double two_b, Work& wk) {
+template <int KM, class SegFn>
+__device__ __forceinline__ double score_seq_seg(SegFn seg, int S, int k, double lam, double dlt, double c0, double T_half_plus_a, double two_b,
+                                                Work& wk) {
   double acc_ld = 0.0, acc_q = 0.0;
   double bt_cur[KM], bt_prev[KM];
 #pragma unroll
   for (int i = 0; i < KM; ++i) bt_cur[i] = bt_prev[i] = 0.0;
-  int lo = 0;
+  seg.begin();
   for (int h = 0; h < S; ++h) {
-    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
     double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM], wv[KM];
-    load_segment<KM>(t, c, lo, hi, G, g, s);
+    seg(h, G, g, s);
     if (h == 1) {  // bt[1] from this segment's own data with lambda^2
       form_a<KM>(G, lam, A);
       ldl_factor<KM>(A, dinv);
 #pragma unroll
       for (int i = 0; i < KM; ++i) bt_cur[i] = lam * g[i];
       solve_ldl<KM>(A, dinv, bt_cur);
-      wk.segment(c.k, false);
+      wk.segment(k, false);
     }
     const double w = (h == 0) ? lam : dlt;
     form_a<KM>(G, w, A);
     acc_ld += log(ldl_factor<KM>(A, dinv));
     acc_q += segment_q<KM, true>(G, g, s, bt_cur, w, A, dinv, wv);
-    wk.segment(c.k, true);
+    wk.segment(k, true);
     if (h >= 1) {  // bt[h+1] = A_dlt(h)^-1 (bt[h-1] + dlt g_h)
       double nxt[KM];
 #pragma unroll
@@ -318,30 +345,33 @@ __device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, T
         bt_cur[i] = nxt[i];
       }
     }
-    lo = hi;
   }
   wk.eval();
   return c0 - 0.5 * acc_ld - T_half_plus_a * log(two_b + acc_q);
+}
+template <int KM, class TauFn>
+__device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, double dlt,
+                                            double c0, double T_half_plus_a, double two_b, Work& wk) {
+  return score_seq_seg<KM>(seg_from_table<KM>(t, c, tau, S), S, c.k, lam, dlt, c0, T_half_plus_a, two_b, wk);
 }
 
 // ----- a9: muSampler's Gaussian (samplers.py:307-351) on sufficient statistics ----------------------------
 // Q = I + sum_h A_h^-1 G_h / s2 (precision), m0 = sum_h A_h^-1 g_h / s2 (mean numerator WITHOUT the mu_in term).
 // sig2(h) is a callable: the same sigma^2 for every segment (glob), or the segment-specific sigma^2_h of vvMuSampler
 // (samplers.py:353-394).
-template <int KM, class TauFn, class SigFn>
-__device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, SigFn sig2,
-                                             double (&Q)[KM * (KM + 1) / 2], double (&m0)[KM], Work& wk) {
+template <int KM, class SegFn, class SigFn>
+__device__ __forceinline__ void mu_posterior_seg(SegFn seg, int S, int k, double lam, SigFn sig2, double (&Q)[KM * (KM + 1) / 2],
+                                                 double (&m0)[KM], Work& wk) {
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
     m0[i] = 0.0;
 #pragma unroll
     for (int j = 0; j <= i; ++j) Q[DBN_TRI(i, j)] = (i == j) ? 1.0 : 0.0;
   }
-  int lo = 0;
+  seg.begin();
   for (int h = 0; h < S; ++h) {
-    const int hi = DBN_SEG_END(tau(h), h, S, t.N);
     double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM];
-    load_segment<KM>(t, c, lo, hi, G, g, s);
+    seg(h, G, g, s);
     form_a<KM>(G, lam, A);
     ldl_factor<KM>(A, dinv);
     const double is2 = 1.0 / sig2(h);
@@ -360,9 +390,13 @@ __device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, 
 #pragma unroll
       for (int i = col; i < KM; ++i) Q[DBN_TRI(i, col)] += x[i] * is2;
     }
-    wk.segment(c.k, true);
-    lo = hi;
+    wk.segment(k, true);
   }
+}
+template <int KM, class TauFn, class SigFn>
+__device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, SigFn sig2,
+                                             double (&Q)[KM * (KM + 1) / 2], double (&m0)[KM], Work& wk) {
+  mu_posterior_seg<KM>(seg_from_table<KM>(t, c, tau, S), S, c.k, lam, sig2, Q, m0, wk);
 }
 
 }  // namespace dbn

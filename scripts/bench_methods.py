@@ -4,7 +4,7 @@
    mTOR / a 40-gene synthetic series.  Data come from the golden fixtures (the series the reference ships) so that the
    script runs on the GPU box.  One JSON line per case: unit-iterations/s with the table resident (CUDA events).
 
-       python scripts/bench_methods.py [> profiles/r1_v9/methods.jsonl]
+       python scripts/bench_methods.py [label-substring] [> profiles/r1_v9/methods.jsonl]
 """
 import glob
 import json
@@ -58,6 +58,13 @@ def run(label, data, method, chains, window, reps, **kw):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ''   # substring filter on the case label
+    global run
+    run_all = run
+
+    def run(label, *a, **k):
+        if only in label:
+            run_all(label, *a, **k)
     yeast, mtor = series('yeast'), series('mtor')
     syn40, _, _ = make_synthetic(40, 400, 3, 4, 5)
     run('c2 yeast nh-dbn, 64 chains', yeast, 'varying_nh_dbn', 64, 100, 20)
