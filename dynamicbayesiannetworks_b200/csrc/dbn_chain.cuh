@@ -22,6 +22,7 @@ struct ChainArgs {
   int unit0;    // grid index node * C + chain of local unit 0
   int n_genes;  // nodes = genes; tb.n = n_genes * lag candidate feature columns (column l * n_genes + g = lag-(l+1) copy of gene g)
   int lag;
+  int lanes;    // lanes of a warp that hold a unit (32 = every lane; fewer spread a small unit count over more warps and SMs)
   int it0;      // global index of the first iteration of this launch
   int n_iter;
   unsigned int chain_offset;
@@ -283,7 +284,10 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
   __shared__ int s_tas[SMAX * CHAIN_BLOCK];
   __shared__ double s_sigv[VV ? SMAX * CHAIN_BLOCK : 1];   // VV: sigma^2_h of the current iteration
   const int tid = threadIdx.x;
-  const int u_raw = blockIdx.x * CHAIN_BLOCK + tid;
+  // unit of this thread: dense, or `lanes` units per warp when the unit count does not fill the device (diverging lanes of
+  // a warp serialise; a unit alone in its warp runs at single-thread latency, profiles/r2_small)
+  const int u_raw = a.lanes >= 32 ? blockIdx.x * CHAIN_BLOCK + tid
+                                  : ((tid & 31) < a.lanes ? (blockIdx.x * (CHAIN_BLOCK / 32) + (tid >> 5)) * a.lanes + (tid & 31) : a.U);
   const bool active = u_raw < a.U;   // lanes past the end run zero iterations so warp-wide reductions stay full
   const int u = active ? u_raw : 0;
   const int n_it = active ? a.n_iter : 0;

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   if (tid < 8) s_tot[tid] = 0ull;
   if (tid == 8) s_done = 0u;
   __syncthreads();  // kernel entry: every warp is converged here
-  const int u_raw = blockIdx.x * FAST_BLOCK + tid;
+  const int u_raw = a.lanes >= 32 ? blockIdx.x * FAST_BLOCK + tid   // see dbn_chain.cuh
+                                  : ((tid & 31) < a.lanes ? (blockIdx.x * (FAST_BLOCK / 32) + (tid >> 5)) * a.lanes + (tid & 31) : a.U);
   const bool active = u_raw < a.U;
   const int u = active ? u_raw : 0;
   const int node = (a.unit0 + u) / a.C;

@@ -227,6 +227,8 @@ struct dbn_handle {
   // full-parents globally coupled chain: global mean [n][U], per-block matrix workspace (large n only)
   double *st_mu_fp = nullptr, *d_fp_ws = nullptr, *d_fp_bsc = nullptr;
   int fp_grid = 0;
+  int sm_count = 0;   // multiprocessors of the device (read once in dbn_chain_init)
+  int lanes_env = 0;  // DBN_LANES override (0: automatic)
   unsigned long long* d_counts = nullptr;
   long long counts_elems = 0;
   unsigned long long* d_counters = nullptr;
@@ -646,6 +648,11 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p) {
   if (h->unit_count < 0) h->unit0 = 0;
   CU(h, cudaSetDevice(h->cfg.device));
   free_chain(h);
+  CU(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->cfg.device));
+  {
+    const char* ev = getenv("DBN_LANES");
+    h->lanes_env = (ev && atoi(ev) >= 1 && atoi(ev) <= 32) ? atoi(ev) : 0;
+  }
   h->rp = *p;
   h->U = (int)U;
   h->it_done = 0;
@@ -819,7 +826,21 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   const bool fast = p.method == DBN_H_DBN || p.method == DBN_NH_DBN;
   const int block = fast ? FAST_BLOCK : CHAIN_BLOCK;
   const size_t smem = fast ? fast_smem_bytes(km) : chain_smem_bytes(km);
-  const unsigned grid = (unsigned)((h->U + block - 1) / block);
+  // small unit counts are spread over more warps: `lanes` units per warp, chosen so that the warps about fill the device
+  // (DBN_LANES overrides: A/B measurements in profiles/r2_small)
+  int lanes = 32;
+  {
+    // measured (profiles/r2_small/lanes_ab.txt): the h / nh kernel gains down to one unit per warp (c2, 320 units: 8.7e6 ->
+    // 1.4e7 unit-iterations/s); the coupled kernel is fastest at 16 and loses below (c3, 2816 units: 4.0e7 / 4.3e7 / 1.8e7 at
+    // 32 / 16 / 4 -- the gathered table no longer stays in the L1 of a few SMs)
+    const long long slots = (long long)h->sm_count * (fast ? 12 : 8);   // resident warps of the kernel
+    const int min_lanes = fast ? 1 : 16;
+    while (lanes > min_lanes && (h->U + lanes / 2 - 1) / (lanes / 2) <= slots) lanes /= 2;   // halve while the warps still fit one wave
+    if (h->lanes_env) lanes = h->lanes_env;
+  }
+  a.lanes = lanes;
+  const int upb = lanes >= 32 ? block : lanes * (block / 32);   // units per block
+  const unsigned grid = (unsigned)((h->U + upb - 1) / upb);
   if (fast) CUX((trace ? launch_fast_trace : launch_fast_plain)(p.method, km, grid, block, smem, h->stream, a));
   else CUX((trace ? launch_chain_trace : launch_chain_plain)(p.method, km, grid, block, smem, h->stream, a));
   h->cache_valid = true;
