@@ -581,8 +581,19 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
           }
           __syncthreads();
           const double rho = s - 2.0 * fp_dot(mu, g, k, red) + fp_dot(mu, tmp, k, red);
-          fp_factor_inv(A, W, ld, k, t, stage);
-          fp_trmv(W, ld, k, x, t, stage);
+          // large k (solve form): the Gibbs pass needs A^-1 only applied to vectors, so the factor and the inverted diagonal
+          // blocks suffice (blocked two-vector solves, dbn_fp_big.cuh) and the k^3 / 3 of the full inverse factor is saved.
+          // Trace builds also form W (the traced covariance diagonal reads it); seq needs it for the beta-tilde recursion.
+          const bool solve_form = BIG && !SEQM;
+          if (solve_form) {
+            fpb_factor(A, W, ld, k, t, stage, TRACE);
+            fpb_solve_fwd2(A, W, ld, k, x, rhs, stage);   // x <- L^-1 v, rhs <- L^-1 (mu + w g)
+            for (int i = tid; i < k; i += FP_BLOCK) t[i] = x[i];
+            __syncthreads();
+          } else {
+            fp_factor_inv(A, W, ld, k, t, stage);
+            fp_trmv(W, ld, k, x, t, stage);
+          }
           const double q_h = rho - w * fp_dot(t, t, k, red);
           q_sum += q_h;
           double sig_h = 1.0;
@@ -601,12 +612,29 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             __syncthreads();
             sig_h = sigv[h];
           }
-          fp_trmv(W, ld, k, rhs, t, stage);
-          fp_trmv_t(W, ld, k, t, mean, stage, red);
+          if (solve_form) {
+            if (!replay) {
+              fp_normals(z, k, gchain, unode, uit, (uint32_t)(h * 512), key);
+            } else {
+              for (int i = tid; i < k; i += FP_BLOCK) z[i] = 0.0;
+              __syncthreads();
+            }
+            fpb_solve_bwd2(A, W, ld, k, rhs, z, stage);   // rhs <- L^-T L^-1 (mu + w g) = posterior mean, z <- L^-T z
+            for (int i = tid; i < k; i += FP_BLOCK) {
+              mean[i] = rhs[i];
+              e[i] = z[i];
+            }
+            __syncthreads();
+          } else {
+            fp_trmv(W, ld, k, rhs, t, stage);
+            fp_trmv_t(W, ld, k, t, mean, stage, red);
+          }
           ++n_segs;
           if (!replay) {
-            fp_normals(z, k, gchain, unode, uit, (uint32_t)(h * 512), key);
-            fp_trmv_t(W, ld, k, z, e, stage, red);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
+            if (!solve_form) {
+              fp_normals(z, k, gchain, unode, uit, (uint32_t)(h * 512), key);
+              fp_trmv_t(W, ld, k, z, e, stage, red);  // e = L^-T z ; beta = mean + sqrt(sig2 lam) e   (samplers.py:214-216)
+            }
             for (int i = tid; i < k; i += FP_BLOCK) tmp[i] = mean[i] - mu[i];
             __syncthreads();
             if constexpr (VVM) {
@@ -948,9 +976,20 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             rhs[i] = av_cur[i] / sig2 + mu[i];
           }
           __syncthreads();
-          const double ldq_cur = fp_factor_inv(Q, W, ld, k, t, stage);
-          fp_trmv(W, ld, k, rhs, t, stage);
-          fp_trmv_t(W, ld, k, t, mean, stage, red);
+          double ldq_cur;
+          if (BIG) {   // solve form (see the Gibbs pass): mean = Q^-1 rhs by two blocked solves, no inverse factor
+            ldq_cur = fpb_factor(Q, W, ld, k, t, stage, false);
+            for (int i = tid; i < k; i += FP_BLOCK) z[i] = 0.0;
+            __syncthreads();
+            fpb_solve_fwd2(Q, W, ld, k, rhs, z, stage);
+            fpb_solve_bwd2(Q, W, ld, k, rhs, z, stage);
+            for (int i = tid; i < k; i += FP_BLOCK) mean[i] = rhs[i];
+            __syncthreads();
+          } else {
+            ldq_cur = fp_factor_inv(Q, W, ld, k, t, stage);
+            fp_trmv(W, ld, k, rhs, t, stage);
+            fp_trmv_t(W, ld, k, t, mean, stage, red);
+          }
           if (TRACE && td)
             for (int i = tid; i < k; i += FP_BLOCK) td[10 + k + i] = mean[i];
           for (int i = tid; i < k; i += FP_BLOCK) x[i] = mu[i] - mean[i];
@@ -969,7 +1008,21 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             rhs[i] = av_star[i] / sig2;
           }
           __syncthreads();
-          const double ldq_star = fp_factor_inv(Q, W, ld, k, t, stage);
+          double ldq_star;
+          if (BIG) {
+            ldq_star = fpb_factor(Q, W, ld, k, t, stage, false);
+            for (int i = tid; i < k; i += FP_BLOCK) z[i] = 0.0;
+            __syncthreads();
+            fpb_solve_fwd2(Q, W, ld, k, rhs, z, stage);
+            if (!replay) fp_normals(z, k, gchain, unode, uit, 8192u, key);
+            fpb_solve_bwd2(Q, W, ld, k, rhs, z, stage);   // rhs <- Q^-1 rhs = mean, z <- L^-T z (cov = Q^-1)
+            for (int i = tid; i < k; i += FP_BLOCK) {
+              mean[i] = rhs[i];
+              mu_star[i] = replay ? rd[3 + i] : rhs[i] + z[i];
+            }
+            __syncthreads();
+          } else {
+          ldq_star = fp_factor_inv(Q, W, ld, k, t, stage);
           fp_trmv(W, ld, k, rhs, t, stage);
           fp_trmv_t(W, ld, k, t, mean, stage, red);
           if (replay) {
@@ -980,6 +1033,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
             fp_trmv_t(W, ld, k, z, e, stage, red);  // cov = Q^-1 = W^T W
             for (int i = tid; i < k; i += FP_BLOCK) mu_star[i] = mean[i] + e[i];
             __syncthreads();
+          }
           }
           if (TRACE && td)
             for (int i = tid; i < k; i += FP_BLOCK) td[10 + 2 * k + i] = mean[i];

@@ -31,7 +31,14 @@
 namespace dbn {
 
 constexpr int FPB_THREADS = 512;
-constexpr int FPB_TM = 64, FPB_TN = 128, FPB_KD = 16, FPB_NSTAGE = 4;
+#ifndef DBN_FPB_KD
+#define DBN_FPB_KD 32   // 32 rows x 2 stages measured 7 % faster than 16 x 4 on the factorisation (half the barriers), profiles/r2_c5/ring_ab.txt
+#endif
+#ifndef DBN_FPB_NSTAGE
+#define DBN_FPB_NSTAGE 2
+#endif
+constexpr int FPB_TM = 64, FPB_TN = 128, FPB_KD = DBN_FPB_KD, FPB_NSTAGE = DBN_FPB_NSTAGE;
+static_assert(FPB_KD % 16 == 0 && FPB_KD * FPB_NSTAGE == 64, "ring = 64 factor rows (it also holds the staged tile and the diagonal block)");
 // row strides in shared memory: = 4 mod 16 doubles, so that the 4 (factor rows) x 8 (entries) operand fragment of a DMMA
 // is read by each half-warp from 32 different banks
 constexpr int FPB_LDX = FPB_TM + 4, FPB_LDY = FPB_TN + 4;
@@ -124,12 +131,14 @@ __device__ inline void fpb_gemm(FpbAcc& acc, const FpbCoord& co, const double* _
   auto load = [&](int s) {
     double* buf = pipe + (s % FPB_NSTAGE) * FPB_STAGE;
     const int j = j_lo + s * FPB_KD;
-    {
-      const bool v = xv && j + xr < j_hi;
-      fpb_cp16(buf + xr * FPB_LDX + xc, xsrc + (long long)(v ? j + xr : j_lo) * ld, v);
+#pragma unroll
+    for (int h = 0; h < FPB_KD / 16; ++h) {
+      const int r = xr + 16 * h;
+      const bool v = xv && j + r < j_hi;
+      fpb_cp16(buf + r * FPB_LDX + xc, xsrc + (long long)(v ? j + r : j_lo) * ld, v);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < FPB_KD / 8; ++h) {
       const int r = yr + 8 * h;
       const bool v = yv && j + r < j_hi;
       fpb_cp16(buf + FPB_KD * FPB_LDX + r * FPB_LDY + yc, ysrc + (long long)(v ? j + r : j_lo) * ld, v);
@@ -168,7 +177,9 @@ __device__ __forceinline__ void fpb_apply_li(FpbAcc& acc, const FpbCoord& co, co
 }
 
 // A = U^T U in place (see the header), idiag[j] = 1 / U[j][j]; W != nullptr: also W = L^-1.  Returns ln det A.
-static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, int k, double* idiag, double* sm) {
+// full_w == false: only the 64 x 64 diagonal blocks of W (the inverted diagonal blocks of L) are written -- what the blocked
+// triangular solves below need; the k^3 / 3 of the full inverse is skipped.
+static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, int k, double* idiag, double* sm, bool full_w = true) {
   __builtin_assume(__isShared(sm));   // generic pointer across the call: without the hint every access below is a generic LD / ST
   __builtin_assume(__isShared(idiag));
   double* const pipe = sm;
@@ -327,7 +338,7 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
         }
       }
     }
-    if (W) {
+    if (W && full_w) {
       // ---- block row p0 of L^-1 left of the diagonal block: -Li (U[b0..p0, p0..]^T W[b0..p0, b0..])
       for (int b0 = 0; b0 < p0; b0 += FPB_TN) {
         FpbAcc acc;
@@ -358,6 +369,132 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
   }
   __syncthreads();
   return -2.0 * (log(mant) + (double)expo * 0.69314718055994530942);
+}
+
+// Blocked triangular solves with two right-hand sides at once (x0, x1 in shared memory, overwritten by the solutions), from the
+// factor U (upper triangle of A) and the inverted diagonal blocks Li_pp (diagonal blocks of W): one pass over the factor
+// serves both vectors.
+//   forward:  x <- L^-1 x.  Panel by panel: x_p <- Li_pp x_p, then every later entry i loses sum_{j in p} U[j][i] x_j (thread per
+//   entry: the rows of U are read coalesced).
+static __device__ __noinline__ void fpb_solve_fwd2(const double* A, const double* W, int ld, int k, double* x0, double* x1, double* sm) {
+  __builtin_assume(__isShared(sm));
+  __builtin_assume(__isShared(x0));
+  __builtin_assume(__isShared(x1));
+  double* red = sm + FPB_OFF_RED;   // [512] partial sums of x0, [.. + 512) of x1 live in the pivot-column slots + li tail: use the ring instead
+  double* red1 = sm;                // the ring is free between products
+  const int tid = threadIdx.x;
+  for (int p0 = 0; p0 < k; p0 += 64) {
+    // diagonal solve: row a = tid / 8, the eight threads of a row split its entries
+    {
+      const int a = tid >> 3, g = tid & 7;
+      double s0 = 0.0, s1 = 0.0;
+      if (p0 + a < k) {
+        const double* w = W + (long long)(p0 + a) * ld + p0;
+        for (int c = g; c <= a; c += 8) {
+          const double l = w[c];
+          s0 = fma(l, x0[p0 + c], s0);
+          s1 = fma(l, x1[p0 + c], s1);
+        }
+      }
+      __syncthreads();   // every thread has read x_p of the previous update
+      red[tid] = s0;
+      red1[tid] = s1;
+      __syncthreads();
+      if (tid < 128) {
+        const int a2 = tid & 63;
+        const double* r = (tid < 64 ? red : red1) + a2 * 8;
+        const double v = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        if (p0 + a2 < k) (tid < 64 ? x0 : x1)[p0 + a2] = v;
+      }
+      __syncthreads();
+    }
+    // update of the entries behind the panel
+    const int nb = min(64, k - p0);
+    for (int i = p0 + 64 + tid; i < k; i += FPB_THREADS) {
+      const double* u = A + (long long)p0 * ld + i;
+      double s0[2] = {0.0, 0.0}, s1[2] = {0.0, 0.0};
+      int j = 0;
+      for (; j + 8 <= nb; j += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = u[(long long)(j + q) * ld];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          s0[q & 1] = fma(v[q], x0[p0 + j + q], s0[q & 1]);
+          s1[q & 1] = fma(v[q], x1[p0 + j + q], s1[q & 1]);
+        }
+      }
+      for (; j < nb; ++j) {
+        const double v = u[(long long)j * ld];
+        s0[0] = fma(v, x0[p0 + j], s0[0]);
+        s1[0] = fma(v, x1[p0 + j], s1[0]);
+      }
+      x0[i] -= s0[0] + s0[1];
+      x1[i] -= s1[0] + s1[1];
+    }
+    __syncthreads();   // the next panel's entries are final
+  }
+}
+
+//   backward: x <- L^-T x = U^-1 x.  Panels bottom-up: x_p loses U[p, behind p] x_behind (16 threads per row), then x_p <- Li_pp^T x_p.
+static __device__ __noinline__ void fpb_solve_bwd2(const double* A, const double* W, int ld, int k, double* x0, double* x1, double* sm) {
+  __builtin_assume(__isShared(sm));
+  __builtin_assume(__isShared(x0));
+  __builtin_assume(__isShared(x1));
+  double* red = sm + FPB_OFF_RED;
+  double* red1 = sm;
+  const int tid = threadIdx.x;
+  for (int p0 = ((k - 1) / 64) * 64; p0 >= 0; p0 -= 64) {
+    // row sums over the columns behind the panel: 16 threads per row, 32 rows per pass
+    for (int r0 = 0; r0 < 64; r0 += FPB_THREADS / 16) {
+      const int a = r0 + (tid >> 4), sl = tid & 15;
+      double s0 = 0.0, s1 = 0.0;
+      if (p0 + a < k) {
+        const double* u = A + (long long)(p0 + a) * ld;
+        for (int j = p0 + 64 + sl; j < k; j += 16) {
+          const double v = u[j];
+          s0 = fma(v, x0[j], s0);
+          s1 = fma(v, x1[j], s1);
+        }
+      }
+      __syncthreads();
+      red[tid] = s0;
+      red1[tid] = s1;
+      __syncthreads();
+      if (tid < 64) {
+        const int a2 = r0 + (tid & 31);
+        const double* r = (tid < 32 ? red : red1) + (tid & 31) * 16;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v += r[q];
+        if (p0 + a2 < k) (tid < 32 ? x0 : x1)[p0 + a2] -= v;
+      }
+    }
+    __syncthreads();
+    // diagonal solve with Li_pp^T: entry a = tid % 64, the eight groups tid / 64 split the rows c >= a
+    {
+      const int a = tid & 63, g = tid >> 6;
+      double s0 = 0.0, s1 = 0.0;
+      if (p0 + a < k) {
+        for (int c = a + g; c < 64 && p0 + c < k; c += 8) {
+          const double l = W[(long long)(p0 + c) * ld + p0 + a];
+          s0 = fma(l, x0[p0 + c], s0);
+          s1 = fma(l, x1[p0 + c], s1);
+        }
+      }
+      __syncthreads();
+      red[tid] = s0;
+      red1[tid] = s1;
+      __syncthreads();
+      if (tid < 128) {
+        const int a2 = tid & 63;
+        const double* r = (tid < 64 ? red : red1) + a2;
+        const double v = ((r[0] + r[64]) + (r[128] + r[192])) + ((r[256] + r[320]) + (r[384] + r[448]));
+        if (p0 + a2 < k) (tid < 64 ? x0 : x1)[p0 + a2] = v;
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // M += scale (I - W^T W) = scale (I - A^-1), full symmetric M

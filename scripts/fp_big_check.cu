@@ -24,17 +24,17 @@ using namespace dbn;
 
 __global__ void __launch_bounds__(FPB_THREADS, 1)
     check_kernel(const double* __restrict__ A0, double* ws, int k, int ld, int repeats, double* logdet, double* xin, double* tout, double* yout,
-                 long long* cycles) {
+                 long long* cycles, double* s0out, double* s1out, long long* solve_cycles) {
   extern __shared__ __align__(16) double sm[];
   double* A = ws + (long long)blockIdx.x * 3 * ld * k;
   double* W = A + (long long)ld * k;
   double* M = W + (long long)ld * k;
-  double* vec = sm + FPB_SMEM_DOUBLES;   // x | t | y | idiag
-  double* x = vec, *t = vec + ld, *y = vec + 2 * ld, *idiag = vec + 3 * ld;
+  double* vec = sm + FPB_SMEM_DOUBLES;   // x | t | y | idiag | s0 | s1
+  double* x = vec, *t = vec + ld, *y = vec + 2 * ld, *idiag = vec + 3 * ld, *s0 = vec + 4 * ld, *s1 = vec + 5 * ld;
   const int tid = threadIdx.x;
   for (int i = tid; i < k; i += FPB_THREADS) x[i] = xin[i];
   for (long long i = tid; i < (long long)k * ld; i += FPB_THREADS) M[i] = 0.0;
-  long long c_f = 0, c_s = 0, c_v = 0;
+  long long c_f = 0, c_s = 0, c_v = 0, c_v2 = 0;
   double ldet = 0.0;
   for (int r = 0; r < repeats; ++r) {
     for (long long i = tid; i < (long long)k * ld; i += FPB_THREADS) A[i] = A0[i];
@@ -47,6 +47,16 @@ __global__ void __launch_bounds__(FPB_THREADS, 1)
     fpb_trmv(W, ld, k, x, t, sm);
     fpb_trmv_t(W, ld, k, t, y);
     long long t3 = clock64();
+    // the blocked solves against the products with the inverse factor: s0 = L^-T L^-1 x (= y), s1 = L^-T L^-1 (2 x)
+    for (int i = tid; i < k; i += FPB_THREADS) {
+      s0[i] = x[i];
+      s1[i] = 2.0 * x[i];
+    }
+    __syncthreads();
+    fpb_solve_fwd2(A, W, ld, k, s0, s1, sm);
+    fpb_solve_bwd2(A, W, ld, k, s0, s1, sm);
+    long long t4 = clock64();
+    c_v2 += t4 - t3;
     c_f += t1 - t0;
     c_s += t2 - t1;
     c_v += t3 - t2;
@@ -56,11 +66,14 @@ __global__ void __launch_bounds__(FPB_THREADS, 1)
     cycles[blockIdx.x * 3 + 0] = c_f / repeats;
     cycles[blockIdx.x * 3 + 1] = c_s / repeats;
     cycles[blockIdx.x * 3 + 2] = c_v / repeats;
+    solve_cycles[blockIdx.x] = c_v2 / repeats;
   }
   if (blockIdx.x == gridDim.x - 1)
     for (int i = tid; i < k; i += FPB_THREADS) {
       tout[i] = t[i];
       yout[i] = y[i];
+      s0out[i] = s0[i];
+      s1out[i] = s1[i];
     }
 }
 
@@ -105,7 +118,8 @@ int main(int argc, char** argv) {
       Wh[(size_t)i * k + c] = s / L[(size_t)i * k + i];
     }
   double *dA0, *dws, *dld, *dx, *dt, *dy;
-  long long* dcyc;
+  long long* dcyc, *dcyc2;
+  double *ds0, *ds1;
   CK(cudaMalloc(&dA0, A.size() * 8));
   CK(cudaMalloc(&dws, (size_t)blocks * 3 * ld * k * 8));
   CK(cudaMemset(dws, 0xFF, (size_t)blocks * 3 * ld * k * 8));   // NaN garbage: nothing may depend on untouched workspace
@@ -114,14 +128,17 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dt, k * 8));
   CK(cudaMalloc(&dy, k * 8));
   CK(cudaMalloc(&dcyc, blocks * 3 * 8));
+  CK(cudaMalloc(&dcyc2, blocks * 8));
+  CK(cudaMalloc(&ds0, k * 8));
+  CK(cudaMalloc(&ds1, k * 8));
   CK(cudaMemcpy(dA0, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dx, x.data(), k * 8, cudaMemcpyHostToDevice));
-  const size_t smem = (size_t)(FPB_SMEM_DOUBLES + 4 * ld) * 8;
+  const size_t smem = (size_t)(FPB_SMEM_DOUBLES + 6 * ld) * 8;
   CK(cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  check_kernel<<<blocks, FPB_THREADS, smem>>>(dA0, dws, k, ld, 1, dld, dx, dt, dy, dcyc);
+  check_kernel<<<blocks, FPB_THREADS, smem>>>(dA0, dws, k, ld, 1, dld, dx, dt, dy, dcyc, ds0, ds1, dcyc2);
   CK(cudaDeviceSynchronize());
   // ---- correctness (last block, one repeat)
   std::vector<double> hA((size_t)k * ld), hW((size_t)k * ld), hM((size_t)k * ld), ht(k), hy(k), hld(blocks);
@@ -162,14 +179,21 @@ int main(int argc, char** argv) {
       ey = fmax(ey, fabs(hy[a] - s));
     }
   }
+  double es = 0;
+  {
+    std::vector<double> h0(k), h1(k);
+    CK(cudaMemcpy(h0.data(), ds0, k * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h1.data(), ds1, k * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < k; ++i) es = fmax(es, fmax(fabs(h0[i] - hy[i]), fabs(h1[i] - 2.0 * hy[i])));
+  }
   for (int b = 0; b < blocks; ++b) eL = fmax(eL, fabs(hld[b] - ldet_ref));
-  printf("k=%d ld=%d blocks=%d  max abs err: U %.3e  W %.3e  M %.3e  t %.3e  y %.3e  logdet %.3e (ref %.6f)\n", k, ld, blocks, eU, eW, eM, et, ey, eL,
+  printf("k=%d ld=%d blocks=%d  max abs err: U %.3e  W %.3e  M %.3e  t %.3e  y %.3e  solves %.3e  logdet %.3e (ref %.6f)\n", k, ld, blocks, eU, eW, eM, et, ey, es, eL,
          ldet_ref);
-  const bool ok = eU < 1e-10 && eW < 1e-10 && eM < 1e-10 && et < 1e-10 && ey < 1e-10 && eL < 1e-9;
+  const bool ok = eU < 1e-10 && eW < 1e-10 && eM < 1e-10 && et < 1e-10 && ey < 1e-10 && es < 1e-10 && eL < 1e-9;
   // ---- timing
   CK(cudaMemset(dws, 0, (size_t)blocks * 3 * ld * k * 8));
   CK(cudaEventRecord(e0));
-  check_kernel<<<blocks, FPB_THREADS, smem>>>(dA0, dws, k, ld, repeats, dld, dx, dt, dy, dcyc);
+  check_kernel<<<blocks, FPB_THREADS, smem>>>(dA0, dws, k, ld, repeats, dld, dx, dt, dy, dcyc, ds0, ds1, dcyc2);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -191,6 +215,13 @@ int main(int argc, char** argv) {
   printf("kernel %.3f ms for %d x %d segments: %.2f TFLOP/s executed (k^3 per segment)\n", ms, blocks, repeats, blocks * (double)repeats * k3 * 2 / 2 / (ms * 1e-3) / 1e12);
   printf("cycles per segment and block: factor+inverse %.0f (%.1f us, %.1f %% of the SM's DFMA peak), syrk %.0f (%.1f us, %.1f %%), trmv pair %.0f (%.1f us)\n", cf,
          cf / ghz * 1e-3, 100.0 * (2.0 * k3 / 3.0) / (cf * 128.0), cs, cs / ghz * 1e-3, 100.0 * (k3 / 3.0) / (cs * 128.0), cv, cv / ghz * 1e-3);
+  {
+    std::vector<long long> c2(blocks);
+    CK(cudaMemcpy(c2.data(), dcyc2, blocks * 8, cudaMemcpyDeviceToHost));
+    double a = 0;
+    for (int b = 0; b < blocks; ++b) a += c2[b];
+    printf("two-vector forward + backward solve: %.0f cycles (%.1f us)\n", a / blocks, a / blocks / ghz * 1e-3);
+  }
   printf("%s\n", ok ? "OK" : "FAILED");
   return ok ? 0 : 1;
 }
