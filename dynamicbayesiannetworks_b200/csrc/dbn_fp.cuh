@@ -110,22 +110,22 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
   const int nb = tb.zz_size + node * (tb.n + 2);
   if (FP_BLOCK > 128) {
     // large k: a warp per matrix row, lanes along the row (table entries of a row are contiguous but for the node's own column);
-    // eight table loads in flight per lane before the first store (one pair per step left the loop waiting for DRAM:
+    // sixteen table loads in flight per lane before the first store (one pair per step left the loop waiting for DRAM:
     // 15 % of all stall samples of the c5 launch, profiles/r2_c5/c5_fp_glob_stall_lines.txt)
     for (int a = threadIdx.x >> 5; a < k; a += FP_BLOCK >> 5) {
       const int fa = fp_col(a, node);
       const long long ro = (long long)fa * (fa + 1) / 2;
-      for (int b0 = threadIdx.x & 31; b0 <= a; b0 += 128) {
-        double vh[4], vl[4];
+      for (int b0 = threadIdx.x & 31; b0 <= a; b0 += 256) {
+        double vh[8], vl[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int b = b0 + 32 * u;
           const long long off = ro + fp_col(b <= a ? b : a, node);
           vh[u] = __ldg(ph + off);
           vl[u] = __ldg(pl + off);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int b = b0 + 32 * u;
           if (b <= a) {
             const double v = lam * (vh[u] - vl[u]) + (a == b ? 1.0 : 0.0);

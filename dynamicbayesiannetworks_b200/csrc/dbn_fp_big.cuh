@@ -237,7 +237,14 @@ static __device__ __noinline__ double fpb_factor(double* A, double* W, int ld, i
           for (int e = 0; e < 2; ++e) {
             const int cc = q0 + g + 8 * e;
             double v = (p0 + r < k && p0 + cc < k) ? pipe[r * FPB_LDY + cc] : (r == cc ? 1.0 : 0.0);
-            for (int m = 0; m < q0; ++m) v = fma(-us[m * FPB_LDX + r], us[m * FPB_LDX + cc], v);
+            double v1 = 0.0, v2 = 0.0, v3 = 0.0;   // four partial sums: the 16 q products are not one dependent chain
+            for (int m = 0; m < q0; m += 4) {
+              v = fma(-us[m * FPB_LDX + r], us[m * FPB_LDX + cc], v);
+              v1 = fma(-us[(m + 1) * FPB_LDX + r], us[(m + 1) * FPB_LDX + cc], v1);
+              v2 = fma(-us[(m + 2) * FPB_LDX + r], us[(m + 2) * FPB_LDX + cc], v2);
+              v3 = fma(-us[(m + 3) * FPB_LDX + r], us[(m + 3) * FPB_LDX + cc], v3);
+            }
+            v = (v + v1) + (v2 + v3);
             d[e] = v;
             t2[e] = (r == cc) ? 1.0 : 0.0;
           }
