@@ -835,7 +835,9 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
     // 32 / 16 / 4 -- the gathered table no longer stays in the L1 of a few SMs)
     const long long slots = (long long)h->sm_count * (fast ? 12 : 8);   // resident warps of the kernel
     const int min_lanes = fast ? 1 : 16;
-    while (lanes > min_lanes && (h->U + lanes / 2 - 1) / (lanes / 2) <= slots) lanes /= 2;   // halve while the warps still fit one wave
+    // halve while the warps fill at most half a wave (c4 data, profiles/r2_small/lanes_c4.txt: 12 800 units are fastest at 16 per
+    // warp, 25 600 and more at 32)
+    while (lanes > min_lanes && (h->U + lanes / 2 - 1) / (lanes / 2) <= slots / 2) lanes /= 2;
     if (h->lanes_env) lanes = h->lanes_env;
   }
   a.lanes = lanes;
