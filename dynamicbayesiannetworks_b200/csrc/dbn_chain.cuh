@@ -709,7 +709,9 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
         if constexpr (GLOB) {
           // moves.py:476-491: mu* ~ muSampler(0 | pi*), reverse density muSampler(mu | pi) at the current mu
           // (VV: moves.py:361-375; vvMuSampler has segment-specific variances and no mu_in term, samplers.py:353-394)
-          mu_posterior_seg<KM>(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, lam, sig_of, Qs, m0s, wk);
+          // one sweep per parent set (not VV): the muSampler sums also give the log-ML at any mean (ml_from_sums)
+          constexpr bool ONE = !VV;
+          const MuSums sums_s = mu_posterior_seg<KM, ONE>(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {
@@ -727,9 +729,15 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             gs.sample(z, mu_star);
           }
           const double ld_star = gs.logpdf(mu_star, Qs, ks);
-          ml_star = score(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, mu_star);
-          ml_cur = score(seg_cur(), S, k, mu);
-          mu_posterior_seg<KM>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
+          if constexpr (ONE) {
+            ml_star = ml_from_sums<KM>(sums_s, Qs, m0s, sig2, lam, mu_star, a.c0, a.T_half_plus_a, a.two_b, wk);
+            const MuSums sums_c = mu_posterior_seg<KM, true>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
+            ml_cur = ml_from_sums<KM>(sums_c, Qc, m0c, sig2, lam, mu, a.c0, a.T_half_plus_a, a.two_b, wk);
+          } else {
+            ml_star = score(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, mu_star);
+            ml_cur = score(seg_cur(), S, k, mu);
+            mu_posterior_seg<KM>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
+          }
           have_qc = true;
           double mc[KM];
 #pragma unroll
@@ -877,7 +885,18 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           __threadfence_block();
         }
         const SegFromCache<KM, decltype(tau_star)> seg_star{cu, U, tau_star, Ss, N, r_new, r_from, r_shift, st};
-        double ml_cur = have_ml_now ? ml_now : score(seg_cur(), S, k, mu);  // moves.py:184-191 / :67-69
+        double ml_cur = NAN;
+        if constexpr (GLOB && !VV) {   // one sweep: muSampler sums of the current state and its log-ML (moves.py:67-73)
+          if (!have_qc) {
+            const MuSums sums_c = mu_posterior_seg<KM, true>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
+            ml_cur = ml_from_sums<KM>(sums_c, Qc, m0c, sig2, lam, mu, a.c0, a.T_half_plus_a, a.two_b, wk);
+            have_qc = true;
+          } else {
+            ml_cur = ml_now;
+          }
+        } else {
+          ml_cur = have_ml_now ? ml_now : score(seg_cur(), S, k, mu);  // moves.py:184-191 / :67-69
+        }
         double ml_star, log_ratio;
         const double lprior = log_cp_prior(tau_star, Ss, a.log_p, a.log_1mp) - log_cp_prior(tau_cur, S, a.log_p, a.log_1mp);
         double mu_star[KM];
@@ -899,7 +918,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
           gc.setup(Qc, mc);
           const double ld_cur = gc.logpdf(mu, Qc, k);
           double Qs[KT], m0s[KM];
-          mu_posterior_seg<KM>(seg_star, Ss, k, lam, sig_of, Qs, m0s, wk);
+          const MuSums sums_s = mu_posterior_seg<KM, true>(seg_star, Ss, k, lam, sig_of, Qs, m0s, wk);
           GaussQ<KM> gs;
           gs.setup(Qs, m0s);
           if (replay) {
@@ -917,7 +936,7 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             gs.sample(z, mu_star);
           }
           const double ld_star = gs.logpdf(mu_star, Qs, k);
-          ml_star = score(seg_star, Ss, k, mu_star);
+          ml_star = ml_from_sums<KM>(sums_s, Qs, m0s, sig2, lam, mu_star, a.c0, a.T_half_plus_a, a.two_b, wk);
           const double lp_star = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu_star));
           const double lp_cur = -0.5 * ((double)k * 1.8378770664093454836 + sqnorm_k<KM>(mu));
           log_ratio = ml_star - ml_cur + lprior + lp_star - lp_cur + ld_cur - ld_star + log_hr;  // moves.py:112-117

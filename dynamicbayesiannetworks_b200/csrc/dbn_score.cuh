@@ -359,9 +359,16 @@ __device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, T
 // Q = I + sum_h A_h^-1 G_h / s2 (precision), m0 = sum_h A_h^-1 g_h / s2 (mean numerator WITHOUT the mu_in term).
 // sig2(h) is a callable: the same sigma^2 for every segment (glob), or the segment-specific sigma^2_h of vvMuSampler
 // (samplers.py:353-394).
-template <int KM, class SegFn, class SigFn>
-__device__ __forceinline__ void mu_posterior_seg(SegFn seg, int S, int k, double lam, SigFn sig2, double (&Q)[KM * (KM + 1) / 2],
-                                                 double (&m0)[KM], Work& wk) {
+// With SUMS the same sweep also returns ld = sum ln det A_h, s = sum y_h^T y_h, c = sum g_h^T A_h^-1 g_h: together with Q
+// and m0 they give the marginal likelihood at ANY mean (ml_from_sums), so the globally coupled moves need one sweep per
+// (parent set, changepoint list) instead of two (muSampler sums, then the score at the mean drawn from them).
+struct MuSums {
+  double ld, s, c;
+};
+template <int KM, bool SUMS = false, class SegFn, class SigFn>
+__device__ __forceinline__ MuSums mu_posterior_seg(SegFn seg, int S, int k, double lam, SigFn sig2, double (&Q)[KM * (KM + 1) / 2],
+                                                   double (&m0)[KM], Work& wk) {
+  MuSums r = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
     m0[i] = 0.0;
@@ -373,12 +380,17 @@ __device__ __forceinline__ void mu_posterior_seg(SegFn seg, int S, int k, double
     double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM];
     seg(h, G, g, s);
     form_a<KM>(G, lam, A);
-    ldl_factor<KM>(A, dinv);
+    const double prod = ldl_factor<KM>(A, dinv);
     const double is2 = 1.0 / sig2(h);
     double x[KM];
 #pragma unroll
     for (int i = 0; i < KM; ++i) x[i] = g[i];
     solve_ldl<KM>(A, dinv, x);
+    if (SUMS) {
+      r.ld += log(prod);
+      r.s += s;
+      r.c += dot<KM>(g, x);
+    }
 #pragma unroll
     for (int i = 0; i < KM; ++i) m0[i] += x[i] * is2;
     // columns of A^-1 G (symmetric): only the lower triangle is accumulated
@@ -392,6 +404,19 @@ __device__ __forceinline__ void mu_posterior_seg(SegFn seg, int S, int k, double
     }
     wk.segment(k, true);
   }
+  return r;
+}
+// log marginal likelihood at prior mean mu from the sums of one sweep (one variance s2 for all segments):
+// sum_h r_h^T C_h^-1 r_h = s - lam c - 2 mu.a + mu^T B mu with a = sum A_h^-1 g_h = s2 m0, B = sum A_h^-1 G_h = s2 (Q - I)
+// (lam G A^-1 = I - A^-1; the same identity the full-parents kernel uses, dbn_fp.cuh)
+template <int KM>
+__device__ __forceinline__ double ml_from_sums(const MuSums& r, const double (&Q)[KM * (KM + 1) / 2], const double (&m0)[KM], double s2,
+                                               double lam, const double (&mu)[KM], double c0, double T_half_plus_a, double two_b, Work& wk) {
+  double Qmu[KM];
+  symv<KM>(Q, mu, Qmu);
+  const double q = r.s - lam * r.c - 2.0 * s2 * dot<KM>(mu, m0) + s2 * (dot<KM>(mu, Qmu) - dot<KM>(mu, mu));
+  wk.eval();
+  return c0 - 0.5 * r.ld - T_half_plus_a * log(two_b + q);
 }
 template <int KM, class TauFn, class SigFn>
 __device__ __forceinline__ void mu_posterior(const Table& t, const Cols<KM>& c, TauFn tau, int S, double lam, SigFn sig2,
