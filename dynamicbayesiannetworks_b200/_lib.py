@@ -89,6 +89,7 @@ SYMBOLS = {
     'dbn_reset_counters': (C.c_int, [_P]),
     'dbn_verify_cache': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'dbn_measure_fp64_peak': (C.c_int, [_P, _dp]),
+    'dbn_score_batch_time': (C.c_int, [_P, _dp]),
 }
 
 _lib = None

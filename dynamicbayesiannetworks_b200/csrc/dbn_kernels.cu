@@ -228,6 +228,11 @@ struct dbn_handle {
   double *st_mu_fp = nullptr, *d_fp_ws = nullptr, *d_fp_bsc = nullptr;
   int fp_grid = 0;
   int sm_count = 0;   // multiprocessors of the device (read once in dbn_chain_init)
+  // dbn_score_batch: grow-only device scratch (round 1 did nine cudaMalloc / cudaFree per call) and the events around its kernel
+  char* d_sb = nullptr;
+  size_t sb_bytes = 0;
+  cudaEvent_t sb_e0 = nullptr, sb_e1 = nullptr;
+  float sb_ms = -1.f;
   int lanes_env = 0;  // DBN_LANES override (0: automatic)
   unsigned long long* d_counts = nullptr;
   long long counts_elems = 0;
@@ -374,6 +379,9 @@ void dbn_destroy(dbn_handle* h) {
   free_stats(h);
   free_chain(h);
   free_dev(h->d_counters);
+  free_dev(h->d_sb);
+  if (h->sb_e0) cudaEventDestroy(h->sb_e0);
+  if (h->sb_e1) cudaEventDestroy(h->sb_e1);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -597,39 +605,49 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
     }
   }
   CU(h, cudaSetDevice(h->cfg.device));
-  int *d_node = nullptr, *d_pi = nullptr, *d_pl = nullptr, *d_tau = nullptr, *d_tl = nullptr;
-  double *d_lam = nullptr, *d_dlt = nullptr, *d_mu = nullptr, *d_out = nullptr;
-  auto cleanup = [&]() {
-    free_dev(d_node); free_dev(d_pi); free_dev(d_pl); free_dev(d_tau); free_dev(d_tl);
-    free_dev(d_lam); free_dev(d_dlt); free_dev(d_mu); free_dev(d_out);
-  };
-#define CUX(expr)                                                                                  \
-  do {                                                                                             \
-    cudaError_t e_ = (expr);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      cleanup();                                                                                   \
-      DBN_FAIL(h, DBN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));                   \
-    }                                                                                              \
-  } while (0)
-  const size_t b4 = (size_t)B * sizeof(int), b8 = (size_t)B * sizeof(double);
-  CUX(cudaMalloc(&d_node, b4)); CUX(cudaMalloc(&d_pi, b4 * PMAX)); CUX(cudaMalloc(&d_pl, b4));
-  CUX(cudaMalloc(&d_tau, b4 * SMAX)); CUX(cudaMalloc(&d_tl, b4));
-  CUX(cudaMalloc(&d_lam, b8)); CUX(cudaMalloc(&d_dlt, b8)); CUX(cudaMalloc(&d_mu, b8 * KMAX)); CUX(cudaMalloc(&d_out, b8));
-  CUX(cudaMemcpyAsync(d_node, node, b4, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_pi, pi, b4 * PMAX, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_pl, pi_len, b4, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_tau, tau, b4 * SMAX, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_tl, tau_len, b4, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_lam, lambda2, b8, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_dlt, delta2, b8, cudaMemcpyHostToDevice, h->stream));
-  CUX(cudaMemcpyAsync(d_mu, mu, b8 * KMAX, cudaMemcpyHostToDevice, h->stream));
+  const size_t b4 = ((size_t)B * sizeof(int) + 255) & ~(size_t)255, b8 = ((size_t)B * sizeof(double) + 255) & ~(size_t)255;
+  const size_t need = b4 * (3 + PMAX + SMAX) + b8 * (3 + KMAX);
+  if (need > h->sb_bytes) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    free_dev(h->d_sb);
+    h->sb_bytes = 0;
+    cudaError_t e = cudaMalloc(&h->d_sb, need);
+    if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "dbn_score_batch: %.1f MB of scratch do not fit: %s", need / 1e6, cudaGetErrorString(e));
+    h->sb_bytes = need;
+  }
+  if (!h->sb_e0) {
+    CU(h, cudaEventCreate(&h->sb_e0));
+    CU(h, cudaEventCreate(&h->sb_e1));
+  }
+  char* q = h->d_sb;
+  auto take = [&](size_t bytes) { char* r = q; q += bytes; return r; };
+  int* d_node = (int*)take(b4); int* d_pi = (int*)take(b4 * PMAX); int* d_pl = (int*)take(b4);
+  int* d_tau = (int*)take(b4 * SMAX); int* d_tl = (int*)take(b4);
+  double* d_lam = (double*)take(b8); double* d_dlt = (double*)take(b8); double* d_mu = (double*)take(b8 * KMAX); double* d_out = (double*)take(b8);
+  const size_t n4 = (size_t)B * sizeof(int), n8 = (size_t)B * sizeof(double);
+  CU(h, cudaMemcpyAsync(d_node, node, n4, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_pi, pi, n4 * PMAX, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_pl, pi_len, n4, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_tau, tau, n4 * SMAX, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_tl, tau_len, n4, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_lam, lambda2, n8, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_dlt, delta2, n8, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_mu, mu, n8 * KMAX, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaEventRecord(h->sb_e0, h->stream));
   score_batch_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(make_table(h), mode, ml_const(T, alpha, beta), T / 2 + alpha, 2 * beta, B,
                                                             d_node, d_pi, d_pl, d_tau, d_tl, d_lam, d_dlt, d_mu, d_out, h->d_counters);
-  CUX(cudaGetLastError());
-  CUX(cudaMemcpyAsync(out_logml, d_out, b8, cudaMemcpyDeviceToHost, h->stream));
-  CUX(cudaStreamSynchronize(h->stream));
-  cleanup();
-#undef CUX
+  CU(h, cudaGetLastError());
+  CU(h, cudaEventRecord(h->sb_e1, h->stream));
+  CU(h, cudaMemcpyAsync(out_logml, d_out, n8, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaEventElapsedTime(&h->sb_ms, h->sb_e0, h->sb_e1));
+  return DBN_OK;
+}
+
+int dbn_score_batch_time(dbn_handle* h, double* ms) {
+  if (!h || !ms) return DBN_ERR_INVALID;
+  if (h->sb_ms < 0.f) DBN_FAIL(h, DBN_ERR_STATE, "dbn_score_batch_time: no dbn_score_batch call yet");
+  *ms = h->sb_ms;
   return DBN_OK;
 }
 

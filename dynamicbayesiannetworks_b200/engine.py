@@ -252,6 +252,12 @@ class DbnEngine:
     def reset_counters(self):
         self._check(self._lib.dbn_reset_counters(self._h), 'dbn_reset_counters')
 
+    def score_batch_ms(self):
+        """dbn_score_batch_time: device time of the scorer kernel of the last score_batch call."""
+        g = C.c_double()
+        self._check(self._lib.dbn_score_batch_time(self._h, C.byref(g)), 'dbn_score_batch_time')
+        return g.value
+
     def fp64_peak_gflops(self):
         g = C.c_double()
         self._check(self._lib.dbn_measure_fp64_peak(self._h, C.byref(g)), 'dbn_measure_fp64_peak')

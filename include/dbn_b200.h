@@ -294,6 +294,10 @@ int dbn_verify_cache(dbn_handle* h, uint64_t out[2]);
 /* dependent-free DFMA microbenchmark: measured FP64 FMA throughput of this device in GFLOP/s */
 int dbn_measure_fp64_peak(dbn_handle* h, double* gflops);
 
+/* device time (CUDA events on the handle's stream, milliseconds) of the scorer kernel of the last dbn_score_batch call:
+ * the throughput figure of kernel 2 (marginalLikelihood.py:91-166 evaluated for a batch) without the host copies */
+int dbn_score_batch_time(dbn_handle* h, double* ms);
+
 #ifdef __cplusplus
 }
 #endif
