@@ -130,7 +130,7 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
           if (b <= a) {
             const double v = lam * (vh[u] - vl[u]) + (a == b ? 1.0 : 0.0);
             A[(long long)a * ld + b] = v;
-            A[(long long)b * ld + a] = v;
+            A[(long long)b * ld + a] = v;   // (dropping the mirrored, scattered store was measured: no gain, profiles/r2_c5 notes)
           }
         }
       }
