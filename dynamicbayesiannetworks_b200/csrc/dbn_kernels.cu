@@ -52,24 +52,109 @@ __global__ void build_v_kernel(const double* __restrict__ raw, const int* __rest
 #define DBN_PREFIX_CPT 4
 #endif
 constexpr int PREFIX_CPT = DBN_PREFIX_CPT;
+// Stage the chunk's rows v_t = [1, x_t, (lagged copies,) y_t], t0 <= t < t0 + len, in shared memory with cp.async, every copy
+// of a thread in flight at once; the caller waits and synchronises.  Round 2 measured where the build's time went
+// (profiles/r2_prefix/where_the_time_goes.txt): without ANY table store it still took 0.067 of 0.088 ms -- synchronous staging
+// loops (25 dependent round trips to L2 per block), the chunk-offset sums and a shared-memory-bound totals pass, not the store
+// stream.  (Staging straight from the series instead of the gathered copy V was measured too: no gain at n = 100, slower at
+// n = 500 -- twice the copy instructions at 8 bytes each.)
+__device__ __forceinline__ void prefix_stage(double* sv, const double* __restrict__ V, int t0, int len, int W) {
+  const double* src = V + (long long)t0 * W;
+  const int total = len * W;
+  const bool aligned = (((long long)t0 * W) & 1) == 0;   // the chunk starts on 16 bytes
+  const int n16 = aligned ? total >> 1 : 0;
+  for (int i = threadIdx.x; i < n16; i += PREFIX_BLOCK) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sv + 2 * i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 2 * i) : "memory");
+  }
+  for (int i = 2 * n16 + threadIdx.x; i < total; i += PREFIX_BLOCK) {   // the odd tail, or everything when not aligned
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sv + i);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // With many chunks (long series, wide rows: BASELINE config 5 has 910) summing the earlier chunks' totals inside the write
 // pass is quadratic in the chunk count; chunk_scan_kernel turns the totals into exclusive running sums once
 // (thread per column, coalesced over columns) and the write pass reads a single offset row (SCANNED).
-constexpr int PREFIX_SCAN_CHUNKS = 96;  // up to here the in-pass sum is cheaper than one more launch (config 4: 63 chunks)
 __global__ void __launch_bounds__(256) chunk_scan_kernel(double* __restrict__ chunk, long long R, int n_chunks) {
   const long long p = blockIdx.x * 256ll + threadIdx.x;
   if (p >= R) return;
   double acc = 0.0;
-  // 16 loads in flight per thread: a load-add-store chain per chunk is one L2 round trip per chunk (19 us for 63 chunks)
-  for (int c0 = 0; c0 < n_chunks; c0 += 16) {
-    double v[16];
+  // 64 loads in flight per thread: a load-add-store chain per chunk is one L2 round trip per chunk (19 us for 63 chunks),
+  // batches of 16 still four (8.9 us, profiles/r2_prefix/launches_before.csv)
+  for (int c0 = 0; c0 < n_chunks; c0 += 64) {
+    double v[64];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < n_chunks) ? __ldcg(chunk + (long long)(c0 + j) * R + p) : 0.0;
+    for (int j = 0; j < 64; ++j) v[j] = (c0 + j < n_chunks) ? __ldcg(chunk + (long long)(c0 + j) * R + p) : 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 64; ++j) {
       if (c0 + j < n_chunks) chunk[(long long)(c0 + j) * R + p] = acc;
       acc += v[j];
     }
+  }
+}
+
+// Per-(chunk, column) totals as a register-tiled product.  A table column is (row entity r, column c): ZZ rows a = 0..nv
+// (value index a, c <= a, offset a (a + 1) / 2 + c) and one ZY | YY row per node i (value index nv + 1 + i, c <= nv + 1, offset
+// zz_size + i (nv + 2) + c); its total over the chunk is sum_t v_t[aidx(r)] v_t[c] (v_t[aidx(r)]^2 for the YY entry c = nv + 1).
+// A warp takes four row entities, a lane the columns lane + 32 j: per time step 4 broadcast + 4 conflict-free shared loads
+// feed 16 FMAs (the write pass's column mapping, used here in round 1, needs 2 loads per FMA and was bound by the
+// shared-memory pipe: 19 us of the 86 us build).
+__global__ void __launch_bounds__(PREFIX_BLOCK) chunk_totals_kernel(const double* __restrict__ V, int N, int W, int nv, int n, int zz_size,
+                                                                    long long R, int Lc, double* __restrict__ chunk) {
+  extern __shared__ __align__(16) double sv[];  // [Lc][W]
+  const int t0 = blockIdx.y * Lc;
+  const int len = min(Lc, N - t0);
+  prefix_stage(sv, V, t0, len, W);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int E = nv + 1 + n;                       // row entities
+  const int e0 = (blockIdx.x * (PREFIX_BLOCK / 32) + warp) * 4;
+  int aidx[4], ncols[4];
+  long long base[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = e0 + r;
+    const bool zz = e <= nv;
+    aidx[r] = e < E ? (zz ? e : e) : 0;            // ZZ row a: v index a; ZY row of node i = e - (nv + 1): v index nv + 1 + i = e
+    ncols[r] = e < E ? (zz ? e + 1 : nv + 2) : 0;
+    base[r] = zz ? (long long)e * (e + 1) / 2 : (long long)zz_size + (long long)(e - nv - 1) * (nv + 2);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (e0 >= E) return;
+  const int maxc = max(max(ncols[0], ncols[1]), max(ncols[2], ncols[3]));
+  double* out = chunk + (long long)blockIdx.y * R;
+  for (int c0 = 0; c0 < maxc; c0 += 128) {
+    double acc[4][4], yy[4];
+    int col[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) col[j] = c0 + lane + 32 * j;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      yy[r] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][j] = 0.0;
+    }
+    for (int t = 0; t < len; ++t) {
+      const double* row = sv + t * W;
+      double a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = row[aidx[r]];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = col[j] <= nv ? row[col[j]] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        yy[r] = fma(a[r], a[r], yy[r]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a[r], b[j], acc[r][j]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col[j] < ncols[r]) out[base[r] + col[j]] = (col[j] == nv + 1) ? yy[r] : acc[r][j];
   }
 }
 
@@ -77,11 +162,10 @@ template <bool WRITE, bool SCANNED = false>
 __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
                                                               const unsigned short* __restrict__ colB, int N, int W, long long R,
                                                               int Lc, double* __restrict__ chunk, double* __restrict__ table) {
-  extern __shared__ double sv[];  // [Lc][W]
+  extern __shared__ __align__(16) double sv[];  // [Lc][W]
   const int t0 = blockIdx.y * Lc;
   const int len = min(Lc, N - t0);
-  for (int i = threadIdx.x; i < len * W; i += PREFIX_BLOCK) sv[i] = V[(long long)t0 * W + i];
-  __syncthreads();
+  prefix_stage(sv, V, t0, len, W);   // in flight while the column maps and the chunk offsets are loaded
   const long long p0 = (long long)blockIdx.x * (PREFIX_BLOCK * PREFIX_CPT) + threadIdx.x;
   int ca[PREFIX_CPT], cb[PREFIX_CPT];
   bool live[PREFIX_CPT];
@@ -94,6 +178,22 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
     cb[j] = live[j] ? colB[p] : 0;
     acc[j] = 0.0;
   }
+  if (WRITE) {
+    // offset of this chunk = sum of the totals of the chunks before it, added in chunk order (coalesced, L2-resident)
+    if constexpr (SCANNED) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j)
+        if (live[j]) acc[j] = __ldcg(chunk + (long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK);
+    } else {
+      for (int c = 0; c < (int)blockIdx.y; ++c) {
+#pragma unroll
+        for (int j = 0; j < PREFIX_CPT; ++j)
+          if (live[j]) acc[j] += chunk[(long long)c * R + p0 + (long long)j * PREFIX_BLOCK];
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   if (!WRITE) {
     for (int t = 0; t < len; ++t) {
 #pragma unroll
@@ -103,18 +203,6 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
     for (int j = 0; j < PREFIX_CPT; ++j)
       if (live[j]) chunk[(long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK] = acc[j];
   } else {
-    // offset of this chunk = sum of the totals of the chunks before it, added in chunk order (coalesced, L2-resident)
-    if constexpr (SCANNED) {
-#pragma unroll
-      for (int j = 0; j < PREFIX_CPT; ++j)
-        if (live[j]) acc[j] = chunk[(long long)blockIdx.y * R + p0 + (long long)j * PREFIX_BLOCK];
-    } else {
-      for (int c = 0; c < (int)blockIdx.y; ++c) {
-#pragma unroll
-        for (int j = 0; j < PREFIX_CPT; ++j)
-          if (live[j]) acc[j] += chunk[(long long)c * R + p0 + (long long)j * PREFIX_BLOCK];
-      }
-    }
     if (blockIdx.y == 0) {
 #pragma unroll
       for (int j = 0; j < PREFIX_CPT; ++j)
@@ -124,8 +212,16 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
     for (int t = 0; t < len; ++t) {
 #pragma unroll
       for (int j = 0; j < PREFIX_CPT; ++j) {
+#if defined(DBN_PREFIX_EXP) && DBN_PREFIX_EXP == 1   // experiment: no shared-memory loads (results wrong, timing only)
+        acc[j] += 1.0;
+#else
         acc[j] = fma(sv[t * W + ca[j]], sv[t * W + cb[j]], acc[j]);
+#endif
+#if defined(DBN_PREFIX_EXP) && DBN_PREFIX_EXP == 2   // experiment: only the chunk's last row is stored
+        if (live[j] && t == len - 1) __stcs(out + (long long)j * PREFIX_BLOCK, acc[j]);
+#else
         if (live[j]) __stcs(out + (long long)j * PREFIX_BLOCK, acc[j]);  // streaming store: the table is far larger than L2
+#endif
       }
       out += R;
     }
@@ -413,15 +509,25 @@ int dbn_sync(dbn_handle* h) {
 
 static int launch_prefix(dbn_handle* h) {
   const int n = h->n, N = h->N, W = h->W;
-  build_v_kernel<<<296, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, h->d_xpos, N, n, h->lag, h->d_V);
-  CU(h, cudaGetLastError());
+  {
+    // one element per thread up to 16 blocks per SM: the gather is two dependent round trips per element, and 296 blocks
+    // walked five elements each in sequence (8.5 us for 400 k elements, now 5.9)
+    const long long total = (long long)N * W;
+    const unsigned gv = (unsigned)std::min<long long>((total + 255) / 256, 148ll * 16);
+    build_v_kernel<<<gv, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, h->d_xpos, N, n, h->lag, h->d_V);
+    CU(h, cudaGetLastError());
+  }
   const size_t smem = (size_t)h->Lc * W * sizeof(double);
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
-  prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  if (getenv("DBN_PREFIX_OLD_TOTALS")) {   // round-1 totals pass (A/B)
+    prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
+  } else {
+    const int row_tiles = (h->nv + 1 + n + 3) / 4;
+    dim3 gt((unsigned)((row_tiles + PREFIX_BLOCK / 32 - 1) / (PREFIX_BLOCK / 32)), (unsigned)h->n_chunks);
+    chunk_totals_kernel<<<gt, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, N, W, h->nv, n, h->zz_size, h->R, h->Lc, h->d_chunk);
+  }
   CU(h, cudaGetLastError());
-  int scan_from = PREFIX_SCAN_CHUNKS;
-  if (const char* e = getenv("DBN_PREFIX_SCAN_FROM")) scan_from = atoi(e);  // tuning knob
-  if (h->n_chunks > scan_from) {
+  if (!getenv("DBN_PREFIX_NO_SCAN")) {   // the 64-way scan costs less than the in-pass sums of the write kernel (0.079 vs 0.082 ms)
     chunk_scan_kernel<<<(unsigned)((h->R + 255) / 256), 256, 0, h->stream>>>(h->d_chunk, h->R, h->n_chunks);
     CU(h, cudaGetLastError());
     prefix_kernel<true, true><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
@@ -501,6 +607,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     CU(h, cudaFuncSetAttribute(prefix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaFuncSetAttribute(prefix_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+    CU(h, cudaFuncSetAttribute(chunk_totals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
     CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_xpos, (size_t)N * sizeof(int)));
