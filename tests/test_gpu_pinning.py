@@ -321,3 +321,45 @@ def test_free_running_gibbs_draw_moments(eng_mod):
         assert np.allclose(lshape, lshape[0])
         assert abs(g.mean() - lshape[0]) < 5 * np.sqrt(lshape[0] / C), node
         assert abs(g.var() / lshape[0] - 1) < 0.15, node
+
+
+@pytest.mark.parametrize('method,series,chains', [('varying_nh_dbn', 'mtor', 64), ('h_dbn', 'yeast', 64), ('seq_coup_nh_dbn', 'mtor', 64),
+                                                   ('glob_coup_nh_dbn', 'mtor', 64)])
+def test_units_per_warp_do_not_change_the_chains(eng_mod, monkeypatch, method, series, chains):
+    """Small unit counts are spread over more warps (DBN_LANES units per warp, chosen from the unit count): the Philox counters
+    are keyed by the (chain, node) of a unit, not by its thread, so every mapping must give the same states and counts."""
+    data = _series(series)
+    got = {}
+    for lanes in ('32', '5', '1', None):   # dense, a ragged value, one unit per warp, automatic
+        if lanes is None:
+            monkeypatch.delenv('DBN_LANES', raising=False)
+        else:
+            monkeypatch.setenv('DBN_LANES', lanes)
+        with eng_mod(n_chains=chains, seed=77) as e:
+            e.build_stats(data)
+            e.chain_init(method, burn_in=0)
+            e.run(30)
+            e.run(45)
+            st = e.state()
+            cnt = e.counts()
+            got[lanes] = (st['S'].copy(), st['tau'].copy(), st['npi'].copy(), st['pi'].copy(), st['lambda2'].copy(),
+                          np.concatenate([np.asarray(v).ravel() for _, v in sorted(cnt.items())]))
+    ref = got['32']
+    for lanes, g in got.items():
+        for a, b, name in zip(g, ref, ('S', 'tau', 'npi', 'pi', 'lambda2', 'counts')):
+            assert np.array_equal(a, b), (method, lanes, name)
+
+
+def test_score_batch_device_time(eng_mod):
+    """dbn_score_batch keeps its device scratch between calls and reports the scorer kernel's device time."""
+    data = _series('yeast')
+    with eng_mod(n_chains=1) as e:
+        e.build_stats(data)
+        with pytest.raises(Exception):
+            e.score_batch_ms()   # no call yet
+        for B in (3, 700, 5):      # the scratch grows and is reused
+            node = [i % e.n for i in range(B)]
+            pi = [[(nd + 1) % e.n] for nd in node]
+            tau = [[e.N + 2]] * B
+            out = e.score_batch(node, pi, tau, 1.0)
+            assert np.isfinite(out).all() and e.score_batch_ms() > 0.0
