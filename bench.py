@@ -296,15 +296,16 @@ def run_reference_arm(args, rank, world):
 
 def c5_sample(device, fp64_peak):
     """BASELINE configs[4] (500 genes, T = 10000, full-parents globally coupled, design width k = 500) on one GPU: a bounded
-    sample -- 500 units (one chain per node) started at the true changepoints, 1 untimed + 2 timed iterations -- of the one
-    contraction-shaped kernel of the path.  Roofline: FP64 (k^3/3 + 4k^2 flops per segment evaluation, counted on
+    sample -- the first 592 of the 4500 (node, chain) units of the 9-chain workload (four full waves of one block per SM),
+    started at the true changepoints, 1 untimed + 2 timed iterations -- of the one contraction-shaped kernel of the path.  Roofline: FP64 (k^3/3 + 4k^2 flops per segment evaluation, counted on
     the device), against the DFMA peak measured in this run."""
     import torch
     from dynamicbayesiannetworks_b200.engine import DbnEngine
     from dynamicbayesiannetworks_b200.synth import make_synthetic
     n, T = 500, 10000
     data, cps, _ = make_synthetic(n, T, n_changepoints=5, max_fan_in=4, seed=20260120)
-    eng = DbnEngine(n_chains=1, device=device, seed=11)
+    chains, units = 9, 592
+    eng = DbnEngine(n_chains=chains, device=device, seed=11, unit_range=(0, units))
     try:
         eng.set_stream(torch.cuda.current_stream().cuda_stream)
         eng.build_stats([data])
@@ -324,8 +325,9 @@ def c5_sample(device, fp64_peak):
     finally:
         eng.close()
     gf = c['algorithmic_flops'] / ms / 1e6
-    return {'workload': 'synthetic fp-glob-dbn: 500 genes, T=10000, 1 chain per node (BASELINE configs[4]), %d timed iterations' % iters,
-            'metric': METRIC, 'value': n * iters / ms * 1e3, 'unit': UNIT, 'ms_per_iteration': ms / iters,
+    return {'workload': 'synthetic fp-glob-dbn: 500 genes, T=10000, %d chains per node (BASELINE configs[4]): units 0..%d of %d, %d timed iterations'
+                        % (chains, units - 1, n * chains, iters),
+            'metric': METRIC, 'value': units * iters / ms * 1e3, 'unit': UNIT, 'ms_per_iteration': ms / iters,
             'ml_evals_per_sec': c['ml_evals'] / ms * 1e3,
             'roofline': {'kernel': 'fp_glob_kernel<glob, BIG>', 'bound': 'fp64', 'achieved': gf / 1e3, 'peak': fp64_peak / 1e3,
                          'unit': 'TFLOP/s', 'frac': gf / fp64_peak, 'peak_source': 'DFMA microbenchmark in this run',

@@ -1055,6 +1055,53 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 // Invariant check (test hook behind dbn_verify_cache): every cached row of every unit must equal the prefix-table row
 // at the end boundary of the corresponding segment, restricted to the unit's column slots, bit for bit.
 // counts[0] += units with at least one differing entry, counts[1] += differing entries.
+// (Re)build the boundary-row cache from the table with one thread per (unit, cached row): canonical slots = parent positions,
+// end boundary of segment j -> row j.  The chain kernel can do this itself (`refresh`), three rows per round trip of its 384
+// threads per SM; as a kernel of its own every row of every unit is in flight at once (the end-to-end step rebuilds table and
+// cache for every new series: 0.33 ms of its 2.2 ms were this gather, scripts/e2e_breakdown.py).
+template <int KM>
+__global__ void __launch_bounds__(256) cache_fill_kernel(const ChainArgs a) {
+  constexpr int KT = FastDims<KM>::KT, NP = FastDims<KM>::NP;
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  const long long U = a.U;
+  if (i >= U * SEG_ROWS) return;
+  const int j = (int)(i / U), u = (int)(i - (long long)j * U);
+  const int S = a.st_S[u];
+  const int npi = a.st_npi[u];
+  int cg[KM];
+  cg[0] = -1;
+#pragma unroll
+  for (int s = 1; s < KM; ++s) cg[s] = (s - 1 < npi) ? a.st_pi[(s - 1) * a.U + u] : -1;
+  if (j == 0) {
+#pragma unroll
+    for (int s = 1; s < KM; ++s) a.st_cg[(s - 1) * a.U + u] = cg[s];
+  }
+  if (j >= S) return;
+  const int node = (a.unit0 + u) / a.C, n = a.tb.n, N = a.tb.N;
+  const int nb = a.tb.zz_size + node * (n + 2);
+  const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N);
+  const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
+  double v[2 * NP];
+#pragma unroll
+  for (int q = 0; q < KM; ++q) {
+    const bool oi = (q == 0) || cg[q] >= 0;
+    const int fi = (q == 0) ? 0 : cg[q] + 1;
+#pragma unroll
+    for (int jj = 0; jj <= q; ++jj) {
+      if (q == 0) continue;   // ZZ(0, 0) = t is not stored
+      const bool oj = (jj == 0) || cg[jj] >= 0;
+      const int fj = (jj == 0) ? 0 : cg[jj] + 1;
+      const int hi = max(fi, fj), lo = min(fi, fj);
+      v[DBN_EZZ(q, jj)] = (oi && oj) ? __ldg(row + hi * (hi + 1) / 2 + lo) : 0.0;
+    }
+    v[KT - 1 + q] = oi ? __ldg(row + nb + fi) : 0.0;
+  }
+  v[KT - 1 + KM] = __ldg(row + nb + n + 1);
+  double2* cu = reinterpret_cast<double2*>(a.cache) + u;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) cu[((long long)j * NP + p) * U] = make_double2(v[2 * p], v[2 * p + 1]);
+}
+
 template <int KM>
 __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* counts) {
   constexpr int KT = FastDims<KM>::KT, NP = FastDims<KM>::NP;

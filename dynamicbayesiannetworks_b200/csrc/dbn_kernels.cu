@@ -968,6 +968,13 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
   a.lanes = lanes;
   const int upb = lanes >= 32 ? block : lanes * (block / 32);   // units per block
   const unsigned grid = (unsigned)((h->U + upb - 1) / upb);
+  if (fast && a.refresh && !getenv("DBN_REFRESH_IN_KERNEL")) {   // rebuild the boundary-row cache with every row of every unit in flight
+    const unsigned gf = (unsigned)(((long long)h->U * SEG_ROWS + 255) / 256);
+    if (km == 4) cache_fill_kernel<4><<<gf, 256, 0, h->stream>>>(a);
+    else cache_fill_kernel<5><<<gf, 256, 0, h->stream>>>(a);
+    CUX(cudaGetLastError());
+    a.refresh = 0;
+  }
   if (fast) CUX((trace ? launch_fast_trace : launch_fast_plain)(p.method, km, grid, block, smem, h->stream, a));
   else CUX((trace ? launch_chain_trace : launch_chain_plain)(p.method, km, grid, block, smem, h->stream, a));
   h->cache_valid = true;
