@@ -735,8 +735,20 @@ __global__ void __launch_bounds__(CHAIN_BLOCK, DBN_CHAIN_MINB) chain_kernel(cons
             ml_cur = ml_from_sums<KM>(sums_c, Qc, m0c, sig2, lam, mu, a.c0, a.T_half_plus_a, a.two_b, wk);
           } else {
             ml_star = score(seg_from_table<KM>(a.tb, cstar, tau_cur, S), S, ks, mu_star);
-            ml_cur = score(seg_cur(), S, k, mu);
-            mu_posterior_seg<KM>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk);
+            // var-glob: the current state's vvLogMargLikelihood (at the known mean) and its muSampler sums in one sweep
+            double acc_vv = 0.0;
+            mu_posterior_seg<KM, false>(seg_cur(), S, k, lam, sig_of, Qc, m0c, wk,
+                                        [&](int len, const double(&G)[KT], const double(&g)[KM], double s, const double(&A)[KT],
+                                            const double(&dinv)[KM], double prod) {
+                                          double wv[KM];
+                                          const double q = segment_q<KM, true>(G, g, s, mu, lam, A, dinv, wv);
+                                          const double Th_half = 0.5 * (double)len;
+                                          acc_vv += lgamma(Th_half + a.a_sig) + vv_c - Th_half * 1.1447298858494002 - 0.5 * log(prod) -
+                                                    (Th_half + a.a_sig) * log(a.two_b + q);
+                                          wk.flops += 12;
+                                        });
+            wk.eval();
+            ml_cur = acc_vv;
           }
           have_qc = true;
           double mc[KM];

@@ -365,9 +365,15 @@ __device__ __forceinline__ double score_seq(const Table& t, const Cols<KM>& c, T
 struct MuSums {
   double ld, s, c;
 };
-template <int KM, bool SUMS = false, class SegFn, class SigFn>
+struct NoSegmentHook {
+  template <class... T>
+  __device__ __forceinline__ void operator()(T&&...) const {}
+};
+// `hook(len, G, g, s, A, dinv, prod)` sees every segment's statistics and factorisation (the var-glob kernel scores the
+// current mean with it in the same sweep: its per-segment log(2b + q_h) terms cannot be recovered from the sums)
+template <int KM, bool SUMS = false, class SegFn, class SigFn, class Hook = NoSegmentHook>
 __device__ __forceinline__ MuSums mu_posterior_seg(SegFn seg, int S, int k, double lam, SigFn sig2, double (&Q)[KM * (KM + 1) / 2],
-                                                   double (&m0)[KM], Work& wk) {
+                                                   double (&m0)[KM], Work& wk, Hook hook = Hook()) {
   MuSums r = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
@@ -378,9 +384,10 @@ __device__ __forceinline__ MuSums mu_posterior_seg(SegFn seg, int S, int k, doub
   seg.begin();
   for (int h = 0; h < S; ++h) {
     double G[KM * (KM + 1) / 2], g[KM], s, A[KM * (KM + 1) / 2], dinv[KM];
-    seg(h, G, g, s);
+    const int len = seg(h, G, g, s);
     form_a<KM>(G, lam, A);
     const double prod = ldl_factor<KM>(A, dinv);
+    hook(len, G, g, s, A, dinv, prod);
     const double is2 = 1.0 / sig2(h);
     double x[KM];
 #pragma unroll
