@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
     for (int i = tid; i < k; i += FP_BLOCK) mu[i] = a.st_mu[(long long)i * a.U + u];
     __syncthreads();
     unsigned long long n_evals = 0, n_segs = 0;
+    unsigned long long n_inv = 0, n_qfac = 0;   // factorisations that also form the inverse and I - A^-1; factorisations of the muSampler precision
 
     for (int li = 0; li < a.n_iter; ++li) {
       const int it = a.it0 + li;
@@ -793,6 +794,8 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
         // sigma^2_h = I + M_w / lam, mean = Q^-1 sum_h A_h^-1 g_h / sigma^2_h (samplers.py:353-379: no mu_in term)
         fp_sweep(a.tb, node, tau_cur, S, lam, A, W, Mc, ld, k, g, t, x, a_cur, red, sc + 3, stage, sigv);
         n_segs += S;
+        n_inv += S;
+        ++n_qfac;
         const double il = 1.0 / lam;
         for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = Mc[i] * il;
         __syncthreads();
@@ -955,8 +958,13 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
           for (int i = tid; i < k * ld; i += FP_BLOCK) Mc[i] = Ms[i] = 0.0;
           __syncthreads();
           FpSummary s_com = {0.0, 0.0, 0.0}, s_old = {0.0, 0.0, 0.0};
-          n_segs += fp_sweep_split(a.tb, node, tau_cur, S, tau_star, Ss, false, lam, A, W, ld, k, Mc, a_cur, s_com, Ms, a_star, s_old, g, t, x,
-                                   red, sc + 3, stage);
+          {
+            const int ne = fp_sweep_split(a.tb, node, tau_cur, S, tau_star, Ss, false, lam, A, W, ld, k, Mc, a_cur, s_com, Ms, a_star, s_old, g, t, x,
+                                          red, sc + 3, stage);
+            n_segs += ne;
+            n_inv += ne;
+            n_qfac += 2;
+          }
           // ... then (Ms, a_star) become the sums of tau, (Mc, a_cur) stay the shared part, to which the second pass adds tau*'s new segments
           for (int i = tid; i < k * ld; i += FP_BLOCK) {   // ... and Q = I + M / (lam s2) of tau in the same pass (diagonal added below)
             const double m = Ms[i] + Mc[i];
@@ -999,8 +1007,12 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
           const double ld_cur = -0.5 * ((double)k * 1.8378770664093454836 - ldq_cur + dQd_cur);
           // ---- proposed changepoints: mu* ~ muSampler(0 | tau*), its density, log-ML at mu* (moves.py:86-93)
           FpSummary ss_ = s_com;
-          n_segs += fp_sweep_split(a.tb, node, tau_star, Ss, tau_cur, S, true, lam, A, W, ld, k, M_star, av_star, ss_, M_star, av_star, ss_, g, t,
-                                   x, red, sc + 3, stage);
+          {
+            const int ne = fp_sweep_split(a.tb, node, tau_star, Ss, tau_cur, S, true, lam, A, W, ld, k, M_star, av_star, ss_, M_star, av_star, ss_, g, t,
+                                          x, red, sc + 3, stage);
+            n_segs += ne;
+            n_inv += ne;
+          }
           for (int i = tid; i < k * ld; i += FP_BLOCK) Q[i] = M_star[i] * ils;
           __syncthreads();
           for (int i = tid; i < k; i += FP_BLOCK) {
@@ -1107,6 +1119,10 @@ __global__ void __launch_bounds__(BIG ? FP_BIG_BLOCK : 128, BIG ? 1 : 5) fp_glob
       // algorithmic bytes / flops of the executed segment factorisations (SURVEY.md 8d with k = n)
       atomicAdd(&a.counters[3], n_segs * 16ull * (unsigned long long)(k * (k + 1) / 2 + k + 1));
       atomicAdd(&a.counters[4], n_segs * (unsigned long long)((long long)k * k * k / 3 + 4ll * k * k + 5 * k));
+      // what the level-3 steps execute: k^3 / 3 per Cholesky factor, another 2 k^3 / 3 where the inverse factor and I - A^-1 are
+      // formed (the muSampler precision needs the explicit k x k matrix).  Slots 5 / 6 (unused by the full-parents methods).
+      atomicAdd(&a.counters[5], SEQM ? n_segs : n_inv);
+      atomicAdd(&a.counters[6], n_segs + n_qfac);
     }
     if (tid < SMAX) a.st_tau[tid * a.U + u] = s_tau[tid];
     for (int i = tid; i < k; i += FP_BLOCK) a.st_mu[(long long)i * a.U + u] = mu[i];

@@ -142,6 +142,7 @@ class DbnEngine:
     def chain_init(self, method, **kw):
         p = run_params(method, self.N, **kw)
         self.params = p
+        self.method = method
         rp = L.DbnRunParams(**p)
         if self.unit_range is not None:
             self._check(self._lib.dbn_set_unit_range(self._h, self.unit_range[0], self.unit_range[1]), 'dbn_set_unit_range')
@@ -240,7 +241,14 @@ class DbnEngine:
         self._check(self._lib.dbn_read_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))), 'dbn_read_counters')
         keys = ('unit_iterations', 'ml_evals', 'segment_evals', 'algorithmic_bytes', 'algorithmic_flops', 'pi_accepts',
                 'segment_factorisations', 'tau_accepts')
-        return {k: int(out[i]) for i, k in enumerate(keys)}
+        d = {k: int(out[i]) for i, k in enumerate(keys)}
+        if self.params is not None and str(getattr(self, 'method', '')).startswith('fp_'):
+            # full-parents kernels: slot 5 = factorisations that also formed the inverse factor and I - A^-1, slot 6 = all k x k
+            # Cholesky factorisations (segments + the muSampler precision): executed level-3 flops = k^3 / 3 per factor + 2 k^3 / 3 per inverse form
+            k = self.n
+            d['inverse_form_evals'] = d.pop('pi_accepts')
+            d['executed_level3_flops'] = (d['segment_factorisations'] + 2 * d['inverse_form_evals']) * (k ** 3) // 3
+        return d
 
     def verify_cache(self):
         """dbn_verify_cache: (units, entries) of the h / nh kernel's segment-statistics cache that differ from what the

@@ -53,7 +53,8 @@ def run(data, cps, chains, iters, peak):
                units=units, iterations=iters, ms_per_iteration=ms / iters, unit_iterations_per_sec=units * iters / ms * 1e3,
                ml_evals_per_sec=c['ml_evals'] / ms * 1e3, segment_evals=c['segment_evals'],
                algorithmic_gflops=c['algorithmic_flops'] / ms / 1e6, fp64_peak_gflops_measured=peak,
-               fp64_frac=c['algorithmic_flops'] / ms / 1e6 / peak, algorithmic_gbs=c['algorithmic_bytes'] / ms / 1e6,
+               fp64_frac=c['algorithmic_flops'] / ms / 1e6 / peak, executed_level3_gflops=c['executed_level3_flops'] / ms / 1e6,
+               executed_fp64_frac=c['executed_level3_flops'] / ms / 1e6 / peak, algorithmic_gbs=c['algorithmic_bytes'] / ms / 1e6,
                prefix_table_gb=info['algorithmic_bytes'] / 1e9, prefix_build_ms=prefix_ms,
                prefix_gbs=info['algorithmic_bytes'] / prefix_ms / 1e6, build_stats_host_call_s=build_s,
                mean_segments=float(st['S'].mean()), finite_state=bool(np.isfinite(st['lambda2']).all() and (st['sigma2'] > 0).all()))
