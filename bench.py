@@ -350,6 +350,10 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak (the contract): 1024 chains per GPU; strong: 1024 chains in total, the flat (node, chain) unit list split over the ranks')
     ap.add_argument('--no-c5', action='store_true', help='skip the BASELINE configs[4] sample (extra.c5)')
+    ap.add_argument('--handles', type=int, default=2,
+                    help='library handles per GPU for the device-resident measurement: each takes a contiguous range of the GPU\'s '
+                         '(node, chain) units and its own stream, so the launches of one range fill the partial last wave of the '
+                         'other (102 400 units are 1.8 waves of resident blocks; measured +10 %%, scripts/two_stream_ab.py). 1 = one handle')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -394,28 +398,60 @@ def main():
     eng.chain_init(METHOD, fan_in=FAN_IN, burn_in=0)
     local_counts = parallel.counts_tensor(eng)
     global_counts = [torch.empty_like(local_counts), torch.empty_like(local_counts)]
-    pending = [None, None]
     units = N_GENES * CHAINS_PER_GPU
     total_units = units if strong else units * world
     step_no = [0]
+
+    # ---- the handles of the device-resident loop.  `eng` (the whole range of this GPU on `stream`) serves the end-to-end
+    # measurement; with --handles H > 1 the timed loop runs H handles of its own, each on a contiguous sub-range of this GPU's
+    # units and on its own stream.  Units are independent and the Philox counters are keyed by (chain, node), so the chains are
+    # the same chains; what changes is that consecutive windows of different ranges overlap on the device.
+    class Part:
+        pass
+    parts = []
+    H = max(1, args.handles)
+    units_here = count if strong else units
+    if units_here <= 148 * 2 * 192:     # at most one wave of resident blocks: nothing to overlap, one handle
+        H = 1
+    for p_i in range(H):
+        pt = Part()
+        if H == 1:
+            pt.eng, pt.stream = eng, stream
+        else:
+            base_first, base_count = (first, count) if strong else (0, units)
+            f_, c_ = parallel.shard_units(base_count, p_i, H)
+            pt.eng = DbnEngine(n_chains=CHAINS_PER_GPU, device=local_rank, seed=0xDB20B200,
+                               chain_offset=0 if strong else rank * CHAINS_PER_GPU, unit_range=(base_first + f_, c_))
+            pt.stream = torch.cuda.Stream()
+            pt.eng.set_stream(pt.stream.cuda_stream)
+            pt.eng.build_stats([data])
+            pt.eng.chain_init(METHOD, fan_in=FAN_IN, burn_in=0)
+        pt.local = local_counts if H == 1 else parallel.counts_tensor(pt.eng)
+        pt.glob = global_counts if H == 1 else [torch.empty_like(pt.local), torch.empty_like(pt.local)]
+        pt.pending = [None, None]
+        parts.append(pt)
 
     def step():
         """One thinning window on every unit, then the all-reduce of the count block over the ranks.  The block is
         snapshotted on the kernel's stream and reduced on NCCL's stream (async_op), so the next window's kernel does
         not wait for the collective; a snapshot buffer is reused only after its reduction has finished."""
-        eng.run(WINDOW)
-        if world > 1 and not DIAG_NOREDUCE:
-            j = step_no[0] & 1
-            step_no[0] += 1
-            if pending[j] is not None:
-                pending[j].wait()
-            _, pending[j] = parallel.allreduce_counts(local_counts, out=global_counts[j], async_op=True)
+        j = step_no[0] & 1
+        step_no[0] += 1
+        for pt in parts:
+            with torch.cuda.stream(pt.stream):
+                pt.eng.run(WINDOW)
+                if world > 1 and not DIAG_NOREDUCE:
+                    if pt.pending[j] is not None:
+                        pt.pending[j].wait()
+                    _, pt.pending[j] = parallel.allreduce_counts(pt.local, out=pt.glob[j], async_op=True)
 
     def drain():
-        for j in (0, 1):
-            if pending[j] is not None:
-                pending[j].wait()
-                pending[j] = None
+        for pt in parts:
+            with torch.cuda.stream(pt.stream):
+                for j in (0, 1):
+                    if pt.pending[j] is not None:
+                        pt.pending[j].wait()
+                        pt.pending[j] = None
 
     def barrier():
         if world > 1:
@@ -429,20 +465,35 @@ def main():
         step()
     drain()
     barrier()
-    eng.reset_counters()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for pt in parts:
+        pt.eng.reset_counters()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in parts]
     barrier()
     t_begin = time.perf_counter()
     ev0.record()
+    for pt in parts:
+        pt.stream.wait_event(ev0)
     for _ in range(K):
         step()
     drain()          # the last reductions are inside the timed region
-    ev1.record()
+    for pt, e1 in zip(parts, ev1):
+        e1.record(pt.stream)
     barrier()
     t_end = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
+    ms = max(ev0.elapsed_time(e1) for e1 in ev1)   # the device time of the slowest handle's stream
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    ctr = eng.counters()
+    ctr = {}
+    for pt in parts:
+        for k_, v_ in pt.eng.counters().items():
+            ctr[k_] = ctr.get(k_, 0) + v_
+    if H > 1:      # the timed handles are done; the end-to-end measurement runs on `eng`, brought to the same chain age first
+        for pt in parts:
+            pt.eng.close()
+        parts = []
+        for _ in range(W + K):
+            eng.run(WINDOW)
+        torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -506,6 +557,10 @@ def main():
             traffic = None
     fp64_peak = eng.fp64_peak_gflops()
     cfg = workload()
+    cfg['handles_per_gpu'] = H
+    if H > 1:
+        cfg['handles'] = ('%d library handles per GPU, each a contiguous range of the GPU\'s (node, chain) units on its own stream: the '
+                          'launches of one range fill the partial last wave of the other (e2e: one handle)' % H)
     if strong:
         cfg['parallelism'] = 'flat (node, chain) unit list split over ranks (1024 chains in total), no data-path collective'
         cfg['chains_total'] = CHAINS_PER_GPU
@@ -534,7 +589,8 @@ def main():
                               'peak_gflops_measured_dfma': fp64_peak}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'steps': Ke, 'what': 'dbn_build_stats(pinned host series) + dbn_run(10 iterations) + (N > 1: reduce of the counts to rank 0) + counts to host, per step'},
-        'gpu_launches': K,
+        'gpu_launches': K * H,
+        'handles_per_gpu': H,
         'clocks': clocks,
     }
     if DIAG_NOREDUCE:

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Does the tail of a window's launch (102 400 units = 1.8 waves of resident blocks) cost throughput?  The same chains as one
+handle on one stream, or as K handles with contiguous unit ranges on K streams (their launches overlap: the second wave of one
+range runs beside the first wave of another).      python scripts/two_stream_ab.py [K=2]"""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dynamicbayesiannetworks_b200.engine import DbnEngine          # noqa: E402
+from dynamicbayesiannetworks_b200.parallel import shard_units      # noqa: E402
+from dynamicbayesiannetworks_b200.synth import make_synthetic     # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+n, T, chains, window, reps = 100, 2000, 1024, 10, 60
+data, cps, _ = make_synthetic(n, T, 3, 4, 20260120)
+
+
+def run(parts):
+    engs, streams = [], []
+    for r in range(parts):
+        first, count = shard_units(n * chains, r, parts)
+        e = DbnEngine(n_chains=chains, seed=11, unit_range=None if parts == 1 else (first, count))
+        s = torch.cuda.Stream()
+        e.set_stream(s.cuda_stream)
+        e.build_stats([data])
+        e.chain_init('varying_nh_dbn', fan_in=4)
+        engs.append(e); streams.append(s)
+    for _ in range(25):
+        for e in engs:
+            e.run(window)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in engs]
+    cur = torch.cuda.current_stream()
+    e0.record(cur)
+    for s in streams:
+        s.wait_event(e0)
+    for _ in range(reps):
+        for e in engs:
+            e.run(window)
+    for s, ev in zip(streams, ends):
+        ev.record(s)
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(ev) for ev in ends)
+    for e in engs:
+        e.close()
+    return ms / reps
+
+
+for parts in (1, K, 1, K):
+    ms = run(parts)
+    print(json.dumps(dict(handles=parts, ms_per_step=ms, unit_iterations_per_sec=n * chains * window / ms * 1e3)), flush=True)
