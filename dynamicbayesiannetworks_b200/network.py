@@ -23,6 +23,8 @@ import numpy as np
 
 from . import _lib as L
 from .engine import DbnEngine
+
+ONE_WAVE_UNITS = 148 * 2 * 192   # resident threads of the h / nh kernel on one B200: beyond this a run is split over two handles
 from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
 from . import scores as S
@@ -156,24 +158,42 @@ class Network():
             raise ValueError('%d units cannot be split over %d ranks' % (n * C, world))
         keep, window = self._plan(mid, n, count, n_iter, world)
         device = parallel.default_device() if self.device is None else self.device
-        with DbnEngine(n_chains=C, device=device, seed=self.seed, unit_range=(first, count)) as eng:
-            eng.build_stats(self.data, lag=self.lag)
-            eng.chain_init(name, fan_in=self.fan_in, burn_in=int(self.burn_in), thin=self.thin)
-            if name in FIXED_CP:   # network.py:178-189: the predefined change points, pseudo changepoint included
-                eng.set_changepoints(self.change_points)
-            N = eng.N
+        # Large h / nh runs without histories use TWO handles per GPU, each a contiguous half of the unit range on its own stream:
+        # 102 400 units are 1.8 waves of resident blocks, and the launches of one half fill the partial last wave of the other
+        # (+10 %, scripts/two_stream_ab.py).  The chains are the same chains (Philox is keyed by (chain, node)).
+        two = (not keep) and mid not in FP_METHODS and name in ('h_dbn', 'varying_nh_dbn', 'fixed_nh_dbn') and count > ONE_WAVE_UNITS
+        ranges = [(first, count)] if not two else [(first + f_, c_) for f_, c_ in (parallel.shard_units(count, i, 2) for i in range(2))]
+        engines = []
+        try:
+            for rg in ranges:
+                eng = DbnEngine(n_chains=C, device=device, seed=self.seed, unit_range=rg)
+                engines.append(eng)
+                eng.build_stats(self.data, lag=self.lag)
+                eng.chain_init(name, fan_in=self.fan_in, burn_in=int(self.burn_in), thin=self.thin)
+                if name in FIXED_CP:   # network.py:178-189: the predefined change points, pseudo changepoint included
+                    eng.set_changepoints(self.change_points)
+            N = engines[0].N
             traces = []
             done = 0
-            run = eng.run_fp if mid in FP_METHODS else eng.run
             while done < n_iter:
                 w = min(window, n_iter - done)
-                if keep:
-                    traces.append(run(w, trace=True))
-                else:
-                    run(w)
+                for eng in engines:      # asynchronous launches, one stream per handle
+                    run = eng.run_fp if mid in FP_METHODS else eng.run
+                    if keep:
+                        traces.append(run(w, trace=True))
+                    else:
+                        run(w)
                 done += w
-            counts = eng.counts() if world == 1 else parallel.global_counts(eng)
-            self.counters = eng.counters()
+            counts, ctrs = None, {}
+            for eng in engines:
+                c_ = eng.counts() if world == 1 else parallel.global_counts(eng)
+                counts = c_ if counts is None else {k: counts[k] + c_[k] for k in counts}
+                for k, v in eng.counters().items():
+                    ctrs[k] = ctrs.get(k, 0) + v
+            self.counters = ctrs
+        finally:
+            for eng in engines:
+                eng.close()
         cat = {k: np.concatenate([t[k] for t in traces], axis=1) for k in traces[0]} if traces else None
         return N, counts, cat, first
 

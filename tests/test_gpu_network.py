@@ -195,3 +195,21 @@ def test_lag2_network_dropin():
         Network(data, 10, 0, 2).infer_network('fp_glob_coup_nh_dbn')
     with pytest.raises(NotImplementedError):
         Network(data, 10, 0, 3).infer_network('varying_nh_dbn')
+
+
+def test_network_two_handles_per_gpu_same_result(monkeypatch):
+    """Runs larger than one wave of resident blocks are split over two handles (two streams) per GPU: the adjacency matrix and
+    the changepoint histogram must be exactly those of the single-handle run."""
+    from dynamicbayesiannetworks_b200 import Network
+    from dynamicbayesiannetworks_b200 import network as NW
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    data, _, _ = make_synthetic(60, 300, 2, 3, 7)
+    chains = NW.ONE_WAVE_UNITS // 60 + 8          # a little more than one wave of units
+    res = {}
+    for label, limit in (('two', NW.ONE_WAVE_UNITS), ('one', 1 << 40)):
+        monkeypatch.setattr(NW, 'ONE_WAVE_UNITS', limit)
+        net = Network([data], 40, 10, 1, n_chains=chains, keep_chain=False)
+        net.infer_network('varying_nh_dbn')
+        res[label] = (np.array(net.proposed_adj_matrix), net.counters['unit_iterations'], net.counters['ml_evals'])
+    assert np.array_equal(res['two'][0], res['one'][0])
+    assert res['two'][1:] == res['one'][1:]
