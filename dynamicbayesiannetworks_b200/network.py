@@ -24,7 +24,10 @@ import numpy as np
 from . import _lib as L
 from .engine import DbnEngine
 
-ONE_WAVE_UNITS = 148 * 2 * 192   # resident threads of the h / nh kernel on one B200: beyond this a run is split over two handles
+# resident threads of the h / nh kernel (2 blocks of 192 per SM) and of the coupled kernel (2 x 128) on one B200: a run with more
+# units than one wave is split over two handles (two streams), whose launches fill each other's partial last wave
+ONE_WAVE_UNITS = 148 * 2 * 192
+ONE_WAVE_UNITS_COUPLED = 148 * 2 * 128
 from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
 from . import scores as S
@@ -158,10 +161,12 @@ class Network():
             raise ValueError('%d units cannot be split over %d ranks' % (n * C, world))
         keep, window = self._plan(mid, n, count, n_iter, world)
         device = parallel.default_device() if self.device is None else self.device
-        # Large h / nh runs without histories use TWO handles per GPU, each a contiguous half of the unit range on its own stream:
+        # Large varying-parents runs without histories use TWO handles per GPU, each a contiguous half of the unit range on its own stream:
         # 102 400 units are 1.8 waves of resident blocks, and the launches of one half fill the partial last wave of the other
         # (+10 %, scripts/two_stream_ab.py).  The chains are the same chains (Philox is keyed by (chain, node)).
-        two = (not keep) and mid not in FP_METHODS and name in ('h_dbn', 'varying_nh_dbn', 'fixed_nh_dbn') and count > ONE_WAVE_UNITS
+        # (measured: c4 nh 6.4e8 -> 7.0e8; mTOR 4096 chains seq 1.95e8 -> 2.35e8, glob 2.2e8 -> 2.67e8, profiles/r2_small/two_handles.txt)
+        fast = name in ('h_dbn', 'varying_nh_dbn', 'fixed_nh_dbn')
+        two = (not keep) and mid not in FP_METHODS and count > (ONE_WAVE_UNITS if fast else ONE_WAVE_UNITS_COUPLED)
         ranges = [(first, count)] if not two else [(first + f_, c_) for f_, c_ in (parallel.shard_units(count, i, 2) for i in range(2))]
         engines = []
         try:

@@ -25,35 +25,53 @@ def series(name):
     return [g['data_seg%d' % s] for s in range(int(g['n_data_segments']))]
 
 
-def run(label, data, method, chains, window, reps, **kw):
-    eng = DbnEngine(n_chains=chains, seed=11)
-    s = torch.cuda.Stream()
-    torch.cuda.set_stream(s)
-    eng.set_stream(s.cuda_stream)
-    eng.build_stats(data)
-    eng.chain_init(method, **kw)
-    if method == 'fixed_nh_dbn':
-        N = eng.N
-        eng.set_changepoints([N // 3, 2 * N // 3, N + 2])
-    step = eng.run_fp if method.startswith('fp_') else eng.run
+def run(label, data, method, chains, window, reps, handles=1, **kw):
+    """handles > 1: the units are split into contiguous ranges, one library handle and stream each (their launches overlap)."""
+    from dynamicbayesiannetworks_b200.parallel import shard_units
+    n = data[0].shape[1]
+    engs = []
+    for h in range(handles):
+        rg = None if handles == 1 else shard_units(n * chains, h, handles)
+        eng = DbnEngine(n_chains=chains, seed=11, unit_range=rg)
+        s = torch.cuda.Stream()
+        eng.set_stream(s.cuda_stream)
+        eng.build_stats(data)
+        eng.chain_init(method, **kw)
+        if method == 'fixed_nh_dbn':
+            N = eng.N
+            eng.set_changepoints([N // 3, 2 * N // 3, N + 2])
+        engs.append((eng, s))
+    steps = [(e.run_fp if method.startswith('fp_') else e.run) for e, _ in engs]
     for _ in range(3):
-        step(window)
+        for st in steps:
+            st(window)
     torch.cuda.synchronize()
-    eng.reset_counters()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for e, _ in engs:
+        e.reset_counters()
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in engs]
     e0.record()
+    for _, s in engs:
+        s.wait_event(e0)
     for _ in range(reps):
-        step(window)
-    e1.record()
+        for st in steps:
+            st(window)
+    for (_, s), ev in zip(engs, ends):
+        ev.record(s)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    c = eng.counters()
+    ms = max(e0.elapsed_time(ev) for ev in ends)
+    c = {}
+    for e, _ in engs:
+        for k, v in e.counters().items():
+            c[k] = c.get(k, 0) + v
+    eng = engs[0][0]
     units = eng.n * chains
-    out = dict(case=label, method=method, n_genes=eng.n, N=eng.N, chains=chains, units=units, iterations=window * reps,
+    out = dict(case=label, method=method, n_genes=eng.n, N=eng.N, chains=chains, units=units, handles=handles, iterations=window * reps,
                ms_per_iteration=ms / (window * reps), unit_iterations_per_sec=units * window * reps / ms * 1e3,
                ml_evals_per_sec=c['ml_evals'] / ms * 1e3, algorithmic_gbs=c['algorithmic_bytes'] / ms / 1e6,
                algorithmic_gflops=c['algorithmic_flops'] / ms / 1e6)
-    eng.close()
+    for e, _ in engs:
+        e.close()
     print(json.dumps(out), flush=True)
 
 
@@ -77,6 +95,10 @@ def main():
     run('mTOR seq-dbn, 4096 chains (device filled)', mtor, 'seq_coup_nh_dbn', 4096, 50, 10)
     run('mTOR glob-dbn, 4096 chains (device filled)', mtor, 'glob_coup_nh_dbn', 4096, 50, 10)
     run('mTOR var-glob-dbn, 4096 chains (device filled)', mtor, 'var_glob_coup_nh_dbn', 4096, 50, 10)
+    run('mTOR nh-dbn, 4096 chains, two handles', mtor, 'varying_nh_dbn', 4096, 50, 10, handles=2)
+    run('mTOR seq-dbn, 4096 chains, two handles', mtor, 'seq_coup_nh_dbn', 4096, 50, 10, handles=2)
+    run('mTOR glob-dbn, 4096 chains, two handles', mtor, 'glob_coup_nh_dbn', 4096, 50, 10, handles=2)
+    run('mTOR var-glob-dbn, 4096 chains, two handles', mtor, 'var_glob_coup_nh_dbn', 4096, 50, 10, handles=2)
     run('yeast fp-glob-dbn, 64 chains', yeast, 'fp_glob_coup_nh_dbn', 64, 20, 5)
     run('mTOR fp-glob-dbn, 256 chains', mtor, 'fp_glob_coup_nh_dbn', 256, 10, 3)
     run('synthetic 40 genes T=400 fp-glob-dbn, 64 chains', [syn40], 'fp_glob_coup_nh_dbn', 64, 5, 2)

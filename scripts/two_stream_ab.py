@@ -11,8 +11,17 @@ from dynamicbayesiannetworks_b200.parallel import shard_units      # noqa: E402
 from dynamicbayesiannetworks_b200.synth import make_synthetic     # noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-n, T, chains, window, reps = 100, 2000, 1024, 10, 60
-data, cps, _ = make_synthetic(n, T, 3, 4, 20260120)
+METHOD = sys.argv[2] if len(sys.argv) > 2 else 'varying_nh_dbn'
+if len(sys.argv) > 3 and sys.argv[3] == 'mtor':      # the mTOR series of the golden fixtures, 4096 chains (bench_methods' device-filled case)
+    import glob
+    import numpy as np
+    g = dict(np.load(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'chain_mtor_varying_nh_dbn.npz'))[0]))
+    DATA = [g['data_seg%d' % s_] for s_ in range(int(g['n_data_segments']))]
+    n, chains, window, reps, FAN = DATA[0].shape[1], 4096, 50, 8, 3
+else:
+    n, T, chains, window, reps, FAN = 100, 2000, 1024, 10, 60, 4
+    data, cps, _ = make_synthetic(n, T, 3, 4, 20260120)
+    DATA = [data]
 
 
 def run(parts):
@@ -22,10 +31,10 @@ def run(parts):
         e = DbnEngine(n_chains=chains, seed=11, unit_range=None if parts == 1 else (first, count))
         s = torch.cuda.Stream()
         e.set_stream(s.cuda_stream)
-        e.build_stats([data])
-        e.chain_init('varying_nh_dbn', fan_in=4)
+        e.build_stats(DATA)
+        e.chain_init(METHOD, fan_in=FAN)
         engs.append(e); streams.append(s)
-    for _ in range(25):
+    for _ in range(3 if window > 10 else 25):
         for e in engs:
             e.run(window)
     torch.cuda.synchronize()
@@ -49,4 +58,4 @@ def run(parts):
 
 for parts in (1, K, 1, K):
     ms = run(parts)
-    print(json.dumps(dict(handles=parts, ms_per_step=ms, unit_iterations_per_sec=n * chains * window / ms * 1e3)), flush=True)
+    print(json.dumps(dict(method=METHOD, units=n * chains, handles=parts, ms_per_step=ms, unit_iterations_per_sec=n * chains * window / ms * 1e3)), flush=True)
