@@ -411,7 +411,7 @@ def main():
     parts = []
     H = max(1, args.handles)
     units_here = count if strong else units
-    if units_here <= 148 * 2 * 192:     # at most one wave of resident blocks: nothing to overlap, one handle
+    if units_here <= 148 * 2 * 128:     # at most one wave of resident blocks (2 x 128 threads per SM): nothing to overlap, one handle
         H = 1
     for p_i in range(H):
         pt = Part()
@@ -577,12 +577,12 @@ def main():
         # bound: the nearest roofline of the two the contract names.  frac = ALGORITHMIC bytes (16 (k(k+1)/2 + k + 1)
         # per executed segment evaluation, counted on the device) / time / measured HBM peak.  The kernel does not move
         # those bytes: unchanged segments come from the per-unit boundary-row cache, so the DRAM traffic ncu measures
-        # (traffic, dram_frac) is lower, and what limits the kernel is dependent-issue latency at 12 warps per SM plus
+        # (traffic, dram_frac) is lower, and what limits the kernel is dependent-issue latency at 8 warps per SM (236 registers per thread) plus
         # instruction delivery (limiter, issue_active_pct; profiles/r2_notes.md).
         'roofline': {'kernel': 'chain_fast_kernel<nh-dbn, KM=5>', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,
                      'dram_frac': (traffic / avg_launch_s / 1e9 / peaks['hbm_gbs']) if traffic else None,
-                     'limiter': 'latency / issue (FP64 dependency chains at 12 warps per SM, ~100 KB loop body), not HBM',
+                     'limiter': 'latency / issue (FP64 dependency chains at 8 warps per SM, ~100 KB loop body), not HBM',
                      'issue_active_pct': issue_active,
                      'algorithmic_bytes_per_launch': per_launch_bytes,
                      'fp64': {'achieved_gflops': ctr['algorithmic_flops'] / K / avg_launch_s / 1e9,

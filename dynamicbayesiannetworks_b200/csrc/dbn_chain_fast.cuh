@@ -39,8 +39,13 @@
 
 namespace dbn {
 
+// Block shape = register budget.  The step needs 236 registers per thread; 2 x 192 threads per SM (rounds 1 and 2a: 12 warps,
+// every shape tried there kept ~12 warps) caps it at 168 and spills.  2 x 128 threads (8 warps per SM, no spills) is 16 % faster
+// on the bench workload with one handle and 17 % with two (7.2e8 / 8.0e8 against 6.2e8 / 6.8e8 unit-iterations/s), and the
+// end-to-end step gains 13 %: profiles/r2_small/block_shape_handles_ab2.txt (64 x 4, 96 x 2, 96 x 3, 112 x 2, 144 x 2, 160 x 2,
+// 176 x 2, 224 x 2 measured beside it).
 #ifndef DBN_FAST_BLOCK
-#define DBN_FAST_BLOCK 192   // 2 blocks of 6 warps per SM measured 2.4 % faster than 3 of 4 (same 12 warps; 168 registers)
+#define DBN_FAST_BLOCK 128
 #endif
 #ifndef DBN_FAST_MINB
 #define DBN_FAST_MINB 2

@@ -958,7 +958,7 @@ int dbn_run(dbn_handle* h, int32_t n_iter, const double* replay_d, const int32_t
     // measured (profiles/r2_small/lanes_ab.txt): the h / nh kernel gains down to one unit per warp (c2, 320 units: 8.7e6 ->
     // 1.4e7 unit-iterations/s); the coupled kernel is fastest at 16 and loses below (c3, 2816 units: 4.0e7 / 4.3e7 / 1.8e7 at
     // 32 / 16 / 4 -- the gathered table no longer stays in the L1 of a few SMs)
-    const long long slots = (long long)h->sm_count * (fast ? 12 : 8);   // resident warps of the kernel
+    const long long slots = (long long)h->sm_count * 8;   // resident warps of either kernel (2 blocks of 128 threads per SM)
     const int min_lanes = fast ? 1 : 16;
     // halve while the warps fill at most half a wave (c4 data, profiles/r2_small/lanes_c4.txt: 12 800 units are fastest at 16 per
     // warp, 25 600 and more at 32)

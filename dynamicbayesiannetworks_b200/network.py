@@ -24,9 +24,9 @@ import numpy as np
 from . import _lib as L
 from .engine import DbnEngine
 
-# resident threads of the h / nh kernel (2 blocks of 192 per SM) and of the coupled kernel (2 x 128) on one B200: a run with more
+# resident threads of the h / nh kernel and of the coupled kernel (2 blocks of 128 per SM each) on one B200: a run with more
 # units than one wave is split over two handles (two streams), whose launches fill each other's partial last wave
-ONE_WAVE_UNITS = 148 * 2 * 192
+ONE_WAVE_UNITS = 148 * 2 * 128
 ONE_WAVE_UNITS_COUPLED = 148 * 2 * 128
 from .methods import method_id, H_DBN, SEQ_DBN, GLOB_DBN, FP_GLOB_DBN, VV_GLOB_DBN, FP_H_DBN, FP_VV_DBN, FP_SEQ_DBN, FP_METHODS, METHOD_NAMES, FIXED_CP
 from . import parallel
