@@ -353,7 +353,7 @@ def main():
     ap.add_argument('--handles', type=int, default=2,
                     help='library handles per GPU for the device-resident measurement: each takes a contiguous range of the GPU\'s '
                          '(node, chain) units and its own stream, so the launches of one range fill the partial last wave of the '
-                         'other (102 400 units are 1.8 waves of resident blocks; measured +10 %%, scripts/two_stream_ab.py). 1 = one handle')
+                         'other (102 400 units are 2.7 waves of resident blocks; measured +12 %%, scripts/two_stream_ab.py). 1 = one handle')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

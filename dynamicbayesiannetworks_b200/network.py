@@ -162,7 +162,7 @@ class Network():
         keep, window = self._plan(mid, n, count, n_iter, world)
         device = parallel.default_device() if self.device is None else self.device
         # Large varying-parents runs without histories use TWO handles per GPU, each a contiguous half of the unit range on its own stream:
-        # 102 400 units are 1.8 waves of resident blocks, and the launches of one half fill the partial last wave of the other
+        # 102 400 units are 2.7 waves of resident blocks (2 x 128 threads per SM), and the launches of one half fill the partial last wave of the other
         # (+10 %, scripts/two_stream_ab.py).  The chains are the same chains (Philox is keyed by (chain, node)).
         # (measured: c4 nh 6.4e8 -> 7.0e8; mTOR 4096 chains seq 1.95e8 -> 2.35e8, glob 2.2e8 -> 2.67e8, profiles/r2_small/two_handles.txt)
         fast = name in ('h_dbn', 'varying_nh_dbn', 'fixed_nh_dbn')

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Does the tail of a window's launch (102 400 units = 1.8 waves of resident blocks) cost throughput?  The same chains as one
+"""Does the tail of a window's launch (102 400 units = 2.7 waves of resident blocks at 2 x 128 threads per SM; 1.8 at the earlier 2 x 192) cost throughput?  The same chains as one
 handle on one stream, or as K handles with contiguous unit ranges on K streams (their launches overlap: the second wave of one
 range runs beside the first wave of another).      python scripts/two_stream_ab.py [K=2]"""
 import json, os, sys
