@@ -585,6 +585,7 @@ def main():
                      'limiter': 'latency / issue (FP64 dependency chains at 8 warps per SM, ~100 KB loop body), not HBM',
                      'issue_active_pct': issue_active,
                      'algorithmic_bytes_per_launch': per_launch_bytes,
+                     'per_launch_means': 'one window of all units of the GPU = one launch per handle (%d); traffic was captured on the one-handle launch of the same units' % H,
                      'fp64': {'achieved_gflops': ctr['algorithmic_flops'] / K / avg_launch_s / 1e9,
                               'peak_gflops_measured_dfma': fp64_peak}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
