@@ -1081,8 +1081,19 @@ int dbn_read_counts(dbn_handle* h, int64_t* out) {
   if (!h || !out) return DBN_ERR_INVALID;
   if (!h->have_chain) DBN_FAIL(h, DBN_ERR_STATE, "dbn_read_counts: call dbn_chain_init first");
   CU(h, cudaSetDevice(h->cfg.device));
-  // through a pinned bounce buffer owned by the handle: a device -> pageable copy runs at a fraction of the link rate
   const size_t bytes = (size_t)h->counts_elems * sizeof(int64_t);
+  {
+    // a PINNED (or registered) destination is written by the copy engine directly: one transfer, no host memcpy
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      CU(h, cudaMemcpyAsync(out, h->d_counts, bytes, cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      return DBN_OK;
+    }
+    cudaGetLastError();
+  }
+  // pageable destination: through a pinned bounce buffer owned by the handle (a device -> pageable copy runs at a fraction of
+  // the link rate)
   if (h->pinned_bytes < bytes) {
     if (h->pinned) cudaFreeHost(h->pinned);
     h->pinned = nullptr;

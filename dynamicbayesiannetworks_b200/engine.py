@@ -214,10 +214,18 @@ class DbnEngine:
             tau_move=ti[:, :, 0], tau_valid=ti[:, :, 1], tau_accept=ti[:, :, 2], S=ti[:, :, 3], S_after=ti[:, :, 4],
             tau_after=ti[:, :, 5:5 + L.SMAX])
 
-    def counts(self):
+    def counts(self, out=None):
+        """Count matrices of the thinned chain (views of one flat int64 block).  `out`: a caller-owned flat int64 array of
+        dbn_counts_size elements to read into -- a PINNED one is written by the copy engine directly (no bounce buffer, no
+        fresh pages per call); the returned matrices are views of it."""
         ne = C.c_int64()
         self._check(self._lib.dbn_counts_size(self._h, C.byref(ne)), 'dbn_counts_size')
-        flat = np.empty(ne.value, dtype=np.int64)
+        if out is None:
+            flat = np.empty(ne.value, dtype=np.int64)
+        else:
+            flat = out
+            if flat.dtype != np.int64 or flat.ndim != 1 or flat.size != ne.value or not flat.flags['C_CONTIGUOUS']:
+                raise ValueError('counts(out=): need a contiguous flat int64 array of %d elements' % ne.value)
         self._check(self._lib.dbn_read_counts(self._h, flat.ctypes.data_as(C.POINTER(C.c_int64))), 'dbn_read_counts')
         return split_counts(flat, self.n, self.N)
 
