@@ -487,13 +487,6 @@ def main():
     for pt in parts:
         for k_, v_ in pt.eng.counters().items():
             ctr[k_] = ctr.get(k_, 0) + v_
-    if H > 1:      # the timed handles are done; the end-to-end measurement runs on `eng`, brought to the same chain age first
-        for pt in parts:
-            pt.eng.close()
-        parts = []
-        for _ in range(W + K):
-            eng.run(WINDOW)
-        torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -506,29 +499,48 @@ def main():
         tot_evals = float(ctr['ml_evals'])
     value = total_units * WINDOW * K / (ms * 1e-3)
 
-    # ---- end-to-end through the C ABI with HOST buffers: per step, H2D of the series + prefix build + one window +
-    # D2H of the count matrices (the chains carry on across steps, so the work per step equals the device-timed one)
+    # ---- end-to-end through the C ABI with HOST buffers: per step and per handle, H2D of the series + prefix build + one
+    # window + D2H of the count matrices (the chains carry on across steps, so the work per step equals the device-timed one).
+    # The handles are the ones of the device-resident loop (each its own table, its own unit range, its own stream) and every
+    # handle's step is strictly sequential (build -> run -> read, the host waits for the read before it queues that handle's
+    # next build); the host queues one handle's next step before it waits for the other's read, so the tail of one handle's
+    # window overlaps the other handle's copies, prefix build and first wave -- the way a caller drives two handles per device
+    # (INTEGRATION.md section 3).  h2d / d2h count every handle's copies.
     Ke = max(5, min(K, 40))
-    h2d = data.nbytes
-    host_counts = torch.empty(local_counts.shape, dtype=local_counts.dtype, pin_memory=True)
-    host_flat = host_counts.numpy().reshape(-1)
+    h2d = data.nbytes * len(parts)
+    for pt in parts:
+        pt.host = torch.empty(pt.local.shape, dtype=pt.local.dtype, pin_memory=True)
+        pt.host_flat = pt.host.numpy().reshape(-1)
     if world > 1:           # untimed: the first collective of a group sets up its communicator
-        parallel.allreduce_counts(local_counts, out=global_counts[0], group=wide)
+        parallel.allreduce_counts(parts[0].local, out=parts[0].glob[0], group=wide)
+
+    def e2e_queue(pt):
+        with torch.cuda.stream(pt.stream):
+            pt.eng.build_stats([data])
+            pt.eng.run(WINDOW)
+            if world > 1:   # the caller reads the counts of ALL chains on rank 0: reduce over the ranks, then device -> pinned host
+                pt.glob[0].copy_(pt.local)
+                dist.reduce(pt.glob[0], dst=0, op=dist.ReduceOp.SUM, group=wide)
+                if rank == 0:
+                    pt.host.copy_(pt.glob[0], non_blocking=True)
+
+    def e2e_read(pt):
+        if world > 1:
+            if rank == 0:
+                pt.stream.synchronize()
+            return pt.host.numel() * pt.host.element_size()
+        cnt = pt.eng.counts(out=pt.host_flat)      # pinned destination: written by the copy engine directly
+        return sum(v.nbytes for v in cnt.values())
+
     barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        eng.build_stats([data])
-        eng.run(WINDOW)
-        if world > 1:       # the caller reads the counts of ALL chains on rank 0: reduce over the ranks, then device -> pinned host
-            global_counts[0].copy_(local_counts)
-            dist.reduce(global_counts[0], dst=0, op=dist.ReduceOp.SUM, group=wide)
-            if rank == 0:
-                host_counts.copy_(global_counts[0], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            d2h = host_counts.numel() * host_counts.element_size()
-        else:
-            cnt = eng.counts(out=host_flat)      # pinned destination: written by the copy engine directly
-            d2h = sum(v.nbytes for v in cnt.values())
+    for s_ in range(Ke):
+        d2h = 0
+        for pt in parts:
+            if s_ > 0:
+                d2h += e2e_read(pt)     # the result of this handle's previous step
+            e2e_queue(pt)
+    d2h = sum(e2e_read(pt) for pt in parts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -536,6 +548,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = total_units * WINDOW * Ke / e2e_s
+    if H > 1:
+        for pt in parts:
+            pt.eng.close()
+        parts = []
 
     if rank != 0:
         if world > 1:
@@ -561,7 +577,7 @@ def main():
     cfg['handles_per_gpu'] = H
     if H > 1:
         cfg['handles'] = ('%d library handles per GPU, each a contiguous range of the GPU\'s (node, chain) units on its own stream: the '
-                          'launches of one range fill the partial last wave of the other (e2e: one handle)' % H)
+                          'launches of one range fill the partial last wave of the other (device-resident loop and e2e alike)' % H)
     if strong:
         cfg['parallelism'] = 'flat (node, chain) unit list split over ranks (1024 chains in total), no data-path collective'
         cfg['chains_total'] = CHAINS_PER_GPU
@@ -590,7 +606,10 @@ def main():
                      'fp64': {'achieved_gflops': ctr['algorithmic_flops'] / K / avg_launch_s / 1e9,
                               'peak_gflops_measured_dfma': fp64_peak}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'steps': Ke, 'what': 'dbn_build_stats(pinned host series) + dbn_run(10 iterations) + (N > 1: reduce of the counts to rank 0) + counts to host, per step'},
+                'steps': Ke, 'handles': H,
+                'what': 'per step and per handle (%d per GPU, each a unit range with its own table and stream): dbn_build_stats(pinned host series) + '
+                        'dbn_run(10 iterations) + (N > 1: reduce of the counts to rank 0) + counts to pinned host; a handle\'s step is sequential, '
+                        'the host queues one handle\'s next step before waiting for the other\'s read' % H},
         'gpu_launches': K * H,
         'handles_per_gpu': H,
         'clocks': clocks,

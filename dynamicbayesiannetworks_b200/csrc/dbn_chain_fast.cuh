@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   double* const cand = s_cand + tid;     // this thread's candidate-column slot: value i at cand[i * FAST_BLOCK]
   double* const cbase = a.cache + 2ll * u;
   auto crow = [&](int row) -> double* { return cbase + (long long)row * NP * (2 * U); };  // pair 0 of cached row `row`
-  const int nb = a.tb.zz_size + node * (n + 2);  // table offset of this node's ZY / YY block
+  const int nb = a.tb.zy_base + node * (n + 2);  // table offset of this node's ZY / YY block
 
   // ---- load state
   int npi = a.st_npi[u];
@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(256) cache_fill_kernel(const ChainArgs a) {
   }
   if (j >= S) return;
   const int node = (a.unit0 + u) / a.C, n = a.tb.n, N = a.tb.N;
-  const int nb = a.tb.zz_size + node * (n + 2);
+  const int nb = a.tb.zy_base + node * (n + 2);
   const int t = DBN_SEG_END(a.st_tau[j * a.U + u], j, S, N);
   const double* __restrict__ row = a.tb.base + (long long)t * a.tb.row_stride;
   double v[2 * NP];
@@ -1114,7 +1114,7 @@ __global__ void cache_verify_kernel(const ChainArgs a, unsigned long long* count
   if (u >= a.U) return;
   const long long U = a.U;
   const int node = (a.unit0 + u) / a.C, n = a.tb.n, N = a.tb.N;
-  const int nb = a.tb.zz_size + node * (n + 2);
+  const int nb = a.tb.zy_base + node * (n + 2);
   const int S = a.st_S[u];
   int cg[KM];
   cg[0] = -1;

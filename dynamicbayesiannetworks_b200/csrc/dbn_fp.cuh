@@ -107,7 +107,7 @@ __device__ inline void fp_load_segment(const Table& tb, int node, int lo, int hi
                                 double* s_out) {
   const double* __restrict__ ph = tb.base + (long long)hi * tb.row_stride;
   const double* __restrict__ pl = tb.base + (long long)lo * tb.row_stride;
-  const int nb = tb.zz_size + node * (tb.n + 2);
+  const int nb = tb.zy_base + node * (tb.n + 2);
   if (FP_BLOCK > 128) {
     // large k: a warp per matrix row, lanes along the row (table entries of a row are contiguous but for the node's own column);
     // sixteen table loads in flight per lane before the first store (one pair per step left the loop waiting for DRAM:

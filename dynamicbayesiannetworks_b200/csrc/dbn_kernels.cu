@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(256) chunk_scan_kernel(double* __restrict__ ch
 }
 
 // Per-(chunk, column) totals as a register-tiled product.  A table column is (row entity r, column c): ZZ rows a = 0..nv
-// (value index a, c <= a, offset a (a + 1) / 2 + c) and one ZY | YY row per node i (value index nv + 1 + i, c <= nv + 1, offset
-// zz_size + i (nv + 2) + c); its total over the chunk is sum_t v_t[aidx(r)] v_t[c] (v_t[aidx(r)]^2 for the YY entry c = nv + 1).
+// (value index a, c <= a, offset a (a + 1) / 2 + c) and one ZY | YY row per node i = node0 + il of the table's `n` nodes (value
+// index nv + 1 + i, c <= nv + 1, offset zz_size + il (nv + 2) + c); its total over the chunk is sum_t v_t[aidx(r)] v_t[c] (v_t[aidx(r)]^2 for the YY entry c = nv + 1).
 // A warp takes four row entities, a lane the columns lane + 32 j: per time step 4 broadcast + 4 conflict-free shared loads
 // feed 16 FMAs (the write pass's column mapping, used here in round 1, needs 2 loads per FMA and was bound by the
 // shared-memory pipe: 19 us of the 86 us build).
-__global__ void __launch_bounds__(PREFIX_BLOCK) chunk_totals_kernel(const double* __restrict__ V, int N, int W, int nv, int n, int zz_size,
-                                                                    long long R, int Lc, double* __restrict__ chunk) {
+__global__ void __launch_bounds__(PREFIX_BLOCK) chunk_totals_kernel(const double* __restrict__ V, int N, int W, int nv, int n, int node0,
+                                                                    int zz_size, long long R, int Lc, double* __restrict__ chunk) {
   extern __shared__ __align__(16) double sv[];  // [Lc][W]
   const int t0 = blockIdx.y * Lc;
   const int len = min(Lc, N - t0);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) chunk_totals_kernel(const double
   for (int r = 0; r < 4; ++r) {
     const int e = e0 + r;
     const bool zz = e <= nv;
-    aidx[r] = e < E ? (zz ? e : e) : 0;            // ZZ row a: v index a; ZY row of node i = e - (nv + 1): v index nv + 1 + i = e
+    aidx[r] = e < E ? (zz ? e : e + node0) : 0;    // ZZ row a: v index a; ZY row of node i = node0 + e - (nv + 1): v index nv + 1 + i
     ncols[r] = e < E ? (zz ? e + 1 : nv + 2) : 0;
     base[r] = zz ? (long long)e * (e + 1) / 2 : (long long)zz_size + (long long)(e - nv - 1) * (nv + 2);
   }
@@ -297,6 +297,7 @@ struct dbn_handle {
   long long raw_rows = 0;
   long long R = 0;
   int zz_size = 0;
+  int tn0 = 0, tnn = 0;       // the table holds the ZY | YY blocks of nodes tn0 .. tn0 + tnn - 1 (the nodes of the handle's unit range)
   double* d_raw = nullptr;
   int* d_xrow = nullptr;
   std::vector<int> seg_len;  // series-segment lengths the row map on the device was built for
@@ -507,6 +508,60 @@ int dbn_sync(dbn_handle* h) {
   return DBN_OK;
 }
 
+// Nodes whose ZY | YY blocks the handle's table needs: every node (no unit range) or the nodes its unit range touches
+// (u = node * n_chains + chain).  A rank / handle of a sharded run then builds and keeps only its own columns: for BASELINE
+// configs[4] at 8 ranks 12.6 GB instead of the 30 GB of the full table (the ZZ block is shared by all nodes).
+static void wanted_nodes(const dbn_handle* h, int n, int* tn0, int* tnn) {
+  *tn0 = 0;
+  *tnn = n;
+  if (h->unit_count < 0 || h->cfg.n_chains < 1) return;
+  const long long C = h->cfg.n_chains;
+  long long first = h->unit0 / C, last = (h->unit0 + h->unit_count - 1) / C;
+  if (first > n - 1) first = n - 1;   // a range past the grid is refused by dbn_chain_init; keep the table well-formed
+  if (last > n - 1) last = n - 1;
+  *tn0 = (int)first;
+  *tnn = (int)(last - first + 1);
+}
+
+// (Re)allocate everything whose size depends on the table's column count for the node range h->tn0, h->tnn and upload the
+// column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[nv+1+i]; YY(i) = v[nv+1+i]^2.  h->n, nv, N, W, zz_size, Lc, n_chunks are set.
+static int layout_columns(dbn_handle* h) {
+  free_dev(h->d_colA);
+  free_dev(h->d_colB);
+  free_dev(h->d_chunk);
+  free_dev(h->d_table);
+  const int nv = h->nv, N = h->N;
+  h->R = (long long)h->zz_size + (long long)h->tnn * (nv + 2);
+  std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
+  {
+    size_t p = 0;
+    for (int a = 0; a <= nv; ++a)
+      for (int b = 0; b <= a; ++b) {
+        ca[p] = (unsigned short)a;
+        cb[p] = (unsigned short)b;
+        ++p;
+      }
+    for (int i = h->tn0; i < h->tn0 + h->tnn; ++i) {
+      for (int a = 0; a <= nv; ++a) {
+        ca[p] = (unsigned short)a;
+        cb[p] = (unsigned short)(nv + 1 + i);
+        ++p;
+      }
+      ca[p] = cb[p] = (unsigned short)(nv + 1 + i);
+      ++p;
+    }
+  }
+  CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
+  CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
+  CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
+  cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
+  if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
+  CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_colB, cb.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));  // ca/cb go out of scope
+  return DBN_OK;
+}
+
 static int launch_prefix(dbn_handle* h) {
   const int n = h->n, N = h->N, W = h->W;
   {
@@ -522,9 +577,9 @@ static int launch_prefix(dbn_handle* h) {
   if (getenv("DBN_PREFIX_OLD_TOTALS")) {   // round-1 totals pass (A/B)
     prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   } else {
-    const int row_tiles = (h->nv + 1 + n + 3) / 4;
+    const int row_tiles = (h->nv + 1 + h->tnn + 3) / 4;
     dim3 gt((unsigned)((row_tiles + PREFIX_BLOCK / 32 - 1) / (PREFIX_BLOCK / 32)), (unsigned)h->n_chunks);
-    chunk_totals_kernel<<<gt, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, N, W, h->nv, n, h->zz_size, h->R, h->Lc, h->d_chunk);
+    chunk_totals_kernel<<<gt, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, N, W, h->nv, h->tnn, h->tn0, h->zz_size, h->R, h->Lc, h->d_chunk);
   }
   CU(h, cudaGetLastError());
   if (!getenv("DBN_PREFIX_NO_SCAN")) {   // the 64-way scan costs less than the in-pass sums of the write kernel (0.079 vs 0.082 ms)
@@ -563,7 +618,9 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
       base += seg_len[s];
     }
   }
-  const bool same_geometry = h->have_stats && h->n == n && h->lag == lag && h->N == (int)N && h->raw_rows == rows;
+  int tn0, tnn;
+  wanted_nodes(h, n, &tn0, &tnn);
+  const bool same_geometry = h->have_stats && h->n == n && h->lag == lag && h->N == (int)N && h->raw_rows == rows && h->tn0 == tn0 && h->tnn == tnn;
   if (!same_geometry) {
     free_stats(h);
     free_chain(h);
@@ -575,27 +632,8 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     h->raw_rows = rows;
     h->W = 1 + nv + n;
     h->zz_size = (nv + 1) * (nv + 2) / 2;
-    h->R = (long long)h->zz_size + (long long)n * (nv + 2);
-    // column map: ZZ(a,b) = v[a] v[b]; ZY(i,a) = v[a] v[nv+1+i]; YY(i) = v[nv+1+i]^2
-    std::vector<unsigned short> ca((size_t)h->R), cb((size_t)h->R);
-    {
-      size_t p = 0;
-      for (int a = 0; a <= nv; ++a)
-        for (int b = 0; b <= a; ++b) {
-          ca[p] = (unsigned short)a;
-          cb[p] = (unsigned short)b;
-          ++p;
-        }
-      for (int i = 0; i < n; ++i) {
-        for (int a = 0; a <= nv; ++a) {
-          ca[p] = (unsigned short)a;
-          cb[p] = (unsigned short)(nv + 1 + i);
-          ++p;
-        }
-        ca[p] = cb[p] = (unsigned short)(nv + 1 + i);
-        ++p;
-      }
-    }
+    h->tn0 = tn0;
+    h->tnn = tnn;
     const size_t row_bytes = (size_t)h->W * sizeof(double);
     int Lc = (int)(96 * 1024 / row_bytes);
     const int Lmax = Lc;
@@ -612,14 +650,8 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_xpos, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_V, (size_t)N * h->W * sizeof(double)));
-    CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
-    CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
-    CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
-    cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
-    if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
-    CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->d_colB, cb.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));  // ca/cb go out of scope
+    int rc = layout_columns(h);
+    if (rc != DBN_OK) return rc;
   }
   // same geometry: the table is rebuilt in place and the chain state (if any) carries on over the new data
   CU(h, cudaMemcpyAsync(h->d_raw, data, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -682,6 +714,7 @@ static Table make_table(const dbn_handle* h) {
   t.n = h->nv;      // candidate feature columns (n genes x lag)
   t.N = h->N;
   t.zz_size = h->zz_size;
+  t.zy_base = h->zz_size - h->tn0 * (h->nv + 2);
   return t;
 }
 
@@ -701,6 +734,9 @@ int dbn_score_batch(dbn_handle* h, int32_t mode, double alpha, double beta, doub
   for (int b = 0; b < B; ++b) {
     if (node[b] < 0 || node[b] >= h->n || pi_len[b] < 0 || pi_len[b] > PMAX || tau_len[b] < 1 || tau_len[b] > SMAX)
       DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d out of range", b);
+    if (node[b] < h->tn0 || node[b] >= h->tn0 + h->tnn)
+      DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d scores node %d, but this handle's table holds nodes %d..%d only (dbn_set_unit_range)", b,
+               node[b], h->tn0, h->tn0 + h->tnn - 1);
     for (int j = 0; j < pi_len[b]; ++j)
       if (pi[b * PMAX + j] < 0 || pi[b * PMAX + j] >= h->nv || pi[b * PMAX + j] % h->n == node[b])
         DBN_FAIL(h, DBN_ERR_INVALID, "dbn_score_batch: item %d has an invalid parent", b);
@@ -844,6 +880,23 @@ int dbn_set_unit_range(dbn_handle* h, int64_t first_unit, int64_t n_units) {
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaStreamSynchronize(h->stream));
     free_chain(h);
+  }
+  if (h->have_stats) {   // the table follows the range's nodes: rebuilt from the series already on the device
+    int tn0, tnn;
+    wanted_nodes(h, h->n, &tn0, &tnn);
+    if (tn0 != h->tn0 || tnn != h->tnn) {
+      CU(h, cudaSetDevice(h->cfg.device));
+      CU(h, cudaStreamSynchronize(h->stream));
+      h->tn0 = tn0;
+      h->tnn = tnn;
+      h->have_stats = false;
+      int rc = layout_columns(h);
+      if (rc != DBN_OK) return rc;
+      rc = launch_prefix(h);
+      if (rc != DBN_OK) return rc;
+      h->have_stats = true;
+      h->cache_valid = false;
+    }
   }
   return DBN_OK;
 }

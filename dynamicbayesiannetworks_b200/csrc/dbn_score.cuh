@@ -18,13 +18,15 @@ namespace dbn {
 
 // ----- prefix table geometry (one row per t = 0..N) -------------------------------------------------------
 // row = [ ZZ packed lower triangle over z = (1, x_0..x_{n-1}) : (n+1)(n+2)/2 doubles |
-//         for each node i: ZY[i][0..n] (sum z_a * y_i), YY[i] (sum y_i^2) : n * (n + 2) doubles ]
+//         for each node i (of the handle's node range): ZY[i][0..n] (sum z_a * y_i), YY[i] (sum y_i^2) : (n + 2) doubles each ]
 struct Table {
   const double* base;
   long long row_stride;  // doubles per row
   int n;
   int N;        // regression rows; table has N+1 rows, row 0 is all zeros
   int zz_size;  // (n+1)(n+2)/2
+  int zy_base;  // offset of node i's ZY | YY block = zy_base + i (n + 2): zz_size when the table holds every node's block,
+                // zz_size - node0 (n + 2) when it holds only the blocks of nodes node0.. (a handle restricted to a unit range)
 };
 
 template <int KM>
@@ -39,7 +41,7 @@ struct Cols {
 template <int KM>
 __device__ __forceinline__ void make_cols(Cols<KM>& c, const Table& t, int node, const int (&f)[KM], int k) {
   c.k = k;
-  const int nb = t.zz_size + node * (t.n + 2);
+  const int nb = t.zy_base + node * (t.n + 2);
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
     const int fi = f[i];

@@ -43,6 +43,8 @@ class DbnEngine:
         self.device = int(device)
         self.unit_range = None if unit_range is None else (int(unit_range[0]), int(unit_range[1]))
         self.n = self.N = None
+        if self.unit_range is not None:     # before build_stats: the table then holds only the ZY | YY blocks of the range's nodes
+            self._check(self._lib.dbn_set_unit_range(self._h, self.unit_range[0], self.unit_range[1]), 'dbn_set_unit_range')
         self.params = None
 
     # ---- plumbing
@@ -96,7 +98,8 @@ class DbnEngine:
         return dict(N=N.value, row_doubles=R.value, algorithmic_bytes=B.value)
 
     def stats_row(self, t):
-        """Table row t split into ZZ[nv+1, nv+1] (symmetric), ZY[n, nv+1] (node, column), YY[n]; nv = n * lag."""
+        """Table row t split into ZZ[nv+1, nv+1] (symmetric), ZY[nodes, nv+1] (node, column), YY[nodes]; nv = n * lag.
+        `nodes` = every node, or the nodes of the engine's unit range (the table holds only their blocks)."""
         info = self.stats_info()
         row = np.empty(info['row_doubles'])
         self._check(self._lib.dbn_read_stats_row(self._h, int(t), _dptr(row)), 'dbn_read_stats_row')
@@ -104,7 +107,7 @@ class DbnEngine:
         zz = np.zeros((nv + 1, nv + 1))
         zz[np.tril_indices(nv + 1)] = row[:(nv + 1) * (nv + 2) // 2]
         zz = zz + np.tril(zz, -1).T
-        blocks = row[(nv + 1) * (nv + 2) // 2:].reshape(n, nv + 2)
+        blocks = row[(nv + 1) * (nv + 2) // 2:].reshape(-1, nv + 2)
         return zz, blocks[:, :nv + 1].copy(), blocks[:, nv + 1].copy()
 
     # ---- kernel 2

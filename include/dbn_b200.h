@@ -121,7 +121,8 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
 int dbn_rebuild_stats(dbn_handle* h);
 /* geometry of the table: regression rows N, doubles per table row, algorithmic bytes of one build */
 int dbn_stats_info(const dbn_handle* h, int32_t* N, int64_t* row_doubles, int64_t* algorithmic_bytes);
-/* copy table row t (0..N) to the host: [ZZ packed | per node: ZY[0..n], YY] (row_doubles values) */
+/* copy table row t (0..N) to the host: [ZZ packed | per node of the table (all, or those of the unit range): ZY[0..n], YY]
+ * (row_doubles values) */
 int dbn_read_stats_row(dbn_handle* h, int32_t t, double* out_row);
 
 /* ---- kernel 2: batched marginal-likelihood scorer ---------------------------------------------------- */
@@ -156,6 +157,10 @@ int dbn_chain_init(dbn_handle* h, const dbn_run_params* p);
  * running the whole grid.  State, trace and replay arrays are indexed by the LOCAL unit (0 .. n_units - 1); the count
  * matrices keep their full [n, ...] shape (rows of nodes outside the slice stay zero) so that they can be summed over
  * ranks.  Takes effect with the next dbn_chain_init (an existing chain is dropped).
+ * The prefix table follows the range: a handle with a unit range builds and keeps the ZZ block and the ZY | YY blocks of the
+ * nodes its range touches only (row = [ZZ | blocks of nodes first_node .. last_node]; dbn_stats_info reports the shorter row,
+ * dbn_score_batch refuses other nodes).  Set the range BEFORE dbn_build_stats to build the smaller table straight away; set
+ * after it, the table is rebuilt for the new nodes from the series already on the device.
  */
 int dbn_set_unit_range(dbn_handle* h, int64_t first_unit, int64_t n_units);
 

@@ -45,6 +45,49 @@ def test_unit_ranges_reproduce_the_full_grid(method):
         assert np.array_equal(acc[k], full_c[k]), (method, k)
 
 
+def test_unit_range_table_holds_only_its_nodes():
+    """A handle restricted to a unit range builds the ZZ block and the ZY | YY blocks of the range's nodes only (a rank
+    keeps its own columns): rows equal the matching slices of the full table's rows, the scorer works on those nodes and refuses
+    the others, and moving the range afterwards rebuilds the table for the new nodes from the series on the device."""
+    from dynamicbayesiannetworks_b200.engine import DbnEngine, DbnError
+    data = _series('yeast')
+    n, C = data[0].shape[1], 3
+    with DbnEngine(n_chains=C) as full:
+        full.build_stats(data)
+        N = full.N
+        info_full = full.stats_info()
+        rows_full = {t: full.stats_row(t) for t in (0, 1, N // 2, N)}
+        ref = full.score_batch([2], [[0, 4]], [[N // 2, N + 2]], [1.3])
+    with DbnEngine(n_chains=C, unit_range=(4, 7)) as e:      # units 4..10 = nodes 1..3
+        e.build_stats(data)
+        info = e.stats_info()
+        assert info['row_doubles'] == (n + 1) * (n + 2) // 2 + 3 * (n + 2)
+        assert info['row_doubles'] < info_full['row_doubles'] and info['algorithmic_bytes'] < info_full['algorithmic_bytes']
+        for t, (zz, zy, yy) in rows_full.items():
+            zz_, zy_, yy_ = e.stats_row(t)
+            assert np.array_equal(zz_, zz) and np.array_equal(zy_, zy[1:4]) and np.array_equal(yy_, yy[1:4]), t
+        assert np.array_equal(e.score_batch([2], [[0, 4]], [[N // 2, N + 2]], [1.3]), ref)
+        with pytest.raises(DbnError, match='holds nodes 1..3 only'):
+            e.score_batch([0], [[1, 4]], [[N // 2, N + 2]], [1.3])
+        # the range moves after the build: nodes 3..4 now
+        e.unit_range = (3 * C + 1, 4)
+        e.chain_init('varying_nh_dbn', burn_in=0)
+        assert e.stats_info()['row_doubles'] == (n + 1) * (n + 2) // 2 + 2 * (n + 2)
+        for t, (zz, zy, yy) in rows_full.items():
+            zz_, zy_, yy_ = e.stats_row(t)
+            assert np.array_equal(zz_, zz) and np.array_equal(zy_, zy[3:5]) and np.array_equal(yy_, yy[3:5]), t
+        e.run(40)
+        assert e.verify_cache() == (0, 0)
+        st = e.state()
+    with DbnEngine(n_chains=C) as full:
+        full.build_stats(data)
+        full.chain_init('varying_nh_dbn', burn_in=0)
+        full.run(40)
+        fs = full.state()
+    for key in ('S', 'npi', 'sigma2', 'lambda2'):
+        assert np.array_equal(st[key], fs[key][3 * C + 1:3 * C + 5]), key
+
+
 @pytest.mark.parametrize('method', ['h_dbn', 'varying_nh_dbn', 'glob_coup_nh_dbn', 'fp_varying_nh_dbn', 'fp_glob_coup_nh_dbn'])
 def test_fit_score_edges_sequence_equals_infer_network(method):
     """The reference's own calling sequence (network.py:413-416) node by node gives what infer_network gives for all
