@@ -514,13 +514,17 @@ def main():
     if world > 1:           # untimed: the first collective of a group sets up its communicator
         parallel.allreduce_counts(parts[0].local, out=parts[0].glob[0], group=wide)
 
+    # the reduce the caller waits for runs on the wide group (NCCL's default CTA count); the 2-CTA group of the overlapped
+    # all-reduce was measured here too (DBN_E2E_GROUP=small, N = 2, two handles): 1.15e9 against 1.24e9
+    e2e_group = (None if os.environ.get('DBN_E2E_GROUP', 'wide') == 'small' else wide) if world > 1 else None
+
     def e2e_queue(pt):
         with torch.cuda.stream(pt.stream):
             pt.eng.build_stats([data])
             pt.eng.run(WINDOW)
             if world > 1:   # the caller reads the counts of ALL chains on rank 0: reduce over the ranks, then device -> pinned host
                 pt.glob[0].copy_(pt.local)
-                dist.reduce(pt.glob[0], dst=0, op=dist.ReduceOp.SUM, group=wide)
+                dist.reduce(pt.glob[0], dst=0, op=dist.ReduceOp.SUM, group=e2e_group)
                 if rank == 0:
                     pt.host.copy_(pt.glob[0], non_blocking=True)
 

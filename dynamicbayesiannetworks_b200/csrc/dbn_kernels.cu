@@ -29,7 +29,8 @@ constexpr int PREFIX_BLOCK = 256;
 // gather the lagged rows: V[t] = [1, x_t, x_{t-1}, .., x_{t-lag+1}, y_t] with x_{t-l} = raw[xrow[t] - l] (zeros for the first l
 // rows of a series segment: the reference pads every lagged copy with zeros, network.py:106-113) and y_t = raw[xrow[t] + 1]
 __global__ void build_v_kernel(const double* __restrict__ raw, const int* __restrict__ xrow, const int* __restrict__ xpos, int N, int n,
-                               int lag, double* __restrict__ V) {
+                               int lag, double* __restrict__ V, unsigned* __restrict__ ticket) {
+  if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;   // block numbering of prefix_onepass_kernel, which runs next
   const int nv = n * lag;          // feature columns: block l = lag-(l+1) copies of the n genes
   const int W = 1 + nv + n;
   const long long total = (long long)N * W;
@@ -228,6 +229,139 @@ __global__ void __launch_bounds__(PREFIX_BLOCK) prefix_kernel(const double* __re
   }
 }
 
+// ---- one-pass build: chunk totals, chunk offsets by decoupled look-back, running sums ------------------------------------
+// The three launches in front of the write pass (totals, scan, and their gaps: 28 of the build's 77 us on configs[3],
+// profiles/r2_prefix/where_the_time_goes.txt) become the prologue of the write pass itself.  A block takes a ticket (blocks are
+// numbered in the order they START, chunk-major, so a block only ever waits for blocks that are already running), stages its
+// chunk's rows, sums its PREFIX_BLOCK * PREFIX_CPT columns over the chunk (the same fma chain from 0 as chunk_totals_kernel:
+// same bits), publishes them as the chunk's AGGREGATE, and finds its offset by looking back over the earlier chunks of its column
+// tile: warp 0 reads 32 predecessor flags per round; the nearest chunk that has published an INCLUSIVE prefix ends the walk,
+// every chunk in between contributes its aggregate.  offset = incl[c] + agg[c + 1] + ... + agg[y - 1] added in chunk order,
+// and incl[c] is itself that left fold, so the offset has the same bits wherever the walk ends -- and the same bits as
+// chunk_scan_kernel's running sums.  The block then publishes its own inclusive prefix and streams its rows out.
+// Flags carry the launch's generation (gen << 2 | state), so nothing is cleared between builds; the ticket counter is zeroed by
+// build_v_kernel, which always runs in front.
+constexpr unsigned PFX_AGG = 1u, PFX_INCL = 2u;
+
+__global__ void __launch_bounds__(PREFIX_BLOCK, 4) prefix_onepass_kernel(const double* __restrict__ V, const unsigned short* __restrict__ colA,
+                                                                      const unsigned short* __restrict__ colB, int N, int W, long long R,
+                                                                      int Lc, int ntx, int n_chunks, unsigned gen, unsigned* __restrict__ ticket,
+                                                                      unsigned* flags, double* agg, double* incl, double* __restrict__ table) {
+  extern __shared__ __align__(16) double sv[];  // [Lc][W]
+  __shared__ unsigned s_ticket;
+  __shared__ int s_incl_c;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int y = (int)(s_ticket / (unsigned)ntx), x = (int)(s_ticket - (unsigned)y * (unsigned)ntx);
+  const int t0 = y * Lc;
+  const int len = min(Lc, N - t0);
+  prefix_stage(sv, V, t0, len, W);   // in flight while the column maps are loaded
+  const long long p0 = (long long)x * (PREFIX_BLOCK * PREFIX_CPT) + threadIdx.x;
+  int ca[PREFIX_CPT], cb[PREFIX_CPT];
+  bool live[PREFIX_CPT];
+  double tot[PREFIX_CPT], acc[PREFIX_CPT];
+#pragma unroll
+  for (int j = 0; j < PREFIX_CPT; ++j) {
+    const long long p = p0 + (long long)j * PREFIX_BLOCK;
+    live[j] = p < R;
+    ca[j] = live[j] ? colA[p] : 0;
+    cb[j] = live[j] ? colB[p] : 0;
+    tot[j] = 0.0;
+    acc[j] = 0.0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int t = 0; t < len; ++t) {
+#pragma unroll
+    for (int j = 0; j < PREFIX_CPT; ++j) tot[j] = fma(sv[t * W + ca[j]], sv[t * W + cb[j]], tot[j]);
+  }
+  volatile unsigned* fl = flags + (long long)x * n_chunks;   // this column tile's flags, one per chunk
+  const unsigned f_agg = (gen << 2) | PFX_AGG, f_incl = (gen << 2) | PFX_INCL;
+  const bool last_chunk = y == n_chunks - 1;
+  if (y > 0) {
+    if (!last_chunk) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j)
+        if (live[j]) __stcg(agg + (long long)y * R + p0 + (long long)j * PREFIX_BLOCK, tot[j]);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) fl[y] = f_agg;
+    }
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      int base = y - 1, found = -2;
+      while (found == -2) {
+        const int c = base - lane;
+        unsigned st;
+        while (true) {
+          st = PFX_INCL;                              // chunks before the first: an inclusive prefix of zero
+          if (c >= 0) {
+            const unsigned f = fl[c];
+            st = (f >> 2) == gen ? (f & 3u) : 0u;
+          }
+          const unsigned ready = __ballot_sync(0xffffffffu, st != 0u);
+          const unsigned inclm = __ballot_sync(0xffffffffu, st == PFX_INCL);
+          const int n_ready = (ready == 0xffffffffu) ? 32 : (__ffs((int)~ready) - 1);   // leading run of published chunks
+          const int first_incl = inclm ? (__ffs((int)inclm) - 1) : 32;
+          if (first_incl < n_ready) {                 // the walk ends at chunk base - first_incl
+            found = base - first_incl;
+            break;
+          }
+          if (n_ready == 32) {                        // 32 aggregates: next window
+            base -= 32;
+            break;
+          }
+        }
+      }
+      if (lane == 0) s_incl_c = found < 0 ? -1 : found;
+      __threadfence();
+    }
+    __syncthreads();
+    const int ci = s_incl_c;
+    if (ci >= 0) {
+#pragma unroll
+      for (int j = 0; j < PREFIX_CPT; ++j)
+        if (live[j]) acc[j] = __ldcg(incl + (long long)ci * R + p0 + (long long)j * PREFIX_BLOCK);
+    }
+    for (int c0 = ci + 1; c0 < y; c0 += 4) {          // 4 x PREFIX_CPT loads in flight, added in chunk order
+      double v[4][PREFIX_CPT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < PREFIX_CPT; ++j)
+          v[i][j] = (c0 + i < y && live[j]) ? __ldcg(agg + (long long)(c0 + i) * R + p0 + (long long)j * PREFIX_BLOCK) : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c0 + i < y) {
+#pragma unroll
+          for (int j = 0; j < PREFIX_CPT; ++j) acc[j] += v[i][j];
+        }
+    }
+  }
+  if (!last_chunk) {
+#pragma unroll
+    for (int j = 0; j < PREFIX_CPT; ++j)
+      if (live[j]) __stcg(incl + (long long)y * R + p0 + (long long)j * PREFIX_BLOCK, acc[j] + tot[j]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) fl[y] = f_incl;
+  }
+  if (y == 0) {
+#pragma unroll
+    for (int j = 0; j < PREFIX_CPT; ++j)
+      if (live[j]) __stcs(table + p0 + (long long)j * PREFIX_BLOCK, 0.0);  // row 0
+  }
+  double* out = table + (long long)(t0 + 1) * R + p0;
+  for (int t = 0; t < len; ++t) {
+#pragma unroll
+    for (int j = 0; j < PREFIX_CPT; ++j) {
+      acc[j] = fma(sv[t * W + ca[j]], sv[t * W + cb[j]], acc[j]);
+      if (live[j]) __stcs(out + (long long)j * PREFIX_BLOCK, acc[j]);  // streaming store: the table is far larger than L2
+    }
+    out += R;
+  }
+}
+
 // =====================================================================================================
 // Kernel 2 — batched scorer (replaces marginalLikelihood.py:91-166)
 // =====================================================================================================
@@ -304,6 +438,10 @@ struct dbn_handle {
   double* d_V = nullptr;
   unsigned short *d_colA = nullptr, *d_colB = nullptr;
   double* d_chunk = nullptr;
+  double* d_incl = nullptr;      // one-pass build: inclusive prefixes per (chunk, column), beside the aggregates in d_chunk
+  unsigned* d_flags = nullptr;   // [column tiles][chunks], generation-stamped
+  unsigned* d_ticket = nullptr;
+  unsigned prefix_gen = 0;
   double* d_table = nullptr;
 
   bool have_stats = false;
@@ -446,6 +584,9 @@ static void free_stats(dbn_handle* h) {
   free_dev(h->d_colA);
   free_dev(h->d_colB);
   free_dev(h->d_chunk);
+  free_dev(h->d_incl);
+  free_dev(h->d_flags);
+  free_dev(h->d_ticket);
   free_dev(h->d_table);
   h->have_stats = false;
 }
@@ -529,6 +670,9 @@ static int layout_columns(dbn_handle* h) {
   free_dev(h->d_colA);
   free_dev(h->d_colB);
   free_dev(h->d_chunk);
+  free_dev(h->d_incl);
+  free_dev(h->d_flags);
+  free_dev(h->d_ticket);
   free_dev(h->d_table);
   const int nv = h->nv, N = h->N;
   h->R = (long long)h->zz_size + (long long)h->tnn * (nv + 2);
@@ -554,6 +698,18 @@ static int layout_columns(dbn_handle* h) {
   CU(h, cudaMalloc(&h->d_colA, (size_t)h->R * sizeof(unsigned short)));
   CU(h, cudaMalloc(&h->d_colB, (size_t)h->R * sizeof(unsigned short)));
   CU(h, cudaMalloc(&h->d_chunk, (size_t)h->n_chunks * h->R * sizeof(double)));
+  // The one-pass build (prefix_onepass_kernel) is kept as a tested alternative, not the default: on one B200 it takes 0.083 ms
+  // against 0.0765 ms for the three-launch build on configs[3] and 12.0 against 8.3 ms at configs[4] size
+  // (profiles/r2_prefix/onepass_ab.txt): every block of a wave is in its prologue (totals, flags, look-back: ~8 us of dependent L2
+  // round trips) at the same time, so the prologues are not hidden behind other blocks' stores, and at n = 500 only two blocks fit an SM.
+  if (getenv("DBN_PREFIX_ONEPASS")) {
+    CU(h, cudaMalloc(&h->d_incl, (size_t)h->n_chunks * h->R * sizeof(double)));
+    const size_t ntx = (size_t)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT));
+    CU(h, cudaMalloc(&h->d_flags, ntx * h->n_chunks * sizeof(unsigned)));
+    CU(h, cudaMemsetAsync(h->d_flags, 0, ntx * h->n_chunks * sizeof(unsigned), h->stream));
+    CU(h, cudaMalloc(&h->d_ticket, sizeof(unsigned)));
+    h->prefix_gen = 0;
+  }
   cudaError_t e = cudaMalloc(&h->d_table, (size_t)(N + 1) * h->R * sizeof(double));
   if (e != cudaSuccess) DBN_FAIL(h, DBN_ERR_NOMEM, "prefix table of %.2f GB does not fit: %s", (double)(N + 1) * h->R * 8 / 1e9, cudaGetErrorString(e));
   CU(h, cudaMemcpyAsync(h->d_colA, ca.data(), (size_t)h->R * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
@@ -569,11 +725,23 @@ static int launch_prefix(dbn_handle* h) {
     // walked five elements each in sequence (8.5 us for 400 k elements, now 5.9)
     const long long total = (long long)N * W;
     const unsigned gv = (unsigned)std::min<long long>((total + 255) / 256, 148ll * 16);
-    build_v_kernel<<<gv, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, h->d_xpos, N, n, h->lag, h->d_V);
+    build_v_kernel<<<gv, 256, 0, h->stream>>>(h->d_raw, h->d_xrow, h->d_xpos, N, n, h->lag, h->d_V, h->d_ticket);
     CU(h, cudaGetLastError());
   }
   const size_t smem = (size_t)h->Lc * W * sizeof(double);
   dim3 grid((unsigned)((h->R + PREFIX_BLOCK * PREFIX_CPT - 1) / (PREFIX_BLOCK * PREFIX_CPT)), (unsigned)h->n_chunks);
+  if (h->d_incl) {   // DBN_PREFIX_ONEPASS: one launch for totals, look-back offsets and the write stream (measured slower, see below)
+    h->prefix_gen = (h->prefix_gen + 1) & 0x3fffffffu;
+    if (h->prefix_gen == 0) {          // the generation wrapped: old stamps could be mistaken for new ones
+      CU(h, cudaMemsetAsync(h->d_flags, 0, (size_t)grid.x * grid.y * sizeof(unsigned), h->stream));
+      h->prefix_gen = 1;
+    }
+    prefix_onepass_kernel<<<grid.x * grid.y, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, (int)grid.x,
+                                                                               h->n_chunks, h->prefix_gen, h->d_ticket, h->d_flags, h->d_chunk,
+                                                                               h->d_incl, h->d_table);
+    CU(h, cudaGetLastError());
+    return DBN_OK;
+  }
   if (getenv("DBN_PREFIX_OLD_TOTALS")) {   // round-1 totals pass (A/B)
     prefix_kernel<false><<<grid, PREFIX_BLOCK, smem, h->stream>>>(h->d_V, h->d_colA, h->d_colB, N, W, h->R, h->Lc, h->d_chunk, h->d_table);
   } else {
@@ -646,6 +814,7 @@ int dbn_build_stats(dbn_handle* h, const double* data, const int32_t* seg_len, i
     CU(h, cudaFuncSetAttribute(prefix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaFuncSetAttribute(prefix_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaFuncSetAttribute(chunk_totals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
+    CU(h, cudaFuncSetAttribute(prefix_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Lc * row_bytes)));
     CU(h, cudaMalloc(&h->d_raw, (size_t)rows * n * sizeof(double)));
     CU(h, cudaMalloc(&h->d_xrow, (size_t)N * sizeof(int)));
     CU(h, cudaMalloc(&h->d_xpos, (size_t)N * sizeof(int)));

@@ -1,5 +1,5 @@
 """Development aid: device time of the prefix build (kernel 1) on BASELINE configs[3] (CUDA events, best and median of 30),
-for the single-launch build and, with DBN_PREFIX_FUSED=0, the round-1 three-launch build."""
+for the default three-launch build and, with DBN_PREFIX_ONEPASS=1, the one-launch build (decoupled look-back)."""
 import sys, os
 sys.path.insert(0, '.')
 import numpy as np
@@ -20,6 +20,6 @@ info = e.stats_info()
 zz, zy, yy = e.stats_row(info['N'])
 X = data[:-1]; Z = np.concatenate([np.ones((X.shape[0], 1)), X], axis=1)
 ok = np.allclose(zz, Z.T @ Z, rtol=1e-11, atol=1e-9) and np.allclose(yy, (data[1:] ** 2).sum(axis=0), rtol=1e-11)
-print('n=%d T=%d fused=%s Lc=%s: prefix rebuild best %.4f ms median %.4f ms -> %.1f / %.1f GB/s algorithmic (%.1f MB); last row ok: %s' % (
-    n, T, os.environ.get('DBN_PREFIX_FUSED', '1'), os.environ.get('DBN_PREFIX_LC'), min(ts), float(np.median(ts)),
+print('n=%d T=%d onepass=%s Lc=%s: prefix rebuild best %.4f ms median %.4f ms -> %.1f / %.1f GB/s algorithmic (%.1f MB); last row ok: %s' % (
+    n, T, os.environ.get('DBN_PREFIX_ONEPASS', '0'), os.environ.get('DBN_PREFIX_LC'), min(ts), float(np.median(ts)),
     info['algorithmic_bytes'] / min(ts) / 1e6, info['algorithmic_bytes'] / float(np.median(ts)) / 1e6, info['algorithmic_bytes'] / 1e6, ok))

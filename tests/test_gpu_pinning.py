@@ -363,3 +363,36 @@ def test_score_batch_device_time(eng_mod):
             tau = [[e.N + 2]] * B
             out = e.score_batch(node, pi, tau, 1.0)
             assert np.isfinite(out).all() and e.score_batch_ms() > 0.0
+
+
+@pytest.mark.parametrize('shape', [(100, 2000), (20, 3001), (7, 130)], ids=lambda s: 'n%d_T%d' % s)
+def test_one_pass_prefix_build_equals_three_pass_build(eng_mod, shape, monkeypatch):
+    """The one-launch prefix build (DBN_PREFIX_ONEPASS: chunk offsets by decoupled look-back inside the write pass; measured slower
+    than the default and kept as an alternative) writes the same bits as the three-launch build (totals, scan, write): both add chunk aggregates to the left in chunk order.  63 / 94 / 5 chunks: two,
+    three and one look-back windows; with a unit range (fewer column tiles) as well; rebuilt several times (generation stamps)."""
+    from dynamicbayesiannetworks_b200.synth import make_synthetic
+    n, T = shape
+    data, _, _ = make_synthetic(n, T, 3, min(4, n - 1), 7)
+    X, Y = O.lagged_matrices([data])
+    N = X.shape[0]
+    Z = np.concatenate([np.ones((N, 1)), X], axis=1)
+    ts = sorted({0, 1, 31, 32, 33, 64, N // 2, N - 33, N - 1, N} & set(range(N + 1)))
+    for rng in (None, (n + 1, 2 * n - 1)):      # unit range: 3 chains per node, units n + 1 .. 3 n - 1 = nodes (n + 1) // 3 .. n - 1
+        monkeypatch.setenv('DBN_PREFIX_ONEPASS', '1')      # read when the table is laid out
+        with eng_mod(n_chains=3, unit_range=rng) as e:
+            e.build_stats([data])
+            for _ in range(3):
+                e.rebuild_stats()
+            one = [e.stats_row(t) for t in ts]
+        monkeypatch.delenv('DBN_PREFIX_ONEPASS')
+        with eng_mod(n_chains=3, unit_range=rng) as e:
+            e.build_stats([data])
+            three = [e.stats_row(t) for t in ts]
+        for t, a, b in zip(ts, one, three):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (shape, rng, t)
+        zz, zy, yy = one[-1]
+        assert_close(zz, Z.T @ Z, 1e-12, 1e-12, what='ZZ[N]')
+        if rng is None:
+            assert_close(zy, (Z.T @ Y).T, 1e-12, 1e-12, what='ZY[N]')
+            assert_close(yy, (Y ** 2).sum(axis=0), 1e-12, 1e-12, what='YY[N]')
