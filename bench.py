@@ -379,7 +379,7 @@ def main():
         # end-to-end read that waits for the reduced counts
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                                 pg_options=parallel.nccl_small_footprint_options(NCCL_OVERLAP_CTAS))
-        wide = dist.new_group(backend='nccl')
+        wide = dist.new_group(backend='nccl')   # (a high-priority NCCL stream for this group was measured at N = 2: no difference)
     K = args.steps
     W = max(3, args.warmup, (BURN_IN_ITERATIONS + WINDOW - 1) // WINDOW)   # >= 200 untimed iterations: a stationary timed region
 
