@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 
   // start the asynchronous copy of cached row j into staging buffer `buf` (the caller commits)
   auto issue_row = [&](int j, int buf) {
-    DBN_CHECK(j >= 0 && j < BSLOTS && buf >= 0 && buf < 2, 2);
+    DBN_CHECK(j >= 0 && j < BSLOTS && buf >= 0 && buf < 3, 2);
     const double* src = crow(j);
     double* dst = sbuf + buf * BUF;
 #pragma unroll
@@ -268,9 +268,18 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     ++n_fact;
   };
 
-  // row 0 of the first Gibbs sweep (every later iteration requests it at its end)
+  // rows 0 and 1 of the first Gibbs sweep, one copy group each (every later iteration requests them at its end).  The Gibbs sweep
+  // keeps TWO rows in flight (the third staging buffer is free until the proposals are drawn): one row ahead, a step waited
+  // for most of an HBM round trip at its top (6.9 % of all stall samples on that line, profiles/r2_b/stalls.txt); measured
+  // 1.271 -> 1.254 ms per step (profiles/r2_small/gibbs_two_rows_in_flight.txt).  The same depth in the parent-set sweep needs
+  // a fourth row buffer and a second candidate slot (99 KB of shared memory per block) and was 19 % SLOWER: the carve-out grows
+  // from 164 to 228 KB and the L1 that serves the scattered table reads shrinks from 92 to 28 KB.
   if (S > 0) issue_row(0, 0);
   cp_async_commit();
+#ifndef DBN_GIBBS_SHALLOW
+  if (S > 1) issue_row(1, 1);
+  cp_async_commit();
+#endif
 
   for (int li = 0; li < a.n_iter; ++li) {
     const int it = a.it0 + li;
@@ -315,10 +324,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     {
       float4 z5 = make_float4(0.f, 0.f, 0.f, 0.f);  // KM = 5: the fifth normal of four consecutive segments
       int bprev = 0;
+#ifndef DBN_GIBBS_SHALLOW
+      int bi = 0;  // h mod 3: row h sits in staging buffer bi, row h - 1 in the one before it (cyclically)
+#endif
       for (int h = 0; h < S; ++h) {
+#ifndef DBN_GIBBS_SHALLOW
+        cp_async_wait<1>();   // row h has landed; row h + 1 may still be on its way
+        const int bp = (bi == 0) ? 2 : bi - 1;
+        const double* sr = sbuf + bi * BUF;
+        const double* sp = sbuf + bp * BUF;
+#else
         cp_async_wait<0>();
         const double* sr = sbuf + (h & 1) * BUF;
         const double* sp = sbuf + ((h & 1) ^ 1) * BUF;
+#endif
         const bool hp = h > 0;
         const int bcur = bnd(h);
         double G[KT], g[KM], s, A[KT], dinv[KM], rs[KM], wv[KM];
@@ -329,7 +348,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
 #pragma unroll
         for (int i = 0; i < KM; ++i) g[i] = DBN_SE(sr, E_ZY + i) - (hp ? DBN_SE(sp, E_ZY + i) : 0.0);
         s = DBN_SE(sr, E_YY) - (hp ? DBN_SE(sp, E_YY) : 0.0);
+#ifndef DBN_GIBBS_SHALLOW
+        if (h + 2 < S) issue_row(h + 2, bp);   // into the buffer of row h - 1, whose values are in registers now
+        bi = (bi == 2) ? 0 : bi + 1;
+#else
         if (h + 1 < S) issue_row(h + 1, (h + 1) & 1);
+#endif
         cp_async_commit();
         form_a<KM>(G, lam, A);
         ldl_factor_rs<KM>(A, dinv, rs);
@@ -1013,6 +1037,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
     // row 0 of the next iteration's Gibbs sweep (after this iteration's own updates of the cached rows)
     if (S > 0 && li + 1 < a.n_iter) issue_row(0, 0);
     cp_async_commit();
+#ifndef DBN_GIBBS_SHALLOW
+    if (S > 1 && li + 1 < a.n_iter) issue_row(1, 1);
+    cp_async_commit();
+#endif
   }
   cp_async_wait<0>();
 
