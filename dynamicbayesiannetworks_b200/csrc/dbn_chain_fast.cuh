@@ -272,8 +272,9 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   // keeps TWO rows in flight (the third staging buffer is free until the proposals are drawn): one row ahead, a step waited
   // for most of an HBM round trip at its top (6.9 % of all stall samples on that line, profiles/r2_b/stalls.txt); measured
   // 1.271 -> 1.254 ms per step (profiles/r2_small/gibbs_two_rows_in_flight.txt).  The same depth in the parent-set sweep needs
-  // a fourth row buffer and a second candidate slot (99 KB of shared memory per block) and was 19 % SLOWER: the carve-out grows
-  // from 164 to 228 KB and the L1 that serves the scattered table reads shrinks from 92 to 28 KB.
+  // a fourth row buffer and a second candidate slot (99 KB of shared memory per block) and was 19 % SLOWER.  What changes with it
+  // is the carve-out (164 -> 228 KB, L1 92 -> 28 KB); the kernel's L1 hit rate is only 1.5 % (profiles/r2_b), so it is not cache
+  // hits that are lost -- the mechanism was not investigated further.
   if (S > 0) issue_row(0, 0);
   cp_async_commit();
 #ifndef DBN_GIBBS_SHALLOW
