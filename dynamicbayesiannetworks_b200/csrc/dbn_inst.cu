@@ -22,12 +22,17 @@
 #include "dbn_fp.cuh"
 #endif
 
+#include <cstdlib>
 namespace dbn {
 
 template <class Fn, class Args>
 static cudaError_t launch_(Fn fn, unsigned grid, int block, size_t smem, cudaStream_t s, const Args& a) {
   if (smem > 16 * 1024) {   // static + dynamic shared memory above 48 KB needs the opt-in as well (the var-glob kernel has 20 KB static)
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (const char* c = getenv("DBN_CARVEOUT")) {   // experiment knob: preferred shared-memory carve-out in percent (profiles/r2_small)
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
     if (e != cudaSuccess) return e;
   }
   fn<<<grid, block, smem, s>>>(a);
