@@ -598,7 +598,7 @@ def main():
         # bound: the nearest roofline of the two the contract names.  frac = ALGORITHMIC bytes (16 (k(k+1)/2 + k + 1)
         # per executed segment evaluation, counted on the device) / time / measured HBM peak.  The kernel does not move
         # those bytes: unchanged segments come from the per-unit boundary-row cache, so the DRAM traffic ncu measures
-        # (traffic, dram_frac) is lower, and what limits the kernel is dependent-issue latency at 8 warps per SM (236 registers per thread) plus
+        # (traffic, dram_frac) is lower, and what limits the kernel is dependent-issue latency at 8 warps per SM (255 registers per thread) plus
         # instruction delivery (limiter, issue_active_pct; profiles/r2_notes.md).
         'roofline': {'kernel': 'chain_fast_kernel<nh-dbn, KM=5>', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peak_kind,

@@ -39,7 +39,7 @@
 
 namespace dbn {
 
-// Block shape = register budget.  The step needs 236 registers per thread; 2 x 192 threads per SM (rounds 1 and 2a: 12 warps,
+// Block shape = register budget.  The step needs 236 registers per thread (255 with two rows in flight in the Gibbs sweep); 2 x 192 threads per SM (rounds 1 and 2a: 12 warps,
 // every shape tried there kept ~12 warps) caps it at 168 and spills.  2 x 128 threads (8 warps per SM, no spills) is 16 % faster
 // on the bench workload with one handle and 17 % with two (7.2e8 / 8.0e8 against 6.2e8 / 6.8e8 unit-iterations/s), and the
 // end-to-end step gains 13 %: profiles/r2_small/block_shape_handles_ab2.txt (64 x 4, 96 x 2, 96 x 3, 112 x 2, 144 x 2, 160 x 2,
