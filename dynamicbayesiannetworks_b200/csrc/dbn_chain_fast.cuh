@@ -68,8 +68,18 @@ struct FastDims {
 // entries of a pair are adjacent, so a row moves as NP 16-byte copies per thread, consecutive threads 16 bytes apart.
 // Entry ids: ZZ(i, j) (i >= j, not both 0) -> DBN_TRI(i, j) - 1; ZY(i) -> KT - 1 + i; YY -> KT - 1 + KM.
 __host__ __device__ inline int fast_cache_row_doubles(int km) { return km * (km + 1) / 2 + km; }
+// The candidate column of the parent-set sweep (<= 6 scattered 8-byte table reads per boundary, the line with 45 % of all
+// long-scoreboard samples in profiles/r2_c/stalls.txt) is requested TWO steps ahead into two alternating slots; the cached rows
+// stay one step ahead (deeper row staging was measured twice and lost).  1.2614 -> 1.2426 ms per step with two handles, 1.4188 ->
+// 1.3815 with one (profiles/r2_small/gibbs_two_rows_in_flight.txt); 78 848 bytes of shared memory per block, still the 164 KB carve-out.
+#ifndef DBN_CAND_SHALLOW
+constexpr int FAST_CAND_SLOTS = 2;
+#else
+constexpr int FAST_CAND_SLOTS = 1;
+#endif
 inline size_t fast_smem_bytes(int km) {
-  return (size_t)(3 * fast_cache_row_doubles(km) + km + 1) * FAST_BLOCK * sizeof(double) + (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(unsigned short);
+  return (size_t)(3 * fast_cache_row_doubles(km) + FAST_CAND_SLOTS * (km + 1)) * FAST_BLOCK * sizeof(double) +
+         (size_t)2 * DBN_SMAX * FAST_BLOCK * sizeof(unsigned short);
 }
 #define DBN_EZZ(i, j) (DBN_TRI(i, j) - 1)
 // entry e of a row whose pair 0 is at `p` (global: pair stride = 2 * U doubles; shared staging: 2 * FAST_BLOCK doubles)
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
   double* const s_row = s_dyn;
   constexpr int BUF = (2 * NP) * FAST_BLOCK;  // doubles per staging buffer
   double* const s_cand = s_dyn + 3 * BUF;
-  unsigned short* const s_tau = reinterpret_cast<unsigned short*>(s_cand + NC * FAST_BLOCK);
+  unsigned short* const s_tau = reinterpret_cast<unsigned short*>(s_cand + FAST_CAND_SLOTS * NC * FAST_BLOCK);
   unsigned short* const s_tas = s_tau + SMAX * FAST_BLOCK;
   const int tid = threadIdx.x;
   __shared__ unsigned long long s_tot[8];  // work counters of the block
@@ -682,7 +692,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       o2d = has_new ? cf * (cf + 1) / 2 + cf : -1;
       o2y = has_new ? nb + cf : -1;
       // request the candidate column (<= KM + 1 table entries) at table row t into the slot `cand`
-      auto request_cand = [&](int t) {
+      auto request_cand = [&](int t, int slot) {
+        double* const cand = s_cand + tid + slot * (NC * FAST_BLOCK);
         DBN_CHECK(t >= 0 && t <= N, 3);
         DBN_CHECK(o2d >= 0 && o2d < a.tb.zz_size && o2y >= a.tb.zz_size && o2y < a.tb.row_stride, 4);
 #pragma unroll
@@ -696,9 +707,13 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       };
       // with row 0 (requested after the Gibbs sweep): the candidate column at the first boundary and the new boundary
       // row of the changepoint proposal (into the third staging buffer, where it stays until the changepoint move)
-      if (has_new && S > 0) request_cand(bnd(0));
+      if (has_new && S > 0) request_cand(bnd(0), 0);
       if (t_new) request_row(trow, b2);
       cp_async_commit();
+#ifndef DBN_CAND_SHALLOW
+      if (has_new && S > 1) request_cand(bnd(1), 1);
+      cp_async_commit();
+#endif
 #ifdef DBN_LATE_DRAWS   // the scattered requests above are in flight while the two gamma variates are drawn
       draw_sigma_lambda();
 #endif
@@ -711,7 +726,12 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
       for (int i = 0; i < KB + 2; ++i) n_prev[i] = 0.0;
       int bprev = 0;
       for (int h = 0; h < S; ++h) {
+#ifndef DBN_CAND_SHALLOW
+        cp_async_wait<1>();   // row h and candidate column h have landed; candidate column h + 1 (the newest group) may not have
+        const double* const cand = s_cand + tid + (h & 1) * (NC * FAST_BLOCK);
+#else
         cp_async_wait<0>();
+#endif
         const double* sr = sbuf + (h & 1) * BUF;
         const double* sp = sbuf + ((h & 1) ^ 1) * BUF;
         const bool hp = h > 0;
@@ -748,11 +768,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, DBN_FAST_MINB) chain_fast_kernel(c
         }
         // this step's operands are in registers: request the next step's (row h + 1 into the buffer of row h - 1, the
         // candidate column at boundary h + 1 into its slot)
+#ifndef DBN_CAND_SHALLOW
+        // two groups per step, the row first: wait<1> at the top of step h + 1 then covers row h + 1 and every older group
+        // (candidate column h + 1 among them) and leaves only the newest one, candidate column h + 2, in flight
+        if (h + 1 < S) issue_row(h + 1, (h + 1) & 1);
+        cp_async_commit();
+        if (has_new && h + 2 < S) request_cand(bnd(h + 2), h & 1);   // this step's slot is free: its values are in registers
+        cp_async_commit();
+#else
         if (h + 1 < S) {
           issue_row(h + 1, (h + 1) & 1);
-          if (has_new) request_cand(bnd(h + 1));
+          if (has_new) request_cand(bnd(h + 1), 0);
         }
         cp_async_commit();
+#endif
         // base factorisation of A_B = I + lam G_B
 #pragma unroll
         for (int p = 0; p < KB; ++p)
